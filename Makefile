@@ -1,0 +1,22 @@
+# Build the sm_100a CUDA library (C-ABI) and the CPU oracle.  nvcc cross-compiles without a GPU.
+NVCC      ?= nvcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function --expt-relaxed-constexpr -Iinclude -Icrazyara_b200/csrc
+CSRC      := crazyara_b200/csrc
+CU_SRCS   := $(wildcard $(CSRC)/*.cu)
+CU_OBJS   := $(patsubst $(CSRC)/%.cu,build/%.o,$(CU_SRCS))
+LIB       := crazyara_b200/libara_b200.so
+
+all: $(LIB)
+
+build/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) $(wildcard include/*.h)
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(LIB): $(CU_OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $^
+
+clean:
+	rm -rf build $(LIB)
+
+.PHONY: all clean

@@ -1,0 +1,439 @@
+// RISE network: blob loader, weight re-layout for the tcgen05 GEMMs, forward launch sequence, C-ABI.
+#include "net.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+
+#include "ara_b200.h"
+#include "net_kernels.cuh"
+
+namespace ara {
+
+namespace {
+
+struct BlobReader {
+    FILE* f = nullptr;
+    ~BlobReader() {
+        if (f) fclose(f);
+    }
+    bool read(void* dst, size_t bytes) { return fread(dst, 1, bytes, f) == bytes; }
+    bool tensor(std::vector<float>& out, size_t expect) {
+        long long count = 0;
+        if (!read(&count, 8)) return false;
+        if (static_cast<size_t>(count) != expect) {
+            set_error("weight blob: tensor has %lld values, expected %zu", count, expect);
+            return false;
+        }
+        out.resize(expect);
+        return read(out.data(), expect * 4);
+    }
+};
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+}  // namespace
+
+template <typename T>
+int Net::dalloc(T** p, size_t count) {
+    void* q = nullptr;
+    ARA_CUDA_OK(cudaMalloc(&q, count * sizeof(T)));
+    ARA_CUDA_OK(cudaMemset(q, 0, count * sizeof(T)));
+    allocs_.push_back(q);
+    *p = static_cast<T*>(q);
+    return 0;
+}
+
+int Net::upload_f32(const float* src, size_t count, size_t padded, float** dst) {
+    if (dalloc(dst, padded) != 0) return -1;
+    ARA_CUDA_OK(cudaMemcpy(*dst, src, count * 4, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// w: [n_out, cin, k, k] fp32 -> fp16 [rows, taps * cw], column = tap * cw + c, rows padded to 256.
+int Net::upload_conv_w(const float* w, int n_out, int cin, int ksize, __half** dst, int* rows) {
+    const int taps = ksize * ksize;
+    const int cw = round_up(cin, 64);
+    const int r = round_up(n_out, 256);
+    std::vector<__half> h(static_cast<size_t>(r) * taps * cw, __float2half(0.0f));
+    for (int n = 0; n < n_out; ++n)
+        for (int c = 0; c < cin; ++c)
+            for (int t = 0; t < taps; ++t)
+                h[(static_cast<size_t>(n) * taps + t) * cw + c] = __float2half_rn(w[(static_cast<size_t>(n) * cin + c) * taps + t]);
+    if (dalloc(dst, h.size()) != 0) return -1;
+    ARA_CUDA_OK(cudaMemcpy(*dst, h.data(), h.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    *rows = r;
+    return 0;
+}
+
+Net::~Net() {
+    cudaSetDevice(device);
+    for (int k = 0; k < 2; ++k)
+        for (auto& g : graphs_[k]) cudaGraphExecDestroy(g.second);
+    for (void* p : allocs_) cudaFree(p);
+    if (stream) cudaStreamDestroy(stream);
+}
+
+int Net::init(const char* blob_path, int dev, int batch_size) {
+    device = dev;
+    batch = batch_size;
+    if (batch < 1) return set_error("ara_net_create: batch %d < 1", batch);
+    batch_cap = round_up(batch < 2 ? 2 : batch, 2);
+    ARA_CUDA_OK(cudaSetDevice(device));
+    {
+        cudaDeviceProp prop;
+        ARA_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10)
+            return set_error("ara_net_create: device %d is sm_%d%d; this library only runs on sm_100a (B200)", device,
+                             prop.major, prop.minor);
+    }
+    ARA_CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    const char* g = getenv("ARA_NO_GRAPH");
+    use_graph = !(g != nullptr && g[0] == '1');
+
+    BlobReader rd;
+    rd.f = fopen(blob_path, "rb");
+    if (!rd.f) return set_error("ara_net_create: cannot open weight blob '%s'", blob_path);
+    char magic[8];
+    if (!rd.read(magic, 8) || memcmp(magic, "ARAB2001", 8) != 0)
+        return set_error("ara_net_create: '%s' is not an ARAB2001 weight blob", blob_path);
+    int h[8];
+    if (!rd.read(h, sizeof(h))) return set_error("ara_net_create: truncated header");
+    hdr.in_channels = h[0];
+    hdr.policy_channels = h[1];
+    hdr.n_blocks = h[2];
+    hdr.channels = h[3];
+    hdr.value_channels = h[4];
+    hdr.value_fc = h[5];
+    hdr.wdl_mode = h[6];
+    hdr.input_version = h[7];
+    if (hdr.channels != 256 || hdr.value_channels != 8 || hdr.value_fc != 256)
+        return set_error("ara_net_create: unsupported trunk geometry (channels %d, value %d/%d)", hdr.channels,
+                         hdr.value_channels, hdr.value_fc);
+    if (hdr.n_blocks < 1 || hdr.n_blocks > 64 || hdr.in_channels < 1 || hdr.in_channels > 256 ||
+        hdr.policy_channels < 1 || hdr.policy_channels > 256)
+        return set_error("ara_net_create: implausible header");
+    blocks.resize(hdr.n_blocks);
+    int max_cop = 0;
+    for (auto& b : blocks) {
+        int t[3];
+        if (!rd.read(t, sizeof(t))) return set_error("ara_net_create: truncated block table");
+        b.c_op = t[0];
+        b.kernel = t[1];
+        b.se_type = t[2];
+        if (b.c_op % 32 != 0 || b.c_op < 32 || (b.kernel != 3 && b.kernel != 5) || b.se_type < 0 || b.se_type > 2)
+            return set_error("ara_net_create: unsupported block (c_op %d kernel %d se %d)", b.c_op, b.kernel, b.se_type);
+        if (b.c_op > max_cop) max_cop = b.c_op;
+    }
+    cin_pad = round_up(hdr.in_channels, 64);
+    ldp = round_up(hdr.policy_channels, 32);
+    const int C = hdr.channels;
+    const size_t rows = static_cast<size_t>(batch_cap) * 64;
+
+    // activation buffers
+    if (dalloc(&d_in_f32, static_cast<size_t>(batch) * hdr.in_channels * 64)) return -1;
+    if (dalloc(&d_in_h, rows * cin_pad)) return -1;
+    if (dalloc(&d_x[0], rows * C)) return -1;
+    if (dalloc(&d_x[1], rows * C)) return -1;
+    if (dalloc(&d_h1, rows * max_cop)) return -1;
+    if (dalloc(&d_h2, rows * max_cop)) return -1;
+    if (dalloc(&d_p1, rows * C)) return -1;
+    if (dalloc(&d_logits, rows * ldp)) return -1;
+    if (dalloc(&d_prob, static_cast<size_t>(batch) * n_labels())) return -1;
+    if (dalloc(&d_value, batch)) return -1;
+    if (dalloc(&d_aux, static_cast<size_t>(batch) * 4)) return -1;
+
+    std::vector<float> t, t2;
+    int wrows = 0;
+    // stem
+    if (!rd.tensor(t, static_cast<size_t>(C) * hdr.in_channels * 9)) return -1;
+    if (upload_conv_w(t.data(), C, hdr.in_channels, 3, &stem_w, &wrows)) return -1;
+    if (!rd.tensor(t, C)) return -1;
+    if (upload_f32(t.data(), C, 256, &stem_b)) return -1;
+    {
+        const int bn = conv_layer_choose_bn(batch, C);
+        if (conv_layer_init(&stem_conv, d_in_h, batch_cap, cin_pad, stem_w, wrows, C, 3, stem_b, 1, nullptr, 0, d_x[0],
+                            nullptr, C, bn))
+            return -1;
+    }
+    bw_.resize(hdr.n_blocks);
+    for (int i = 0; i < hdr.n_blocks; ++i) {
+        const BlockDesc& bd = blocks[i];
+        BlockW& w = bw_[i];
+        __half* xin = d_x[i & 1];
+        __half* xout = d_x[(i + 1) & 1];
+        if (bd.se_type == 1) {
+            if (!rd.tensor(t, 128 * 256)) return -1;  // fc1 [128][256]
+            t2.assign(256 * 128, 0.f);
+            for (int j = 0; j < 128; ++j)
+                for (int k = 0; k < 256; ++k) t2[k * 128 + j] = t[j * 256 + k];
+            if (upload_f32(t2.data(), t2.size(), t2.size(), &w.se_w1t)) return -1;
+            if (!rd.tensor(t, 256 * 128)) return -1;  // fc2 [256][128]
+            t2.assign(128 * 256, 0.f);
+            for (int c = 0; c < 256; ++c)
+                for (int j = 0; j < 128; ++j) t2[j * 256 + c] = t[c * 128 + j];
+            if (upload_f32(t2.data(), t2.size(), t2.size(), &w.se_w2t)) return -1;
+        } else if (bd.se_type == 2) {
+            if (!rd.tensor(t, 256 * 256)) return -1;  // centre tap [out][in]
+            t2.assign(256 * 256, 0.f);
+            for (int c = 0; c < 256; ++c)
+                for (int k = 0; k < 256; ++k) t2[k * 256 + c] = t[c * 256 + k];
+            if (upload_f32(t2.data(), t2.size(), t2.size(), &w.se_w1t)) return -1;
+            if (!rd.tensor(t, 256)) return -1;
+            if (upload_f32(t.data(), 256, 256, &w.se_b)) return -1;
+        }
+        // conv1 1x1 256 -> c_op (+ReLU)
+        if (!rd.tensor(t, static_cast<size_t>(bd.c_op) * C)) return -1;
+        if (upload_conv_w(t.data(), bd.c_op, C, 1, &w.w1, &wrows)) return -1;
+        if (!rd.tensor(t, bd.c_op)) return -1;
+        if (upload_f32(t.data(), bd.c_op, round_up(bd.c_op, 256), &w.b1)) return -1;
+        {
+            const int bn = conv_layer_choose_bn(batch, bd.c_op);
+            if (conv_layer_init(&w.conv1, xin, batch_cap, C, w.w1, wrows, bd.c_op, 1, w.b1, 1, nullptr, 0, d_h1, nullptr,
+                                bd.c_op, bn))
+                return -1;
+        }
+        // depthwise k x k: blob [c_op][k][k] -> device [k*k][c_op]
+        const int kk = bd.kernel * bd.kernel;
+        if (!rd.tensor(t, static_cast<size_t>(bd.c_op) * kk)) return -1;
+        t2.assign(static_cast<size_t>(kk) * bd.c_op, 0.f);
+        for (int c = 0; c < bd.c_op; ++c)
+            for (int q = 0; q < kk; ++q) t2[static_cast<size_t>(q) * bd.c_op + c] = t[static_cast<size_t>(c) * kk + q];
+        if (upload_f32(t2.data(), t2.size(), t2.size(), &w.wd)) return -1;
+        if (!rd.tensor(t, bd.c_op)) return -1;
+        if (upload_f32(t.data(), bd.c_op, bd.c_op, &w.bd)) return -1;
+        // conv2 1x1 c_op -> 256 (+residual)
+        if (!rd.tensor(t, static_cast<size_t>(C) * bd.c_op)) return -1;
+        if (upload_conv_w(t.data(), C, bd.c_op, 1, &w.w2, &wrows)) return -1;
+        if (!rd.tensor(t, C)) return -1;
+        if (upload_f32(t.data(), C, 256, &w.b2)) return -1;
+        {
+            const int bn = conv_layer_choose_bn(batch, C);
+            if (conv_layer_init(&w.conv2, d_h2, batch_cap, bd.c_op, w.w2, wrows, C, 1, w.b2, 0, xin, C, xout, nullptr, C,
+                                bn))
+                return -1;
+        }
+    }
+    __half* xfinal = d_x[hdr.n_blocks & 1];
+    // value head
+    if (!rd.tensor(t, 8 * 256)) return -1;
+    if (upload_f32(t.data(), t.size(), t.size(), &vh_wv)) return -1;
+    if (!rd.tensor(t, 8)) return -1;
+    if (upload_f32(t.data(), 8, 8, &vh_bv)) return -1;
+    if (!hdr.wdl_mode) {
+        if (!rd.tensor(t, 256 * 512)) return -1;  // fc1 [256][512]
+        t2.assign(512 * 256, 0.f);
+        for (int o = 0; o < 256; ++o)
+            for (int i = 0; i < 512; ++i) t2[i * 256 + o] = t[o * 512 + i];
+        if (upload_f32(t2.data(), t2.size(), t2.size(), &vh_w1t)) return -1;
+        if (!rd.tensor(t, 256)) return -1;
+        if (upload_f32(t.data(), 256, 256, &vh_b1)) return -1;
+        if (!rd.tensor(t, 256)) return -1;
+        if (upload_f32(t.data(), 256, 256, &vh_w2)) return -1;
+        if (!rd.tensor(t, 1)) return -1;
+        if (upload_f32(t.data(), 1, 1, &vh_b2)) return -1;
+    } else {
+        if (!rd.tensor(t, 3 * 512)) return -1;
+        if (upload_f32(t.data(), t.size(), t.size(), &vh_wdl_w)) return -1;
+        if (!rd.tensor(t, 3)) return -1;
+        if (upload_f32(t.data(), 3, 4, &vh_wdl_b)) return -1;
+        if (!rd.tensor(t, 512)) return -1;
+        if (upload_f32(t.data(), 512, 512, &vh_plys_w)) return -1;
+        if (!rd.tensor(t, 1)) return -1;
+        if (upload_f32(t.data(), 1, 1, &vh_plys_b)) return -1;
+    }
+    // policy head
+    if (!rd.tensor(t, static_cast<size_t>(C) * C * 9)) return -1;
+    if (upload_conv_w(t.data(), C, C, 3, &pol_w1, &wrows)) return -1;
+    if (!rd.tensor(t, C)) return -1;
+    if (upload_f32(t.data(), C, 256, &pol_b1)) return -1;
+    {
+        const int bn = conv_layer_choose_bn(batch, C);
+        if (conv_layer_init(&pol_conv1, xfinal, batch_cap, C, pol_w1, wrows, C, 3, pol_b1, 1, nullptr, 0, d_p1, nullptr, C,
+                            bn))
+            return -1;
+    }
+    if (!rd.tensor(t, static_cast<size_t>(hdr.policy_channels) * C * 9)) return -1;
+    if (upload_conv_w(t.data(), hdr.policy_channels, C, 3, &pol_w2, &wrows)) return -1;
+    {
+        const int bn = conv_layer_choose_bn(batch, hdr.policy_channels);
+        if (conv_layer_init(&pol_conv2, d_p1, batch_cap, C, pol_w2, wrows, hdr.policy_channels, 3, nullptr, 0, nullptr, 0,
+                            nullptr, d_logits, ldp, bn))
+            return -1;
+    }
+    {
+        char tail;
+        if (fread(&tail, 1, 1, rd.f) != 0) return set_error("ara_net_create: trailing bytes in weight blob");
+    }
+    ARA_CUDA_OK(cudaFuncSetAttribute(policy_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     n_labels() * 4));
+    ARA_CUDA_OK(cudaFuncSetAttribute(nchw_f32_to_nhwc_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     hdr.in_channels * 65 * 4));
+    ARA_CUDA_OK(cudaDeviceSynchronize());
+    return 0;
+}
+
+int Net::enqueue(int n, cudaStream_t s, bool from_f32) {
+    if (from_f32) {
+        nchw_f32_to_nhwc_f16_kernel<<<n, 256, hdr.in_channels * 65 * 4, s>>>(d_in_f32, d_in_h, hdr.in_channels, cin_pad);
+        ++launches;
+    }
+    if (conv_layer_launch(&stem_conv, n, s)) return -1;
+    ++launches;
+    for (int i = 0; i < hdr.n_blocks; ++i) {
+        const BlockDesc& bd = blocks[i];
+        BlockW& w = bw_[i];
+        __half* xin = d_x[i & 1];
+        if (bd.se_type != 0) {
+            se_kernel<<<n, 256, 0, s>>>(xin, w.se_w1t, w.se_w2t, w.se_b, bd.se_type);
+            ++launches;
+        }
+        if (conv_layer_launch(&w.conv1, n, s)) return -1;
+        const long long total = static_cast<long long>(n) * 64 * (bd.c_op / 8);
+        const int grid = static_cast<int>((total + 255) / 256);
+        if (bd.kernel == 3)
+            dwconv_kernel<3><<<grid, 256, 0, s>>>(d_h1, w.wd, w.bd, d_h2, n, bd.c_op);
+        else
+            dwconv_kernel<5><<<grid, 256, 0, s>>>(d_h1, w.wd, w.bd, d_h2, n, bd.c_op);
+        if (conv_layer_launch(&w.conv2, n, s)) return -1;
+        launches += 3;
+    }
+    __half* xfinal = d_x[hdr.n_blocks & 1];
+    ValueHeadW vw{vh_wv, vh_bv, vh_w1t, vh_b1, vh_w2, vh_b2, vh_wdl_w, vh_wdl_b, vh_plys_w, vh_plys_b, hdr.wdl_mode};
+    value_head_kernel<<<n, 256, 0, s>>>(xfinal, vw, d_value, d_aux);
+    if (conv_layer_launch(&pol_conv1, n, s)) return -1;
+    if (conv_layer_launch(&pol_conv2, n, s)) return -1;
+    policy_softmax_kernel<<<n, 256, n_labels() * 4, s>>>(d_logits, d_prob, hdr.policy_channels, ldp);
+    launches += 4;
+    ARA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int Net::forward_device(int n, cudaStream_t s) {
+    if (n < 1 || n > batch) return set_error("forward: n=%d outside [1,%d]", n, batch);
+    if (!use_graph) return enqueue(n, s, false);
+    auto it = graphs_[0].find(n);
+    if (it == graphs_[0].end()) {
+        // warm-up launch outside capture (sets function attributes), then capture
+        if (enqueue(n, s, false)) return -1;
+        ARA_CUDA_OK(cudaStreamSynchronize(s));
+        const long long before = launches;
+        cudaGraph_t g;
+        ARA_CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        int rc = enqueue(n, s, false);
+        cudaError_t e = cudaStreamEndCapture(s, &g);
+        launches = before;
+        if (rc) return -1;
+        ARA_CUDA_OK(e);
+        cudaGraphExec_t ge;
+        ARA_CUDA_OK(cudaGraphInstantiate(&ge, g, 0));
+        cudaGraphDestroy(g);
+        it = graphs_[0].emplace(n, ge).first;
+    }
+    ARA_CUDA_OK(cudaGraphLaunch(it->second, s));
+    launches += kernels_per_forward(false);
+    return 0;
+}
+
+int Net::forward_from_f32_device(int n, cudaStream_t s) {
+    if (n < 1 || n > batch) return set_error("forward: n=%d outside [1,%d]", n, batch);
+    if (!use_graph) return enqueue(n, s, true);
+    auto it = graphs_[1].find(n);
+    if (it == graphs_[1].end()) {
+        if (enqueue(n, s, true)) return -1;
+        ARA_CUDA_OK(cudaStreamSynchronize(s));
+        const long long before = launches;
+        cudaGraph_t g;
+        ARA_CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        int rc = enqueue(n, s, true);
+        cudaError_t e = cudaStreamEndCapture(s, &g);
+        launches = before;
+        if (rc) return -1;
+        ARA_CUDA_OK(e);
+        cudaGraphExec_t ge;
+        ARA_CUDA_OK(cudaGraphInstantiate(&ge, g, 0));
+        cudaGraphDestroy(g);
+        it = graphs_[1].emplace(n, ge).first;
+    }
+    ARA_CUDA_OK(cudaGraphLaunch(it->second, s));
+    launches += kernels_per_forward(true);
+    return 0;
+}
+
+int Net::kernels_per_forward(bool from_f32) const {
+    int k = from_f32 ? 1 : 0;
+    k += 1;  // stem
+    for (const auto& b : blocks) k += 3 + (b.se_type != 0 ? 1 : 0);
+    k += 4;  // value head, policy conv x2, softmax
+    return k;
+}
+
+int Net::predict(const float* planes_host, int n, float* value_host, float* prob_host, float* aux_host) {
+    ARA_CUDA_OK(cudaSetDevice(device));
+    if (n < 1 || n > batch) return set_error("ara_net_predict: n=%d outside [1,%d]", n, batch);
+    if (planes_host == nullptr || value_host == nullptr) return set_error("ara_net_predict: null planes/value buffer");
+    ARA_CUDA_OK(cudaMemcpyAsync(d_in_f32, planes_host, static_cast<size_t>(n) * hdr.in_channels * 64 * 4,
+                                cudaMemcpyHostToDevice, stream));
+    if (forward_from_f32_device(n, stream)) return -1;
+    ARA_CUDA_OK(cudaMemcpyAsync(value_host, d_value, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, stream));
+    if (prob_host != nullptr)
+        ARA_CUDA_OK(cudaMemcpyAsync(prob_host, d_prob, static_cast<size_t>(n) * n_labels() * 4, cudaMemcpyDeviceToHost,
+                                    stream));
+    if (aux_host != nullptr && hdr.wdl_mode)
+        ARA_CUDA_OK(cudaMemcpyAsync(aux_host, d_aux, static_cast<size_t>(n) * 4 * 4, cudaMemcpyDeviceToHost, stream));
+    ARA_CUDA_OK(cudaStreamSynchronize(stream));
+    return 0;
+}
+
+}  // namespace ara
+
+// ------------------------------------------------------------------------------------------- C-ABI
+using ara::Net;
+
+extern "C" ara_net_t ara_net_create(const char* weights_path, int device, int batch_size) {
+    std::unique_ptr<Net> net(new Net());
+    if (net->init(weights_path, device, batch_size) != 0) return nullptr;
+    return reinterpret_cast<ara_net_t>(net.release());
+}
+
+extern "C" void ara_net_destroy(ara_net_t h) { delete reinterpret_cast<Net*>(h); }
+
+extern "C" int ara_net_shape(ara_net_t h, int* in_channels, int* n_labels, int* n_aux, int* is_policy_map,
+                             int* input_version, int* batch_size) {
+    if (h == nullptr) return ara::set_error("ara_net_shape: null handle");
+    Net* net = reinterpret_cast<Net*>(h);
+    if (in_channels) *in_channels = net->hdr.in_channels;
+    if (n_labels) *n_labels = net->n_labels();
+    if (n_aux) *n_aux = net->n_aux();
+    if (is_policy_map) *is_policy_map = 1;
+    if (input_version) *input_version = net->hdr.input_version;
+    if (batch_size) *batch_size = net->batch;
+    return 0;
+}
+
+extern "C" int ara_net_predict(ara_net_t h, const float* planes, int n, float* value, float* prob, float* aux) {
+    if (h == nullptr) return ara::set_error("ara_net_predict: null handle");
+    return reinterpret_cast<Net*>(h)->predict(planes, n, value, prob, aux);
+}
+
+extern "C" int ara_net_forward_device(ara_net_t h, const float* planes_dev, int n, float** value_dev, float** prob_dev) {
+    if (h == nullptr) return ara::set_error("ara_net_forward_device: null handle");
+    Net* net = reinterpret_cast<Net*>(h);
+    if (cudaSetDevice(net->device) != cudaSuccess) return ara::set_error("cudaSetDevice failed");
+    if (planes_dev != nullptr) {
+        cudaError_t e = cudaMemcpyAsync(net->d_in_f32, planes_dev, static_cast<size_t>(n) * net->hdr.in_channels * 64 * 4,
+                                        cudaMemcpyDeviceToDevice, net->stream);
+        if (e != cudaSuccess) return ara::set_error("ara_net_forward_device: %s", cudaGetErrorString(e));
+        if (net->forward_from_f32_device(n, net->stream)) return -1;
+    } else {
+        if (net->forward_device(n, net->stream)) return -1;
+    }
+    cudaError_t e = cudaStreamSynchronize(net->stream);
+    if (e != cudaSuccess) return ara::set_error("ara_net_forward_device: %s", cudaGetErrorString(e));
+    if (value_dev) *value_dev = net->d_value;
+    if (prob_dev) *prob_dev = net->d_prob;
+    return 0;
+}
+
+extern "C" long long ara_net_launch_count(ara_net_t h) { return h ? reinterpret_cast<Net*>(h)->launches : 0; }

@@ -1,0 +1,90 @@
+"""Host-side mirror of the reference's NeuralNetAPI (engine/src/nn/neuralnetapi.h:148-311) over the C-ABI.
+
+Same names and argument meaning as the reference class: predict(inputPlanes, valueOutput, probOutputs,
+auxiliaryOutputs) on caller-owned host buffers; shape getters.  No fallback: construction raises AraError when the
+CUDA library or an sm_100 device is missing.
+"""
+import ctypes
+
+import numpy as np
+
+from ._lib import AraError, check, lib
+
+
+def _fptr(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+
+
+class NeuralNetAPI:
+    def __init__(self, ctx="gpu", deviceID=0, batchSize=8, modelDirectory="", enableTensorrt=True):
+        if ctx != "gpu":
+            raise AraError("crazyara_b200 has no CPU context (ctx must be 'gpu')")
+        L = lib()
+        L.ara_net_create.restype = ctypes.c_void_p
+        L.ara_net_create.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int]
+        L.ara_net_destroy.argtypes = [ctypes.c_void_p]
+        L.ara_net_shape.argtypes = [ctypes.c_void_p] + [ctypes.POINTER(ctypes.c_int)] * 6
+        L.ara_net_predict.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.c_int,
+                                      ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float),
+                                      ctypes.POINTER(ctypes.c_float)]
+        L.ara_net_forward_device.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                             ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p)]
+        L.ara_net_launch_count.restype = ctypes.c_longlong
+        L.ara_net_launch_count.argtypes = [ctypes.c_void_p]
+        self._h = L.ara_net_create(modelDirectory.encode(), deviceID, batchSize)
+        if not self._h:
+            raise AraError(L.ara_last_error().decode())
+        v = [ctypes.c_int() for _ in range(6)]
+        check(L.ara_net_shape(self._h, *[ctypes.byref(x) for x in v]))
+        self.nbInputChannels, self.nbPolicyValues, self.nbAuxiliaryOutputs = v[0].value, v[1].value, v[2].value
+        self.isPolicyMap, self.version, self.batchSize = bool(v[3].value), v[4].value, v[5].value
+        self.deviceID = deviceID
+
+    # reference getters (nn/neuralnetapi.h:116-293)
+    def get_batch_size(self):
+        return self.batchSize
+
+    def get_nb_input_values_total(self):
+        return self.nbInputChannels * 64
+
+    def get_nb_policy_values(self):
+        return self.nbPolicyValues
+
+    def get_nb_auxiliary_outputs(self):
+        return self.nbAuxiliaryOutputs
+
+    def is_policy_map(self):
+        return self.isPolicyMap
+
+    def get_version(self):
+        return self.version
+
+    def predict(self, inputPlanes, valueOutput, probOutputs, auxiliaryOutputs=None, n=None):
+        """inputPlanes: float32 [n, C, 8, 8] host array; outputs are written in place (caller-owned buffers)."""
+        n = self.batchSize if n is None else n
+        for a in (inputPlanes, valueOutput, probOutputs):
+            if a.dtype != np.float32 or not a.flags["C_CONTIGUOUS"]:
+                raise AraError("predict buffers must be C-contiguous float32")
+        aux = _fptr(auxiliaryOutputs) if auxiliaryOutputs is not None else None
+        check(lib().ara_net_predict(self._h, _fptr(inputPlanes), n, _fptr(valueOutput), _fptr(probOutputs), aux))
+
+    def forward_device(self, planes_dev_ptr, n):
+        """planes already in HBM ([n, C, 8, 8] fp32 device pointer, or 0 to use the encoded NHWC input buffer).
+        Returns (value_dev_ptr, prob_dev_ptr)."""
+        v, p = ctypes.c_void_p(), ctypes.c_void_p()
+        check(lib().ara_net_forward_device(self._h, ctypes.c_void_p(planes_dev_ptr), n, ctypes.byref(v), ctypes.byref(p)))
+        return v.value, p.value
+
+    def launch_count(self):
+        return lib().ara_net_launch_count(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().ara_net_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,70 @@
+"""GPU network (tcgen05 fp16 operands, fp32 accumulate) vs the fp32 oracle, through the C-ABI with host buffers.
+
+Tolerances: the reference's default engine precision is float16 (engine/src/uci/optionsuci.cpp:144); our
+activations are fp16 with fp32 accumulation, so value / probabilities agree with the fp32 oracle to ~1e-3
+(written below), not 1e-4 (that bound applies to an fp32 path)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import net as onet
+from tests.golden.gen_net_golden import golden_input
+
+VALUE_ATOL = 4e-3
+LOGIT_ATOL = 2.5e-2
+PROB_RTOL = 3e-2
+
+
+def _make_net(tmp_path, arch, batch, version):
+    from crazyara_b200.nn import NeuralNetAPI
+    from crazyara_b200.weights import export_blob
+    sd = onet.make_state_dict(arch, 0)
+    blob = export_blob(sd, arch, str(tmp_path / f"{arch['name']}.arab"), input_version=version)
+    return NeuralNetAPI("gpu", 0, batch, blob), sd
+
+
+CASES = [("risev2", 34, 81, 8, 8), ("risev2", 34, 81, 64, 64), ("risev2", 34, 81, 1, 1), ("risev33", 52, 76, 64, 64),
+         ("risev33", 52, 76, 8, 5), ("risev2", 63, 84, 16, 16)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,cin,pch,batch,n", CASES)
+def test_net_predict_matches_oracle(tmp_path, name, cin, pch, batch, n):
+    arch = onet.arch_risev2(cin, pch) if name == "risev2" else onet.arch_risev33(cin, pch, True)
+    net, sd = _make_net(tmp_path, arch, batch, 10 if name == "risev2" else 30)
+    assert net.get_nb_policy_values() == pch * 64 and net.get_nb_input_values_total() == cin * 64
+    x = golden_input(arch, n=n, seed=5)
+    value = np.full(batch, np.nan, np.float32)
+    prob = np.full((batch, pch * 64), np.nan, np.float32)
+    aux = np.full((batch, 4), np.nan, np.float32)
+    xin = np.zeros((batch, cin, 8, 8), np.float32)
+    xin[:n] = x
+    net.predict(xin, value, prob, aux if arch["wdl"] else None, n=n)
+    ref = onet.forward(sd, arch, x)
+    assert np.isfinite(value[:n]).all() and np.isfinite(prob[:n]).all()
+    np.testing.assert_allclose(prob[:n].sum(1), 1.0, atol=1e-4)
+    np.testing.assert_allclose(value[:n], ref["value"], atol=VALUE_ATOL)
+    logit_gpu = np.log(prob[:n]) - np.log(prob[:n]).mean(1, keepdims=True)
+    logit_ref = ref["policy_logits"] - ref["policy_logits"].mean(1, keepdims=True)
+    assert np.abs(logit_gpu - logit_ref).max() < LOGIT_ATOL
+    np.testing.assert_allclose(prob[:n], ref["prob"], rtol=PROB_RTOL, atol=1e-7)
+    if arch["wdl"]:
+        np.testing.assert_allclose(aux[:n], ref["aux"], atol=6e-3)
+    # second call must give bit-identical results (graph replay, no stale state)
+    value2, prob2 = value.copy(), prob.copy()
+    net.predict(xin, value2, prob2, None, n=n)
+    assert np.array_equal(value2[:n], value[:n]) and np.array_equal(prob2[:n], prob[:n])
+    net.close()
+
+
+@pytest.mark.gpu
+def test_net_create_fails_loudly_on_bad_blob(tmp_path):
+    from crazyara_b200 import AraError
+    from crazyara_b200.nn import NeuralNetAPI
+    p = tmp_path / "bad.arab"
+    p.write_bytes(b"not a blob")
+    with pytest.raises(AraError):
+        NeuralNetAPI("gpu", 0, 8, str(p))
+    with pytest.raises(AraError):
+        NeuralNetAPI("gpu", 0, 8, str(tmp_path / "missing.arab"))

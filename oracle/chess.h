@@ -11,6 +11,7 @@
  */
 #ifndef ORACLE_CHESS_H
 #define ORACLE_CHESS_H
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus

@@ -125,12 +125,37 @@ int opolicy_nb_labels(int mode) { build(mode); return g_sets[mode].n; }
 int opolicy_nb_policy_channels(int mode) { return mode == OMODE_CRAZYHOUSE ? 81 : (mode == OMODE_CHESS ? 76 : 84); }
 const char* opolicy_label(int mode, int idx) { build(mode); return g_sets[mode].s[idx]; }
 int opolicy_flat_plane_idx(int mode, int idx) { build(mode); return g_sets[mode].flat[idx]; }
+/* string -> small integer key: drops 0..511 (piece*64+sq), other moves 512 + from*64*8 + to*8 + promo */
+static int label_key(const char* l) {
+    if (l[1] == '@') {
+        const char* order = "PNBRQ";
+        const char* q = strchr(order, l[0]);
+        if (!q) return -1;
+        return (int)(q - order) * 64 + (l[3] - '1') * 8 + (l[2] - 'a');
+    }
+    int promo = 0;
+    if (l[4]) {
+        const char* order = "nbrqk";
+        const char* q = strchr(order, l[4]);
+        if (!q) return -1;
+        promo = (int)(q - order) + 1;
+    }
+    const int from = (l[1] - '1') * 8 + (l[0] - 'a'), to = (l[3] - '1') * 8 + (l[2] - 'a');
+    if (from < 0 || from > 63 || to < 0 || to > 63) return -1;
+    return 512 + (from * 64 + to) * 8 + promo;
+}
+static int16_t g_lookup[3][512 + 64 * 64 * 8];
+static int g_lookup_built[3];
 int opolicy_label_index(int mode, const char* uci) {
     build(mode);
-    const LabelSet* L = &g_sets[mode];
-    for (int i = 0; i < L->n; ++i)
-        if (strcmp(L->s[i], uci) == 0) return i;
-    return -1;
+    if (!g_lookup_built[mode]) {
+        const LabelSet* L = &g_sets[mode];
+        for (size_t i = 0; i < sizeof(g_lookup[mode]) / sizeof(int16_t); ++i) g_lookup[mode][i] = -1;
+        for (int i = 0; i < L->n; ++i) g_lookup[mode][label_key(L->s[i])] = (int16_t)i;
+        g_lookup_built[mode] = 1;
+    }
+    const int k = label_key(uci);
+    return k < 0 ? -1 : g_lookup[mode][k];
 }
 void opolicy_mirror(const char* uci, char* out) {
     strcpy(out, uci);

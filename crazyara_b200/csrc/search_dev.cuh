@@ -1,0 +1,940 @@
+// GPU MCTS: flat SoA node / edge pools in HBM and the warp-level search primitives that walk them.
+//
+// One warp owns one tree.  Playouts of a tree are SEQUENTIAL inside the warp (each playout sees the virtual visits
+// of the previous one, exactly as the reference's single search thread does) -- lanes parallelise the child argmax,
+// move legality, plane encoding, the repetition scan and the prior sort; independent trees run on independent warps.
+//
+// Reference semantics restated here (engine/src of QueensGambit/CrazyAra):
+//   select   node.cpp:1150-1167 select_child_node, :1056-1063 get_current_u_values, :1243-1246 get_current_cput
+//   virtual  node.cpp:507-529 apply_virtual_loss_to_child, node.h:199-246 revert_virtual_loss_and_update,
+//            node.cpp:661-679 revert_virtual_loss, node.h:819-843 backup_value
+//   expand   node.cpp:82-106 Node ctor, :880-904 check_for_terminal, :571-580 increment_no_visit_idx,
+//            searchthread.cpp:164-271 get_new_child_to_evaluate, :347-380 create_mini_batch
+//   scatter  searchthread.cpp:290-324, node.cpp:961-979 set_probabilities_for_moves, util/blazeutil.h:78-88,
+//            node.cpp:464-470 sort_moves_by_probabilities, :634-644 prepare_node_for_visits
+//   solver   node.cpp:108-173, :265-297, :365-453, :1006-1010
+//   results  node.cpp:1070-1148, evalinfo.cpp:112-121, :195-249
+// Everything is __host__ __device__ over the lane abstraction so the whole search also runs as a 1-lane emulation on
+// the CPU for unit tests (tests/hostemu); that build is scaffolding, not a fallback.
+#pragma once
+#include <math.h>
+
+#include "chess_dev.cuh"
+#include "planes_dev.cuh"
+
+namespace ara {
+
+constexpr int kMaxDepth = 256;
+constexpr int kNoCheckmate = 65535;
+constexpr float kQInit = -1.0f;
+enum : int { VS_VIRTUAL_LOSS = 0, VS_VIRTUAL_VISIT = 1, VS_VIRTUAL_OFFSET = 2, VS_VIRTUAL_MIX = 3 };
+enum : int { NT_WIN = 0, NT_DRAW = 1, NT_LOSS = 2, NT_UNSOLVED = 3 };
+enum : int { NF_TERMINAL = 1, NF_HAS_NN = 2, NF_HAS_D = 4, NF_SORTED = 8 };
+
+// Same layout as OSettings (oracle/mcts.h) and ara_search_settings_t (include/ara_b200.h).
+struct SearchParams {
+    int batch_size;
+    float dirichlet_epsilon;
+    float dirichlet_alpha;
+    float node_policy_temperature;
+    float q_value_weight;
+    float q_veto_delta;
+    float cpuct_init;
+    float cpuct_base;
+    int mcts_solver;
+    int virtual_style;
+    unsigned virtual_mix_threshold;
+    unsigned simulations;
+    unsigned nodes;
+    unsigned long long seed;
+    int mode;
+    int input_version;
+};
+
+struct alignas(16) NodeHdr {  // 64 B: one line per visited node on the select path
+    double value_sum;
+    uint64_t key;
+    uint32_t real_visits;
+    uint32_t visit_sum;
+    uint32_t free_visits;
+    uint32_t edge_base;
+    int32_t parent;
+    uint16_t n_moves;
+    uint16_t no_visit_idx;
+    uint16_t checkmate_idx;
+    uint16_t end_in_ply;
+    uint16_t n_unsolved;
+    uint16_t parent_ci;
+    int16_t repetition;
+    uint8_t node_type;
+    uint8_t flags;
+    uint32_t pad_[3];
+};
+static_assert(sizeof(NodeHdr) == 64, "NodeHdr must be 64 bytes");
+
+struct TreeState {
+    int n_nodes;
+    int n_edges;
+    int n_new;
+    int n_coll;
+    int done;      // search loop condition failed (limits reached / root solved)
+    int error;     // 1 node pool, 2 edge pool, 3 depth overflow
+    unsigned iterations;
+    unsigned evals;
+    unsigned long long sum_select_k;
+    unsigned long long sum_depth;
+};
+
+struct TreeDev {
+    NodeHdr* hdr;
+    Board* board;
+    float* P;
+    float* Q;
+    uint32_t* N;
+    int32_t* child;
+    Move* move;
+    uint8_t* vl;
+    uint8_t* etype;
+    TreeState* st;
+    int32_t* new_node;      // [B]
+    int32_t* traj_node;     // [2B][kMaxDepth]   rows 0..B-1 new leaves, B..2B-1 collisions
+    uint16_t* traj_ci;      // [2B][kMaxDepth]
+    int32_t* traj_len;      // [2B]
+    const uint64_t* hist_keys;  // positions before the root, oldest first
+    const int16_t* hist_reps;
+    int hist_len;
+    const float* cput_lut;  // cput for visit_sum < cput_lut_len, computed on the host with the host libm
+    int cput_lut_len;
+    int max_nodes;
+    int max_edges;
+    int slot_base;  // first row of this tree in the network batch
+};
+
+struct WarpScratch {  // per-warp shared memory (stack on the host)
+    Board parent;
+    Board child;
+    Move scratch[kMaxMoves];
+    Move legal[kMaxMoves];
+    uint64_t path_key[kMaxDepth];
+    int16_t path_rep[kMaxDepth];
+    int32_t traj_node[kMaxDepth];
+    uint16_t traj_ci[kMaxDepth];
+    float sort_p[kMaxMoves];
+    int shared_n;
+    int bcast[4];
+};
+
+// ------------------------------------------------------------------ small helpers
+ARA_HD int virtual_style_of(const SearchParams& sp, uint32_t visits) {  // node.h:87-95
+    if (sp.virtual_style == VS_VIRTUAL_MIX) return visits > sp.virtual_mix_threshold ? VS_VIRTUAL_LOSS : VS_VIRTUAL_VISIT;
+    return sp.virtual_style;
+}
+ARA_HD float node_value(const NodeHdr& h) { return static_cast<float>(h.value_sum / h.real_visits); }
+ARA_HD void node_set_value(NodeHdr& h, float v) {  // node.cpp:716-720
+    ++h.real_visits;
+    h.value_sum = static_cast<double>(v * static_cast<float>(h.real_visits));
+}
+ARA_HD float current_cput(const TreeDev& t, const SearchParams& sp, uint32_t visit_sum) {
+    if (static_cast<int>(visit_sum) < t.cput_lut_len) return t.cput_lut[visit_sum];
+    return logf((static_cast<float>(visit_sum) + sp.cpuct_base + 1) / sp.cpuct_base) + sp.cpuct_init;
+}
+template <typename T>
+ARA_HD T bcast0(T v) {
+    return ARA_SHFL(v, 0);
+}
+
+// copy one 128-byte board between memories, cooperatively
+ARA_HD void copy_board(Board* dst, const Board* src) {
+#if defined(__CUDA_ARCH__)
+    if (ARA_LANE < 8) reinterpret_cast<uint4*>(dst)[ARA_LANE] = reinterpret_cast<const uint4*>(src)[ARA_LANE];
+#else
+    *dst = *src;
+#endif
+    ARA_WARP_SYNC();
+}
+
+// ------------------------------------------------------------------ select (warp argmax, first maximum wins)
+ARA_HD int select_child(const TreeDev& t, const SearchParams& sp, int nid) {
+    NodeHdr& h = t.hdr[nid];
+    if (ARA_LANE == 0 && !(h.flags & NF_HAS_D)) h.flags |= NF_HAS_D | NF_SORTED;  // prepare_node_for_visits (lazy flag)
+    ARA_WARP_SYNC();
+    const int k = h.no_visit_idx;
+    if (k == 1) return 0;
+    if (h.checkmate_idx != kNoCheckmate) return h.checkmate_idx;
+    const uint32_t vs = h.visit_sum;
+    const float cput = current_cput(t, sp, vs);
+    const double sq = sqrt(static_cast<double>(vs));
+    const uint32_t e = h.edge_base;
+    float best_v = 0.0f;
+    int best_i = 0x7fffffff;
+    for (int i = ARA_LANE; i < k; i += ARA_WARP_N) {
+        const float u = static_cast<float>(static_cast<double>(cput * t.P[e + i]) * (sq / (static_cast<double>(t.N[e + i]) + 1.0)));
+        const float v = t.Q[e + i] + u;
+        if (best_i == 0x7fffffff || v > best_v) {
+            best_v = v;
+            best_i = i;
+        }
+    }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best_v, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, best_i, off);
+        if (oi != 0x7fffffff && (best_i == 0x7fffffff || ov > best_v || (ov == best_v && oi < best_i))) {
+            best_v = ov;
+            best_i = oi;
+        }
+    }
+#endif
+    if (ARA_LANE == 0) t.st->sum_select_k += static_cast<unsigned long long>(k);
+    return best_i;
+}
+
+// lane 0 only
+ARA_HD void apply_virtual_loss(const TreeDev& t, const SearchParams& sp, int nid, int ci) {  // node.cpp:507-529
+    NodeHdr& h = t.hdr[nid];
+    const uint32_t e = h.edge_base + ci;
+    if (virtual_style_of(sp, t.N[e]) == VS_VIRTUAL_LOSS)
+        t.Q[e] = static_cast<float>((static_cast<double>(t.Q[e]) * t.N[e] - 1) / static_cast<double>(t.N[e] + 1));
+    ++t.N[e];
+    ++h.visit_sum;
+    ++t.vl[e];
+}
+
+// ------------------------------------------------------------------ MCTS solver (lane 0 only; TWO_PLAYER, no tablebases)
+ARA_HD void disable_action(const TreeDev& t, uint32_t e) {
+    t.P[e] = 0.0f;
+    t.Q[e] = static_cast<float>(-2147483647);
+}
+ARA_HD bool at_least_one_drawn_child(const TreeDev& t, const NodeHdr& h) {
+    bool drawn = false;
+    for (int i = 0; i < h.no_visit_idx; ++i) {
+        const int c = t.child[h.edge_base + i];
+        if (c < 0) return false;
+        const NodeHdr& ch = t.hdr[c];
+        if (!(ch.flags & NF_HAS_D) || (ch.node_type != NT_DRAW && ch.node_type != NT_WIN)) return false;
+        if (ch.node_type == NT_DRAW) drawn = true;
+    }
+    return drawn;
+}
+ARA_HD bool only_won_children(const TreeDev& t, const NodeHdr& h) {
+    for (int i = 0; i < h.no_visit_idx; ++i) {
+        const int c = t.child[h.edge_base + i];
+        if (c < 0 || t.hdr[c].node_type != NT_WIN) return false;
+    }
+    return true;
+}
+ARA_HD void define_end_ply(const TreeDev& t, NodeHdr& h, const NodeHdr& ch) {  // node.cpp:265-289
+    if (h.node_type == NT_LOSS) {
+        for (int i = 0; i < h.no_visit_idx; ++i) {
+            const int c = t.child[h.edge_base + i];
+            if (c >= 0 && t.hdr[c].end_in_ply + 1 > h.end_in_ply) h.end_in_ply = static_cast<uint16_t>(t.hdr[c].end_in_ply + 1);
+        }
+        return;
+    }
+    if (h.node_type == NT_DRAW) {
+        for (int i = 0; i < h.no_visit_idx; ++i) {
+            const int c = t.child[h.edge_base + i];
+            if (c >= 0 && t.hdr[c].node_type == NT_DRAW && t.hdr[c].end_in_ply + 1 < h.end_in_ply)
+                h.end_in_ply = static_cast<uint16_t>(t.hdr[c].end_in_ply + 1);
+        }
+        return;
+    }
+    h.end_in_ply = static_cast<uint16_t>(ch.end_in_ply + 1);
+}
+ARA_HD void update_solved_terminal(const TreeDev& t, NodeHdr& h, const NodeHdr& ch, int ci, int target) {
+    define_end_ply(t, h, ch);
+    node_set_value(h, static_cast<float>(target));
+    t.Q[h.edge_base + ci] = static_cast<float>(target);
+}
+ARA_HD bool solve_for_terminal(const TreeDev& t, int nid, int ci) {  // node.cpp:365-453
+    NodeHdr& h = t.hdr[nid];
+    const int c = t.child[h.edge_base + ci];
+    const NodeHdr& ch = t.hdr[c];
+    if (!(ch.flags & NF_HAS_D)) return false;
+    if (ch.node_type == NT_UNSOLVED) return false;
+    if (h.node_type != NT_UNSOLVED) return false;
+    const uint32_t e = h.edge_base + ci;
+    if (t.etype[e] == NT_UNSOLVED) {
+        --h.n_unsolved;
+        t.etype[e] = ch.node_type;
+        if (ch.node_type == NT_WIN) disable_action(t, e);
+    }
+    if (ch.node_type == NT_LOSS) {
+        h.node_type = NT_WIN;
+        update_solved_terminal(t, h, ch, ci, 1);
+        h.checkmate_idx = static_cast<uint16_t>(ci);
+        return true;
+    }
+    if (h.n_unsolved == 0 && ch.node_type == NT_WIN && only_won_children(t, h)) {
+        h.node_type = NT_LOSS;
+        update_solved_terminal(t, h, ch, ci, -1);
+        return true;
+    }
+    if (h.n_unsolved == 0 && ch.node_type != NT_LOSS && at_least_one_drawn_child(t, h)) {
+        h.node_type = NT_DRAW;
+        update_solved_terminal(t, h, ch, ci, 0);
+        return true;
+    }
+    return false;
+}
+
+// ------------------------------------------------------------------ backup (lane 0 only)
+ARA_HD void revert_virtual_loss_and_update(const TreeDev& t, const SearchParams& sp, int nid, int ci, float value,
+                                           bool free_backup, bool solve) {  // node.h:199-246
+    NodeHdr& h = t.hdr[nid];
+    const uint32_t e = h.edge_base + ci;
+    h.value_sum += value;
+    ++h.real_visits;
+    if (t.N[e] == 1) {
+        t.Q[e] = value;
+    } else {
+        const int style = virtual_style_of(sp, t.N[e]);
+        if (style == VS_VIRTUAL_LOSS) {
+            t.Q[e] = static_cast<float>((static_cast<double>(t.Q[e]) * t.N[e] + 1 + value) / t.N[e]);
+        } else if (style == VS_VIRTUAL_VISIT) {
+            const uint32_t real = t.N[e] - t.vl[e];
+            t.Q[e] = static_cast<float>((static_cast<double>(t.Q[e]) * real + value) / (real + 1));
+        }
+    }
+    --t.vl[e];
+    if (free_backup) ++h.free_visits;
+    if (solve) solve_for_terminal(t, nid, ci);
+}
+ARA_HD void backup_value(const TreeDev& t, const SearchParams& sp, float value, const int32_t* tn, const uint16_t* tc,
+                         int len, bool free_backup, bool solve) {  // node.h:819-843 (transposition branches are dead)
+    for (int i = len - 1; i >= 0; --i) {
+        value = -value;
+        revert_virtual_loss_and_update(t, sp, tn[i], tc[i], value, free_backup, solve);
+    }
+}
+ARA_HD void revert_virtual_loss(const TreeDev& t, const SearchParams& sp, int nid, int ci) {  // node.cpp:661-679
+    NodeHdr& h = t.hdr[nid];
+    const uint32_t e = h.edge_base + ci;
+    if (virtual_style_of(sp, t.N[e]) == VS_VIRTUAL_LOSS)
+        t.Q[e] = static_cast<float>((static_cast<double>(t.Q[e]) * t.N[e] + 1) / (t.N[e] - 1));
+    --t.N[e];
+    --h.visit_sum;
+    --t.vl[e];
+}
+
+// ------------------------------------------------------------------ repetition over (pre-root history + tree path)
+// ws.path_key/rep[0..depth) hold root..current; ws.child is the new position (depth plies below the root).
+ARA_HD int repetition_on_path(const TreeDev& t, const WarpScratch& ws, int depth) {
+    const Board& b = ws.child;
+    const int total = t.hist_len + depth;  // number of earlier positions
+    int end = repetition_end(b);
+    if (end > total) end = total;
+    for (int base = 4; base <= end; base += 2 * ARA_WARP_N) {
+        const int i = base + 2 * ARA_LANE;
+        bool hit = false;
+        int rep = 0;
+        if (i <= end) {
+            const int idx = total - i;
+            const uint64_t k = idx < t.hist_len ? t.hist_keys[idx] : ws.path_key[idx - t.hist_len];
+            if (k == b.key) {
+                hit = true;
+                rep = idx < t.hist_len ? t.hist_reps[idx] : ws.path_rep[idx - t.hist_len];
+            }
+        }
+        const uint32_t m = ARA_BALLOT(hit);
+        if (m) {
+#if defined(__CUDA_ARCH__)
+            const int src = __ffs(m) - 1;
+#else
+            const int src = 0;
+#endif
+            const int ri = ARA_SHFL(rep, src);
+            const int ii = ARA_SHFL(i, src);
+            return ri ? -ii : ii;
+        }
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------ expansion
+// Creates the node for ws.child (already moved), child `ci` of `parent` (or the root if parent < 0).
+// Returns the new node id (uniform), or -1 on pool exhaustion.  *is_terminal receives the terminal verdict.
+template <class PlaneWriter>
+ARA_HD int expand_node(const TreeDev& t, const SearchParams& sp, WarpScratch& ws, int parent, int ci, int depth,
+                       const PlaneWriter* writer_for_slot, int* is_terminal) {
+    Board& b = ws.child;
+    // repetition info needs the key: done by do_move
+    const int rep = repetition_on_path(t, ws, depth);
+    if (ARA_LANE == 0) b.repetition = static_cast<int16_t>(rep);
+    ARA_WARP_SYNC();
+    const int n_moves = gen_legal(b, ws.scratch, ws.legal, &ws.shared_n);
+    const bool checked = in_check(b);
+    const int tt = terminal_type(b, n_moves, checked);
+    int nid = -1;
+    if (ARA_LANE == 0) {
+        TreeState& st = *t.st;
+        if (st.n_nodes >= t.max_nodes) {
+            st.error = 1;
+        } else if (tt == TERM_NONE && st.n_edges + n_moves > t.max_edges) {
+            st.error = 2;
+        } else {
+            nid = st.n_nodes++;
+            NodeHdr h;
+            h.value_sum = 0.0;
+            h.key = b.key;
+            h.real_visits = 0;
+            h.visit_sum = 0;
+            h.free_visits = 0;
+            h.edge_base = 0;
+            h.parent = parent;
+            h.n_moves = static_cast<uint16_t>(n_moves);
+            h.no_visit_idx = 1;
+            h.checkmate_idx = kNoCheckmate;
+            h.end_in_ply = 0;
+            h.n_unsolved = static_cast<uint16_t>(n_moves);
+            h.parent_ci = static_cast<uint16_t>(ci < 0 ? 0 : ci);
+            h.repetition = b.repetition;
+            h.node_type = NT_UNSOLVED;
+            h.flags = 0;
+            h.pad_[0] = h.pad_[1] = h.pad_[2] = 0;
+            if (tt != TERM_NONE) {  // check_for_terminal node.cpp:880-904 + mark_as_terminal
+                h.flags = NF_TERMINAL | NF_HAS_D | NF_SORTED;
+                h.no_visit_idx = 0;
+                if (tt == TERM_WIN) {
+                    node_set_value(h, 1.0f);
+                    h.node_type = NT_WIN;
+                } else if (tt == TERM_DRAW) {
+                    node_set_value(h, 0.0f);
+                    h.node_type = NT_DRAW;
+                    h.n_moves = 0;
+                } else {
+                    node_set_value(h, -1.0f);
+                    h.node_type = NT_LOSS;
+                }
+            } else {
+                h.edge_base = static_cast<uint32_t>(st.n_edges);
+                st.n_edges += n_moves;
+            }
+            t.hdr[nid] = h;
+            if (parent >= 0) t.child[t.hdr[parent].edge_base + ci] = nid;
+        }
+    }
+    nid = bcast0(nid);
+    *is_terminal = tt != TERM_NONE;
+    if (nid < 0) return -1;
+    copy_board(&t.board[nid], &b);
+    if (tt == TERM_NONE) {
+        const uint32_t e = t.hdr[nid].edge_base;
+        for (int i = ARA_LANE; i < n_moves; i += ARA_WARP_N) {
+            const Move m = ws.legal[i];
+            t.move[e + i] = m;
+            // the policy-vector index is parked in P until the network results arrive (set_probabilities_for_moves)
+            const int pidx = policy_map_index(m, b.stm, b.chess960);
+#if defined(__CUDA_ARCH__)
+            t.P[e + i] = __int_as_float(pidx);
+#else
+            union { int i; float f; } u;
+            u.i = pidx;
+            t.P[e + i] = u.f;
+#endif
+            t.Q[e + i] = kQInit;
+            t.N[e + i] = 0;
+            t.child[e + i] = -1;
+            t.vl[e + i] = 0;
+            t.etype[e + i] = NT_UNSOLVED;
+        }
+        if (writer_for_slot != nullptr) encode_planes(b, sp.mode, sp.input_version, true, *writer_for_slot);
+    }
+    ARA_WARP_SYNC();
+    return nid;
+}
+
+// ------------------------------------------------------------------ scatter of network results into a new node
+// prob: this node's row of the soft-maxed policy; value: its value output.  Warp-collective.
+ARA_HD void fill_nn_results(const TreeDev& t, const SearchParams& sp, WarpScratch& ws, int nid, float value,
+                            const float* prob) {
+    NodeHdr& h = t.hdr[nid];
+    const int n = h.n_moves;
+    const uint32_t e = h.edge_base;
+    // set_probabilities_for_moves
+    for (int i = ARA_LANE; i < n; i += ARA_WARP_N) {
+#if defined(__CUDA_ARCH__)
+        const int pidx = __float_as_int(t.P[e + i]);
+#else
+        union { int i; float f; } u;
+        u.f = t.P[e + i];
+        const int pidx = u.i;
+#endif
+        ws.sort_p[i] = prob[pidx];
+        ws.scratch[i] = t.move[e + i];
+        ws.legal[i] = static_cast<Move>(pidx);  // tie-break key (policy indices are < 65536)
+    }
+    ARA_WARP_SYNC();
+    // apply_temperature (blazeutil.h:78-88): no renormalisation at T == 1
+    if (sp.node_policy_temperature != 1.0f) {
+        const float inv_t = 1.0f / sp.node_policy_temperature;
+        float part = 0.0f;
+        for (int i = ARA_LANE; i < n; i += ARA_WARP_N) {
+            const float p = powf(ws.sort_p[i], inv_t);
+            ws.sort_p[i] = p;
+            part += p;
+        }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+#endif
+        ARA_WARP_SYNC();
+        for (int i = ARA_LANE; i < n; i += ARA_WARP_N) ws.sort_p[i] = ws.sort_p[i] / part;
+        ARA_WARP_SYNC();
+    }
+    // sort_moves_by_probabilities: descending prior; the reference's std::sort leaves ties unspecified, we order
+    // them by ascending policy-vector index (independent of move-generation order).  Rank counting, O(n^2 / 32).
+    for (int i = ARA_LANE; i < n; i += ARA_WARP_N) {
+        const float p = ws.sort_p[i];
+        const Move pi = ws.legal[i];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) {
+            const float q = ws.sort_p[j];
+            rank += (q > p || (q == p && ws.legal[j] < pi)) ? 1 : 0;
+        }
+        t.P[e + rank] = p;
+        t.move[e + rank] = ws.scratch[i];
+    }
+    if (ARA_LANE == 0) {
+        node_set_value(h, value);  // node_assign_value
+        h.flags |= NF_HAS_NN;
+    }
+    ARA_WARP_SYNC();
+}
+
+// ------------------------------------------------------------------ Dirichlet noise (libstdc++ gamma_distribution<float>
+// over minstd_rand0, util/blazeutil.h:113-124) with an explicit seed.  Lane 0 only.
+struct MinStd {
+    uint32_t x;
+};
+ARA_HD uint32_t minstd_next(MinStd& g) {
+    g.x = static_cast<uint32_t>((static_cast<uint64_t>(g.x) * 16807ULL) % 2147483647ULL);
+    return g.x;
+}
+ARA_HD float canonical_f(MinStd& g) {
+    const float sum = static_cast<float>(minstd_next(g) - 1u);
+    float r = sum / 2147483648.0f;
+    if (r >= 1.0f) r = 0.99999994f;  // nextafterf(1, 0)
+    return r;
+}
+ARA_HD float gamma_f(MinStd& g, float alpha) {
+    const float malpha = alpha < 1.0f ? alpha + 1.0f : alpha;
+    const float a1 = malpha - 1.0f / 3.0f;
+    const float a2 = 1.0f / sqrtf(9.0f * a1);
+    bool saved_ok = false;
+    float saved = 0.0f, u, v, n;
+    do {
+        do {
+            if (saved_ok) {
+                saved_ok = false;
+                n = saved;
+            } else {
+                float x, y, r2;
+                do {
+                    x = static_cast<float>(2.0f * canonical_f(g) - 1.0);
+                    y = static_cast<float>(2.0f * canonical_f(g) - 1.0);
+                    r2 = x * x + y * y;
+                } while (r2 > 1.0 || r2 == 0.0);
+                const float mult = sqrtf(-2 * logf(r2) / r2);
+                saved = x * mult;
+                saved_ok = true;
+                n = y * mult;
+            }
+            v = 1.0f + a2 * n;
+        } while (v <= 0.0);
+        v = v * v * v;
+        u = canonical_f(g);
+    } while (u > 1.0f - 0.0331 * n * n * n * n && (logf(u) > (0.5 * n * n + a1 * (1.0 - v + logf(v)))));
+    if (alpha == malpha) return a1 * v * 1.0f;
+    do u = canonical_f(g);
+    while (u == 0.0);
+    return powf(u, 1.0f / alpha) * a1 * v * 1.0f;
+}
+// MCTSAgent::evaluate_board_state :311-316: noise on the (sorted) root priors, then open all children.  Lane 0.
+ARA_HD void apply_dirichlet_to_root(const TreeDev& t, const SearchParams& sp, WarpScratch& ws) {
+    NodeHdr& h = t.hdr[0];
+    const int n = h.n_moves;
+    MinStd g;
+    g.x = static_cast<uint32_t>(sp.seed % 2147483647ULL);
+    if (g.x == 0) g.x = 1;
+    float sum = 0.0f;
+    for (int i = 0; i < n; ++i) {
+        ws.sort_p[i] = gamma_f(g, sp.dirichlet_alpha);
+        sum += ws.sort_p[i];
+    }
+    for (int i = 0; i < n; ++i) {
+        const float noise = ws.sort_p[i] / sum;
+        t.P[h.edge_base + i] = (1 - sp.dirichlet_epsilon) * t.P[h.edge_base + i] + sp.dirichlet_epsilon * noise;
+    }
+    h.no_visit_idx = static_cast<uint16_t>(n);  // fully_expand_node (edges are pre-initialised)
+    h.flags |= NF_SORTED | NF_HAS_D;
+}
+
+// ------------------------------------------------------------------ one mini-batch: SearchThread::create_mini_batch
+// PlaneWriterFactory::make(slot) returns the writer for network-batch row `slot`.
+template <class WriterFactory>
+ARA_HD void create_mini_batch(const TreeDev& t, const SearchParams& sp, WarpScratch& ws, const WriterFactory& wf) {
+    TreeState& st = *t.st;
+    if (st.done || st.error) {
+        if (ARA_LANE == 0) st.n_new = 0, st.n_coll = 0;
+        return;
+    }
+    // run_search_thread loop condition (searchthread.cpp:326-340, :418-426), checked before every iteration
+    {
+        const NodeHdr& r = t.hdr[0];
+        const uint32_t node_count = r.visit_sum - r.free_visits;
+        const bool limits_ok = (sp.nodes == 0 || node_count < sp.nodes) && (sp.simulations == 0 || r.visit_sum < sp.simulations);
+        if (!(limits_ok && r.node_type == NT_UNSOLVED) || r.n_moves <= 1) {
+            if (ARA_LANE == 0) st.done = 1, st.n_new = 0, st.n_coll = 0;
+            return;
+        }
+    }
+    const int B = sp.batch_size;
+    int n_new = 0, n_coll = 0, n_term = 0;
+    while (n_new < B && n_coll != B && n_term < 2 * B) {
+        int cur = 0, depth = 0, type = -1, leaf = -1;  // type: 0 new, 1 collision, 2 terminal
+        for (;;) {
+            if (depth >= kMaxDepth) {
+                if (ARA_LANE == 0) st.error = 3;
+                type = -2;
+                break;
+            }
+            const int ci = select_child(t, sp, cur);
+            const NodeHdr& h = t.hdr[cur];
+            if (ARA_LANE == 0) {
+                apply_virtual_loss(t, sp, cur, ci);
+                ws.traj_node[depth] = cur;
+                ws.traj_ci[depth] = static_cast<uint16_t>(ci);
+                ws.path_key[depth] = h.key;
+                ws.path_rep[depth] = h.repetition;
+            }
+            ARA_WARP_SYNC();
+            depth++;
+            const int next = t.child[h.edge_base + ci];
+            if (next < 0) {
+                copy_board(&ws.child, &t.board[cur]);
+                if (ARA_LANE == 0) {
+                    do_move(ws.child, t.move[h.edge_base + ci]);
+                    // increment_no_visit_idx: open the next-best sibling (its edge slots are pre-initialised)
+                    if (t.hdr[cur].no_visit_idx < t.hdr[cur].n_moves) ++t.hdr[cur].no_visit_idx;
+                }
+                ARA_WARP_SYNC();
+                int is_term = 0;
+                const auto writer = wf.make(t.slot_base + n_new);
+                leaf = expand_node(t, sp, ws, cur, ci, depth, &writer, &is_term);
+                if (leaf < 0) {
+                    type = -2;
+                    break;
+                }
+                type = is_term ? 2 : 0;
+                break;
+            }
+            const NodeHdr& nh = t.hdr[next];
+            if (nh.flags & NF_TERMINAL) {
+                type = 2;
+                leaf = next;
+                break;
+            }
+            if (!(nh.flags & NF_HAS_NN)) {
+                type = 1;
+                leaf = next;
+                break;
+            }
+            cur = next;
+        }
+        if (type == -2) break;
+        if (ARA_LANE == 0) {
+            st.sum_depth += static_cast<unsigned long long>(depth);
+            if (type == 2) {
+                backup_value(t, sp, node_value(t.hdr[leaf]), ws.traj_node, ws.traj_ci, depth, true, sp.mcts_solver != 0);
+            } else {
+                const int row = type == 1 ? B + n_coll : n_new;
+                for (int i = 0; i < depth; ++i) {
+                    t.traj_node[row * kMaxDepth + i] = ws.traj_node[i];
+                    t.traj_ci[row * kMaxDepth + i] = ws.traj_ci[i];
+                }
+                t.traj_len[row] = depth;
+                if (type == 0) t.new_node[n_new] = leaf;
+            }
+        }
+        ARA_WARP_SYNC();
+        if (type == 2) ++n_term;
+        else if (type == 1) ++n_coll;
+        else ++n_new;
+    }
+    if (ARA_LANE == 0) {
+        st.n_new = n_new;
+        st.n_coll = n_coll;
+        st.iterations++;
+        st.evals += static_cast<unsigned>(n_new);
+    }
+    ARA_WARP_SYNC();
+}
+
+// set_nn_results_to_child_nodes + backup_value_outputs + backup_collisions (searchthread.cpp:301-324)
+ARA_HD void apply_results(const TreeDev& t, const SearchParams& sp, WarpScratch& ws, const float* values,
+                          const float* probs, int n_labels) {
+    const TreeState& st = *t.st;
+    const int B = sp.batch_size;
+    const int n_new = st.n_new, n_coll = st.n_coll;
+    for (int b = 0; b < n_new; ++b) {
+        const int slot = t.slot_base + b;
+        fill_nn_results(t, sp, ws, t.new_node[b], values[slot], probs + static_cast<size_t>(slot) * n_labels);
+    }
+    if (ARA_LANE == 0) {
+        for (int b = 0; b < n_new; ++b)
+            backup_value(t, sp, node_value(t.hdr[t.new_node[b]]), t.traj_node + b * kMaxDepth, t.traj_ci + b * kMaxDepth,
+                         t.traj_len[b], false, false);
+        for (int c = 0; c < n_coll; ++c) {
+            const int row = B + c;
+            for (int i = t.traj_len[row] - 1; i >= 0; --i)
+                revert_virtual_loss(t, sp, t.traj_node[row * kMaxDepth + i], t.traj_ci[row * kMaxDepth + i]);
+        }
+        t.st->n_new = 0;
+        t.st->n_coll = 0;
+    }
+    ARA_WARP_SYNC();
+}
+
+// Root creation: MCTSAgent::create_new_root_node (mctsagent.cpp:180-196), first half (before the network call).
+template <class WriterFactory>
+ARA_HD void create_root(const TreeDev& t, const SearchParams& sp, WarpScratch& ws, const Board* root_board,
+                        const WriterFactory& wf) {
+    copy_board(&ws.child, root_board);
+    if (ARA_LANE == 0) {
+        TreeState& st = *t.st;
+        st.n_nodes = 0;
+        st.n_edges = 0;
+        st.n_new = 0;
+        st.n_coll = 0;
+        st.done = 0;
+        st.error = 0;
+        st.iterations = 0;
+        st.evals = 0;
+        st.sum_select_k = 0;
+        st.sum_depth = 0;
+    }
+    ARA_WARP_SYNC();
+    // the root keeps the repetition info it arrived with (set by the host from the game history)
+    const int saved_rep = root_board->repetition;
+    int is_term = 0;
+    const auto writer = wf.make(t.slot_base);
+    // expand_node recomputes repetition from history; for the root depth = 0 means "history only"
+    const int nid = expand_node(t, sp, ws, -1, -1, 0, &writer, &is_term);
+    (void)saved_rep;
+    if (ARA_LANE == 0 && nid == 0) {
+        TreeState& st = *t.st;
+        if (is_term || t.hdr[0].n_moves == 0) {
+            st.done = 1;
+        } else {
+            st.n_new = 1;  // the root is the single "new node" of the first network call
+            t.new_node[0] = 0;
+            t.traj_len[0] = 0;
+            st.evals = 1;
+        }
+    }
+    ARA_WARP_SYNC();
+}
+// second half: after the network results were scattered by apply_results (root trajectory is empty)
+ARA_HD void finalize_root(const TreeDev& t, const SearchParams& sp, WarpScratch& ws) {
+    if (ARA_LANE == 0 && !t.st->done && !t.st->error) {
+        NodeHdr& h = t.hdr[0];
+        h.flags |= NF_HAS_D | NF_SORTED;  // prepare_node_for_visits
+        if (sp.dirichlet_epsilon > 0.009f && h.n_moves > 1) apply_dirichlet_to_root(t, sp, ws);
+    }
+    ARA_WARP_SYNC();
+}
+
+// ------------------------------------------------------------------ results (lane 0): update_eval_info
+struct SearchResult {
+    int n_moves;
+    int no_visit_idx;
+    int best_idx;
+    int node_type;
+    int pv_len;
+    float root_value;
+    float best_move_q;
+    unsigned visit_sum;
+    unsigned free_visits;
+    unsigned iterations;
+    unsigned evals;
+    int tree_nodes;
+    int error;
+    unsigned long long sum_select_k;
+    unsigned long long sum_depth;
+    Move moves[kMaxMoves];
+    uint32_t visits[kMaxMoves];
+    float q[kMaxMoves];
+    float prior[kMaxMoves];
+    double policy[kMaxMoves];
+    Move pv[kMaxDepth];
+};
+
+ARA_HD int mcts_policy(const TreeDev& t, const SearchParams& sp, const NodeHdr& h, double* out) {  // node.cpp:1070-1109
+    const int k = h.no_visit_idx;
+    const uint32_t e = h.edge_base;
+    for (int i = 0; i < h.n_moves; ++i) out[i] = 0.0;
+    if (h.node_type == NT_WIN) {
+        for (int i = 0; i < k; ++i) {
+            const int c = t.child[e + i];
+            if (c >= 0 && (t.hdr[c].flags & NF_HAS_D) && t.hdr[c].node_type == NT_LOSS) out[i] = 1.0;
+        }
+    } else if (h.node_type == NT_LOSS) {
+        int longest = 0, end = 0;
+        for (int i = 0; i < k; ++i) {
+            const int c = t.child[e + i];
+            if (c >= 0 && (t.hdr[c].flags & NF_HAS_D) && t.hdr[c].end_in_ply > end) end = t.hdr[c].end_in_ply, longest = i;
+        }
+        out[longest] = 1.0;
+    } else {
+        for (int i = 0; i < k; ++i) out[i] = static_cast<double>(t.N[e + i]);
+        if (h.n_unsolved != h.n_moves && h.node_type != NT_LOSS)
+            for (int i = 0; i < k; ++i) {
+                const int c = t.child[e + i];
+                if (c >= 0 && (t.hdr[c].flags & NF_HAS_D) && t.hdr[c].node_type == NT_WIN) out[i] = 0;
+            }
+        if (sp.q_value_weight > 0) {
+            int best_q = 0;
+            for (int i = 1; i < k; ++i)
+                if (t.Q[e + i] > t.Q[e + best_q]) best_q = i;
+            double first = out[0], second = 2.2250738585072014e-308;
+            int first_arg = 0, second_arg = 0;
+            for (int i = 1; i < k; ++i) {
+                if (out[i] > first) {
+                    second = first;
+                    second_arg = first_arg;
+                    first = out[i];
+                    first_arg = i;
+                } else if (out[i] > second) {
+                    second = out[i];
+                    second_arg = i;
+                }
+            }
+            const int best = first_arg;
+            if (sp.q_veto_delta != 0 && best_q != best && t.Q[e + best_q] > t.Q[e + best] + sp.q_veto_delta && t.N[e + best_q] > 1) {
+                if (out[best] > out[best_q]) {
+                    const double save = out[best_q];
+                    out[best_q] = out[best];
+                    out[best] = save;
+                }
+            } else if (best != second_arg && t.Q[e + second_arg] > t.Q[e + best]) {
+                const float q_diff = t.Q[e + second_arg] - t.Q[e + best];
+                out[second_arg] += q_diff * sp.q_value_weight * out[best];
+            }
+        }
+    }
+    double sum = 0;
+    for (int i = 0; i < k; ++i) sum += out[i];
+    for (int i = 0; i < k; ++i) out[i] /= sum;
+    int b = 0;
+    for (int i = 1; i < k; ++i)
+        if (out[i] > out[b]) b = i;
+    return b;
+}
+ARA_HD int best_action_index(const TreeDev& t, const SearchParams& sp, const NodeHdr& h, bool fast, double* tmp) {
+    if (h.checkmate_idx != kNoCheckmate) return h.checkmate_idx;
+    if (h.node_type == NT_LOSS) {
+        int longest = 0, idx = 0;
+        for (int i = 0; i < h.n_moves; ++i) {
+            const int c = t.child[h.edge_base + i];
+            if (c >= 0 && t.hdr[c].end_in_ply > longest) longest = t.hdr[c].end_in_ply, idx = i;
+        }
+        return idx;
+    }
+    if (fast) {
+        int b = 0;
+        for (int i = 1; i < h.no_visit_idx; ++i)
+            if (t.N[h.edge_base + i] > t.N[h.edge_base + b]) b = i;
+        return b;
+    }
+    return mcts_policy(t, sp, h, tmp);
+}
+ARA_HD float value_display(const NodeHdr& h) {
+    if (h.node_type == NT_WIN) return 1.0f;
+    if (h.node_type == NT_LOSS) return -1.0f;
+    if (h.node_type == NT_DRAW) return 0.0f;
+    return node_value(h);
+}
+ARA_HD void collect_result(const TreeDev& t, const SearchParams& sp, SearchResult* r) {  // lane 0
+    const TreeState& st = *t.st;
+    const NodeHdr& h = t.hdr[0];
+    r->error = st.error;
+    r->tree_nodes = st.n_nodes;
+    r->iterations = st.iterations;
+    r->evals = st.evals;
+    r->sum_select_k = st.sum_select_k;
+    r->sum_depth = st.sum_depth;
+    r->n_moves = h.n_moves;
+    const bool has_d = (h.flags & NF_HAS_D) != 0;
+    r->no_visit_idx = has_d ? h.no_visit_idx : 0;
+    r->node_type = has_d ? h.node_type : NT_UNSOLVED;
+    r->visit_sum = has_d ? h.visit_sum : 0;
+    r->free_visits = has_d ? h.free_visits : 0;
+    r->root_value = h.real_visits ? node_value(h) : 0.0f;
+    r->best_idx = -1;
+    r->best_move_q = 0.0f;
+    r->pv_len = 0;
+    if (h.n_moves == 0 || (h.flags & NF_TERMINAL)) return;
+    const uint32_t e = h.edge_base;
+    for (int i = 0; i < h.n_moves; ++i) {
+        r->moves[i] = t.move[e + i];
+        r->visits[i] = i < h.no_visit_idx ? t.N[e + i] : 0;
+        r->q[i] = i < h.no_visit_idx ? t.Q[e + i] : -1.0f;
+        r->prior[i] = t.P[e + i];
+        r->policy[i] = 0.0;
+    }
+    if (!(h.flags & NF_HAS_NN)) return;
+    // get_best_action_index(root, fast = false) and the posterior (evalinfo.cpp:199-206)
+    int bi = 0;
+    if (h.n_moves == 1) {
+        r->policy[0] = 1.0;
+    } else {
+        bi = mcts_policy(t, sp, h, r->policy);
+    }
+    if (h.checkmate_idx != kNoCheckmate) bi = h.checkmate_idx;
+    else if (h.node_type == NT_LOSS) bi = best_action_index(t, sp, h, true, nullptr);
+    r->best_idx = bi;
+    // set_eval_for_single_pv (evalinfo.cpp:123-178) + get_principal_variation (node.cpp:1111-1121)
+    int n = 0;
+    r->pv[n++] = t.move[e + bi];
+    int c = t.child[e + bi];
+    if (c < 0) {
+        r->best_move_q = kQInit;
+    } else {
+        const NodeHdr& ch = t.hdr[c];
+        r->best_move_q = (ch.flags & NF_HAS_D) ? -value_display(ch) : -node_value(ch);
+        while (c >= 0 && (t.hdr[c].flags & NF_HAS_D) && !(t.hdr[c].flags & NF_TERMINAL) && n < kMaxDepth) {
+            const NodeHdr& cur = t.hdr[c];
+            const int ci = best_action_index(t, sp, cur, true, nullptr);
+            r->pv[n++] = t.move[cur.edge_base + ci];
+            c = t.child[cur.edge_base + ci];
+        }
+    }
+    r->pv_len = n;
+}
+
+// ------------------------------------------------------------------ hash-derived fake network (test backend)
+// Same definition as oracle/fake.c: every output is (9-bit integer) * 2^k, exact in fp32.
+ARA_HD uint64_t zmix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+ARA_HD float fake_value(uint64_t key) {
+    const uint64_t h0 = zmix64(key ^ 0x9E3779B97F4A7C15ULL);
+    return static_cast<float>(static_cast<int>((h0 >> 11) & 0xFFFF) - 32768) * (1.0f / 65536.0f);
+}
+ARA_HD float fake_prob(uint64_t key, int i) {
+    const uint64_t h = zmix64(key + static_cast<uint64_t>(i + 1) * 0xD6E8FEB86659FD93ULL);
+    const uint32_t lo = static_cast<uint32_t>(h) | 0x80u;
+#if defined(__CUDA_ARCH__)
+    const int tz = __ffs(static_cast<int>(lo)) - 1;
+#else
+    const int tz = __builtin_ctz(lo);
+#endif
+    const int m = static_cast<int>((h >> 40) & 0xFF);
+    return static_cast<float>(256 + m) * (1.0f / 65536.0f) * static_cast<float>(1 << tz);
+}
+
+}  // namespace ara

@@ -266,8 +266,9 @@ static void node_free(ONode* n) {
     free(n);
 }
 
-/* sort_moves_by_probabilities node.cpp:464-470.  std::sort on a permutation is unstable for equal priors; the
- * oracle (and the product) fix the tie-break to "original order" so that both agree. */
+/* sort_moves_by_probabilities node.cpp:464-470.  std::sort on a permutation is unstable for equal priors, i.e. the
+ * reference leaves the order of tied moves unspecified; the oracle (and the product) break ties by ascending
+ * policy-vector index, which does not depend on the move generator's emission order. */
 typedef struct {
     float p;
     uint32_t a;
@@ -278,11 +279,11 @@ static int cmp_desc(const void* x, const void* y) {
     const SortItem* b = (const SortItem*)y;
     if (a->p > b->p) return -1;
     if (a->p < b->p) return 1;
-    return a->i - b->i;
+    return a->i - b->i; /* i = policy-vector index */
 }
 static void prepare_node_for_visits(ONode* n) { /* node.cpp:634-644 */
     SortItem* it = (SortItem*)malloc(sizeof(SortItem) * (size_t)(n->n_actions > 0 ? n->n_actions : 1));
-    for (int i = 0; i < n->n_actions; ++i) it[i].p = n->policy[i], it[i].a = n->actions[i], it[i].i = i;
+    for (int i = 0; i < n->n_actions; ++i) it[i].p = n->policy[i], it[i].a = n->actions[i], it[i].i = n->pidx[i];
     qsort(it, (size_t)n->n_actions, sizeof(SortItem), cmp_desc);
     for (int i = 0; i < n->n_actions; ++i) n->policy[i] = it[i].p, n->actions[i] = it[i].a;
     free(it);

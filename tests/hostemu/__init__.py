@@ -105,3 +105,92 @@ class HeState:
 
     def board_bytes(self):
         return ctypes.string_at(self.L.he_board(self.h), 128)
+
+
+class SearchResult(ctypes.Structure):
+    _fields_ = [("n_moves", ctypes.c_int), ("no_visit_idx", ctypes.c_int), ("best_idx", ctypes.c_int),
+                ("node_type", ctypes.c_int), ("pv_len", ctypes.c_int), ("root_value", ctypes.c_float),
+                ("best_move_q", ctypes.c_float), ("visit_sum", ctypes.c_uint), ("free_visits", ctypes.c_uint),
+                ("iterations", ctypes.c_uint), ("evals", ctypes.c_uint), ("tree_nodes", ctypes.c_int),
+                ("error", ctypes.c_int), ("sum_select_k", ctypes.c_ulonglong), ("sum_depth", ctypes.c_ulonglong),
+                ("moves", ctypes.c_uint16 * 512), ("visits", ctypes.c_uint32 * 512), ("q", ctypes.c_float * 512),
+                ("prior", ctypes.c_float * 512), ("policy", ctypes.c_double * 512), ("pv", ctypes.c_uint16 * 256)]
+
+
+def result_to_dict(r, uci_fn):
+    import numpy as np
+    k = r.n_moves
+    d = dict(moves=[uci_fn(m) for m in r.moves[:k]], visits=np.array(r.visits[:k], np.uint32),
+             q=np.array(r.q[:k], np.float32), prior=np.array(r.prior[:k], np.float32),
+             policy=np.array(r.policy[:k], np.float64), root_value=r.root_value, visit_sum=r.visit_sum,
+             free_visits=r.free_visits, nodes=r.visit_sum - r.free_visits, best_idx=r.best_idx,
+             best_move_q=r.best_move_q, node_type=r.node_type, pv_len=r.pv_len, iterations=r.iterations,
+             evals=r.evals, tree_nodes=r.tree_nodes, sum_select_k=r.sum_select_k, sum_depth=r.sum_depth,
+             error=r.error, pv=[uci_fn(m) for m in r.pv[:r.pv_len]])
+    if k > 0 and r.best_idx >= 0:
+        d["best_move"] = d["moves"][r.best_idx]
+    return d
+
+
+class HeSearch:
+    """Host emulation of the GPU search, driven like oracle.search.Search."""
+
+    def __init__(self, settings, max_nodes=1 << 16, max_edges=1 << 21):
+        import numpy as np
+        self.np = np
+        self.L = L = lib()
+        L.he_search_new.restype = ctypes.c_void_p
+        L.he_search_new.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        for n in ("he_search_free", "he_search_channels", "he_search_n_labels", "he_search_create_mini_batch",
+                  "he_search_done", "he_search_error"):
+            getattr(L, n).argtypes = [ctypes.c_void_p]
+        L.he_search_planes.restype = ctypes.c_void_p
+        L.he_search_planes.argtypes = [ctypes.c_void_p]
+        L.he_search_set_root.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.he_search_root_results.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.he_search_apply_results.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.he_search_batch_keys.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.he_search_result.restype = ctypes.POINTER(SearchResult)
+        L.he_search_result.argtypes = [ctypes.c_void_p]
+        L.he_fake_eval.argtypes = [ctypes.c_ulonglong, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        assert L.he_sizeof_result() == ctypes.sizeof(SearchResult)
+        self.settings = settings
+        self.h = L.he_search_new(ctypes.byref(settings), max_nodes, max_edges)
+        self.channels = L.he_search_channels(self.h)
+        self.n_labels = L.he_search_n_labels(self.h)
+        self.batch = settings.batch_size
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.he_search_free(self.h)
+            self.h = None
+
+    def _planes(self, n):
+        ptr = self.L.he_search_planes(self.h)
+        arr = self.np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_float)),
+                                         shape=(self.batch, self.channels, 8, 8))
+        return arr[:n].copy()
+
+    def _keys(self, n):
+        k = self.np.zeros(max(n, 1), self.np.uint64)
+        self.L.he_search_batch_keys(self.h, k.ctypes.data)
+        return k[:n]
+
+    def run(self, he_state, net_fn, with_keys=False):
+        L, h, np = self.L, self.h, self.np
+        n = L.he_search_set_root(h, he_state.h)
+        if n:
+            v, p = net_fn(self._planes(1), self._keys(1)) if with_keys else net_fn(self._planes(1))
+            v, p = np.ascontiguousarray(v, np.float32), np.ascontiguousarray(p, np.float32)
+            L.he_search_root_results(h, v.ctypes.data, p.ctypes.data)
+            while True:
+                n = L.he_search_create_mini_batch(h)
+                if L.he_search_done(h):
+                    break
+                if n > 0:
+                    v, p = net_fn(self._planes(n), self._keys(n)) if with_keys else net_fn(self._planes(n))
+                    v, p = np.ascontiguousarray(v, np.float32), np.ascontiguousarray(p, np.float32)
+                else:
+                    v, p = np.zeros(1, np.float32), np.zeros(1, np.float32)
+                L.he_search_apply_results(h, v.ctypes.data, p.ctypes.data)
+        return result_to_dict(L.he_search_result(h).contents, he_state.uci)

@@ -63,3 +63,133 @@ int he_planes(const HeState* s, int mode, int version, int normalize, float* out
 int he_sizeof_board() { return static_cast<int>(sizeof(Board)); }
 const void* he_board(const HeState* s) { return &s->b; }
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// 1-lane emulation of the GPU search (search_dev.cuh) with host arrays standing in for the HBM pools.
+#include <cmath>
+
+#include "search_dev.cuh"
+
+struct HostWriterFactory {
+    float* base;
+    int channels;
+    NchwF32Writer make(int slot) const { return NchwF32Writer{base + static_cast<size_t>(slot) * channels * 64}; }
+};
+
+struct HeSearch {
+    SearchParams sp;
+    TreeDev t;
+    TreeState st;
+    std::vector<NodeHdr> hdr;
+    std::vector<Board> board;
+    std::vector<float> P, Q;
+    std::vector<uint32_t> N;
+    std::vector<int32_t> child;
+    std::vector<Move> move;
+    std::vector<uint8_t> vl, etype;
+    std::vector<int32_t> new_node, traj_node, traj_len;
+    std::vector<uint16_t> traj_ci;
+    std::vector<uint64_t> hist_keys;
+    std::vector<int16_t> hist_reps;
+    std::vector<float> lut;
+    std::vector<float> planes;
+    WarpScratch ws;
+    int channels, n_labels;
+    Board root;
+    SearchResult result;
+};
+
+extern "C" {
+
+HeSearch* he_search_new(const SearchParams* sp, int max_nodes, int max_edges) {
+    HeSearch* s = new HeSearch();
+    s->sp = *sp;
+    const int B = sp->batch_size;
+    s->hdr.resize(max_nodes);
+    s->board.resize(max_nodes);
+    s->P.resize(max_edges);
+    s->Q.resize(max_edges);
+    s->N.resize(max_edges);
+    s->child.resize(max_edges);
+    s->move.resize(max_edges);
+    s->vl.resize(max_edges);
+    s->etype.resize(max_edges);
+    s->new_node.resize(B);
+    s->traj_node.resize(2 * B * kMaxDepth);
+    s->traj_ci.resize(2 * B * kMaxDepth);
+    s->traj_len.resize(2 * B);
+    s->channels = planes_channels(sp->mode, sp->input_version);
+    s->n_labels = (sp->mode == MODE_CRAZYHOUSE ? 81 : (sp->mode == MODE_CHESS ? 76 : 84)) * 64;
+    s->planes.assign(static_cast<size_t>(B) * s->channels * 64, 0.0f);
+    const int lut_len = 1 << 16;
+    s->lut.resize(lut_len);
+    for (int i = 0; i < lut_len; ++i) s->lut[i] = logf((static_cast<float>(i) + sp->cpuct_base + 1) / sp->cpuct_base) + sp->cpuct_init;
+    memset(&s->st, 0, sizeof(s->st));
+    TreeDev& t = s->t;
+    t.hdr = s->hdr.data();
+    t.board = s->board.data();
+    t.P = s->P.data();
+    t.Q = s->Q.data();
+    t.N = s->N.data();
+    t.child = s->child.data();
+    t.move = s->move.data();
+    t.vl = s->vl.data();
+    t.etype = s->etype.data();
+    t.st = &s->st;
+    t.new_node = s->new_node.data();
+    t.traj_node = s->traj_node.data();
+    t.traj_ci = s->traj_ci.data();
+    t.traj_len = s->traj_len.data();
+    t.hist_keys = nullptr;
+    t.hist_reps = nullptr;
+    t.hist_len = 0;
+    t.cput_lut = s->lut.data();
+    t.cput_lut_len = lut_len;
+    t.max_nodes = max_nodes;
+    t.max_edges = max_edges;
+    t.slot_base = 0;
+    return s;
+}
+void he_search_free(HeSearch* s) { delete s; }
+int he_search_channels(const HeSearch* s) { return s->channels; }
+int he_search_n_labels(const HeSearch* s) { return s->n_labels; }
+const float* he_search_planes(const HeSearch* s) { return s->planes.data(); }
+
+int he_search_set_root(HeSearch* s, const HeState* root) {
+    s->root = root->b;
+    s->hist_keys = root->keys;
+    s->hist_reps = root->reps;
+    s->t.hist_keys = s->hist_keys.data();
+    s->t.hist_reps = s->hist_reps.data();
+    s->t.hist_len = static_cast<int>(s->hist_keys.size());
+    HostWriterFactory wf{s->planes.data(), s->channels};
+    create_root(s->t, s->sp, s->ws, &s->root, wf);
+    return s->st.n_new;
+}
+void he_search_root_results(HeSearch* s, const float* values, const float* probs) {
+    apply_results(s->t, s->sp, s->ws, values, probs, s->n_labels);
+    finalize_root(s->t, s->sp, s->ws);
+}
+int he_search_create_mini_batch(HeSearch* s) {
+    HostWriterFactory wf{s->planes.data(), s->channels};
+    create_mini_batch(s->t, s->sp, s->ws, wf);
+    return s->st.n_new;
+}
+void he_search_apply_results(HeSearch* s, const float* values, const float* probs) {
+    apply_results(s->t, s->sp, s->ws, values, probs, s->n_labels);
+}
+int he_search_done(const HeSearch* s) { return s->st.done || s->st.error; }
+int he_search_error(const HeSearch* s) { return s->st.error; }
+void he_search_batch_keys(const HeSearch* s, unsigned long long* out) {
+    for (int i = 0; i < s->st.n_new; ++i) out[i] = s->hdr[s->new_node[i]].key;
+}
+const SearchResult* he_search_result(HeSearch* s) {
+    collect_result(s->t, s->sp, &s->result);
+    return &s->result;
+}
+void he_fake_eval(unsigned long long key, int n_labels, float* value, float* prob) {
+    *value = fake_value(key);
+    for (int i = 0; i < n_labels; ++i) prob[i] = fake_prob(key, i);
+}
+int he_sizeof_result() { return static_cast<int>(sizeof(SearchResult)); }
+}

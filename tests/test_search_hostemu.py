@@ -1,0 +1,75 @@
+"""The GPU search code (crazyara_b200/csrc/search_dev.cuh) run as a 1-lane host emulation against the search
+oracle (oracle/mcts.c) with the hash-derived fake backend: visit counts, Q values, priors, posterior, root value,
+best move, node counters must agree BIT-EXACTLY (the GPU run of the same comparison is tests/test_search_gpu.py)."""
+import numpy as np
+import pytest
+
+from oracle import search as osr
+from oracle.chess import Position
+from tests.hostemu import HeSearch, HeState
+
+CASES = [
+    # variant, vid, mode, fen, is960, moves-to-play-first, batch, sims, extra settings
+    ("crazyhouse", 1, "crazyhouse", None, False, [], 8, 400, {}),
+    ("crazyhouse", 1, "crazyhouse", None, False, [], 64, 1600, {}),
+    ("chess", 0, "chess", None, False, ["e2e4", "c7c5", "g1f3"], 64, 1600, {}),
+    ("chess", 0, "chess", None, False, [], 1, 100, {}),
+    ("chess", 0, "chess", "bqnb1rkr/pp3ppp/3ppn2/2p5/5P2/P2P4/NPP1P1PP/BQ1BNRKR w HFhf - 2 9", True, [], 8, 300, {}),
+    ("kingofthehill", 2, "lichess", None, False, ["e2e4", "e7e5", "e1e2", "e8e7", "e2e3", "e7e6"], 16, 600, {}),
+    ("3check", 3, "lichess", None, False, ["e2e4", "f7f6", "d1h5", "g7g6"], 16, 600, {}),
+    # mate-in-few positions: exercise the MCTS solver and terminal (free) backups
+    ("chess", 0, "chess", "6k1/5ppp/8/8/8/8/8/R3K2R w KQ - 0 1", False, [], 8, 400, {}),
+    ("chess", 0, "chess", "7k/5Q2/6K1/8/8/8/8/8 w - - 0 1", False, [], 4, 200, {}),
+    ("crazyhouse", 1, "crazyhouse", "4R2b/1N3rkb/1p2P1pp/p2P4/2P1P3/8/PP4Q1/3R3K[QRBBNNNPPPPpp] w - - 2 53", False, [], 8, 300, {}),
+    # virtual loss style, solver off, nodes limit
+    ("crazyhouse", 1, "crazyhouse", None, False, ["e2e4"], 16, 500, dict(virtual_style=0)),
+    ("crazyhouse", 1, "crazyhouse", None, False, ["e2e4"], 16, 0, dict(nodes=300, mcts_solver=0, virtual_mix_threshold=20)),
+    ("chess", 0, "chess", None, False, ["d2d4"], 32, 800, dict(q_value_weight=0.0, q_veto_delta=0.0)),
+]
+
+
+def _run_both(variant, vid, mode, fen, is960, premoves, batch, sims, extra):
+    st = osr.default_settings(mode, batch_size=batch, simulations=sims, node_policy_temperature=1.0, **extra)
+    pos = Position(fen, variant, is960)
+    he = HeState(pos.fen(), vid, is960)
+    for u in premoves:
+        pos.push_uci(u)
+        he.do_move(he.move_from_uci(u))
+    S = osr.Search(st)
+    ro = S.run(pos, osr.fake_net(S.n_labels), with_keys=True)
+    H = HeSearch(st)
+    rh = H.run(he, osr.fake_net(H.n_labels), with_keys=True)
+    return ro, rh
+
+
+def assert_same_search(ro, rh):
+    assert rh["error"] == 0
+    assert ro["moves"] == rh["moves"]
+    assert np.array_equal(ro["visits"], rh["visits"])
+    assert np.array_equal(ro["q"], rh["q"])
+    assert np.array_equal(ro["prior"], rh["prior"])
+    assert np.array_equal(ro["policy"], rh["policy"])
+    for k in ("visit_sum", "free_visits", "nodes", "best_idx", "node_type", "iterations", "evals", "tree_nodes",
+              "sum_select_k", "sum_depth", "pv_len"):
+        assert ro[k] == rh[k], k
+    assert ro["root_value"] == rh["root_value"] and ro["best_move_q"] == rh["best_move_q"]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[f"{c[0]}-b{c[6]}-s{c[7]}-{i}" for i, c in enumerate(CASES)])
+def test_hostemu_search_equals_oracle(case):
+    ro, rh = _run_both(*case)
+    assert ro["visit_sum"] > 0
+    assert_same_search(ro, rh)
+
+
+def test_fake_backends_identical():
+    import ctypes
+    from oracle.search import _lib
+    from tests.hostemu import lib as helib
+    for key in (0, 1, 0xDEADBEEFCAFEF00D, 2**64 - 1, 123456789):
+        vo, po = np.zeros(1, np.float32), np.zeros(5184, np.float32)
+        vh, ph = np.zeros(1, np.float32), np.zeros(5184, np.float32)
+        _lib().ofake_eval(key, 5184, vo.ctypes.data, po.ctypes.data)
+        HeSearch(osr.default_settings("crazyhouse"))  # sets argtypes
+        helib().he_fake_eval(key, 5184, vh.ctypes.data, ph.ctypes.data)
+        assert vo[0] == vh[0] and np.array_equal(po, ph)

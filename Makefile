@@ -9,9 +9,12 @@ LIB       := crazyara_b200/libara_b200.so
 
 all: $(LIB)
 
+build/search.o: EXTRA := -fmad=false
+build/rules_kernels.o: EXTRA := -fmad=false
+
 build/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) $(wildcard include/*.h)
 	@mkdir -p build
-	$(NVCC) $(NVFLAGS) -c $< -o $@
+	$(NVCC) $(NVFLAGS) $(EXTRA) -c $< -o $@
 
 $(LIB): $(CU_OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $^

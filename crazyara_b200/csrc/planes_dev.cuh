@@ -30,7 +30,7 @@ struct NchwF32Writer {  // the reference's [C,8,8] float layout (State::get_stat
 struct NhwcF16Writer {  // [64, cpad] fp16: the stem convolution's A operand
     __half* out;
     int cpad;
-    __device__ __forceinline__ void put(int c, int sq, float v) const { out[sq * cpad + c] = __float2half_rn(v); }
+    ARA_HD void put(int c, int sq, float v) const { out[sq * cpad + c] = __float2half_rn(v); }
 };
 #endif
 

@@ -1,0 +1,391 @@
+// GPU MCTS engine: kernels around search_dev.cuh, the host-side driver (MCTSAgent::evaluate_board_state /
+// SearchThread::thread_iteration of the reference) and the C-ABI.
+//
+// Per search iteration three things are enqueued on one stream, with no host round trip in between:
+//   select_kernel  (one warp per tree: create_mini_batch -> planes written straight into the network's NHWC input)
+//   network        (tcgen05 conv stack, CUDA graph; or the hash-derived fake backend for search-parity tests)
+//   apply_kernel   (scatter priors/values into the new nodes, backups, collision reverts)
+// The host only looks at the per-tree `done` flag once per chunk of iterations.
+// This translation unit is compiled with -fmad=false: the PUCT / Q arithmetic must round exactly like the
+// reference's (and the oracle's) scalar C++ code.
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "abi_common.h"
+#include "ara_b200.h"
+#include "net.h"
+#include "search_dev.cuh"
+
+namespace ara {
+
+struct DevWriterFactory {
+    __half* base;
+    int cpad;
+    ARA_HD NhwcF16Writer make(int slot) const { return NhwcF16Writer{base + static_cast<size_t>(slot) * 64 * cpad, cpad}; }
+};
+struct NullWriterFactory {  // fake backend: no planes needed
+    struct W {
+        ARA_HD void put(int, int, float) const {}
+    };
+    ARA_HD W make(int) const { return W{}; }
+};
+
+__global__ void __launch_bounds__(32) root_kernel(const TreeDev* trees, SearchParams sp, const Board* roots, __half* in_h,
+                                                  int cpad) {
+    __shared__ WarpScratch ws;
+    const TreeDev t = trees[blockIdx.x];
+    if (in_h != nullptr) {
+        DevWriterFactory wf{in_h, cpad};
+        create_root(t, sp, ws, &roots[blockIdx.x], wf);
+    } else {
+        NullWriterFactory wf;
+        create_root(t, sp, ws, &roots[blockIdx.x], wf);
+    }
+}
+
+__global__ void __launch_bounds__(32) select_kernel(const TreeDev* trees, SearchParams sp, __half* in_h, int cpad) {
+    __shared__ WarpScratch ws;
+    const TreeDev t = trees[blockIdx.x];
+    if (in_h != nullptr) {
+        DevWriterFactory wf{in_h, cpad};
+        create_mini_batch(t, sp, ws, wf);
+    } else {
+        NullWriterFactory wf;
+        create_mini_batch(t, sp, ws, wf);
+    }
+}
+
+__global__ void __launch_bounds__(32) apply_kernel(const TreeDev* trees, SearchParams sp, const float* values,
+                                                   const float* probs, int n_labels, int finalize) {
+    __shared__ WarpScratch ws;
+    const TreeDev t = trees[blockIdx.x];
+    apply_results(t, sp, ws, values, probs, n_labels);
+    if (finalize) finalize_root(t, sp, ws);
+}
+
+__global__ void __launch_bounds__(32) result_kernel(const TreeDev* trees, SearchParams sp, SearchResult* out) {
+    const TreeDev t = trees[blockIdx.x];
+    if (threadIdx.x == 0) collect_result(t, sp, &out[blockIdx.x]);
+}
+
+// Fake backend: value/prob rows of the pending new nodes from their Zobrist keys (oracle/fake.c definition).
+__global__ void fake_eval_kernel(const TreeDev* trees, int n_trees, int batch, float* values, float* probs, int n_labels) {
+    const int slot = blockIdx.x;  // tree * batch + b
+    const int tree = slot / batch, b = slot - tree * batch;
+    if (tree >= n_trees) return;
+    const TreeDev t = trees[tree];
+    if (b >= t.st->n_new) return;
+    const uint64_t key = t.hdr[t.new_node[b]].key;
+    if (threadIdx.x == 0) values[slot] = fake_value(key);
+    for (int i = threadIdx.x; i < n_labels; i += blockDim.x) probs[static_cast<size_t>(slot) * n_labels + i] = fake_prob(key, i);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+class Search {
+   public:
+    ~Search();
+    int init(Net* net, const SearchParams& sp, int device, int n_trees, int max_nodes);
+    int set_position(int tree, const Board& root, const uint64_t* hist_keys, const int16_t* hist_reps, int hist_len);
+    int go();
+    int fetch_results();
+    SearchParams sp{};
+    int n_trees = 0;
+    std::vector<SearchResult> results;
+    long long launches = 0;
+    double last_go_ms = 0.0;
+
+   private:
+    template <typename T>
+    int dalloc(T** p, size_t count);
+    int iterate(int count);
+    Net* net_ = nullptr;
+    int device_ = 0;
+    cudaStream_t stream_ = nullptr;
+    bool own_stream_ = false;
+    int max_nodes_ = 0, max_edges_ = 0, n_labels_ = 0, hist_cap_ = 512;
+    std::vector<void*> allocs_;
+    std::vector<TreeDev> h_trees_;
+    TreeDev* d_trees_ = nullptr;
+    Board* d_roots_ = nullptr;
+    std::vector<Board> h_roots_;
+    std::vector<TreeState*> d_states_;
+    std::vector<uint64_t*> d_hist_keys_;
+    std::vector<int16_t*> d_hist_reps_;
+    float* d_lut_ = nullptr;
+    float *d_values_ = nullptr, *d_probs_ = nullptr;  // fake backend buffers
+    SearchResult* d_results_ = nullptr;
+    int* h_done_ = nullptr;  // pinned
+    cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+};
+
+template <typename T>
+int Search::dalloc(T** p, size_t count) {
+    void* q = nullptr;
+    ARA_CUDA_OK(cudaMalloc(&q, count * sizeof(T)));
+    ARA_CUDA_OK(cudaMemset(q, 0, count * sizeof(T)));
+    allocs_.push_back(q);
+    *p = static_cast<T*>(q);
+    return 0;
+}
+
+Search::~Search() {
+    cudaSetDevice(device_);
+    if (stream_) cudaStreamSynchronize(stream_);
+    for (void* p : allocs_) cudaFree(p);
+    if (h_done_) cudaFreeHost(h_done_);
+    if (ev0_) cudaEventDestroy(ev0_);
+    if (ev1_) cudaEventDestroy(ev1_);
+    if (own_stream_ && stream_) cudaStreamDestroy(stream_);
+}
+
+int Search::init(Net* net, const SearchParams& params, int device, int trees, int max_nodes) {
+    sp = params;
+    net_ = net;
+    device_ = net ? net->device : device;
+    n_trees = trees;
+    if (sp.batch_size < 1 || sp.batch_size > 1024) return set_error("ara_search_create: batch_size %d out of range", sp.batch_size);
+    if (n_trees < 1) return set_error("ara_search_create: n_trees %d < 1", n_trees);
+    if (planes_channels(sp.mode, sp.input_version) < 0)
+        return set_error("ara_search_create: unsupported mode %d / input version %d", sp.mode, sp.input_version);
+    ARA_CUDA_OK(cudaSetDevice(device_));
+    {
+        cudaDeviceProp prop;
+        ARA_CUDA_OK(cudaGetDeviceProperties(&prop, device_));
+        if (prop.major < 10) return set_error("ara_search_create: device %d is not sm_100 (B200)", device_);
+    }
+    n_labels_ = (sp.mode == MODE_CRAZYHOUSE ? 81 : (sp.mode == MODE_CHESS ? 76 : 84)) * 64;
+    if (net_ != nullptr) {
+        if (net_->batch < n_trees * sp.batch_size)
+            return set_error("ara_search_create: network batch %d < trees %d x Batch_Size %d", net_->batch, n_trees, sp.batch_size);
+        if (net_->n_labels() != n_labels_ || net_->hdr.in_channels != planes_channels(sp.mode, sp.input_version))
+            return set_error("ara_search_create: network shape (C=%d, L=%d) does not match mode/version (C=%d, L=%d)",
+                             net_->hdr.in_channels, net_->n_labels(), planes_channels(sp.mode, sp.input_version), n_labels_);
+        stream_ = net_->stream;
+    } else {
+        ARA_CUDA_OK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+        own_stream_ = true;
+        if (dalloc(&d_values_, static_cast<size_t>(n_trees) * sp.batch_size)) return -1;
+        if (dalloc(&d_probs_, static_cast<size_t>(n_trees) * sp.batch_size * n_labels_)) return -1;
+    }
+    if (max_nodes <= 0) {
+        const unsigned budget = sp.simulations ? sp.simulations : (sp.nodes ? sp.nodes * 2 : 0);
+        if (budget == 0) return set_error("ara_search_create: max_nodes must be given when neither Simulations nor Nodes is set");
+        max_nodes = static_cast<int>(budget) + 4 * sp.batch_size + 64;
+    }
+    max_nodes_ = max_nodes;
+    max_edges_ = max_nodes * 64 + 1024;
+    const int B = sp.batch_size;
+    // cput look-up table with the HOST libm: bit-identical to the reference's scalar code (node.cpp:1243-1246)
+    {
+        int len = max_nodes_ + 8;
+        if (len > (1 << 22)) len = 1 << 22;
+        std::vector<float> lut(len);
+        for (int i = 0; i < len; ++i) lut[i] = logf((static_cast<float>(i) + sp.cpuct_base + 1) / sp.cpuct_base) + sp.cpuct_init;
+        if (dalloc(&d_lut_, lut.size())) return -1;
+        ARA_CUDA_OK(cudaMemcpy(d_lut_, lut.data(), lut.size() * 4, cudaMemcpyHostToDevice));
+        h_trees_.resize(n_trees);
+        for (auto& t : h_trees_) t.cput_lut_len = len;
+    }
+    d_states_.resize(n_trees);
+    d_hist_keys_.resize(n_trees);
+    d_hist_reps_.resize(n_trees);
+    for (int i = 0; i < n_trees; ++i) {
+        TreeDev& t = h_trees_[i];
+        if (dalloc(&t.hdr, max_nodes_) || dalloc(&t.board, max_nodes_)) return -1;
+        if (dalloc(&t.P, max_edges_) || dalloc(&t.Q, max_edges_) || dalloc(&t.N, max_edges_) || dalloc(&t.child, max_edges_) ||
+            dalloc(&t.move, max_edges_) || dalloc(&t.vl, max_edges_) || dalloc(&t.etype, max_edges_))
+            return -1;
+        if (dalloc(&t.st, 1)) return -1;
+        if (dalloc(&t.new_node, B) || dalloc(&t.traj_node, static_cast<size_t>(2) * B * kMaxDepth) ||
+            dalloc(&t.traj_ci, static_cast<size_t>(2) * B * kMaxDepth) || dalloc(&t.traj_len, 2 * B))
+            return -1;
+        if (dalloc(&d_hist_keys_[i], hist_cap_) || dalloc(&d_hist_reps_[i], hist_cap_)) return -1;
+        t.hist_keys = d_hist_keys_[i];
+        t.hist_reps = d_hist_reps_[i];
+        t.hist_len = 0;
+        t.cput_lut = d_lut_;
+        t.max_nodes = max_nodes_;
+        t.max_edges = max_edges_;
+        t.slot_base = i * B;
+        d_states_[i] = t.st;
+    }
+    if (dalloc(&d_trees_, n_trees) || dalloc(&d_roots_, n_trees) || dalloc(&d_results_, n_trees)) return -1;
+    h_roots_.resize(n_trees);
+    results.resize(n_trees);
+    ARA_CUDA_OK(cudaMallocHost(&h_done_, sizeof(int) * n_trees));
+    ARA_CUDA_OK(cudaEventCreate(&ev0_));
+    ARA_CUDA_OK(cudaEventCreate(&ev1_));
+    return 0;
+}
+
+int Search::set_position(int tree, const Board& root, const uint64_t* hist_keys, const int16_t* hist_reps, int hist_len) {
+    if (tree < 0 || tree >= n_trees) return set_error("ara_search_set_position: tree %d out of range", tree);
+    ARA_CUDA_OK(cudaSetDevice(device_));
+    h_roots_[tree] = root;
+    // keep the most recent hist_cap_ plies (rule50 bounds the look-back to 100 plies in chess; crazyhouse looks back
+    // over the whole game, truncated here to hist_cap_ plies)
+    int skip = hist_len > hist_cap_ ? hist_len - hist_cap_ : 0;
+    const int len = hist_len - skip;
+    if (len > 0) {
+        ARA_CUDA_OK(cudaMemcpyAsync(d_hist_keys_[tree], hist_keys + skip, sizeof(uint64_t) * len, cudaMemcpyHostToDevice, stream_));
+        ARA_CUDA_OK(cudaMemcpyAsync(d_hist_reps_[tree], hist_reps + skip, sizeof(int16_t) * len, cudaMemcpyHostToDevice, stream_));
+    }
+    h_trees_[tree].hist_len = len;
+    ARA_CUDA_OK(cudaStreamSynchronize(stream_));
+    return 0;
+}
+
+int Search::iterate(int count) {
+    __half* in_h = net_ ? net_->d_in_h : nullptr;
+    const int cpad = net_ ? net_->cin_pad : 0;
+    const int B = sp.batch_size;
+    for (int it = 0; it < count; ++it) {
+        select_kernel<<<n_trees, 32, 0, stream_>>>(d_trees_, sp, in_h, cpad);
+        if (net_) {
+            if (net_->forward_device(n_trees * B, stream_)) return -1;
+            apply_kernel<<<n_trees, 32, 0, stream_>>>(d_trees_, sp, net_->d_value, net_->d_prob, n_labels_, 0);
+        } else {
+            fake_eval_kernel<<<n_trees * B, 128, 0, stream_>>>(d_trees_, n_trees, B, d_values_, d_probs_, n_labels_);
+            apply_kernel<<<n_trees, 32, 0, stream_>>>(d_trees_, sp, d_values_, d_probs_, n_labels_, 0);
+            ++launches;
+        }
+        launches += 2;
+    }
+    ARA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int Search::go() {
+    ARA_CUDA_OK(cudaSetDevice(device_));
+    ARA_CUDA_OK(cudaEventRecord(ev0_, stream_));
+    ARA_CUDA_OK(cudaMemcpyAsync(d_trees_, h_trees_.data(), sizeof(TreeDev) * n_trees, cudaMemcpyHostToDevice, stream_));
+    ARA_CUDA_OK(cudaMemcpyAsync(d_roots_, h_roots_.data(), sizeof(Board) * n_trees, cudaMemcpyHostToDevice, stream_));
+    __half* in_h = net_ ? net_->d_in_h : nullptr;
+    const int cpad = net_ ? net_->cin_pad : 0;
+    const int B = sp.batch_size;
+    // root: create, evaluate (set_root_node_predictions), scatter, prepare_node_for_visits (+ Dirichlet)
+    root_kernel<<<n_trees, 32, 0, stream_>>>(d_trees_, sp, d_roots_, in_h, cpad);
+    if (net_) {
+        // the root of tree i sits in batch row i * B; a single-tree search only needs row 0
+        if (net_->forward_device(n_trees == 1 ? 1 : n_trees * B, stream_)) return -1;
+        apply_kernel<<<n_trees, 32, 0, stream_>>>(d_trees_, sp, net_->d_value, net_->d_prob, n_labels_, 1);
+    } else {
+        fake_eval_kernel<<<n_trees * B, 128, 0, stream_>>>(d_trees_, n_trees, B, d_values_, d_probs_, n_labels_);
+        apply_kernel<<<n_trees, 32, 0, stream_>>>(d_trees_, sp, d_values_, d_probs_, n_labels_, 1);
+        ++launches;
+    }
+    launches += 2;
+    ARA_CUDA_OK(cudaGetLastError());
+    // main loop: enqueue the iterations the visit budget certainly needs, then poll `done` in small chunks
+    unsigned budget = sp.simulations ? sp.simulations : sp.nodes;
+    int first = budget ? static_cast<int>(budget / (static_cast<unsigned>(B) * 1u)) : 8;
+    if (first < 1) first = 1;
+    bool all_done = false;
+    int chunk = first;
+    int guard = 0;
+    bool polled_root = false;
+    while (!all_done) {
+        if (polled_root && iterate(chunk)) return -1;
+        for (int i = 0; i < n_trees; ++i)
+            ARA_CUDA_OK(cudaMemcpyAsync(&h_done_[i], &d_states_[i]->done, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+        ARA_CUDA_OK(cudaStreamSynchronize(stream_));
+        all_done = true;
+        for (int i = 0; i < n_trees; ++i) all_done = all_done && (h_done_[i] != 0);
+        // errors also stop the loop: they set done through the error flag check below
+        if (!all_done) {
+            int err = 0;
+            for (int i = 0; i < n_trees && !err; ++i) {
+                TreeState st;
+                ARA_CUDA_OK(cudaMemcpy(&st, d_states_[i], sizeof(st), cudaMemcpyDeviceToHost));
+                err = st.error;
+            }
+            if (err) return set_error("ara_search_go: device search error %d (1 node pool, 2 edge pool, 3 depth > %d)", err, kMaxDepth);
+        }
+        if (polled_root) chunk = 2;
+        polled_root = true;
+        if (++guard > (1 << 22)) return set_error("ara_search_go: search did not terminate");
+    }
+    ARA_CUDA_OK(cudaEventRecord(ev1_, stream_));
+    ARA_CUDA_OK(cudaEventSynchronize(ev1_));
+    float ms = 0.0f;
+    ARA_CUDA_OK(cudaEventElapsedTime(&ms, ev0_, ev1_));
+    last_go_ms = ms;
+    return 0;
+}
+
+int Search::fetch_results() {
+    ARA_CUDA_OK(cudaSetDevice(device_));
+    result_kernel<<<n_trees, 32, 0, stream_>>>(d_trees_, sp, d_results_);
+    ++launches;
+    ARA_CUDA_OK(cudaMemcpyAsync(results.data(), d_results_, sizeof(SearchResult) * n_trees, cudaMemcpyDeviceToHost, stream_));
+    ARA_CUDA_OK(cudaStreamSynchronize(stream_));
+    for (const auto& r : results)
+        if (r.error) return set_error("search error %d on device (1 node pool, 2 edge pool, 3 depth overflow)", r.error);
+    return 0;
+}
+
+}  // namespace ara
+
+// --------------------------------------------------------------------------------------------------------- C-ABI
+using ara::Search;
+static_assert(sizeof(ara_search_settings_t) == sizeof(ara::SearchParams), "settings layout");
+static_assert(sizeof(ara_search_result_t) == sizeof(ara::SearchResult), "result layout");
+static_assert(sizeof(ara_board_t) == sizeof(ara::Board), "board layout");
+
+extern "C" void ara_search_default_settings(ara_search_settings_t* s, int mode) {
+    // uci/optionsuci.cpp:66-220 (non-RL build)
+    memset(s, 0, sizeof(*s));
+    s->batch_size = mode == ara::MODE_CHESS ? 64 : 16;
+    s->dirichlet_epsilon = 0.0f;
+    s->dirichlet_alpha = 0.2f;
+    s->node_policy_temperature = 1.7f;
+    s->q_value_weight = 1.0f;
+    s->q_veto_delta = 0.4f;
+    s->cpuct_init = 2.5f;
+    s->cpuct_base = 19652.0f;
+    s->mcts_solver = 1;
+    s->virtual_style = ara::VS_VIRTUAL_MIX;
+    s->virtual_mix_threshold = 1000;
+    s->seed = 42;
+    s->mode = mode;
+    s->input_version = mode == ara::MODE_CHESS ? 3 : 1;
+}
+
+extern "C" ara_search_t ara_search_create(ara_net_t net, const ara_search_settings_t* settings, int device, int n_trees,
+                                          int max_nodes) {
+    if (settings == nullptr) {
+        ara::set_error("ara_search_create: null settings");
+        return nullptr;
+    }
+    ara::SearchParams sp;
+    memcpy(&sp, settings, sizeof(sp));
+    std::unique_ptr<Search> s(new Search());
+    if (s->init(reinterpret_cast<ara::Net*>(net), sp, device, n_trees, max_nodes) != 0) return nullptr;
+    return reinterpret_cast<ara_search_t>(s.release());
+}
+extern "C" void ara_search_destroy(ara_search_t h) { delete reinterpret_cast<Search*>(h); }
+
+extern "C" int ara_search_set_position(ara_search_t h, int tree, const ara_board_t* root, const unsigned long long* hist_keys,
+                                       const short* hist_reps, int hist_len) {
+    if (h == nullptr || root == nullptr) return ara::set_error("ara_search_set_position: null argument");
+    ara::Board b;
+    memcpy(&b, root, sizeof(b));
+    return reinterpret_cast<Search*>(h)->set_position(tree, b, reinterpret_cast<const uint64_t*>(hist_keys), hist_reps, hist_len);
+}
+extern "C" int ara_search_go(ara_search_t h) {
+    if (h == nullptr) return ara::set_error("ara_search_go: null handle");
+    Search* s = reinterpret_cast<Search*>(h);
+    if (s->go()) return -1;
+    return s->fetch_results();
+}
+extern "C" int ara_search_result(ara_search_t h, int tree, ara_search_result_t* out) {
+    if (h == nullptr || out == nullptr) return ara::set_error("ara_search_result: null argument");
+    Search* s = reinterpret_cast<Search*>(h);
+    if (tree < 0 || tree >= s->n_trees) return ara::set_error("ara_search_result: tree %d out of range", tree);
+    memcpy(out, &s->results[tree], sizeof(*out));
+    return 0;
+}
+extern "C" double ara_search_last_go_ms(ara_search_t h) { return h ? reinterpret_cast<Search*>(h)->last_go_ms : 0.0; }
+extern "C" long long ara_search_launch_count(ara_search_t h) { return h ? reinterpret_cast<Search*>(h)->launches : 0; }

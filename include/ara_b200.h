@@ -43,6 +43,119 @@ int ara_net_forward_device(ara_net_t net, const float* planes_dev, int n, float*
 /* Number of CUDA kernels this net has launched so far (bench bookkeeping). */
 long long ara_net_launch_count(ara_net_t net);
 
+/* ---- Position seam: replaces State / BoardState for the supported variants (engine/src/state.h:287-509,
+ * environments/chess_related/boardstate.{h,cpp}).  A position is one opaque 128-byte line (bitboards, pockets,
+ * castling rooks, counters, Zobrist key, last 8 moves); it is what the device kernels read.
+ * Variants: 0 chess (incl. chess960), 1 crazyhouse, 2 King of the Hill, 3 Three-check.
+ * Moves are 16-bit: from | to<<6 | flag<<12 (flag 0 normal, 1-4 promotion N/B/R/Q, 5 en passant,
+ * 6 castling king-from -> rook-from, 8+pt drop with from == to).
+ */
+typedef struct ara_board_s {
+    unsigned long long w[16];
+} ara_board_t;
+
+/* State::set(fen, isChess960, variant) / State::fen() / StateConstants::action_to_uci -- host control plane */
+int ara_board_from_fen(const char* fen, int variant, int is960, ara_board_t* out);
+int ara_board_to_fen(const ara_board_t* board, char* buf, int buf_len);
+int ara_move_to_uci(unsigned short move, int is960, char* buf8);
+
+/* State::get_state_planes(normalize, float* planes, version) (state.h:354; board_to_planes,
+ * inputrepresentation.cpp:628-680) for n positions at once: one warp per position on the GPU.
+ * mode: 0 MODE_CRAZYHOUSE, 1 MODE_CHESS, 2 MODE_LICHESS (the reference's compile-time product mode);
+ * version: 1, 2, 3.  planes_out: [n, C, 8, 8] fp32, C = 34/51/64, 39/52, 63/80.  Host buffers. */
+int ara_encode_planes(const ara_board_t* boards, int n, int mode, int version, int normalize, float* planes_out);
+/* device-resident variant: boards_dev [n] in HBM -> planes_dev [n,C,8,8] fp32 and/or planes_half_nhwc_dev
+ * [n, 64, cpad] fp16 (the stem convolution's input layout); asynchronous on `stream`. */
+int ara_encode_planes_device(const void* boards_dev, int n, int mode, int version, int normalize, float* planes_dev,
+                             void* planes_half_nhwc_dev, int cpad, void* stream);
+
+/* State::legal_actions() + State::is_terminal() + StateConstants::action_to_index<normal, mirrored?> for n positions
+ * (boardstate.cpp:61-69, :143-226, boardstate.h:73-97): moves_out [n][512], counts [n], terminal [n] (TerminalType:
+ * 0 loss, 1 draw, 2 win, 4 none; repetition taken from the board's stored repetition info), policy_idx [n][512]
+ * (index into the policy-map vector).  terminal / policy_idx may be NULL.  Host buffers, GPU kernel. */
+int ara_legal_moves(const ara_board_t* boards, int n, unsigned short* moves_out, int* counts, int* terminal, int* policy_idx);
+
+/* Game state with history (BoardState: position + the StateInfo chain that repetition detection walks).  Host control
+ * plane for UCI "position ... moves ..." and the self-play loop; hands roots to ara_search_set_position. */
+typedef struct ara_state_s* ara_state_t;
+ara_state_t ara_state_create(const char* fen_or_null, int variant, int is960); /* State::set / State::init */
+ara_state_t ara_state_clone(ara_state_t s);                                    /* State::clone */
+void ara_state_destroy(ara_state_t s);
+int ara_state_do_move(ara_state_t s, unsigned short move);                     /* State::do_action */
+int ara_state_do_uci(ara_state_t s, const char* uci);                          /* uci_to_action + do_action */
+int ara_state_board(ara_state_t s, ara_board_t* out);
+int ara_state_history(ara_state_t s, const unsigned long long** keys, const short** reps, int* len);
+int ara_state_fen(ara_state_t s, char* buf, int buf_len);                      /* State::fen */
+int ara_state_legal_moves(ara_state_t s, unsigned short* moves_out);           /* returns the count */
+int ara_state_side_to_move(ara_state_t s);
+int ara_state_is_terminal(ara_state_t s);                                      /* TerminalType */
+
+/* ---- Search seam: replaces MCTSAgent::evaluate_board_state + SearchThread::thread_iteration + Node
+ * (agents/mctsagent.cpp:292-337, searchthread.cpp:403-426, node.{h,cpp}) with a device-resident tree.
+ * ara_search_settings_t carries SearchSettings + SearchLimits (agents/config/searchsettings.h:51-98,
+ * searchlimits.h:37-61) with the reference's UCI defaults (uci/optionsuci.cpp:66-220).
+ */
+typedef struct ara_search_s* ara_search_t;
+typedef struct ara_search_settings_s {
+    int batch_size;                 /* Batch_Size */
+    float dirichlet_epsilon;        /* Centi_Dirichlet_Epsilon / 100 */
+    float dirichlet_alpha;          /* Centi_Dirichlet_Alpha / 100 */
+    float node_policy_temperature;  /* Centi_Node_Temperature / 100 */
+    float q_value_weight;           /* Centi_Q_Value_Weight / 100 */
+    float q_veto_delta;             /* Centi_Q_Veto_Delta / 100 */
+    float cpuct_init;               /* Centi_CPuct_Init / 100 */
+    float cpuct_base;               /* CPuct_Base */
+    int mcts_solver;                /* MCTS_Solver */
+    int virtual_style;              /* 0 virtual_loss, 1 virtual_visit, 3 virtual_mix */
+    unsigned virtual_mix_threshold; /* Virtual_Mix_Threshold */
+    unsigned simulations;           /* SearchLimits::simulations (0 = no limit) */
+    unsigned nodes;                 /* SearchLimits::nodes (0 = no limit) */
+    unsigned long long seed;        /* explicit seed of the Dirichlet generator (the reference has none) */
+    int mode;                       /* 0 MODE_CRAZYHOUSE, 1 MODE_CHESS, 2 MODE_LICHESS */
+    int input_version;              /* input representation version 1, 2, 3 */
+} ara_search_settings_t;
+
+/* What update_eval_info (evalinfo.cpp:195-249) exposes: per root move visits / Q / prior / MCTS posterior, best
+ * move, root value, node counters (nodes = visit_sum - free_visits, evalinfo.cpp:73-85), principal variation. */
+typedef struct ara_search_result_s {
+    int n_moves;
+    int no_visit_idx;
+    int best_idx;
+    int node_type; /* 0 win, 1 draw, 2 loss, 3 unsolved */
+    int pv_len;
+    float root_value;
+    float best_move_q;
+    unsigned visit_sum;
+    unsigned free_visits;
+    unsigned iterations;
+    unsigned evals;
+    int tree_nodes;
+    int error;
+    unsigned long long sum_select_k; /* sum over selections of the number of open children read (HBM accounting) */
+    unsigned long long sum_depth;
+    unsigned short moves[512];
+    unsigned int visits[512];
+    float q[512];
+    float prior[512];
+    double policy[512];
+    unsigned short pv[256];
+} ara_search_result_t;
+
+void ara_search_default_settings(ara_search_settings_t* s, int mode);
+/* net: handle whose batch size is >= n_trees * batch_size, or NULL to run the hash-derived fake backend (search-parity
+ * tests).  n_trees independent positions are searched concurrently, one warp per tree, sharing each network batch.
+ * max_nodes <= 0 sizes the node pool from the Simulations / Nodes limit. */
+ara_search_t ara_search_create(ara_net_t net, const ara_search_settings_t* settings, int device, int n_trees, int max_nodes);
+void ara_search_destroy(ara_search_t s);
+/* root position of tree `tree` plus the (key, repetition) history of the game before it, oldest first */
+int ara_search_set_position(ara_search_t s, int tree, const ara_board_t* root, const unsigned long long* hist_keys,
+                            const short* hist_reps, int hist_len);
+/* runs all trees to their limits (synchronous) and fetches the results */
+int ara_search_go(ara_search_t s);
+int ara_search_result(ara_search_t s, int tree, ara_search_result_t* out);
+double ara_search_last_go_ms(ara_search_t s);       /* device time of the last go (CUDA events) */
+long long ara_search_launch_count(ara_search_t s); /* search kernels launched so far */
+
 /* ---- debug / unit-test entries (one tcgen05 convolution layer on caller-provided device buffers) */
 int ara_debug_conv(const void* act_half, int boards_cap, int boards, int cin, const void* w_half, int w_rows, int n_out,
                    int ksize, const float* bias, int relu, const void* residual, int ldr, void* out_half,

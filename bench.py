@@ -97,7 +97,18 @@ def cpu_arm(sims, batch, steps, warmup):
     from oracle import net as onet
     from oracle import search as osr
     from oracle.chess import Position
-    cores = os.cpu_count() or 1
+    # all host threads torch can use profitably: beyond ~16 threads the 8x8-board convolutions only get slower
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except Exception:
+        avail = os.cpu_count() or 1
+    try:  # cgroup CPU quota (the container may see every host core but only be allowed a few)
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            avail = min(avail, max(1, int(int(q) / int(p))))
+    except Exception:
+        pass
+    cores = max(1, min(avail, int(os.environ.get("ARA_CPU_THREADS", "16"))))
     torch.set_num_threads(cores)
     arch = onet.arch_risev2(34, 81)
     sd = onet.make_state_dict(arch, 0)
@@ -133,6 +144,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--sims", type=int, default=3200)
     ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU arm (profiling runs)")
     ap.add_argument("--cpu-sims", type=int, default=1280, help="bounded CPU sample: simulations per CPU search")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -266,7 +278,7 @@ def main():
                          "kernel": "RISEv2 conv stack (conv_gemm_kernel tcgen05 GEMMs + depthwise/SE/head kernels), per forward of 64 positions",
                          "flop_per_position": flops_pos, "peak_source": peak_src},
         }
-        if world == 1:
+        if world == 1 and not args.no_cpu_baseline:
             nps, ms, cores, _ = cpu_arm(args.cpu_sims, args.batch, 2, 1)
             out["cpu_baseline"] = {"value": nps, "unit": UNIT, "cores": cores, "kind": "port",
                                    "sample": f"2 searches of {args.cpu_sims} simulations (Batch_Size {args.batch}); C oracle "

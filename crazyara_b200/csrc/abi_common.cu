@@ -1,5 +1,7 @@
 #include "abi_common.h"
 
+#include <cstdlib>
+
 namespace ara {
 
 std::string& last_error_ref() {
@@ -15,6 +17,15 @@ int set_error(const char* fmt, ...) {
     va_end(ap);
     last_error_ref() = buf;
     return -1;
+}
+
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("ARA_NO_PDL");
+        v = (e != nullptr && e[0] == '1') ? 0 : 1;
+    }
+    return v == 1;
 }
 
 }  // namespace ara

@@ -81,6 +81,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // PDL: everything above overlapped the tail of the previous kernel; its outputs are only touched below
+    pdl_wait();
+    pdl_launch_dependents();
 
     if (warp == 0) {
         if (lane == 0) {

@@ -101,8 +101,7 @@ static int launch_bn(const ConvLayer* L, const ConvGemmArgs& a, dim3 grid, cudaS
                                          Cfg::kSmemBytes));
         attr_done = true;
     }
-    conv_gemm_kernel<BN, 0><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(L->tm_a, L->tm_b, a);
-    ARA_CUDA_OK(cudaGetLastError());
+    ARA_CUDA_OK(launch_pdl(conv_gemm_kernel<BN, 0>, grid, dim3(kGemmThreads), Cfg::kSmemBytes, stream, L->tm_a, L->tm_b, a));
     return 0;
 }
 

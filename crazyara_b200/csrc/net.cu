@@ -276,7 +276,7 @@ int Net::init(const char* blob_path, int dev, int batch_size) {
 
 int Net::enqueue(int n, cudaStream_t s, bool from_f32) {
     if (from_f32) {
-        nchw_f32_to_nhwc_f16_kernel<<<n, 256, hdr.in_channels * 65 * 4, s>>>(d_in_f32, d_in_h, hdr.in_channels, cin_pad);
+        ARA_CUDA_OK(launch_pdl(nchw_f32_to_nhwc_f16_kernel, dim3(n), dim3(256), hdr.in_channels * 65 * 4, s, d_in_f32, d_in_h, hdr.in_channels, cin_pad));
         ++launches;
     }
     if (conv_layer_launch(&stem_conv, n, s)) return -1;
@@ -286,25 +286,25 @@ int Net::enqueue(int n, cudaStream_t s, bool from_f32) {
         BlockW& w = bw_[i];
         __half* xin = d_x[i & 1];
         if (bd.se_type != 0) {
-            se_kernel<<<n, 256, 0, s>>>(xin, w.se_w1t, w.se_w2t, w.se_b, bd.se_type);
+            ARA_CUDA_OK(launch_pdl(se_kernel, dim3(n), dim3(256), 0, s, xin, w.se_w1t, w.se_w2t, w.se_b, bd.se_type));
             ++launches;
         }
         if (conv_layer_launch(&w.conv1, n, s)) return -1;
         const long long total = static_cast<long long>(n) * 64 * (bd.c_op / 8);
         const int grid = static_cast<int>((total + 255) / 256);
         if (bd.kernel == 3)
-            dwconv_kernel<3><<<grid, 256, 0, s>>>(d_h1, w.wd, w.bd, d_h2, n, bd.c_op);
+            ARA_CUDA_OK(launch_pdl(dwconv_kernel<3>, dim3(grid), dim3(256), 0, s, d_h1, w.wd, w.bd, d_h2, n, bd.c_op));
         else
-            dwconv_kernel<5><<<grid, 256, 0, s>>>(d_h1, w.wd, w.bd, d_h2, n, bd.c_op);
+            ARA_CUDA_OK(launch_pdl(dwconv_kernel<5>, dim3(grid), dim3(256), 0, s, d_h1, w.wd, w.bd, d_h2, n, bd.c_op));
         if (conv_layer_launch(&w.conv2, n, s)) return -1;
         launches += 3;
     }
     __half* xfinal = d_x[hdr.n_blocks & 1];
     ValueHeadW vw{vh_wv, vh_bv, vh_w1t, vh_b1, vh_w2, vh_b2, vh_wdl_w, vh_wdl_b, vh_plys_w, vh_plys_b, hdr.wdl_mode};
-    value_head_kernel<<<n, 256, 0, s>>>(xfinal, vw, d_value, d_aux);
+    ARA_CUDA_OK(launch_pdl(value_head_kernel, dim3(n), dim3(256), 0, s, xfinal, vw, d_value, d_aux));
     if (conv_layer_launch(&pol_conv1, n, s)) return -1;
     if (conv_layer_launch(&pol_conv2, n, s)) return -1;
-    policy_softmax_kernel<<<n, 256, n_labels() * 4, s>>>(d_logits, d_prob, hdr.policy_channels, ldp);
+    ARA_CUDA_OK(launch_pdl(policy_softmax_kernel, dim3(n), dim3(256), n_labels() * 4, s, d_logits, d_prob, hdr.policy_channels, ldp));
     launches += 4;
     ARA_CUDA_OK(cudaGetLastError());
     return 0;

@@ -9,12 +9,16 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "sm100_prims.cuh"
+
 namespace ara {
 
 // ---------------------------------------------------------------------------------------------
 // [n, C, 64] fp32 (reference NCHW planes) -> [n, 64, cpad] fp16 (zero padded channels).  One CTA per board.
 __global__ void nchw_f32_to_nhwc_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, int C, int cpad) {
     extern __shared__ float s_planes[];  // [C][65]
+    pdl_wait();
+    pdl_launch_dependents();
     const int b = blockIdx.x;
     const float* src = in + static_cast<size_t>(b) * C * 64;
     for (int i = threadIdx.x; i < C * 64; i += blockDim.x) {
@@ -35,6 +39,8 @@ __global__ void nchw_f32_to_nhwc_f16_kernel(const float* __restrict__ in, __half
 template <int K>
 __global__ void dwconv_kernel(const __half* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
                               __half* __restrict__ out, int boards, int C) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int vec_per_row = C >> 3;
     const long long total = static_cast<long long>(boards) * 64 * vec_per_row;
     const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -92,6 +98,8 @@ __global__ void __launch_bounds__(256) se_kernel(__half* __restrict__ x, const f
                                                    int mode) {
     __shared__ float s_pool[256];
     __shared__ float s_hid[128];
+    pdl_wait();
+    pdl_launch_dependents();
     const int b = blockIdx.x;
     const int c = threadIdx.x;
     __half* xb = x + static_cast<size_t>(b) * 64 * 256;
@@ -149,6 +157,8 @@ __global__ void __launch_bounds__(256) value_head_kernel(const __half* __restric
     __shared__ float s_wv[8 * 256];
     __shared__ float s_f[512];
     __shared__ float s_red[8];
+    pdl_wait();
+    pdl_launch_dependents();
     const int b = blockIdx.x;
     const int t = threadIdx.x;
     const __half* xb = x + static_cast<size_t>(b) * 64 * 256;
@@ -218,6 +228,8 @@ __global__ void __launch_bounds__(256) policy_softmax_kernel(const float* __rest
     extern __shared__ float s_l[];  // [P*64] in output order
     __shared__ float s_red[8];
     __shared__ float s_bcast;
+    pdl_wait();
+    pdl_launch_dependents();
     const int b = blockIdx.x;
     const int t = threadIdx.x;
     const int L = P * 64;

@@ -1,0 +1,92 @@
+"""Self-play arena: many concurrent games per GPU, each game one device-resident search tree.
+
+Counterpart of the reference's SelfPlay::go / generate_game loop (engine/src/rl/selfplay.cpp:192-261, :367-385) and its
+"one process per GPU" deployment (engine/src/rl/README.md:84-97).  The reference plays ONE game at a time per process;
+here `n_games` games advance in lock-step on one GPU: every move, all trees are searched together (one warp per tree,
+their leaves share each network batch), then every game samples / plays its move on the host.  Games never interact,
+so multi-GPU scaling is N independent processes -- no collective.
+
+Move selection follows Agent::set_best_move / MCTSAgent play settings (agents/agent.cpp:38-53): argmax of the MCTS
+posterior, or a sample from posterior^(1/T) during the first `temperature_moves` plies (RL defaults:
+DeepCrazyhouse/configs/rl_config.py:34-65).  Training-sample export (zarr) is out of scope.
+"""
+import time
+
+import numpy as np
+
+from .engine import BoardState, MCTSAgent, TERMINAL_NONE, default_settings
+
+
+def rl_settings(mode, **kw):
+    """UCIConfig of the reference's RL loop (rl_config.py:34-65)."""
+    base = dict(batch_size=8, nodes=800, simulations=3200, dirichlet_alpha=0.3, dirichlet_epsilon=0.25,
+                node_policy_temperature=1.0, q_value_weight=0.0, mcts_solver=1)
+    base.update(kw)
+    return default_settings(mode, **base)
+
+
+class Arena:
+    def __init__(self, net, settings, variant, n_games, device=0, is960=False, temperature=0.8, temperature_moves=15,
+                 max_plies=512, seed=0, max_nodes=0):
+        self.variant, self.is960 = variant, is960
+        self.n_games = n_games
+        self.temperature, self.temperature_moves, self.max_plies = temperature, temperature_moves, max_plies
+        self.rng = np.random.default_rng(seed)
+        self.agent = MCTSAgent(net, settings, device, n_games, max_nodes)
+        self.states = [self._new_state() for _ in range(n_games)]
+        self.plies = [0] * n_games
+        self.finished = []  # (plies, terminal type, side to move at the end)
+        self.nodes = 0
+        self.search_ms = 0.0
+
+    def _new_state(self):
+        return BoardState().set("", self.is960, self.variant)
+
+    def _pick(self, res, ply):
+        pol = res["policy"]
+        if ply < self.temperature_moves and self.temperature > 0 and pol.sum() > 0:
+            p = np.power(pol, 1.0 / self.temperature)
+            p = p / p.sum()
+            return int(self.rng.choice(len(p), p=p))
+        return int(res["best_idx"])
+
+    def step(self):
+        """One move in every running game."""
+        for t, st in enumerate(self.states):
+            self.agent.set_position(st, t)
+        self.agent.evaluate_board_state()
+        self.search_ms += self.agent.last_go_ms()
+        for t, st in enumerate(self.states):
+            res = self.agent.result(t)
+            self.nodes += int(res["nodes"])
+            if len(res["moves"]) == 0:
+                term = st.is_terminal()
+                self.finished.append((self.plies[t], term, st.side_to_move()))
+                self.states[t], self.plies[t] = self._new_state(), 0
+                continue
+            idx = self._pick(res, self.plies[t])
+            st.do_uci(res["moves"][idx])
+            self.plies[t] += 1
+            term = st.is_terminal()
+            if term != TERMINAL_NONE or self.plies[t] >= self.max_plies:
+                self.finished.append((self.plies[t], term, st.side_to_move()))
+                self.states[t], self.plies[t] = self._new_state(), 0
+
+    def run(self, min_games=0, max_steps=1 << 30, max_seconds=1e30):
+        t0 = time.perf_counter()
+        steps = 0
+        while steps < max_steps and (time.perf_counter() - t0) < max_seconds:
+            self.step()
+            steps += 1
+            if min_games and len(self.finished) >= min_games:
+                break
+        wall = time.perf_counter() - t0
+        moves = steps * self.n_games
+        return dict(games=len(self.finished), steps=steps, moves=moves, wall_s=wall,
+                    games_per_hour=len(self.finished) / wall * 3600.0 if wall > 0 else 0.0,
+                    moves_per_s=moves / wall if wall > 0 else 0.0, nodes=self.nodes,
+                    nps=self.nodes / (self.search_ms / 1000.0) if self.search_ms > 0 else 0.0,
+                    avg_plies=float(np.mean([g[0] for g in self.finished])) if self.finished else 0.0)
+
+    def close(self):
+        self.agent.close()

@@ -226,127 +226,194 @@ ARA_HD bool variant_end(const Board& b) {
     return false;
 }
 
-// ------------------------------------------------------------------ pseudo-legal generation (one lane)
-ARA_HD int add_targets(Move* out, int n, int from, uint64_t targets, int flag) {
-    while (targets) {
-        const int t = lsb64(targets);
-        targets &= targets - 1;
-        out[n++] = make_move(from, t, flag);
+// ------------------------------------------------------------------ legal move generation (warp-cooperative)
+// Work is split by SQUARE: virtual lane l owns squares l and l+32.  Phases (separated by warp syncs; on the host the
+// 32 virtual lanes are simply looped, so the very same partitioning is unit-tested on the CPU):
+//   A  per own piece: pseudo-legal target set + move count; per empty square: number of droppable piece types
+//   B  exclusive prefix sums -> write offsets
+//   C  emission of the pseudo-legal list
+//   D  legality: only moves that CAN expose the king (king moves, en passant, castling, pieces on a line with the king,
+//      everything when in check) go through the full "apply and look at the king" test; survivors are compacted in order.
+struct MoveGenScratch {
+    uint64_t tgt[64];
+    uint16_t cnt[64];
+    uint16_t dcnt[64];
+    uint16_t off[64];
+    uint16_t doff[64];
+    int n_pseudo;
+    int castle_mask;  // bit 0: O-O possible, bit 1: O-O-O possible
+    int checked;
+};
+
+#if defined(__CUDA_ARCH__)
+#define ARA_FOR_VLANES(l) for (int l = ARA_LANE, once_ = 1; once_; once_ = 0)
+#else
+#define ARA_FOR_VLANES(l) for (int l = 0; l < 32; ++l)
+#endif
+
+ARA_HD uint64_t piece_targets(const Board& b, int sq, int pt, int us, uint64_t own, uint64_t opp, uint64_t occ) {
+    const uint64_t s = bit(sq);
+    switch (pt) {
+        case PT_PAWN: {
+            const uint64_t empty = ~occ;
+            uint64_t t;
+            if (us == 0) {
+                const uint64_t one = (s << 8) & empty;
+                t = one | (((one & (0xFFULL << 16)) << 8) & empty);
+            } else {
+                const uint64_t one = (s >> 8) & empty;
+                t = one | (((one & (0xFFULL << 40)) >> 8) & empty);
+            }
+            uint64_t caps = opp;
+            if (b.ep != 0xFF) caps |= bit(b.ep);
+            return t | (pawn_attacks_bb(s, us) & caps);
+        }
+        case PT_KNIGHT: return knight_attacks_bb(s) & ~own;
+        case PT_BISHOP: return bishop_attacks_bb(s, occ) & ~own;
+        case PT_ROOK: return rook_attacks_bb(s, occ) & ~own;
+        case PT_QUEEN: return (rook_attacks_bb(s, occ) | bishop_attacks_bb(s, occ)) & ~own;
+        default: return king_attacks_bb(s) & ~own;
     }
-    return n;
 }
 
-ARA_HD int gen_pseudo(const Board& b, Move* out) {
-    int n = 0;
+// castling rights that are currently executable (Position::castling_impeded + the "not through check" rule);
+// the 960 "attacker hidden behind the castling rook" case is left to the final legality test
+ARA_HD int castle_mask_of(const Board& b, int ksq, uint64_t occ, uint64_t opp) {
     const int us = b.stm, them = us ^ 1;
-    const uint64_t own = b.by_color[us], opp = b.by_color[them], occ = own | opp, empty = ~occ;
-    // pawns
-    {
-        const uint64_t pawns = pieces(b, us, PT_PAWN);
-        const uint64_t promo_rank = us ? kRank1 : kRank8;
-        const uint64_t third = us ? (0xFFULL << 40) : (0xFFULL << 16);
-        const int up = us ? -8 : 8;
-        uint64_t one = (us ? (pawns >> 8) : (pawns << 8)) & empty;
-        uint64_t two = (us ? ((one & third) >> 8) : ((one & third) << 8)) & empty;
-        uint64_t cap_l = us ? ((pawns >> 9) & ~kFileH) : ((pawns << 7) & ~kFileH);  // towards file a
-        uint64_t cap_r = us ? ((pawns >> 7) & ~kFileA) : ((pawns << 9) & ~kFileA);  // towards file h
-        const int dl = us ? -9 : 7, dr = us ? -7 : 9;
-        uint64_t t;
-        for (t = one & ~promo_rank; t; t &= t - 1) { const int s = lsb64(t); out[n++] = make_move(s - up, s, MF_NORMAL); }
-        for (t = two; t; t &= t - 1) { const int s = lsb64(t); out[n++] = make_move(s - 2 * up, s, MF_NORMAL); }
-        for (t = cap_l & opp & ~promo_rank; t; t &= t - 1) { const int s = lsb64(t); out[n++] = make_move(s - dl, s, MF_NORMAL); }
-        for (t = cap_r & opp & ~promo_rank; t; t &= t - 1) { const int s = lsb64(t); out[n++] = make_move(s - dr, s, MF_NORMAL); }
-        for (t = one & promo_rank; t; t &= t - 1) {
-            const int s = lsb64(t);
-            for (int f = MF_PROMO_Q; f >= MF_PROMO_N; --f) out[n++] = make_move(s - up, s, f);
+    int mask = 0;
+    for (int side = 0; side < 2; ++side) {
+        const int rs = b.castle_rook[us * 2 + side];
+        if (rs == 0xFF) continue;
+        int kto, rto;
+        castle_targets(us, side == 0, &kto, &rto);
+        const uint64_t path = (between_incl(ksq, kto) | between_incl(rs, rto)) & ~(bit(ksq) | bit(rs));
+        if (path & occ) continue;
+        uint64_t kpath = between_incl(ksq, kto) & ~bit(ksq);
+        bool ok = true;
+        while (kpath && ok) {
+            const int s = lsb64(kpath);
+            kpath &= kpath - 1;
+            if (attackers_of(b, s, occ, them, opp)) ok = false;
         }
-        for (t = cap_l & opp & promo_rank; t; t &= t - 1) {
-            const int s = lsb64(t);
-            for (int f = MF_PROMO_Q; f >= MF_PROMO_N; --f) out[n++] = make_move(s - dl, s, f);
-        }
-        for (t = cap_r & opp & promo_rank; t; t &= t - 1) {
-            const int s = lsb64(t);
-            for (int f = MF_PROMO_Q; f >= MF_PROMO_N; --f) out[n++] = make_move(s - dr, s, f);
-        }
-        if (b.ep != 0xFF) {
-            const uint64_t e = bit(b.ep);
-            if (cap_l & e) out[n++] = make_move(b.ep - dl, b.ep, MF_EP);
-            if (cap_r & e) out[n++] = make_move(b.ep - dr, b.ep, MF_EP);
-        }
+        if (ok) mask |= 1 << side;
     }
-    uint64_t bb;
-    for (bb = pieces(b, us, PT_KNIGHT); bb; bb &= bb - 1) { const int s = lsb64(bb); n = add_targets(out, n, s, knight_attacks_bb(bit(s)) & ~own, MF_NORMAL); }
-    for (bb = pieces(b, us, PT_BISHOP); bb; bb &= bb - 1) { const int s = lsb64(bb); n = add_targets(out, n, s, bishop_attacks_bb(bit(s), occ) & ~own, MF_NORMAL); }
-    for (bb = pieces(b, us, PT_ROOK); bb; bb &= bb - 1) { const int s = lsb64(bb); n = add_targets(out, n, s, rook_attacks_bb(bit(s), occ) & ~own, MF_NORMAL); }
-    for (bb = pieces(b, us, PT_QUEEN); bb; bb &= bb - 1) {
-        const int s = lsb64(bb);
-        n = add_targets(out, n, s, (rook_attacks_bb(bit(s), occ) | bishop_attacks_bb(bit(s), occ)) & ~own, MF_NORMAL);
-    }
+    return mask;
+}
+
+// Returns the number of legal moves written to `out` (uniform across lanes); mg.checked tells whether the side to move
+// is in check.  `scratch` receives the pseudo-legal list.
+ARA_HD int gen_legal(const Board& b, MoveGenScratch& mg, Move* scratch, Move* out) {
+    const int us = b.stm, them = us ^ 1;
+    const uint64_t own = b.by_color[us], opp = b.by_color[them], occ = own | opp;
     const int ksq = king_square(b, us);
-    if (ksq >= 0) {
-        n = add_targets(out, n, ksq, king_attacks_bb(bit(ksq)) & ~own, MF_NORMAL);
-        // castling: rights, empty path (bar king and castling rook), king not in check and not crossing attacked squares
-        if ((b.castle_rook[us * 2] != 0xFF || b.castle_rook[us * 2 + 1] != 0xFF) &&
-            attackers_of(b, ksq, occ, them, opp) == 0) {
-            for (int side = 0; side < 2; ++side) {
-                const int rs = b.castle_rook[us * 2 + side];
-                if (rs == 0xFF) continue;
-                int kto, rto;
-                castle_targets(us, side == 0, &kto, &rto);
-                const uint64_t path = (between_incl(ksq, kto) | between_incl(rs, rto)) & ~(bit(ksq) | bit(rs));
-                if (path & occ) continue;
-                uint64_t kpath = between_incl(ksq, kto) & ~bit(ksq);
-                bool ok = true;
-                while (kpath && ok) {
-                    const int s = lsb64(kpath);
-                    kpath &= kpath - 1;
-                    if (attackers_of(b, s, occ, them, opp)) ok = false;
+    const bool checked = ksq >= 0 && attackers_of(b, ksq, occ, them, opp) != 0;
+    if (ARA_LANE == 0) {
+        mg.checked = checked ? 1 : 0;
+        mg.castle_mask = 0;
+    }
+    ARA_WARP_SYNC();
+    if (variant_end(b)) return 0;
+    const bool house = b.variant == V_CRAZYHOUSE;
+    int hand_types = 0, hand_nonpawn = 0;
+    if (house)
+        for (int pt = 0; pt < 5; ++pt)
+            if (b.hand[us][pt]) {
+                ++hand_types;
+                if (pt != PT_PAWN) ++hand_nonpawn;
+            }
+    const uint64_t promo_from = us ? (0xFFULL << 8) : (0xFFULL << 48);
+    // ---- phase A
+    ARA_FOR_VLANES(l) {
+        for (int sq = l; sq < 64; sq += 32) {
+            uint64_t t = 0;
+            int c = 0, d = 0;
+            if (own & bit(sq)) {
+                const int pt = piece_type_on(b, sq);
+                t = piece_targets(b, sq, pt, us, own, opp, occ);
+                c = popc64(t);
+                if (pt == PT_PAWN && (bit(sq) & promo_from)) c *= 4;
+                if (pt == PT_KING && !checked && (b.castle_rook[us * 2] != 0xFF || b.castle_rook[us * 2 + 1] != 0xFF)) {
+                    const int cm = castle_mask_of(b, sq, occ, opp);
+                    mg.castle_mask = cm;
+                    c += (cm & 1) + ((cm >> 1) & 1);
+                } else if (pt == PT_KING) {
+                    mg.castle_mask = 0;
                 }
-                if (ok) out[n++] = make_move(ksq, rs, MF_CASTLE);
+            } else if (house && !(occ & bit(sq))) {
+                d = ((sq >> 3) == 0 || (sq >> 3) == 7) ? hand_nonpawn : hand_types;
+            }
+            mg.tgt[sq] = t;
+            mg.cnt[sq] = static_cast<uint16_t>(c);
+            mg.dcnt[sq] = static_cast<uint16_t>(d);
+        }
+    }
+    ARA_WARP_SYNC();
+    // ---- phase B (lane 0: 128 additions)
+    if (ARA_LANE == 0) {
+        int acc = 0;
+        for (int sq = 0; sq < 64; ++sq) {
+            mg.off[sq] = static_cast<uint16_t>(acc);
+            acc += mg.cnt[sq];
+        }
+        for (int sq = 0; sq < 64; ++sq) {
+            mg.doff[sq] = static_cast<uint16_t>(acc);
+            acc += mg.dcnt[sq];
+        }
+        mg.n_pseudo = acc;
+    }
+    ARA_WARP_SYNC();
+    // ---- phase C
+    ARA_FOR_VLANES(l) {
+        for (int sq = l; sq < 64; sq += 32) {
+            uint64_t t = mg.tgt[sq];
+            if (t || mg.cnt[sq]) {
+                int o = mg.off[sq];
+                const int pt = piece_type_on(b, sq);
+                const bool promo = pt == PT_PAWN && (bit(sq) & promo_from);
+                for (; t; t &= t - 1) {
+                    const int to = lsb64(t);
+                    if (promo) {
+                        for (int f = MF_PROMO_Q; f >= MF_PROMO_N; --f) scratch[o++] = make_move(sq, to, f);
+                    } else {
+                        const bool ep = pt == PT_PAWN && b.ep != 0xFF && to == b.ep && ((to ^ sq) & 7) != 0;
+                        scratch[o++] = make_move(sq, to, ep ? MF_EP : MF_NORMAL);
+                    }
+                }
+                if (pt == PT_KING) {
+                    const int cm = mg.castle_mask;
+                    if (cm & 1) scratch[o++] = make_move(sq, b.castle_rook[us * 2], MF_CASTLE);
+                    if (cm & 2) scratch[o++] = make_move(sq, b.castle_rook[us * 2 + 1], MF_CASTLE);
+                }
+            }
+            if (mg.dcnt[sq]) {
+                int o = mg.doff[sq];
+                const bool edge = (sq >> 3) == 0 || (sq >> 3) == 7;
+                for (int pt = 0; pt < 5; ++pt)
+                    if (b.hand[us][pt] && !(pt == PT_PAWN && edge)) scratch[o++] = make_move(sq, sq, MF_DROP + pt);
             }
         }
     }
-    if (b.variant == V_CRAZYHOUSE) {
-        for (int pt = 0; pt < 5; ++pt) {
-            if (b.hand[us][pt] == 0) continue;
-            uint64_t t = empty;
-            if (pt == PT_PAWN) t &= ~(kRank1 | kRank8);
-            for (; t; t &= t - 1) { const int s = lsb64(t); out[n++] = make_move(s, s, MF_DROP + pt); }
-        }
-    }
-    return n;
-}
-
-// Legal moves, warp-cooperative: lane 0 generates the pseudo-legal list into `scratch` (shared between the lanes),
-// all lanes test legality, survivors are compacted in order into `out`.  Returns the count (uniform).
-ARA_HD int gen_legal(const Board& b, Move* scratch, Move* out, int* shared_n) {
-    if (variant_end(b)) return 0;
-    if (ARA_LANE == 0) *shared_n = gen_pseudo(b, scratch);
     ARA_WARP_SYNC();
-    const int n = *shared_n;
+    // ---- phase D
+    const int n = mg.n_pseudo;
+    const uint64_t king_lines = ksq >= 0 ? (rook_attacks_bb(bit(ksq), 0) | bishop_attacks_bb(bit(ksq), 0)) : 0;
     int k = 0;
     for (int base = 0; base < n; base += ARA_WARP_N) {
         const int i = base + ARA_LANE;
-        const bool ok = i < n && leaves_king_safe(b, scratch[i]);
+        bool ok = false;
+        if (i < n) {
+            const Move m = scratch[i];
+            const int flag = mv_flag(m), from = mv_from(m);
+            const bool risky = checked || flag == MF_EP || flag == MF_CASTLE ||
+                               (flag < MF_DROP && (from == ksq || (bit(from) & king_lines)));
+            ok = !risky || leaves_king_safe(b, m);
+        }
         const uint32_t mask = ARA_BALLOT(ok);
         if (ok) out[k + ARA_POPC_BELOW(mask)] = scratch[i];
         k += ARA_POPC(mask);
     }
     ARA_WARP_SYNC();
     return k;
-}
-// does the side to move have any legal move? (early exit)
-ARA_HD bool has_legal_move(const Board& b, Move* scratch, int* shared_n) {
-    if (variant_end(b)) return false;
-    if (ARA_LANE == 0) *shared_n = gen_pseudo(b, scratch);
-    ARA_WARP_SYNC();
-    const int n = *shared_n;
-    for (int base = 0; base < n; base += ARA_WARP_N) {
-        const int i = base + ARA_LANE;
-        const bool ok = i < n && leaves_king_safe(b, scratch[i]);
-        if (ARA_BALLOT(ok)) return true;
-    }
-    return false;
 }
 
 // ------------------------------------------------------------------ do_move (Position::do_move + Board::do_move)

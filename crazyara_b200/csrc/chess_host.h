@@ -211,8 +211,8 @@ inline std::string move_to_uci(Move m, bool chess960) {  // UCI::move of the eng
 
 inline std::vector<Move> legal_moves_host(const Board& b) {
     Move scratch[kMaxMoves], out[kMaxMoves];
-    int n_shared = 0;
-    const int n = gen_legal(b, scratch, out, &n_shared);
+    MoveGenScratch mg;
+    const int n = gen_legal(b, mg, scratch, out);
     return std::vector<Move>(out, out + n);
 }
 

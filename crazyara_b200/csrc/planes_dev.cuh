@@ -2,9 +2,15 @@
 //
 // Semantics: engine/src/environments/chess_related/inputrepresentation.cpp (board_to_planes :628-680 and the
 // per-version bodies :426-624) with the constants of boardstate.h:207-245.  The reference's compile-time MODE_*
-// is the run-time `mode`.  Unlike the reference (one thread filling plane after plane) the encoder is organised
-// per SQUARE: every lane owns squares {lane, lane+32} and emits their whole channel vector, which is contiguous in
-// the NHWC layout the tcgen05 stem convolution reads.
+// is the run-time `mode`.
+//
+// Every plane of every layout is either a bitboard plane (value v on the squares of a 64-bit mask) or a constant
+// plane, so the encoder walks the layout once and hands each channel to a sink as (mask in OUTPUT coordinates, v):
+//   * NCHW fp32 sink (the reference's [C,8,8] float tensor, State::get_state_planes): lanes write 2 squares each,
+//     coalesced 256 B per plane;
+//   * NHWC fp16 sink (the tcgen05 stem convolution's A operand): lane l keeps the descriptors of channels l, l+32,
+//     l+64 and then writes row after row, 64 contiguous bytes per warp store.
+// The reference fills plane after plane with a bit-serial loop (set_bits_from_bitmap :33-46).
 #pragma once
 #include "chess_dev.cuh"
 #if defined(__CUDACC__)
@@ -22,117 +28,129 @@ ARA_HD int planes_channels(int mode, int version) {
     return version == 3 ? 80 : 63;
 }
 
-struct NchwF32Writer {  // the reference's [C,8,8] float layout (State::get_state_planes)
-    float* out;
-    ARA_HD void put(int c, int sq, float v) const { out[c * 64 + sq] = v; }
-};
-#if defined(__CUDACC__)
-struct NhwcF16Writer {  // [64, cpad] fp16: the stem convolution's A operand
-    __half* out;
-    int cpad;
-    ARA_HD void put(int c, int sq, float v) const { out[sq * cpad + c] = __float2half_rn(v); }
-};
-#endif
+ARA_HD uint64_t bswap64_portable(uint64_t x) {  // flip_vertical (sfutil.cpp:178)
+    x = ((x & 0x00FF00FF00FF00FFULL) << 8) | ((x >> 8) & 0x00FF00FF00FF00FFULL);
+    x = ((x & 0x0000FFFF0000FFFFULL) << 16) | ((x >> 16) & 0x0000FFFF0000FFFFULL);
+    return (x << 32) | (x >> 32);
+}
 
 struct PlaneCtx {
     const Board* b;
     int mode, flip, me, you;
     bool normalize;
-    uint64_t own, opp, checkers, promoted;
+    uint64_t own, opp, checkers;
     int cnt[2][6];
     bool opp_bishops;
 };
 
-ARA_HD int variant_channel(int variant) { return variant + 1; }  // chess 1, crazyhouse 2, koth 3, 3check 4 (boardstate.h:269-279)
+ARA_HD PlaneCtx make_plane_ctx(const Board& b, int mode, bool normalize) {
+    PlaneCtx p;
+    p.b = &b;
+    p.mode = mode;
+    p.flip = b.stm != 0;  // racing kings (never flipped) is not a supported variant
+    p.me = b.stm;
+    p.you = b.stm ^ 1;
+    p.normalize = normalize;
+    p.own = b.by_color[p.me];
+    p.opp = b.by_color[p.you];
+    p.checkers = checkers_bb(b);
+    for (int pt = 0; pt < 6; ++pt) {
+        p.cnt[0][pt] = popc64(b.by_type[pt] & p.own);
+        p.cnt[1][pt] = popc64(b.by_type[pt] & p.opp);
+    }
+    const uint64_t wb = pieces(b, 0, PT_BISHOP), bb = pieces(b, 1, PT_BISHOP);
+    p.opp_bishops = false;
+    if (popc64(wb) == 1 && popc64(bb) == 1) {
+        const int ws = lsb64(wb), bs = lsb64(bb);
+        p.opp_bishops = (((ws >> 3) + (ws & 7)) & 1) != (((bs >> 3) + (bs & 7)) & 1);
+    }
+    return p;
+}
 
-template <class W>
-ARA_HD void encode_square(const PlaneCtx& p, int version, int sq, const W& w) {
+// Calls sink(mask, value) once per channel, in channel order.  mask is already in output coordinates.
+template <class Sink>
+ARA_HD void for_each_plane(const PlaneCtx& p, int version, Sink& sink) {
     const Board& b = *p.b;
-    const int src = p.flip ? (sq ^ 56) : sq;  // board square shown at output square sq
-    const uint64_t sbit = bit(src);
     const float max_prisoners = p.mode == MODE_CRAZYHOUSE ? 32.0f : 16.0f;
     const float max_no_progress = p.mode == MODE_CRAZYHOUSE ? 40.0f : 50.0f;
-    int c = 0;
-#define EMIT(v) w.put(c++, sq, (v))
+    auto bb_plane = [&](uint64_t bb) { sink(p.flip ? bswap64_portable(bb) : bb, 1.0f); };
+    auto const_plane = [&](float v) { sink(v != 0.0f ? ~0ULL : 0ULL, v); };
+    auto square_plane = [&](int sq, bool on) { sink(on ? bit(p.flip ? (sq ^ 56) : sq) : 0ULL, 1.0f); };
+
     auto pieces_planes = [&]() {
         for (int k = 0; k < 2; ++k) {
             const int col = k == 0 ? p.me : p.you;
-            for (int pt = 0; pt < 6; ++pt) EMIT((b.by_type[pt] & b.by_color[col] & sbit) ? 1.0f : 0.0f);
+            for (int pt = 0; pt < 6; ++pt) bb_plane(b.by_type[pt] & b.by_color[col]);
         }
     };
-    auto repetition_planes = [&]() {
-        const int rep = b.repetition == 0 ? 0 : 1;  // Board::number_repetitions never returns 2 (board.cpp:132-141)
-        EMIT(rep >= 1 ? 1.0f : 0.0f);
-        EMIT(0.0f);
+    auto repetition_planes = [&]() {  // Board::number_repetitions never returns 2 (board.cpp:132-141)
+        const_plane(b.repetition != 0 ? 1.0f : 0.0f);
+        const_plane(0.0f);
     };
     auto pockets_planes = [&]() {
         for (int k = 0; k < 2; ++k) {
             const int col = k == 0 ? p.me : p.you;
             for (int pt = 0; pt < 5; ++pt) {
                 const int cnt = b.variant == V_CRAZYHOUSE ? b.hand[col][pt] : 0;
-                EMIT(cnt > 0 ? (p.normalize ? cnt / max_prisoners : static_cast<float>(cnt)) : 0.0f);
+                const_plane(cnt > 0 ? (p.normalize ? cnt / max_prisoners : static_cast<float>(cnt)) : 0.0f);
             }
         }
     };
     auto promoted_planes = [&]() {
-        EMIT((p.promoted & p.own & sbit) ? 1.0f : 0.0f);
-        EMIT((p.promoted & p.opp & sbit) ? 1.0f : 0.0f);
+        bb_plane(b.promoted & p.own);
+        bb_plane(b.promoted & p.opp);
     };
-    auto ep_plane = [&]() { EMIT((b.ep != 0xFF && b.ep == src) ? 1.0f : 0.0f); };
-    auto color_plane = [&]() { EMIT(p.me == 0 ? 1.0f : 0.0f); };
+    auto ep_plane = [&]() { square_plane(b.ep & 63, b.ep != 0xFF); };
+    auto color_plane = [&]() { const_plane(p.me == 0 ? 1.0f : 0.0f); };
     auto move_count_plane = [&]() {
         const float v = static_cast<float>((b.game_ply / 2) + 1);
-        EMIT(p.normalize ? v / 500.0f : v);
+        const_plane(p.normalize ? v / 500.0f : v);
     };
-    auto castling_planes = [&]() {
+    auto castling_planes = [&]() {  // me-OO, me-OOO, you-OO, you-OOO (:174-213)
         for (int k = 0; k < 2; ++k) {
             const int col = k == 0 ? p.me : p.you;
-            for (int side = 0; side < 2; ++side) EMIT(b.castle_rook[col * 2 + side] != 0xFF ? 1.0f : 0.0f);
+            for (int side = 0; side < 2; ++side) const_plane(b.castle_rook[col * 2 + side] != 0xFF ? 1.0f : 0.0f);
         }
     };
     auto no_progress_plane = [&]() {
         const float v = static_cast<float>(b.rule50);
-        EMIT(p.normalize ? v / max_no_progress : v);
+        const_plane(p.normalize ? v / max_no_progress : v);
     };
-    auto remaining_checks_planes = [&]() {
+    auto remaining_checks_planes = [&]() {  // :221-242
         for (int k = 0; k < 2; ++k) {
             const int col = k == 0 ? p.me : p.you;
             const int g = b.variant == V_THREECHECK ? checks_given(b, col) : 0;
-            EMIT(g != 0 ? 1.0f : 0.0f);
-            EMIT(g >= 2 ? 1.0f : 0.0f);
+            const_plane(g != 0 ? 1.0f : 0.0f);
+            const_plane(g >= 2 ? 1.0f : 0.0f);
         }
     };
-    auto variant_960_planes = [&]() {
-        const int vc = variant_channel(b.variant);
-        for (int k = 0; k < 9; ++k) EMIT((k == 0 ? b.chess960 != 0 : k == vc) ? 1.0f : 0.0f);
+    auto variant_960_planes = [&]() {  // :246-260, CHANNEL_MAPPING_VARIANTS boardstate.h:269-279
+        const int vc = b.variant + 1;
+        for (int k = 0; k < 9; ++k) const_plane((k == 0 ? b.chess960 != 0 : k == vc) ? 1.0f : 0.0f);
     };
-    auto last_moves_planes = [&]() {
+    auto last_moves_planes = [&]() {  // :262-282
         for (int i = 0; i < 8; ++i) {
-            if (i < b.n_last) {
-                const Move m = b.last_moves[i];
-                EMIT((!mv_is_drop(m) && mv_from(m) == src) ? 1.0f : 0.0f);
-                EMIT(mv_to(m) == src ? 1.0f : 0.0f);
-            } else {
-                EMIT(0.0f);
-                EMIT(0.0f);
-            }
+            const bool have = i < b.n_last;
+            const Move m = have ? b.last_moves[i] : 0;
+            square_plane(mv_from(m), have && !mv_is_drop(m));
+            square_plane(mv_to(m), have);
         }
     };
-    auto is960_plane = [&]() { EMIT(b.chess960 ? 1.0f : 0.0f); };
+    auto is960_plane = [&]() { const_plane(b.chess960 ? 1.0f : 0.0f); };
     auto masks_planes = [&]() {
-        EMIT((p.own & sbit) ? 1.0f : 0.0f);
-        EMIT((p.opp & sbit) ? 1.0f : 0.0f);
+        bb_plane(p.own);
+        bb_plane(p.opp);
     };
-    auto checkerboard_plane = [&]() { EMIT((((sq >> 3) + (sq & 7)) & 1) ? 1.0f : 0.0f); };  // not flipped (:301-313)
-    auto rel_count = [&](float rel) { EMIT(rel != 0 ? (p.normalize ? rel / 8.0f : rel) : 0.0f); };
+    auto checkerboard_plane = [&]() { sink(0x55AA55AA55AA55AAULL, 1.0f); };  // written unflipped, [0,0] = 0 (:301-313)
+    auto rel_count = [&](float rel) { const_plane(rel != 0 ? (p.normalize ? rel / 8.0f : rel) : 0.0f); };
     auto material_diff_planes = [&](int npt) {
         for (int pt = 0; pt < npt; ++pt) rel_count(static_cast<float>(p.cnt[0][pt] - p.cnt[1][pt]));
     };
     auto material_count_planes = [&](int npt) {
         for (int pt = 0; pt < npt; ++pt) rel_count(static_cast<float>(p.cnt[0][pt]));
     };
-    auto opp_bishops_plane = [&]() { EMIT(p.opp_bishops ? 1.0f : 0.0f); };
-    auto checkers_plane = [&]() { EMIT((p.checkers & sbit) ? 1.0f : 0.0f); };
+    auto opp_bishops_plane = [&]() { const_plane(p.opp_bishops ? 1.0f : 0.0f); };
+    auto checkers_plane = [&]() { bb_plane(p.checkers); };
     auto chess_v3 = [&]() {  // :536-566
         pieces_planes(); repetition_planes(); ep_plane(); castling_planes(); no_progress_plane(); last_moves_planes();
         is960_plane(); masks_planes(); checkerboard_plane(); material_diff_planes(5); opp_bishops_plane();
@@ -158,44 +176,64 @@ ARA_HD void encode_square(const PlaneCtx& p, int version, int sq, const W& w) {
         }
     } else {  // lichess v3 :599-624
         pieces_planes(); repetition_planes(); pockets_planes(); promoted_planes(); ep_plane();
-        EMIT(0.0f); EMIT(0.0f);  // colour info and move count are skipped
+        const_plane(0.0f); const_plane(0.0f);  // colour info and move count are skipped
         castling_planes(); no_progress_plane(); remaining_checks_planes(); variant_960_planes(); last_moves_planes();
         masks_planes(); checkerboard_plane(); material_diff_planes(6); opp_bishops_plane(); checkers_plane();
         material_count_planes(6);
     }
-#undef EMIT
 }
 
-ARA_HD PlaneCtx make_plane_ctx(const Board& b, int mode, bool normalize) {
-    PlaneCtx p;
-    p.b = &b;
-    p.mode = mode;
-    p.flip = b.stm != 0;  // racing kings (no flip) is not a supported variant
-    p.me = b.stm;
-    p.you = b.stm ^ 1;
-    p.normalize = normalize;
-    p.own = b.by_color[p.me];
-    p.opp = b.by_color[p.you];
-    p.checkers = checkers_bb(b);
-    p.promoted = b.promoted;
-    for (int pt = 0; pt < 6; ++pt) {
-        p.cnt[0][pt] = popc64(b.by_type[pt] & p.own);
-        p.cnt[1][pt] = popc64(b.by_type[pt] & p.opp);
+// ---- sinks ------------------------------------------------------------------------------------------------------
+struct NchwF32Sink {  // [C, 8, 8] fp32; all lanes take part, 2 squares each
+    float* out;
+    int c = 0;
+    ARA_HD void operator()(uint64_t mask, float v) {
+        for (int sq = ARA_LANE; sq < 64; sq += ARA_WARP_N) out[c * 64 + sq] = ((mask >> sq) & 1) ? v : 0.0f;
+        ++c;
     }
-    const uint64_t wb = pieces(b, 0, PT_BISHOP), bb = pieces(b, 1, PT_BISHOP);
-    p.opp_bishops = false;
-    if (popc64(wb) == 1 && popc64(bb) == 1) {
-        const int ws = lsb64(wb), bs = lsb64(bb);
-        p.opp_bishops = (((ws >> 3) + (ws & 7)) & 1) != (((bs >> 3) + (bs & 7)) & 1);
-    }
-    return p;
-}
+};
 
-// all lanes of the warp call this; every lane encodes squares lane, lane+32 (all 64 on the host)
-template <class W>
-ARA_HD void encode_planes(const Board& b, int mode, int version, bool normalize, const W& w) {
+struct LaneCaptureSink {  // keeps the descriptors of channels lane, lane+32, lane+64
+    int lane;
+    int c = 0;
+    uint64_t m0 = 0, m1 = 0, m2 = 0;
+    float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f;
+    ARA_HD void operator()(uint64_t mask, float v) {
+        if (c == lane) { m0 = mask; v0 = v; }
+        if (c == lane + 32) { m1 = mask; v1 = v; }
+        if (c == lane + 64) { m2 = mask; v2 = v; }
+        ++c;
+    }
+};
+
+// the reference layout; warp-collective (1 lane on the host)
+ARA_HD void encode_planes_nchw_f32(const Board& b, int mode, int version, bool normalize, float* out) {
     const PlaneCtx p = make_plane_ctx(b, mode, normalize);
-    for (int sq = ARA_LANE; sq < 64; sq += ARA_WARP_N) encode_square(p, version, sq, w);
+    NchwF32Sink sink{out};
+    for_each_plane(p, version, sink);
 }
+
+#if defined(__CUDACC__)
+// [64, cpad] fp16 rows (cpad = 64 or 128); channels >= C are written as zero.  Device only, warp-collective.
+__device__ __forceinline__ void encode_planes_nhwc_f16(const Board& b, int mode, int version, __half* out, int cpad) {
+    const PlaneCtx p = make_plane_ctx(b, mode, true);
+    LaneCaptureSink sink;
+    sink.lane = threadIdx.x & 31;
+    for_each_plane(p, version, sink);
+    const int lane = sink.lane;
+    const __half h0 = __float2half_rn(sink.v0), h1 = __float2half_rn(sink.v1), h2 = __float2half_rn(sink.v2);
+    const __half z = __float2half_rn(0.0f);
+#pragma unroll 4
+    for (int sq = 0; sq < 64; ++sq) {
+        __half* row = out + sq * cpad;
+        row[lane] = ((sink.m0 >> sq) & 1) ? h0 : z;
+        row[lane + 32] = ((sink.m1 >> sq) & 1) ? h1 : z;
+        if (cpad > 64) {
+            row[lane + 64] = ((sink.m2 >> sq) & 1) ? h2 : z;
+            row[lane + 96] = z;
+        }
+    }
+}
+#endif
 
 }  // namespace ara

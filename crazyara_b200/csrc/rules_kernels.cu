@@ -22,8 +22,7 @@ encode_planes_f32_kernel(const Board* boards, int n, int mode, int version, int 
     if (i >= n) return;
     if (ARA_LANE < 8) reinterpret_cast<uint4*>(&sb[w])[ARA_LANE] = reinterpret_cast<const uint4*>(&boards[i])[ARA_LANE];
     __syncwarp();
-    NchwF32Writer wr{out + static_cast<size_t>(i) * channels * 64};
-    encode_planes(sb[w], mode, version, normalize != 0, wr);
+    encode_planes_nchw_f32(sb[w], mode, version, normalize != 0, out + static_cast<size_t>(i) * channels * 64);
 }
 
 __global__ void __launch_bounds__(32 * kWarpsPerBlock)
@@ -34,23 +33,22 @@ encode_planes_f16_kernel(const Board* boards, int n, int mode, int version, __ha
     if (i >= n) return;
     if (ARA_LANE < 8) reinterpret_cast<uint4*>(&sb[w])[ARA_LANE] = reinterpret_cast<const uint4*>(&boards[i])[ARA_LANE];
     __syncwarp();
-    NhwcF16Writer wr{out + static_cast<size_t>(i) * 64 * cpad, cpad};
-    encode_planes(sb[w], mode, version, true, wr);
+    encode_planes_nhwc_f16(sb[w], mode, version, out + static_cast<size_t>(i) * 64 * cpad, cpad);
 }
 
 __global__ void __launch_bounds__(32 * kWarpsPerBlock)
 legal_moves_kernel(const Board* boards, int n, Move* moves_out, int* counts, int* terminal, int* policy_idx) {
     __shared__ Board sb[kWarpsPerBlock];
     __shared__ Move scratch[kWarpsPerBlock][kMaxMoves];
-    __shared__ int shared_n[kWarpsPerBlock];
+    __shared__ MoveGenScratch mg[kWarpsPerBlock];
     const int w = threadIdx.x >> 5;
     const int i = blockIdx.x * kWarpsPerBlock + w;
     if (i >= n) return;
     if (ARA_LANE < 8) reinterpret_cast<uint4*>(&sb[w])[ARA_LANE] = reinterpret_cast<const uint4*>(&boards[i])[ARA_LANE];
     __syncwarp();
     Move* out = moves_out + static_cast<size_t>(i) * kMaxMoves;
-    const int cnt = gen_legal(sb[w], scratch[w], out, &shared_n[w]);
-    const bool checked = in_check(sb[w]);
+    const int cnt = gen_legal(sb[w], mg[w], scratch[w], out);
+    const bool checked = mg[w].checked != 0;
     if (policy_idx != nullptr)
         for (int k = ARA_LANE; k < cnt; k += 32)
             policy_idx[static_cast<size_t>(i) * kMaxMoves + k] = policy_map_index(out[k], sb[w].stm, sb[w].chess960);
@@ -123,7 +121,7 @@ extern "C" int ara_encode_planes_device(const void* boards_dev, int n, int mode,
     if (planes_dev != nullptr)
         encode_planes_f32_kernel<<<grid, 32 * kWarpsPerBlock, 0, (cudaStream_t)stream>>>((const Board*)boards_dev, n, mode, version, normalize, planes_dev, c);
     if (planes_half_nhwc_dev != nullptr) {
-        if (cpad < c || cpad % 8 != 0) return set_error("ara_encode_planes_device: bad cpad %d", cpad);
+        if (cpad < c || (cpad != 64 && cpad != 128)) return set_error("ara_encode_planes_device: cpad %d must be 64 or 128", cpad);
         encode_planes_f16_kernel<<<grid, 32 * kWarpsPerBlock, 0, (cudaStream_t)stream>>>((const Board*)boards_dev, n, mode, version, (__half*)planes_half_nhwc_dev, cpad);
     }
     ARA_CUDA_OK(cudaGetLastError());

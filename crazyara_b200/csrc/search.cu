@@ -23,13 +23,22 @@ namespace ara {
 struct DevWriterFactory {
     __half* base;
     int cpad;
-    ARA_HD NhwcF16Writer make(int slot) const { return NhwcF16Writer{base + static_cast<size_t>(slot) * 64 * cpad, cpad}; }
+    struct Target {
+        __half* out;
+        int cpad;
+        ARA_HD void encode(const Board& b, int mode, int version) const {
+#if defined(__CUDA_ARCH__)
+            encode_planes_nhwc_f16(b, mode, version, out, cpad);
+#endif
+        }
+    };
+    ARA_HD Target make(int slot) const { return Target{base + static_cast<size_t>(slot) * 64 * cpad, cpad}; }
 };
 struct NullWriterFactory {  // fake backend: no planes needed
-    struct W {
-        ARA_HD void put(int, int, float) const {}
+    struct Target {
+        ARA_HD void encode(const Board&, int, int) const {}
     };
-    ARA_HD W make(int) const { return W{}; }
+    ARA_HD Target make(int) const { return Target{}; }
 };
 
 __global__ void __launch_bounds__(32) root_kernel(const TreeDev* trees, SearchParams sp, const Board* roots, __half* in_h,

@@ -120,7 +120,7 @@ struct WarpScratch {  // per-warp shared memory (stack on the host)
     int32_t traj_node[kMaxDepth];
     uint16_t traj_ci[kMaxDepth];
     float sort_p[kMaxMoves];
-    int shared_n;
+    MoveGenScratch mg;
     int bcast[4];
 };
 
@@ -363,8 +363,8 @@ ARA_HD int expand_node(const TreeDev& t, const SearchParams& sp, WarpScratch& ws
     const int rep = repetition_on_path(t, ws, depth);
     if (ARA_LANE == 0) b.repetition = static_cast<int16_t>(rep);
     ARA_WARP_SYNC();
-    const int n_moves = gen_legal(b, ws.scratch, ws.legal, &ws.shared_n);
-    const bool checked = in_check(b);
+    const int n_moves = gen_legal(b, ws.mg, ws.scratch, ws.legal);
+    const bool checked = ws.mg.checked != 0;
     const int tt = terminal_type(b, n_moves, checked);
     int nid = -1;
     if (ARA_LANE == 0) {
@@ -439,7 +439,7 @@ ARA_HD int expand_node(const TreeDev& t, const SearchParams& sp, WarpScratch& ws
             t.vl[e + i] = 0;
             t.etype[e + i] = NT_UNSOLVED;
         }
-        if (writer_for_slot != nullptr) encode_planes(b, sp.mode, sp.input_version, true, *writer_for_slot);
+        if (writer_for_slot != nullptr) writer_for_slot->encode(b, sp.mode, sp.input_version);
     }
     ARA_WARP_SYNC();
     return nid;
@@ -644,16 +644,20 @@ ARA_HD void create_mini_batch(const TreeDev& t, const SearchParams& sp, WarpScra
             cur = next;
         }
         if (type == -2) break;
-        if (ARA_LANE == 0) {
-            st.sum_depth += static_cast<unsigned long long>(depth);
-            if (type == 2) {
+        if (type == 2) {
+            if (ARA_LANE == 0) {
+                st.sum_depth += static_cast<unsigned long long>(depth);
+                // terminal: free backup, sequential leaf -> root because the MCTS solver propagates bottom-up
                 backup_value(t, sp, node_value(t.hdr[leaf]), ws.traj_node, ws.traj_ci, depth, true, sp.mcts_solver != 0);
-            } else {
-                const int row = type == 1 ? B + n_coll : n_new;
-                for (int i = 0; i < depth; ++i) {
-                    t.traj_node[row * kMaxDepth + i] = ws.traj_node[i];
-                    t.traj_ci[row * kMaxDepth + i] = ws.traj_ci[i];
-                }
+            }
+        } else {
+            const int row = type == 1 ? B + n_coll : n_new;
+            for (int i = ARA_LANE; i < depth; i += ARA_WARP_N) {
+                t.traj_node[row * kMaxDepth + i] = ws.traj_node[i];
+                t.traj_ci[row * kMaxDepth + i] = ws.traj_ci[i];
+            }
+            if (ARA_LANE == 0) {
+                st.sum_depth += static_cast<unsigned long long>(depth);
                 t.traj_len[row] = depth;
                 if (type == 0) t.new_node[n_new] = leaf;
             }
@@ -682,15 +686,25 @@ ARA_HD void apply_results(const TreeDev& t, const SearchParams& sp, WarpScratch&
         const int slot = t.slot_base + b;
         fill_nn_results(t, sp, ws, t.new_node[b], values[slot], probs + static_cast<size_t>(slot) * n_labels);
     }
-    if (ARA_LANE == 0) {
-        for (int b = 0; b < n_new; ++b)
-            backup_value(t, sp, node_value(t.hdr[t.new_node[b]]), t.traj_node + b * kMaxDepth, t.traj_ci + b * kMaxDepth,
-                         t.traj_len[b], false, false);
-        for (int c = 0; c < n_coll; ++c) {
-            const int row = B + c;
-            for (int i = t.traj_len[row] - 1; i >= 0; --i)
-                revert_virtual_loss(t, sp, t.traj_node[row * kMaxDepth + i], t.traj_ci[row * kMaxDepth + i]);
+    // backup_value (node.h:819-843) without solver: the levels of one trajectory are distinct nodes/edges, so lane i
+    // updates depth i (value sign alternates with the distance to the leaf); consecutive backups that share an edge
+    // share its depth and therefore its lane, which preserves the reference's update order edge by edge.
+    for (int b = 0; b < n_new; ++b) {
+        const float leaf_v = node_value(t.hdr[t.new_node[b]]);
+        const int len = t.traj_len[b];
+        for (int i = ARA_LANE; i < len; i += ARA_WARP_N) {
+            const float v = ((len - i) & 1) ? -leaf_v : leaf_v;
+            revert_virtual_loss_and_update(t, sp, t.traj_node[b * kMaxDepth + i], t.traj_ci[b * kMaxDepth + i], v, false, false);
         }
+    }
+    for (int c = 0; c < n_coll; ++c) {
+        const int row = B + c;
+        const int len = t.traj_len[row];
+        for (int i = ARA_LANE; i < len; i += ARA_WARP_N)
+            revert_virtual_loss(t, sp, t.traj_node[row * kMaxDepth + i], t.traj_ci[row * kMaxDepth + i]);
+    }
+    ARA_WARP_SYNC();
+    if (ARA_LANE == 0) {
         t.st->n_new = 0;
         t.st->n_coll = 0;
     }

@@ -47,17 +47,16 @@ unsigned long long he_key_scratch(const HeState* s) { return compute_key(s->b); 
 int he_in_check(const HeState* s) { return in_check(s->b) ? 1 : 0; }
 int he_repetition(const HeState* s) { return s->b.repetition; }
 int he_terminal(const HeState* s) {
-    Move scratch[kMaxMoves];
-    int n = 0;
-    const bool any = has_legal_move(s->b, scratch, &n);
-    return terminal_type(s->b, any ? 1 : 0, in_check(s->b));
+    Move scratch[kMaxMoves], out[kMaxMoves];
+    MoveGenScratch mg;
+    const int n = gen_legal(s->b, mg, scratch, out);
+    return terminal_type(s->b, n, mg.checked != 0);
 }
 int he_policy_index(const HeState* s, uint16_t m) { return policy_map_index(m, s->b.stm, s->b.chess960); }
 int he_planes(const HeState* s, int mode, int version, int normalize, float* out) {
     const int c = planes_channels(mode, version);
     if (c < 0) return -1;
-    NchwF32Writer w{out};
-    encode_planes(s->b, mode, version, normalize != 0, w);
+    encode_planes_nchw_f32(s->b, mode, version, normalize != 0, out);
     return c;
 }
 int he_sizeof_board() { return static_cast<int>(sizeof(Board)); }
@@ -73,7 +72,11 @@ const void* he_board(const HeState* s) { return &s->b; }
 struct HostWriterFactory {
     float* base;
     int channels;
-    NchwF32Writer make(int slot) const { return NchwF32Writer{base + static_cast<size_t>(slot) * channels * 64}; }
+    struct Target {
+        float* out;
+        void encode(const Board& b, int mode, int version) const { encode_planes_nchw_f32(b, mode, version, true, out); }
+    };
+    Target make(int slot) const { return Target{base + static_cast<size_t>(slot) * channels * 64}; }
 };
 
 struct HeSearch {

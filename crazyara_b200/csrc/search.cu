@@ -99,6 +99,12 @@ class Search {
     int set_position(int tree, const Board& root, const uint64_t* hist_keys, const int16_t* hist_reps, int hist_len);
     int go();
     int fetch_results();
+    int debug_cycles(int tree, unsigned long long* out8) {
+        TreeState st;
+        ARA_CUDA_OK(cudaMemcpy(&st, d_states_[tree], sizeof(st), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < 8; ++i) out8[i] = st.prof[i];
+        return 0;
+    }
     SearchParams sp{};
     int n_trees = 0;
     std::vector<SearchResult> results;
@@ -452,6 +458,10 @@ extern "C" int ara_search_profile(ara_search_t h, double* select_ms, double* net
     if (apply_ms) *apply_ms = s->apply_ms;
     if (net_forwards) *net_forwards = s->net_forwards;
     return 0;
+}
+extern "C" int ara_search_debug_cycles(ara_search_t h, int tree, unsigned long long* out8) {
+    if (h == nullptr || out8 == nullptr) return ara::set_error("ara_search_debug_cycles: null argument");
+    return reinterpret_cast<Search*>(h)->debug_cycles(tree, out8);
 }
 extern "C" double ara_search_last_go_ms(ara_search_t h) { return h ? reinterpret_cast<Search*>(h)->last_go_ms : 0.0; }
 extern "C" long long ara_search_launch_count(ara_search_t h) { return h ? reinterpret_cast<Search*>(h)->launches : 0; }

@@ -83,7 +83,22 @@ struct TreeState {
     unsigned evals;
     unsigned long long sum_select_k;
     unsigned long long sum_depth;
+    // SM-clock cycles spent per phase of create_mini_batch (lane 0): 0 descent, 1 board copy + do_move, 2 repetition +
+    // move generation, 3 node/edge allocation + init, 4 plane encoding, 5 terminal backups, 6 trajectory bookkeeping
+    unsigned long long prof[8];
 };
+
+#if defined(__CUDA_ARCH__)
+#define ARA_CLOCK() clock64()
+#else
+#define ARA_CLOCK() 0LL
+#endif
+#define ARA_PROF(st, idx, t0)                                                      \
+    do {                                                                           \
+        const long long now_ = ARA_CLOCK();                                        \
+        if (ARA_LANE == 0) (st).prof[idx] += static_cast<unsigned long long>(now_ - (t0)); \
+        (t0) = now_;                                                               \
+    } while (0)
 
 struct TreeDev {
     NodeHdr* hdr;
@@ -360,12 +375,14 @@ ARA_HD int expand_node(const TreeDev& t, const SearchParams& sp, WarpScratch& ws
                        const PlaneWriter* writer_for_slot, int* is_terminal) {
     Board& b = ws.child;
     // repetition info needs the key: done by do_move
+    long long tp = ARA_CLOCK();
     const int rep = repetition_on_path(t, ws, depth);
     if (ARA_LANE == 0) b.repetition = static_cast<int16_t>(rep);
     ARA_WARP_SYNC();
     const int n_moves = gen_legal(b, ws.mg, ws.scratch, ws.legal);
     const bool checked = ws.mg.checked != 0;
     const int tt = terminal_type(b, n_moves, checked);
+    ARA_PROF(*t.st, 2, tp);
     int nid = -1;
     if (ARA_LANE == 0) {
         TreeState& st = *t.st;
@@ -439,7 +456,9 @@ ARA_HD int expand_node(const TreeDev& t, const SearchParams& sp, WarpScratch& ws
             t.vl[e + i] = 0;
             t.etype[e + i] = NT_UNSOLVED;
         }
+        ARA_PROF(*t.st, 3, tp);
         if (writer_for_slot != nullptr) writer_for_slot->encode(b, sp.mode, sp.input_version);
+        ARA_PROF(*t.st, 4, tp);
     }
     ARA_WARP_SYNC();
     return nid;
@@ -594,6 +613,7 @@ ARA_HD void create_mini_batch(const TreeDev& t, const SearchParams& sp, WarpScra
     int n_new = 0, n_coll = 0, n_term = 0;
     while (n_new < B && n_coll != B && n_term < 2 * B) {
         int cur = 0, depth = 0, type = -1, leaf = -1;  // type: 0 new, 1 collision, 2 terminal
+        long long tq = ARA_CLOCK();
         for (;;) {
             if (depth >= kMaxDepth) {
                 if (ARA_LANE == 0) st.error = 3;
@@ -613,6 +633,7 @@ ARA_HD void create_mini_batch(const TreeDev& t, const SearchParams& sp, WarpScra
             depth++;
             const int next = t.child[h.edge_base + ci];
             if (next < 0) {
+                ARA_PROF(st, 0, tq);
                 copy_board(&ws.child, &t.board[cur]);
                 if (ARA_LANE == 0) {
                     do_move(ws.child, t.move[h.edge_base + ci]);
@@ -620,6 +641,7 @@ ARA_HD void create_mini_batch(const TreeDev& t, const SearchParams& sp, WarpScra
                     if (t.hdr[cur].no_visit_idx < t.hdr[cur].n_moves) ++t.hdr[cur].no_visit_idx;
                 }
                 ARA_WARP_SYNC();
+                ARA_PROF(st, 1, tq);
                 int is_term = 0;
                 const auto writer = wf.make(t.slot_base + n_new);
                 leaf = expand_node(t, sp, ws, cur, ci, depth, &writer, &is_term);
@@ -628,6 +650,7 @@ ARA_HD void create_mini_batch(const TreeDev& t, const SearchParams& sp, WarpScra
                     break;
                 }
                 type = is_term ? 2 : 0;
+                tq = ARA_CLOCK();
                 break;
             }
             const NodeHdr& nh = t.hdr[next];
@@ -644,6 +667,7 @@ ARA_HD void create_mini_batch(const TreeDev& t, const SearchParams& sp, WarpScra
             cur = next;
         }
         if (type == -2) break;
+        if (type != 0) ARA_PROF(st, 0, tq);
         if (type == 2) {
             if (ARA_LANE == 0) {
                 st.sum_depth += static_cast<unsigned long long>(depth);
@@ -663,6 +687,7 @@ ARA_HD void create_mini_batch(const TreeDev& t, const SearchParams& sp, WarpScra
             }
         }
         ARA_WARP_SYNC();
+        ARA_PROF(st, type == 2 ? 5 : 6, tq);
         if (type == 2) ++n_term;
         else if (type == 1) ++n_coll;
         else ++n_new;
@@ -728,6 +753,7 @@ ARA_HD void create_root(const TreeDev& t, const SearchParams& sp, WarpScratch& w
         st.evals = 0;
         st.sum_select_k = 0;
         st.sum_depth = 0;
+        for (int i = 0; i < 8; ++i) st.prof[i] = 0;
     }
     ARA_WARP_SYNC();
     // the root keeps the repetition info it arrived with (set by the host from the game history)

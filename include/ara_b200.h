@@ -156,6 +156,9 @@ int ara_search_result(ara_search_t s, int tree, ara_search_result_t* out);
 /* per-phase device times of the last go (CUDA events on the search stream); enable before ara_search_go */
 int ara_search_set_profile(ara_search_t s, int on);
 int ara_search_profile(ara_search_t s, double* select_ms, double* net_ms, double* apply_ms, long long* net_forwards);
+/* SM-clock cycles per phase of the select kernel in the last go (0 descent, 1 do_move, 2 movegen, 3 node init,
+ * 4 plane encode, 5 terminal backup, 6 bookkeeping) -- profiling aid */
+int ara_search_debug_cycles(ara_search_t s, int tree, unsigned long long* out8);
 double ara_search_last_go_ms(ara_search_t s);       /* device time of the last go (CUDA events) */
 long long ara_search_launch_count(ara_search_t s); /* search kernels launched so far */
 

@@ -1,0 +1,31 @@
+"""Self-play arena: concurrent games, one device tree each (games/hr leg of the metric)."""
+import pytest
+
+
+@pytest.mark.gpu
+def test_arena_plays_legal_games_fake_backend():
+    from crazyara_b200.selfplay import Arena, rl_settings
+    st = rl_settings("crazyhouse", batch_size=8, nodes=60, simulations=240)
+    arena = Arena(None, st, variant=1, n_games=6, temperature_moves=8, max_plies=40, seed=3)
+    res = arena.run(min_games=6, max_steps=60)
+    assert res["games"] >= 6 and res["moves"] > 0 and res["nodes"] > 0
+    assert all(p <= 40 for p, _, _ in arena.finished)
+    arena.close()
+
+
+@pytest.mark.gpu
+def test_arena_real_net_chess960(tmp_path):
+    from crazyara_b200.nn import NeuralNetAPI
+    from crazyara_b200.selfplay import Arena, rl_settings
+    from crazyara_b200.weights import export_blob
+    from oracle import net as onet
+    arch = onet.arch_risev33(52, 76, True)
+    blob = export_blob(onet.make_state_dict(arch, 0), arch, str(tmp_path / "v33.arab"), input_version=30)
+    n_games, B = 8, 8
+    net = NeuralNetAPI("gpu", 0, n_games * B, blob)
+    st = rl_settings("chess", batch_size=B, nodes=100, simulations=400, input_version=3)
+    arena = Arena(net, st, variant=0, n_games=n_games, max_plies=12, seed=1)
+    res = arena.run(min_games=8, max_steps=14)
+    assert res["games"] >= 8 and res["nps"] > 0
+    arena.close()
+    net.close()

@@ -41,36 +41,50 @@ struct NullWriterFactory {  // fake backend: no planes needed
     ARA_HD Target make(int) const { return Target{}; }
 };
 
-__global__ void __launch_bounds__(32) root_kernel(const TreeDev* trees, SearchParams sp, const Board* roots, __half* in_h,
-                                                  int cpad) {
+__global__ void __launch_bounds__(32) root_kernel(const TreeDev* trees, SearchParams sp, const Board* roots) {
     __shared__ WarpScratch ws;
     const TreeDev t = trees[blockIdx.x];
+    create_root(t, sp, ws, &roots[blockIdx.x]);
+}
+
+// one warp per tree: the sequential part of SearchThread::create_mini_batch
+__global__ void __launch_bounds__(32) select_kernel(const TreeDev* trees, SearchParams sp) {
+    __shared__ WarpScratch ws;
+    const TreeDev t = trees[blockIdx.x];
+    create_mini_batch(t, sp, ws);
+}
+
+// one warp per (tree, new leaf): move lists, edges, policy indices, input planes of all new leaves in parallel
+__global__ void __launch_bounds__(32) expand_kernel(const TreeDev* trees, SearchParams sp, int batch, __half* in_h, int cpad) {
+    __shared__ WarpScratch ws;
+    const int tree = blockIdx.x / batch, b = blockIdx.x - tree * batch;
+    const TreeDev t = trees[tree];
+    if (b >= t.st->n_new || t.st->error) return;
+    const int nid = t.new_node[b];
     if (in_h != nullptr) {
-        DevWriterFactory wf{in_h, cpad};
-        create_root(t, sp, ws, &roots[blockIdx.x], wf);
+        const DevWriterFactory wf{in_h, cpad};
+        const auto target = wf.make(t.slot_base + b);
+        expand_pending(t, sp, ws, nid, &target);
     } else {
-        NullWriterFactory wf;
-        create_root(t, sp, ws, &roots[blockIdx.x], wf);
+        expand_pending(t, sp, ws, nid, static_cast<const NullWriterFactory::Target*>(nullptr));
     }
 }
 
-__global__ void __launch_bounds__(32) select_kernel(const TreeDev* trees, SearchParams sp, __half* in_h, int cpad) {
+// one warp per (tree, new leaf): priors of the legal moves out of the soft-maxed policy, temperature, sort, value
+__global__ void __launch_bounds__(32) scatter_kernel(const TreeDev* trees, SearchParams sp, int batch, const float* values,
+                                                     const float* probs, int n_labels) {
     __shared__ WarpScratch ws;
-    const TreeDev t = trees[blockIdx.x];
-    if (in_h != nullptr) {
-        DevWriterFactory wf{in_h, cpad};
-        create_mini_batch(t, sp, ws, wf);
-    } else {
-        NullWriterFactory wf;
-        create_mini_batch(t, sp, ws, wf);
-    }
+    const int tree = blockIdx.x / batch, b = blockIdx.x - tree * batch;
+    const TreeDev t = trees[tree];
+    if (b >= t.st->n_new || t.st->error) return;
+    scatter_pending(t, sp, ws, b, values, probs, n_labels);
 }
 
-__global__ void __launch_bounds__(32) apply_kernel(const TreeDev* trees, SearchParams sp, const float* values,
-                                                   const float* probs, int n_labels, int finalize) {
+// one warp per tree: value backups along the stored trajectories, collision reverts
+__global__ void __launch_bounds__(32) backup_kernel(const TreeDev* trees, SearchParams sp, int finalize) {
     __shared__ WarpScratch ws;
     const TreeDev t = trees[blockIdx.x];
-    apply_results(t, sp, ws, values, probs, n_labels);
+    backup_results(t, sp);
     if (finalize) finalize_root(t, sp, ws);
 }
 
@@ -290,23 +304,25 @@ int Search::iterate(int count) {
     __half* in_h = net_ ? net_->d_in_h : nullptr;
     const int cpad = net_ ? net_->cin_pad : 0;
     const int B = sp.batch_size;
+    const float* values = net_ ? net_->d_value : d_values_;
+    const float* probs = net_ ? net_->d_prob : d_probs_;
     for (int it = 0; it < count; ++it) {
         if (profile) prof_event();
-        select_kernel<<<n_trees, 32, 0, stream_>>>(d_trees_, sp, in_h, cpad);
+        select_kernel<<<n_trees, 32, 0, stream_>>>(d_trees_, sp);
+        expand_kernel<<<n_trees * B, 32, 0, stream_>>>(d_trees_, sp, B, in_h, cpad);
         if (profile) prof_event();
         if (net_) {
             if (net_->forward_device(n_trees * B, stream_)) return -1;
-            if (profile) prof_event();
-            apply_kernel<<<n_trees, 32, 0, stream_>>>(d_trees_, sp, net_->d_value, net_->d_prob, n_labels_, 0);
         } else {
             fake_eval_kernel<<<n_trees * B, 128, 0, stream_>>>(d_trees_, n_trees, B, d_values_, d_probs_, n_labels_);
-            if (profile) prof_event();
-            apply_kernel<<<n_trees, 32, 0, stream_>>>(d_trees_, sp, d_values_, d_probs_, n_labels_, 0);
             ++launches;
         }
         if (profile) prof_event();
+        scatter_kernel<<<n_trees * B, 32, 0, stream_>>>(d_trees_, sp, B, values, probs, n_labels_);
+        backup_kernel<<<n_trees, 32, 0, stream_>>>(d_trees_, sp, 0);
+        if (profile) prof_event();
         ++net_forwards;
-        launches += 2;
+        launches += 4;
     }
     ARA_CUDA_OK(cudaGetLastError());
     return 0;
@@ -322,18 +338,20 @@ int Search::go() {
     __half* in_h = net_ ? net_->d_in_h : nullptr;
     const int cpad = net_ ? net_->cin_pad : 0;
     const int B = sp.batch_size;
-    // root: create, evaluate (set_root_node_predictions), scatter, prepare_node_for_visits (+ Dirichlet)
-    root_kernel<<<n_trees, 32, 0, stream_>>>(d_trees_, sp, d_roots_, in_h, cpad);
+    // root: create, expand, evaluate (set_root_node_predictions), scatter, prepare_node_for_visits (+ Dirichlet)
+    root_kernel<<<n_trees, 32, 0, stream_>>>(d_trees_, sp, d_roots_);
+    expand_kernel<<<n_trees * B, 32, 0, stream_>>>(d_trees_, sp, B, in_h, cpad);
     if (net_) {
         // the root of tree i sits in batch row i * B; a single-tree search only needs row 0
         if (net_->forward_device(n_trees == 1 ? 1 : n_trees * B, stream_)) return -1;
-        apply_kernel<<<n_trees, 32, 0, stream_>>>(d_trees_, sp, net_->d_value, net_->d_prob, n_labels_, 1);
     } else {
         fake_eval_kernel<<<n_trees * B, 128, 0, stream_>>>(d_trees_, n_trees, B, d_values_, d_probs_, n_labels_);
-        apply_kernel<<<n_trees, 32, 0, stream_>>>(d_trees_, sp, d_values_, d_probs_, n_labels_, 1);
         ++launches;
     }
-    launches += 2;
+    scatter_kernel<<<n_trees * B, 32, 0, stream_>>>(d_trees_, sp, B, net_ ? net_->d_value : d_values_,
+                                                     net_ ? net_->d_prob : d_probs_, n_labels_);
+    backup_kernel<<<n_trees, 32, 0, stream_>>>(d_trees_, sp, 1);
+    launches += 4;
     ARA_CUDA_OK(cudaGetLastError());
     // main loop: enqueue the iterations the visit budget certainly needs, then poll `done` in small chunks
     unsigned budget = sp.simulations ? sp.simulations : sp.nodes;

@@ -68,7 +68,8 @@ struct alignas(16) NodeHdr {  // 64 B: one line per visited node on the select p
     int16_t repetition;
     uint8_t node_type;
     uint8_t flags;
-    uint32_t pad_[3];
+    float cput;  // get_current_cput(visit_sum), refreshed by whoever changes visit_sum: keeps the LUT off the select path
+    uint32_t pad_[2];
 };
 static_assert(sizeof(NodeHdr) == 64, "NodeHdr must be 64 bytes");
 
@@ -169,25 +170,33 @@ ARA_HD void copy_board(Board* dst, const Board* src) {
 }
 
 // ------------------------------------------------------------------ select (warp argmax, first maximum wins)
-ARA_HD int select_child(const TreeDev& t, const SearchParams& sp, int nid) {
+// Returns the selected child index; *child_out receives that child's node id (-1 if not expanded).  The dependent
+// load chain per tree level is: node header -> edge arrays (P, N, Q and the child ids together) -> next header.
+ARA_HD int select_child(const TreeDev& t, const SearchParams& sp, int nid, int* child_out) {
     NodeHdr& h = t.hdr[nid];
-    if (ARA_LANE == 0 && !(h.flags & NF_HAS_D)) h.flags |= NF_HAS_D | NF_SORTED;  // prepare_node_for_visits (lazy flag)
-    ARA_WARP_SYNC();
+    const uint8_t flags = h.flags;
     const int k = h.no_visit_idx;
-    if (k == 1) return 0;
-    if (h.checkmate_idx != kNoCheckmate) return h.checkmate_idx;
+    const int cm = h.checkmate_idx;
     const uint32_t vs = h.visit_sum;
-    const float cput = current_cput(t, sp, vs);
-    const double sq = sqrt(static_cast<double>(vs));
     const uint32_t e = h.edge_base;
+    const float cput = h.cput;
+    if (ARA_LANE == 0 && !(flags & NF_HAS_D)) h.flags = flags | NF_HAS_D | NF_SORTED;  // prepare_node_for_visits (lazy flag)
+    if (k == 1 || cm != kNoCheckmate) {
+        const int ci = k == 1 ? 0 : cm;
+        *child_out = t.child[e + ci];
+        return ci;
+    }
+    const double sq = sqrt(static_cast<double>(vs));
     float best_v = 0.0f;
-    int best_i = 0x7fffffff;
+    int best_i = 0x7fffffff, best_c = -1;
     for (int i = ARA_LANE; i < k; i += ARA_WARP_N) {
+        const int c = t.child[e + i];
         const float u = static_cast<float>(static_cast<double>(cput * t.P[e + i]) * (sq / (static_cast<double>(t.N[e + i]) + 1.0)));
         const float v = t.Q[e + i] + u;
         if (best_i == 0x7fffffff || v > best_v) {
             best_v = v;
             best_i = i;
+            best_c = c;
         }
     }
 #if defined(__CUDA_ARCH__)
@@ -195,13 +204,16 @@ ARA_HD int select_child(const TreeDev& t, const SearchParams& sp, int nid) {
     for (int off = 16; off > 0; off >>= 1) {
         const float ov = __shfl_xor_sync(0xffffffffu, best_v, off);
         const int oi = __shfl_xor_sync(0xffffffffu, best_i, off);
+        const int oc = __shfl_xor_sync(0xffffffffu, best_c, off);
         if (oi != 0x7fffffff && (best_i == 0x7fffffff || ov > best_v || (ov == best_v && oi < best_i))) {
             best_v = ov;
             best_i = oi;
+            best_c = oc;
         }
     }
 #endif
     if (ARA_LANE == 0) t.st->sum_select_k += static_cast<unsigned long long>(k);
+    *child_out = best_c;
     return best_i;
 }
 
@@ -212,7 +224,9 @@ ARA_HD void apply_virtual_loss(const TreeDev& t, const SearchParams& sp, int nid
     if (virtual_style_of(sp, t.N[e]) == VS_VIRTUAL_LOSS)
         t.Q[e] = static_cast<float>((static_cast<double>(t.Q[e]) * t.N[e] - 1) / static_cast<double>(t.N[e] + 1));
     ++t.N[e];
-    ++h.visit_sum;
+    const uint32_t vs = h.visit_sum + 1;
+    h.visit_sum = vs;
+    h.cput = current_cput(t, sp, vs);
     ++t.vl[e];
 }
 
@@ -329,7 +343,9 @@ ARA_HD void revert_virtual_loss(const TreeDev& t, const SearchParams& sp, int ni
     if (virtual_style_of(sp, t.N[e]) == VS_VIRTUAL_LOSS)
         t.Q[e] = static_cast<float>((static_cast<double>(t.Q[e]) * t.N[e] + 1) / (t.N[e] - 1));
     --t.N[e];
-    --h.visit_sum;
+    const uint32_t vs = h.visit_sum - 1;
+    h.visit_sum = vs;
+    h.cput = current_cput(t, sp, vs);
     --t.vl[e];
 }
 
@@ -368,28 +384,63 @@ ARA_HD int repetition_on_path(const TreeDev& t, const WarpScratch& ws, int depth
 }
 
 // ------------------------------------------------------------------ expansion
+// Expansion is split in two so that only what the reference's SEQUENTIAL semantics need stays in the per-tree loop:
+//   expand_node_seq   (inside create_mini_batch, one warp per tree): repetition info, terminal verdict, node id,
+//                     header, board, child link.  The verdict needs "is there any legal move", answered without the
+//                     full list whenever some piece that is not on a line with the king has a pseudo-legal move.
+//   expand_pending    (one warp per NEW leaf, all leaves of all trees in parallel): full legal move list, edge
+//                     allocation + initialisation, policy indices, input planes.
+
+// Does the side to move have a legal move?  Warp-collective; *checked_out = side to move is in check.
+ARA_HD bool any_legal_move(const Board& b, WarpScratch& ws, bool* checked_out) {
+    const int us = b.stm, them = us ^ 1;
+    const uint64_t own = b.by_color[us], opp = b.by_color[them], occ = own | opp;
+    const int ksq = king_square(b, us);
+    const bool checked = ksq >= 0 && attackers_of(b, ksq, occ, them, opp) != 0;
+    *checked_out = checked;
+    if (variant_end(b)) return false;
+    if (!checked) {
+        if (b.variant == V_CRAZYHOUSE) {
+            const uint64_t empty = ~occ;
+            bool nonpawn = false;
+            for (int pt = PT_KNIGHT; pt <= PT_QUEEN; ++pt) nonpawn = nonpawn || b.hand[us][pt] != 0;
+            if ((nonpawn && empty) || (b.hand[us][PT_PAWN] && (empty & ~(kRank1 | kRank8)))) return true;
+        }
+        // a piece that is not aligned with its king cannot be pinned: any pseudo-legal move of it is legal
+        // (en passant excluded: it can uncover a rank attack through two removed pawns)
+        const uint64_t king_lines = ksq >= 0 ? (rook_attacks_bb(bit(ksq), 0) | bishop_attacks_bb(bit(ksq), 0) | bit(ksq)) : 0;
+        const uint64_t ep_bit = b.ep != 0xFF ? bit(b.ep) : 0;
+        bool found = false;
+        for (int sq = ARA_LANE; sq < 64; sq += ARA_WARP_N) {
+            if (!(own & bit(sq)) || (king_lines & bit(sq))) continue;
+            const int pt = piece_type_on(b, sq);
+            uint64_t tg = piece_targets(b, sq, pt, us, own, opp, occ);
+            if (pt == PT_PAWN) tg &= ~ep_bit;
+            if (tg) found = true;
+        }
+        if (ARA_BALLOT(found)) return true;
+    }
+    return gen_legal(b, ws.mg, ws.scratch, ws.legal) > 0;
+}
+
 // Creates the node for ws.child (already moved), child `ci` of `parent` (or the root if parent < 0).
 // Returns the new node id (uniform), or -1 on pool exhaustion.  *is_terminal receives the terminal verdict.
-template <class PlaneWriter>
-ARA_HD int expand_node(const TreeDev& t, const SearchParams& sp, WarpScratch& ws, int parent, int ci, int depth,
-                       const PlaneWriter* writer_for_slot, int* is_terminal) {
+ARA_HD int expand_node_seq(const TreeDev& t, const SearchParams& sp, WarpScratch& ws, int parent, int ci, int depth,
+                           int* is_terminal) {
     Board& b = ws.child;
-    // repetition info needs the key: done by do_move
     long long tp = ARA_CLOCK();
     const int rep = repetition_on_path(t, ws, depth);
     if (ARA_LANE == 0) b.repetition = static_cast<int16_t>(rep);
     ARA_WARP_SYNC();
-    const int n_moves = gen_legal(b, ws.mg, ws.scratch, ws.legal);
-    const bool checked = ws.mg.checked != 0;
-    const int tt = terminal_type(b, n_moves, checked);
+    bool checked = false;
+    const bool any = any_legal_move(b, ws, &checked);
+    const int tt = terminal_type(b, any ? 1 : 0, checked);
     ARA_PROF(*t.st, 2, tp);
     int nid = -1;
     if (ARA_LANE == 0) {
         TreeState& st = *t.st;
         if (st.n_nodes >= t.max_nodes) {
             st.error = 1;
-        } else if (tt == TERM_NONE && st.n_edges + n_moves > t.max_edges) {
-            st.error = 2;
         } else {
             nid = st.n_nodes++;
             NodeHdr h;
@@ -400,16 +451,17 @@ ARA_HD int expand_node(const TreeDev& t, const SearchParams& sp, WarpScratch& ws
             h.free_visits = 0;
             h.edge_base = 0;
             h.parent = parent;
-            h.n_moves = static_cast<uint16_t>(n_moves);
+            h.n_moves = 0;  // filled by expand_pending
             h.no_visit_idx = 1;
             h.checkmate_idx = kNoCheckmate;
             h.end_in_ply = 0;
-            h.n_unsolved = static_cast<uint16_t>(n_moves);
+            h.n_unsolved = 0;
             h.parent_ci = static_cast<uint16_t>(ci < 0 ? 0 : ci);
             h.repetition = b.repetition;
             h.node_type = NT_UNSOLVED;
             h.flags = 0;
-            h.pad_[0] = h.pad_[1] = h.pad_[2] = 0;
+            h.cput = current_cput(t, sp, 0);
+            h.pad_[0] = h.pad_[1] = 0;
             if (tt != TERM_NONE) {  // check_for_terminal node.cpp:880-904 + mark_as_terminal
                 h.flags = NF_TERMINAL | NF_HAS_D | NF_SORTED;
                 h.no_visit_idx = 0;
@@ -419,14 +471,10 @@ ARA_HD int expand_node(const TreeDev& t, const SearchParams& sp, WarpScratch& ws
                 } else if (tt == TERM_DRAW) {
                     node_set_value(h, 0.0f);
                     h.node_type = NT_DRAW;
-                    h.n_moves = 0;
                 } else {
                     node_set_value(h, -1.0f);
                     h.node_type = NT_LOSS;
                 }
-            } else {
-                h.edge_base = static_cast<uint32_t>(st.n_edges);
-                st.n_edges += n_moves;
             }
             t.hdr[nid] = h;
             if (parent >= 0) t.child[t.hdr[parent].edge_base + ci] = nid;
@@ -436,8 +484,42 @@ ARA_HD int expand_node(const TreeDev& t, const SearchParams& sp, WarpScratch& ws
     *is_terminal = tt != TERM_NONE;
     if (nid < 0) return -1;
     copy_board(&t.board[nid], &b);
-    if (tt == TERM_NONE) {
-        const uint32_t e = t.hdr[nid].edge_base;
+    ARA_PROF(*t.st, 3, tp);
+    return nid;
+}
+
+// Second half of the expansion of node `nid` (non-terminal, freshly created by expand_node_seq).  Warp-collective;
+// different nodes are processed by different warps concurrently, the edge pool is claimed with one atomic.
+template <class PlaneTarget>
+ARA_HD void expand_pending(const TreeDev& t, const SearchParams& sp, WarpScratch& ws, int nid, const PlaneTarget* target) {
+    copy_board(&ws.child, &t.board[nid]);
+    const Board& b = ws.child;
+    const int n_moves = gen_legal(b, ws.mg, ws.scratch, ws.legal);
+    if (ARA_LANE == 0) {
+        TreeState& st = *t.st;
+#if defined(__CUDA_ARCH__)
+        const int e0 = atomicAdd(&st.n_edges, n_moves);
+#else
+        const int e0 = st.n_edges;
+        st.n_edges += n_moves;
+#endif
+        NodeHdr& h = t.hdr[nid];
+        if (e0 + n_moves > t.max_edges) {
+            st.error = 2;
+            h.edge_base = 0;
+            h.n_moves = 0;
+            ws.bcast[0] = -1;
+        } else {
+            h.edge_base = static_cast<uint32_t>(e0);
+            h.n_moves = static_cast<uint16_t>(n_moves);
+            h.n_unsolved = static_cast<uint16_t>(n_moves);
+            ws.bcast[0] = e0;
+        }
+    }
+    ARA_WARP_SYNC();
+    const int e0 = ws.bcast[0];
+    if (e0 >= 0) {
+        const uint32_t e = static_cast<uint32_t>(e0);
         for (int i = ARA_LANE; i < n_moves; i += ARA_WARP_N) {
             const Move m = ws.legal[i];
             t.move[e + i] = m;
@@ -456,12 +538,9 @@ ARA_HD int expand_node(const TreeDev& t, const SearchParams& sp, WarpScratch& ws
             t.vl[e + i] = 0;
             t.etype[e + i] = NT_UNSOLVED;
         }
-        ARA_PROF(*t.st, 3, tp);
-        if (writer_for_slot != nullptr) writer_for_slot->encode(b, sp.mode, sp.input_version);
-        ARA_PROF(*t.st, 4, tp);
+        if (target != nullptr) target->encode(b, sp.mode, sp.input_version);
     }
     ARA_WARP_SYNC();
-    return nid;
 }
 
 // ------------------------------------------------------------------ scatter of network results into a new node
@@ -591,9 +670,9 @@ ARA_HD void apply_dirichlet_to_root(const TreeDev& t, const SearchParams& sp, Wa
 }
 
 // ------------------------------------------------------------------ one mini-batch: SearchThread::create_mini_batch
-// PlaneWriterFactory::make(slot) returns the writer for network-batch row `slot`.
-template <class WriterFactory>
-ARA_HD void create_mini_batch(const TreeDev& t, const SearchParams& sp, WarpScratch& ws, const WriterFactory& wf) {
+// Sequential per tree (one warp).  New leaves are only created here (expand_node_seq); their move lists, edges and
+// input planes are produced afterwards by expand_pending, one warp per leaf.
+ARA_HD void create_mini_batch(const TreeDev& t, const SearchParams& sp, WarpScratch& ws) {
     TreeState& st = *t.st;
     if (st.done || st.error) {
         if (ARA_LANE == 0) st.n_new = 0, st.n_coll = 0;
@@ -620,7 +699,8 @@ ARA_HD void create_mini_batch(const TreeDev& t, const SearchParams& sp, WarpScra
                 type = -2;
                 break;
             }
-            const int ci = select_child(t, sp, cur);
+            int next = -1;
+            const int ci = select_child(t, sp, cur, &next);
             const NodeHdr& h = t.hdr[cur];
             if (ARA_LANE == 0) {
                 apply_virtual_loss(t, sp, cur, ci);
@@ -631,7 +711,6 @@ ARA_HD void create_mini_batch(const TreeDev& t, const SearchParams& sp, WarpScra
             }
             ARA_WARP_SYNC();
             depth++;
-            const int next = t.child[h.edge_base + ci];
             if (next < 0) {
                 ARA_PROF(st, 0, tq);
                 copy_board(&ws.child, &t.board[cur]);
@@ -643,8 +722,7 @@ ARA_HD void create_mini_batch(const TreeDev& t, const SearchParams& sp, WarpScra
                 ARA_WARP_SYNC();
                 ARA_PROF(st, 1, tq);
                 int is_term = 0;
-                const auto writer = wf.make(t.slot_base + n_new);
-                leaf = expand_node(t, sp, ws, cur, ci, depth, &writer, &is_term);
+                leaf = expand_node_seq(t, sp, ws, cur, ci, depth, &is_term);
                 if (leaf < 0) {
                     type = -2;
                     break;
@@ -701,16 +779,18 @@ ARA_HD void create_mini_batch(const TreeDev& t, const SearchParams& sp, WarpScra
     ARA_WARP_SYNC();
 }
 
-// set_nn_results_to_child_nodes + backup_value_outputs + backup_collisions (searchthread.cpp:301-324)
-ARA_HD void apply_results(const TreeDev& t, const SearchParams& sp, WarpScratch& ws, const float* values,
-                          const float* probs, int n_labels) {
+// set_nn_results_to_child_nodes (searchthread.cpp:301-310) for new leaf `b` of the tree: one warp per leaf.
+ARA_HD void scatter_pending(const TreeDev& t, const SearchParams& sp, WarpScratch& ws, int b, const float* values,
+                            const float* probs, int n_labels) {
+    const int slot = t.slot_base + b;
+    fill_nn_results(t, sp, ws, t.new_node[b], values[slot], probs + static_cast<size_t>(slot) * n_labels);
+}
+
+// backup_value_outputs + backup_collisions (searchthread.cpp:312-324): one warp per tree.
+ARA_HD void backup_results(const TreeDev& t, const SearchParams& sp) {
     const TreeState& st = *t.st;
     const int B = sp.batch_size;
     const int n_new = st.n_new, n_coll = st.n_coll;
-    for (int b = 0; b < n_new; ++b) {
-        const int slot = t.slot_base + b;
-        fill_nn_results(t, sp, ws, t.new_node[b], values[slot], probs + static_cast<size_t>(slot) * n_labels);
-    }
     // backup_value (node.h:819-843) without solver: the levels of one trajectory are distinct nodes/edges, so lane i
     // updates depth i (value sign alternates with the distance to the leaf); consecutive backups that share an edge
     // share its depth and therefore its lane, which preserves the reference's update order edge by edge.
@@ -737,9 +817,7 @@ ARA_HD void apply_results(const TreeDev& t, const SearchParams& sp, WarpScratch&
 }
 
 // Root creation: MCTSAgent::create_new_root_node (mctsagent.cpp:180-196), first half (before the network call).
-template <class WriterFactory>
-ARA_HD void create_root(const TreeDev& t, const SearchParams& sp, WarpScratch& ws, const Board* root_board,
-                        const WriterFactory& wf) {
+ARA_HD void create_root(const TreeDev& t, const SearchParams& sp, WarpScratch& ws, const Board* root_board) {
     copy_board(&ws.child, root_board);
     if (ARA_LANE == 0) {
         TreeState& st = *t.st;
@@ -756,16 +834,12 @@ ARA_HD void create_root(const TreeDev& t, const SearchParams& sp, WarpScratch& w
         for (int i = 0; i < 8; ++i) st.prof[i] = 0;
     }
     ARA_WARP_SYNC();
-    // the root keeps the repetition info it arrived with (set by the host from the game history)
-    const int saved_rep = root_board->repetition;
     int is_term = 0;
-    const auto writer = wf.make(t.slot_base);
-    // expand_node recomputes repetition from history; for the root depth = 0 means "history only"
-    const int nid = expand_node(t, sp, ws, -1, -1, 0, &writer, &is_term);
-    (void)saved_rep;
+    // repetition info is recomputed from the game history (depth 0 = history only)
+    const int nid = expand_node_seq(t, sp, ws, -1, -1, 0, &is_term);
     if (ARA_LANE == 0 && nid == 0) {
         TreeState& st = *t.st;
-        if (is_term || t.hdr[0].n_moves == 0) {
+        if (is_term) {
             st.done = 1;
         } else {
             st.n_new = 1;  // the root is the single "new node" of the first network call
@@ -776,7 +850,7 @@ ARA_HD void create_root(const TreeDev& t, const SearchParams& sp, WarpScratch& w
     }
     ARA_WARP_SYNC();
 }
-// second half: after the network results were scattered by apply_results (root trajectory is empty)
+// second half: after expand_pending + network + scatter_pending + backup_results (root trajectory is empty)
 ARA_HD void finalize_root(const TreeDev& t, const SearchParams& sp, WarpScratch& ws) {
     if (ARA_LANE == 0 && !t.st->done && !t.st->error) {
         NodeHdr& h = t.hdr[0];

@@ -165,21 +165,31 @@ int he_search_set_root(HeSearch* s, const HeState* root) {
     s->t.hist_keys = s->hist_keys.data();
     s->t.hist_reps = s->hist_reps.data();
     s->t.hist_len = static_cast<int>(s->hist_keys.size());
+    create_root(s->t, s->sp, s->ws, &s->root);
     HostWriterFactory wf{s->planes.data(), s->channels};
-    create_root(s->t, s->sp, s->ws, &s->root, wf);
+    for (int b = 0; b < s->st.n_new; ++b) {
+        const auto target = wf.make(b);
+        expand_pending(s->t, s->sp, s->ws, s->new_node[b], &target);
+    }
     return s->st.n_new;
 }
 void he_search_root_results(HeSearch* s, const float* values, const float* probs) {
-    apply_results(s->t, s->sp, s->ws, values, probs, s->n_labels);
+    for (int b = 0; b < s->st.n_new; ++b) scatter_pending(s->t, s->sp, s->ws, b, values, probs, s->n_labels);
+    backup_results(s->t, s->sp);
     finalize_root(s->t, s->sp, s->ws);
 }
 int he_search_create_mini_batch(HeSearch* s) {
+    create_mini_batch(s->t, s->sp, s->ws);
     HostWriterFactory wf{s->planes.data(), s->channels};
-    create_mini_batch(s->t, s->sp, s->ws, wf);
+    for (int b = 0; b < s->st.n_new; ++b) {
+        const auto target = wf.make(b);
+        expand_pending(s->t, s->sp, s->ws, s->new_node[b], &target);
+    }
     return s->st.n_new;
 }
 void he_search_apply_results(HeSearch* s, const float* values, const float* probs) {
-    apply_results(s->t, s->sp, s->ws, values, probs, s->n_labels);
+    for (int b = 0; b < s->st.n_new; ++b) scatter_pending(s->t, s->sp, s->ws, b, values, probs, s->n_labels);
+    backup_results(s->t, s->sp);
 }
 int he_search_done(const HeSearch* s) { return s->st.done || s->st.error; }
 int he_search_error(const HeSearch* s) { return s->st.error; }

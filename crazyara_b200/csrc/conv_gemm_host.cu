@@ -23,6 +23,36 @@ static PFN_encodeTiled get_encode_fn() {
     return fn;
 }
 
+// activations [boards_cap, 8, 8, cin] fp16 as a 4-D map with box {64 ch, 8, 8, 2 boards}, 128-B swizzle, zero OOB fill
+int make_act_tensor_map(CUtensorMap* m, const __half* act, int boards_cap, int cin) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (enc == nullptr) return set_error("cuTensorMapEncodeTiled entry point not available");
+    if (cin % 8 != 0 || boards_cap < 2 || (boards_cap & 1)) return set_error("make_act_tensor_map: bad shape (%d, %d)", boards_cap, cin);
+    cuuint64_t dims[4] = {(cuuint64_t)cin, 8, 8, (cuuint64_t)boards_cap};
+    cuuint64_t strides[3] = {(cuuint64_t)cin * 2, (cuuint64_t)cin * 16, (cuuint64_t)cin * 128};
+    cuuint32_t box[4] = {64, 8, 8, 2};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(act), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled(act) failed: %d", (int)r);
+    return 0;
+}
+// weights [rows, k_total] fp16 K-major as a 2-D map with box {64 k, box_rows}
+int make_weight_tensor_map(CUtensorMap* m, const __half* w, int k_total, int rows, int box_rows) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (enc == nullptr) return set_error("cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(w), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
+    return 0;
+}
+
 int conv_layer_choose_bn(int boards, int n_out) {
     const char* env = getenv("ARA_FORCE_BN");
     if (env != nullptr) {

@@ -89,6 +89,10 @@ int Net::init(const char* blob_path, int dev, int batch_size) {
                              prop.major, prop.minor);
     }
     ARA_CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    {
+        const char* f = getenv("ARA_FUSED_BLOCKS");
+        use_fused = !(f != nullptr && f[0] == '0');
+    }
     const char* g = getenv("ARA_NO_GRAPH");
     use_graph = !(g != nullptr && g[0] == '1');
 
@@ -201,8 +205,15 @@ int Net::init(const char* blob_path, int dev, int batch_size) {
         for (int c = 0; c < bd.c_op; ++c)
             for (int q = 0; q < kk; ++q) t2[static_cast<size_t>(q) * bd.c_op + c] = t[static_cast<size_t>(c) * kk + q];
         if (upload_f32(t2.data(), t2.size(), t2.size(), &w.wd)) return -1;
+        const int cpad64 = round_up(bd.c_op, 64);
+        {  // padded copy for the fused block kernel: [k*k][cpad64]
+            std::vector<float> t3(static_cast<size_t>(kk) * cpad64, 0.f);
+            for (int c = 0; c < bd.c_op; ++c)
+                for (int q = 0; q < kk; ++q) t3[static_cast<size_t>(q) * cpad64 + c] = t[static_cast<size_t>(c) * kk + q];
+            if (upload_f32(t3.data(), t3.size(), t3.size(), &w.wd_pad)) return -1;
+        }
         if (!rd.tensor(t, bd.c_op)) return -1;
-        if (upload_f32(t.data(), bd.c_op, bd.c_op, &w.bd)) return -1;
+        if (upload_f32(t.data(), bd.c_op, cpad64, &w.bd)) return -1;
         // conv2 1x1 c_op -> 256 (+residual)
         if (!rd.tensor(t, static_cast<size_t>(C) * bd.c_op)) return -1;
         if (upload_conv_w(t.data(), C, bd.c_op, 1, &w.w2, &wrows)) return -1;
@@ -214,6 +225,10 @@ int Net::init(const char* blob_path, int dev, int batch_size) {
                                 bn))
                 return -1;
         }
+        // the same block as ONE fused kernel (rise_block.cuh); w1 rows / b1 are padded to 256, w2 columns to cpad64
+        if (rise_block_init(&w.fused, xin, batch_cap, w.w1, round_up(bd.c_op, 256), w.w2, wrows, cpad64, bd.c_op, bd.kernel, w.b1,
+                            w.wd_pad, w.bd, w.b2, xout))
+            return -1;
     }
     __half* xfinal = d_x[hdr.n_blocks & 1];
     // value head
@@ -288,6 +303,11 @@ int Net::enqueue(int n, cudaStream_t s, bool from_f32) {
         if (bd.se_type != 0) {
             ARA_CUDA_OK(launch_pdl(se_kernel, dim3(n), dim3(256), 0, s, xin, w.se_w1t, w.se_w2t, w.se_b, bd.se_type));
             ++launches;
+        }
+        if (use_fused) {
+            if (rise_block_launch(&w.fused, n, s)) return -1;
+            ++launches;
+            continue;
         }
         if (conv_layer_launch(&w.conv1, n, s)) return -1;
         const long long total = static_cast<long long>(n) * 64 * (bd.c_op / 8);
@@ -364,7 +384,7 @@ int Net::forward_from_f32_device(int n, cudaStream_t s) {
 int Net::kernels_per_forward(bool from_f32) const {
     int k = from_f32 ? 1 : 0;
     k += 1;  // stem
-    for (const auto& b : blocks) k += 3 + (b.se_type != 0 ? 1 : 0);
+    for (const auto& b : blocks) k += (use_fused ? 1 : 3) + (b.se_type != 0 ? 1 : 0);
     k += 4;  // value head, policy conv x2, softmax
     return k;
 }

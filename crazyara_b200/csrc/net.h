@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "conv_gemm_host.h"
+#include "rise_block_host.h"
 
 namespace ara {
 
@@ -36,6 +37,8 @@ struct BlockW {
     __half* w2 = nullptr;
     float* b2 = nullptr;
     ConvLayer conv1, conv2;
+    float* wd_pad = nullptr;  // [k*k][ceil64(c_op)] for the fused block kernel
+    RiseBlockLayer fused;
 };
 
 class Net {
@@ -74,6 +77,7 @@ class Net {
     float* d_aux = nullptr;      // [batch, 4]
     long long launches = 0;      // kernels launched so far (bench bookkeeping)
     bool use_graph = true;
+    bool use_fused = true;  // one kernel per bottleneck block (ARA_FUSED_BLOCKS=0 selects the three-kernel path)
 
    private:
     int enqueue(int n, cudaStream_t s, bool from_f32);

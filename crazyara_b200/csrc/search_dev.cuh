@@ -137,6 +137,7 @@ struct WarpScratch {  // per-warp shared memory (stack on the host)
     uint16_t traj_ci[kMaxDepth];
     float sort_p[kMaxMoves];
     MoveGenScratch mg;
+    TreeState st_local;  // the tree's counters live in shared memory while the select kernel runs
     int bcast[4];
 };
 
@@ -169,65 +170,152 @@ ARA_HD void copy_board(Board* dst, const Board* src) {
     ARA_WARP_SYNC();
 }
 
-// ------------------------------------------------------------------ select (warp argmax, first maximum wins)
-// Returns the selected child index; *child_out receives that child's node id (-1 if not expanded).  The dependent
-// load chain per tree level is: node header -> edge arrays (P, N, Q and the child ids together) -> next header.
-ARA_HD int select_child(const TreeDev& t, const SearchParams& sp, int nid, int* child_out) {
-    NodeHdr& h = t.hdr[nid];
-    const uint8_t flags = h.flags;
-    const int k = h.no_visit_idx;
-    const int cm = h.checkmate_idx;
-    const uint32_t vs = h.visit_sum;
-    const uint32_t e = h.edge_base;
-    const float cput = h.cput;
-    if (ARA_LANE == 0 && !(flags & NF_HAS_D)) h.flags = flags | NF_HAS_D | NF_SORTED;  // prepare_node_for_visits (lazy flag)
-    if (k == 1 || cm != kNoCheckmate) {
-        const int ci = k == 1 ? 0 : cm;
-        *child_out = t.child[e + ci];
-        return ci;
-    }
-    const double sq = sqrt(static_cast<double>(vs));
-    float best_v = 0.0f;
-    int best_i = 0x7fffffff, best_c = -1;
-    for (int i = ARA_LANE; i < k; i += ARA_WARP_N) {
-        const int c = t.child[e + i];
-        const float u = static_cast<float>(static_cast<double>(cput * t.P[e + i]) * (sq / (static_cast<double>(t.N[e + i]) + 1.0)));
-        const float v = t.Q[e + i] + u;
-        if (best_i == 0x7fffffff || v > best_v) {
-            best_v = v;
-            best_i = i;
-            best_c = c;
-        }
-    }
+// ------------------------------------------------------------------ select + virtual visit (one fused warp step)
+// Node::select_child_node (node.cpp:1150-1167, first maximum wins) followed by apply_virtual_loss_to_child
+// (node.cpp:507-529).  Written for a single in-order warp, where every load->use pair costs a full memory latency:
+//   * the 64-byte header is fetched once (all lanes, same address) and kept in registers;
+//   * cput for visit_sum+1 (needed only to refresh the cached header value) is requested before the argmax;
+//   * every lane loads P, Q, N, vl AND the child id of its candidates and prefetches that child's header line, so the
+//     next level's header is already on its way while the FP64 PUCT arithmetic runs;
+//   * the lane that owns the winning child applies the virtual visit from its registers (stores only), lane 0 updates
+//     the header (stores only).
+// The dependent chain per tree level is therefore: (prefetched) header -> edge arrays -> arithmetic.
+struct SelectStep {
+    int ci;            // selected child index
+    int child;         // its node id (-1: not expanded yet)
+    uint64_t key;      // key / repetition of the node we selected FROM (for the repetition scan of a new leaf)
+    int16_t repetition;
+    uint32_t edge_base;
+    uint16_t n_moves;
+    uint16_t no_visit_idx;
+};
+
+ARA_HD void prefetch_line(const void* p) {
 #if defined(__CUDA_ARCH__)
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, best_v, off);
-        const int oi = __shfl_xor_sync(0xffffffffu, best_i, off);
-        const int oc = __shfl_xor_sync(0xffffffffu, best_c, off);
-        if (oi != 0x7fffffff && (best_i == 0x7fffffff || ov > best_v || (ov == best_v && oi < best_i))) {
-            best_v = ov;
-            best_i = oi;
-            best_c = oc;
-        }
-    }
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    (void)p;
 #endif
-    if (ARA_LANE == 0) t.st->sum_select_k += static_cast<unsigned long long>(k);
-    *child_out = best_c;
-    return best_i;
 }
 
-// lane 0 only
-ARA_HD void apply_virtual_loss(const TreeDev& t, const SearchParams& sp, int nid, int ci) {  // node.cpp:507-529
-    NodeHdr& h = t.hdr[nid];
-    const uint32_t e = h.edge_base + ci;
-    if (virtual_style_of(sp, t.N[e]) == VS_VIRTUAL_LOSS)
-        t.Q[e] = static_cast<float>((static_cast<double>(t.Q[e]) * t.N[e] - 1) / static_cast<double>(t.N[e] + 1));
-    ++t.N[e];
-    const uint32_t vs = h.visit_sum + 1;
-    h.visit_sum = vs;
-    h.cput = current_cput(t, sp, vs);
-    ++t.vl[e];
+ARA_HD SelectStep select_and_visit(const TreeDev& t, const SearchParams& sp, int nid) {
+    NodeHdr* hp = &t.hdr[nid];
+    NodeHdr h;
+#if defined(__CUDA_ARCH__)
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(hp);
+        uint4* dst = reinterpret_cast<uint4*>(&h);
+        dst[0] = src[0];
+        dst[1] = src[1];
+        dst[2] = src[2];
+        dst[3] = src[3];
+    }
+#else
+    h = *hp;
+#endif
+    const int k = h.no_visit_idx;
+    const uint32_t e = h.edge_base;
+    const uint32_t vs_new = h.visit_sum + 1;
+    const float cput_new = current_cput(t, sp, vs_new);  // only stored; issued early so its latency is hidden
+    SelectStep r;
+    r.key = h.key;
+    r.repetition = h.repetition;
+    r.edge_base = e;
+    r.n_moves = h.n_moves;
+    r.no_visit_idx = h.no_visit_idx;
+    float best_v = 0.0f, best_q = 0.0f;
+    int best_i = 0x7fffffff, best_c = -1;
+    uint32_t best_n = 0;
+    uint8_t best_vl = 0;
+    if (k == 1 || h.checkmate_idx != kNoCheckmate) {
+        const int ci = k == 1 ? 0 : h.checkmate_idx;
+        if (ARA_LANE == (ci & (ARA_WARP_N - 1))) {
+            best_i = ci;
+            best_c = t.child[e + ci];
+            best_q = t.Q[e + ci];
+            best_n = t.N[e + ci];
+            best_vl = t.vl[e + ci];
+            if (best_c >= 0) prefetch_line(&t.hdr[best_c]);
+        }
+        best_i = ARA_SHFL(best_i, ci & (ARA_WARP_N - 1));
+        best_c = ARA_SHFL(best_c, ci & (ARA_WARP_N - 1));
+    } else {
+        const float cput = h.cput;
+        const double sq = sqrt(static_cast<double>(h.visit_sum));
+        for (int i = ARA_LANE; i < k; i += ARA_WARP_N) {
+            const int c = t.child[e + i];
+            const float p = t.P[e + i], q = t.Q[e + i];
+            const uint32_t n = t.N[e + i];
+            const uint8_t vl = t.vl[e + i];
+            if (c >= 0) prefetch_line(&t.hdr[c]);
+            const float u = static_cast<float>(static_cast<double>(cput * p) * (sq / (static_cast<double>(n) + 1.0)));
+            const float v = q + u;
+            if (best_i == 0x7fffffff || v > best_v) {
+                best_v = v;
+                best_i = i;
+                best_c = c;
+                best_q = q;
+                best_n = n;
+                best_vl = vl;
+            }
+        }
+#if defined(__CUDA_ARCH__)
+        float rv = best_v;
+        int ri = best_i, rc = best_c;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, rv, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, ri, off);
+            const int oc = __shfl_xor_sync(0xffffffffu, rc, off);
+            if (oi != 0x7fffffff && (ri == 0x7fffffff || ov > rv || (ov == rv && oi < ri))) {
+                rv = ov;
+                ri = oi;
+                rc = oc;
+            }
+        }
+        // the lane whose own best candidate is the global winner keeps best_q/best_n/best_vl of that edge
+        if (ri != best_i) best_i = -1;  // not the owner
+        const int owner_is_me = best_i == ri;
+        best_c = rc;
+        r.ci = ri;
+        r.child = rc;
+        if (owner_is_me) {
+#else
+        r.ci = best_i;
+        r.child = best_c;
+        {
+#endif
+            // apply_virtual_loss_to_child on the owner lane: registers in, stores out
+            const uint32_t ee = e + static_cast<uint32_t>(r.ci);
+            if (virtual_style_of(sp, best_n) == VS_VIRTUAL_LOSS)
+                t.Q[ee] = static_cast<float>((static_cast<double>(best_q) * best_n - 1) / static_cast<double>(best_n + 1));
+            t.N[ee] = best_n + 1;
+            t.vl[ee] = static_cast<uint8_t>(best_vl + 1);
+        }
+        if (ARA_LANE == 0) {
+            t.st->sum_select_k += static_cast<unsigned long long>(k);
+            hp->visit_sum = vs_new;
+            hp->cput = cput_new;
+            if (!(h.flags & NF_HAS_D)) hp->flags = h.flags | NF_HAS_D | NF_SORTED;  // prepare_node_for_visits (lazy flag)
+        }
+        return r;
+    }
+    // single-candidate paths (only one open child / forced win)
+    r.ci = best_i;
+    r.child = best_c;
+    if (ARA_LANE == (r.ci & (ARA_WARP_N - 1))) {
+        const uint32_t ee = e + static_cast<uint32_t>(r.ci);
+        if (virtual_style_of(sp, best_n) == VS_VIRTUAL_LOSS)
+            t.Q[ee] = static_cast<float>((static_cast<double>(best_q) * best_n - 1) / static_cast<double>(best_n + 1));
+        t.N[ee] = best_n + 1;
+        t.vl[ee] = static_cast<uint8_t>(best_vl + 1);
+    }
+    if (ARA_LANE == 0) {
+        hp->visit_sum = vs_new;
+        hp->cput = cput_new;
+        if (!(h.flags & NF_HAS_D)) hp->flags = h.flags | NF_HAS_D | NF_SORTED;
+    }
+    return r;
 }
 
 // ------------------------------------------------------------------ MCTS solver (lane 0 only; TWO_PLAYER, no tablebases)
@@ -672,7 +760,7 @@ ARA_HD void apply_dirichlet_to_root(const TreeDev& t, const SearchParams& sp, Wa
 // ------------------------------------------------------------------ one mini-batch: SearchThread::create_mini_batch
 // Sequential per tree (one warp).  New leaves are only created here (expand_node_seq); their move lists, edges and
 // input planes are produced afterwards by expand_pending, one warp per leaf.
-ARA_HD void create_mini_batch(const TreeDev& t, const SearchParams& sp, WarpScratch& ws) {
+ARA_HD void create_mini_batch_impl(const TreeDev& t, const SearchParams& sp, WarpScratch& ws) {
     TreeState& st = *t.st;
     if (st.done || st.error) {
         if (ARA_LANE == 0) st.n_new = 0, st.n_coll = 0;
@@ -699,15 +787,14 @@ ARA_HD void create_mini_batch(const TreeDev& t, const SearchParams& sp, WarpScra
                 type = -2;
                 break;
             }
-            int next = -1;
-            const int ci = select_child(t, sp, cur, &next);
-            const NodeHdr& h = t.hdr[cur];
+            const SelectStep step = select_and_visit(t, sp, cur);
+            const int ci = step.ci;
+            const int next = step.child;
             if (ARA_LANE == 0) {
-                apply_virtual_loss(t, sp, cur, ci);
                 ws.traj_node[depth] = cur;
                 ws.traj_ci[depth] = static_cast<uint16_t>(ci);
-                ws.path_key[depth] = h.key;
-                ws.path_rep[depth] = h.repetition;
+                ws.path_key[depth] = step.key;
+                ws.path_rep[depth] = step.repetition;
             }
             ARA_WARP_SYNC();
             depth++;
@@ -715,9 +802,9 @@ ARA_HD void create_mini_batch(const TreeDev& t, const SearchParams& sp, WarpScra
                 ARA_PROF(st, 0, tq);
                 copy_board(&ws.child, &t.board[cur]);
                 if (ARA_LANE == 0) {
-                    do_move(ws.child, t.move[h.edge_base + ci]);
+                    do_move(ws.child, t.move[step.edge_base + ci]);
                     // increment_no_visit_idx: open the next-best sibling (its edge slots are pre-initialised)
-                    if (t.hdr[cur].no_visit_idx < t.hdr[cur].n_moves) ++t.hdr[cur].no_visit_idx;
+                    if (step.no_visit_idx < step.n_moves) t.hdr[cur].no_visit_idx = static_cast<uint16_t>(step.no_visit_idx + 1);
                 }
                 ARA_WARP_SYNC();
                 ARA_PROF(st, 1, tq);
@@ -776,6 +863,18 @@ ARA_HD void create_mini_batch(const TreeDev& t, const SearchParams& sp, WarpScra
         st.iterations++;
         st.evals += static_cast<unsigned>(n_new);
     }
+    ARA_WARP_SYNC();
+}
+
+ARA_HD void create_mini_batch(const TreeDev& t_in, const SearchParams& sp, WarpScratch& ws) {
+    // every `st.x += ...` of the sequential loop would otherwise be a global-memory round trip on the critical path
+    TreeDev t = t_in;
+    if (ARA_LANE == 0) ws.st_local = *t_in.st;
+    ARA_WARP_SYNC();
+    t.st = &ws.st_local;
+    create_mini_batch_impl(t, sp, ws);
+    ARA_WARP_SYNC();
+    if (ARA_LANE == 0) *t_in.st = ws.st_local;
     ARA_WARP_SYNC();
 }
 

@@ -77,7 +77,7 @@ class Net {
     float* d_aux = nullptr;      // [batch, 4]
     long long launches = 0;      // kernels launched so far (bench bookkeeping)
     bool use_graph = true;
-    bool use_fused = true;  // one kernel per bottleneck block (ARA_FUSED_BLOCKS=0 selects the three-kernel path)
+    bool use_fused = false;  // ARA_FUSED_BLOCKS=1: one kernel per bottleneck block (rise_block.cuh)
 
    private:
     int enqueue(int n, cudaStream_t s, bool from_f32);

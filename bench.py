@@ -236,17 +236,8 @@ def main():
     sampler.join(timeout=2)
     launches = agent.launch_count() + net.launch_count() - launches0
 
-    total_nodes, max_dev_ms, max_wall = float(nodes), dev_ms, wall_s
-    if dist is not None:
-        t = torch.tensor([float(nodes)], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        total_nodes = t.item()
-        m = torch.tensor([dev_ms, wall_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(m, op=dist.ReduceOp.MAX)
-        max_dev_ms, max_wall = m[0].item(), m[1].item()
-        lt = torch.tensor([float(launches)], device="cuda", dtype=torch.float64)
-        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
-        launches = int(lt.item())
+    from crazyara_b200.multi import aggregate_counters
+    total_nodes, max_dev_ms, max_wall, launches = aggregate_counters(nodes, dev_ms, wall_s, launches, dist, "cuda")
 
     if rank == 0:
         peaks = {}

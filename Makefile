@@ -19,6 +19,14 @@ build/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) $(wild
 $(LIB): $(CU_OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $^
 
+# profiling build: clock64 probes inside the descent (tools/prof_select.py with ARA_B200_LIB=build/libara_b200_fine.so)
+build/search_fine.o: $(CSRC)/search.cu $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) $(wildcard include/*.h)
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -fmad=false -DARA_PROF_FINE -c $< -o $@
+build/libara_b200_fine.so: build/search_fine.o $(filter-out build/search.o,$(CU_OBJS))
+	$(NVCC) $(ARCH) -shared -o $@ $^
+fine: build/libara_b200_fine.so
+
 clean:
 	rm -rf build $(LIB)
 

@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libara_b200.so")
+# ARA_B200_LIB selects another build of the same CUDA library (e.g. the -DARA_PROF_FINE profiling build)
+LIB_PATH = os.environ.get("ARA_B200_LIB") or os.path.join(_HERE, "libara_b200.so")
 
 _lib = None
 

@@ -258,11 +258,13 @@ int Search::init(Net* net, const SearchParams& params, int device, int trees, in
         TreeDev& t = h_trees_[i];
         if (dalloc(&t.hdr, max_nodes_) || dalloc(&t.board, max_nodes_)) return -1;
         if (dalloc(&t.P, max_edges_) || dalloc(&t.Q, max_edges_) || dalloc(&t.N, max_edges_) || dalloc(&t.child, max_edges_) ||
+            dalloc(&t.cbase, max_edges_) ||
             dalloc(&t.move, max_edges_) || dalloc(&t.vl, max_edges_) || dalloc(&t.etype, max_edges_))
             return -1;
         if (dalloc(&t.st, 1)) return -1;
         if (dalloc(&t.new_node, B) || dalloc(&t.traj_node, static_cast<size_t>(2) * B * kMaxDepth) ||
-            dalloc(&t.traj_ci, static_cast<size_t>(2) * B * kMaxDepth) || dalloc(&t.traj_len, 2 * B))
+            dalloc(&t.traj_ci, static_cast<size_t>(2) * B * kMaxDepth) || dalloc(&t.traj_len, 2 * B) ||
+            dalloc(&t.traj_edge, static_cast<size_t>(2) * B * kMaxDepth) || dalloc(&t.new_value, B))
             return -1;
         if (dalloc(&d_hist_keys_[i], hist_cap_) || dalloc(&d_hist_reps_[i], hist_cap_)) return -1;
         t.hist_keys = d_hist_keys_[i];

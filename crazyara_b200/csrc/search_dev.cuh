@@ -68,8 +68,8 @@ struct alignas(16) NodeHdr {  // 64 B: one line per visited node on the select p
     int16_t repetition;
     uint8_t node_type;
     uint8_t flags;
-    float cput;  // get_current_cput(visit_sum), refreshed by whoever changes visit_sum: keeps the LUT off the select path
-    uint32_t pad_[2];
+    float cput;      // get_current_cput(visit_sum) and
+    double sqrt_vs;  // sqrt(double(visit_sum)): refreshed by whoever changes visit_sum, which keeps both off the select path
 };
 static_assert(sizeof(NodeHdr) == 64, "NodeHdr must be 64 bytes");
 
@@ -101,6 +101,22 @@ struct TreeState {
         (t0) = now_;                                                               \
     } while (0)
 
+// -DARA_PROF_FINE: split the descent into edge wait (slot 4), PUCT arithmetic + reductions (slot 7) and child-header
+// wait (slot 5).  The clock is read through an asm that consumes `dep`, so it cannot be scheduled before dep arrives.
+#if defined(ARA_PROF_FINE) && defined(__CUDA_ARCH__)
+#define ARA_FINE(stp, idx, t0, dep)                                                         \
+    do {                                                                                    \
+        long long now_;                                                                     \
+        asm volatile("mov.u64 %0, %%clock64;" : "=l"(now_) : "r"(static_cast<int>(dep)) : "memory"); \
+        if (ARA_LANE == 0) (stp)->prof[idx] += static_cast<unsigned long long>(now_ - (t0)); \
+        (t0) = now_;                                                                        \
+    } while (0)
+#define ARA_FINE_T0(t0) long long t0 = clock64()
+#else
+#define ARA_FINE(stp, idx, t0, dep) do { } while (0)
+#define ARA_FINE_T0(t0) do { } while (0)
+#endif
+
 struct TreeDev {
     NodeHdr* hdr;
     Board* board;
@@ -108,6 +124,7 @@ struct TreeDev {
     float* Q;
     uint32_t* N;
     int32_t* child;
+    uint32_t* cbase;  // edge_base of the child behind every edge: lets one round trip fetch a child's header AND edges
     Move* move;
     uint8_t* vl;
     uint8_t* etype;
@@ -115,7 +132,9 @@ struct TreeDev {
     int32_t* new_node;      // [B]
     int32_t* traj_node;     // [2B][kMaxDepth]   rows 0..B-1 new leaves, B..2B-1 collisions
     uint16_t* traj_ci;      // [2B][kMaxDepth]
+    uint32_t* traj_edge;    // [2B][kMaxDepth]   absolute edge index (edge_base + ci) of every step
     int32_t* traj_len;      // [2B]
+    float* new_value;       // [B] network value of every new leaf (written by the scatter step)
     const uint64_t* hist_keys;  // positions before the root, oldest first
     const int16_t* hist_reps;
     int hist_len;
@@ -135,6 +154,7 @@ struct WarpScratch {  // per-warp shared memory (stack on the host)
     int16_t path_rep[kMaxDepth];
     int32_t traj_node[kMaxDepth];
     uint16_t traj_ci[kMaxDepth];
+    uint32_t traj_edge[kMaxDepth];
     float sort_p[kMaxMoves];
     MoveGenScratch mg;
     TreeState st_local;  // the tree's counters live in shared memory while the select kernel runs
@@ -172,24 +192,16 @@ ARA_HD void copy_board(Board* dst, const Board* src) {
 
 // ------------------------------------------------------------------ select + virtual visit (one fused warp step)
 // Node::select_child_node (node.cpp:1150-1167, first maximum wins) followed by apply_virtual_loss_to_child
-// (node.cpp:507-529).  Written for a single in-order warp, where every load->use pair costs a full memory latency:
-//   * the 64-byte header is fetched once (all lanes, same address) and kept in registers;
-//   * cput for visit_sum+1 (needed only to refresh the cached header value) is requested before the argmax;
-//   * every lane loads P, Q, N, vl AND the child id of its candidates and prefetches that child's header line, so the
-//     next level's header is already on its way while the FP64 PUCT arithmetic runs;
-//   * the lane that owns the winning child applies the virtual visit from its registers (stores only), lane 0 updates
-//     the header (stores only).
-// The dependent chain per tree level is therefore: (prefetched) header -> edge arrays -> arithmetic.
-struct SelectStep {
-    int ci;            // selected child index
-    int child;         // its node id (-1: not expanded yet)
-    uint64_t key;      // key / repetition of the node we selected FROM (for the repetition scan of a new leaf)
-    int16_t repetition;
-    uint32_t edge_base;
-    uint16_t n_moves;
-    uint16_t no_visit_idx;
-};
-
+// (node.cpp:507-529).  Written for a single in-order warp, where every load->use pair costs a full memory latency and
+// every dependent arithmetic chain is exposed.  Per tree level the chain is
+//     edge arrays (one round trip; the header refresh values sqrt(visit_sum+1) and cput(visit_sum+1) are computed
+//     while it is in flight) -> FP64 PUCT term -> two warp reductions -> child header (one round trip; the virtual
+//     visit and the header update are stored while it is in flight).
+//   * the caller hands in the 64-byte header in registers (it came back from the previous level's step);
+//   * sqrt(visit_sum) and cput(visit_sum) are cached in the header by whoever changes visit_sum;
+//   * the argmax is redux.max over an order-preserving integer image of Q+U, then redux.min over the indices of the
+//     lanes that hold the maximum (first maximum wins, as in the reference);
+//   * the lane that owns the winning edge applies the virtual visit from its registers, lane 0 updates the header.
 ARA_HD void prefetch_line(const void* p) {
 #if defined(__CUDA_ARCH__)
     asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
@@ -198,122 +210,177 @@ ARA_HD void prefetch_line(const void* p) {
 #endif
 }
 
-ARA_HD SelectStep select_and_visit(const TreeDev& t, const SearchParams& sp, int nid) {
-    NodeHdr* hp = &t.hdr[nid];
-    NodeHdr h;
+ARA_HD void load_hdr(NodeHdr* dst, const NodeHdr* src) {
 #if defined(__CUDA_ARCH__)
-    {
-        const uint4* src = reinterpret_cast<const uint4*>(hp);
-        uint4* dst = reinterpret_cast<uint4*>(&h);
-        dst[0] = src[0];
-        dst[1] = src[1];
-        dst[2] = src[2];
-        dst[3] = src[3];
-    }
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    const uint4 a = s4[0], b = s4[1], c = s4[2], d = s4[3];
+    d4[0] = a;
+    d4[1] = b;
+    d4[2] = c;
+    d4[3] = d;
 #else
-    h = *hp;
+    *dst = *src;
 #endif
+}
+
+// the per-edge statistics one lane holds for one candidate child
+struct EdgeRegs {
+    int c;         // child node id (-1: not expanded yet)
+    float p, q;
+    uint32_t n;
+    uint32_t cb;   // edge_base of the child (valid once the child has been expanded)
+    uint8_t vl;
+};
+ARA_HD EdgeRegs load_edge(const TreeDev& t, uint32_t idx) {
+    EdgeRegs x;
+    x.c = t.child[idx];
+    x.p = t.P[idx];
+    x.q = t.Q[idx];
+    x.n = t.N[idx];
+    x.cb = t.cbase[idx];
+    x.vl = t.vl[idx];
+    return x;
+}
+// order-preserving integer image of a float (x + 0 folds -0 into +0, so equal floats have equal images)
+ARA_HD uint32_t float_image(float v) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t fb = __float_as_uint(v + 0.0f);
+#else
+    union { float f; uint32_t u; } cv;
+    cv.f = v + 0.0f;
+    const uint32_t fb = cv.u;
+#endif
+    return (fb & 0x80000000u) ? ~fb : (fb | 0x80000000u);
+}
+
+struct SelectStep {
+    int ci;        // selected child index
+    int child;     // its node id (-1: not expanded yet)
+    NodeHdr ch;    // header of `child` (valid when child >= 0)
+    EdgeRegs pre;  // and this lane's edge of it (edge index ARA_LANE)
+};
+
+struct SelectPick {
+    int ci;        // winning child index (same in every lane)
+    bool owner;    // this lane holds the winning edge in `x`
+    EdgeRegs x;
+};
+
+// Exact arithmetic of the reference (get_current_u_values, node.cpp:1056-1063: float cput*P, then double): first
+// maximum of Q + U over the open children.
+ARA_HD SelectPick pick_exact(const TreeDev& t, const NodeHdr& h, const EdgeRegs& pre) {
     const int k = h.no_visit_idx;
     const uint32_t e = h.edge_base;
-    const uint32_t vs_new = h.visit_sum + 1;
-    const float cput_new = current_cput(t, sp, vs_new);  // only stored; issued early so its latency is hidden
-    SelectStep r;
-    r.key = h.key;
-    r.repetition = h.repetition;
-    r.edge_base = e;
-    r.n_moves = h.n_moves;
-    r.no_visit_idx = h.no_visit_idx;
-    float best_v = 0.0f, best_q = 0.0f;
-    int best_i = 0x7fffffff, best_c = -1;
-    uint32_t best_n = 0;
-    uint8_t best_vl = 0;
-    if (k == 1 || h.checkmate_idx != kNoCheckmate) {
-        const int ci = k == 1 ? 0 : h.checkmate_idx;
-        if (ARA_LANE == (ci & (ARA_WARP_N - 1))) {
-            best_i = ci;
-            best_c = t.child[e + ci];
-            best_q = t.Q[e + ci];
-            best_n = t.N[e + ci];
-            best_vl = t.vl[e + ci];
-            if (best_c >= 0) prefetch_line(&t.hdr[best_c]);
-        }
-        best_i = ARA_SHFL(best_i, ci & (ARA_WARP_N - 1));
-        best_c = ARA_SHFL(best_c, ci & (ARA_WARP_N - 1));
-    } else {
-        const float cput = h.cput;
-        const double sq = sqrt(static_cast<double>(h.visit_sum));
-        for (int i = ARA_LANE; i < k; i += ARA_WARP_N) {
-            const int c = t.child[e + i];
-            const float p = t.P[e + i], q = t.Q[e + i];
-            const uint32_t n = t.N[e + i];
-            const uint8_t vl = t.vl[e + i];
-            if (c >= 0) prefetch_line(&t.hdr[c]);
-            const float u = static_cast<float>(static_cast<double>(cput * p) * (sq / (static_cast<double>(n) + 1.0)));
-            const float v = q + u;
-            if (best_i == 0x7fffffff || v > best_v) {
-                best_v = v;
-                best_i = i;
-                best_c = c;
-                best_q = q;
-                best_n = n;
-                best_vl = vl;
-            }
-        }
-#if defined(__CUDA_ARCH__)
-        float rv = best_v;
-        int ri = best_i, rc = best_c;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, rv, off);
-            const int oi = __shfl_xor_sync(0xffffffffu, ri, off);
-            const int oc = __shfl_xor_sync(0xffffffffu, rc, off);
-            if (oi != 0x7fffffff && (ri == 0x7fffffff || ov > rv || (ov == rv && oi < ri))) {
-                rv = ov;
-                ri = oi;
-                rc = oc;
-            }
-        }
-        // the lane whose own best candidate is the global winner keeps best_q/best_n/best_vl of that edge
-        if (ri != best_i) best_i = -1;  // not the owner
-        const int owner_is_me = best_i == ri;
-        best_c = rc;
-        r.ci = ri;
-        r.child = rc;
-        if (owner_is_me) {
-#else
-        r.ci = best_i;
-        r.child = best_c;
-        {
-#endif
-            // apply_virtual_loss_to_child on the owner lane: registers in, stores out
-            const uint32_t ee = e + static_cast<uint32_t>(r.ci);
-            if (virtual_style_of(sp, best_n) == VS_VIRTUAL_LOSS)
-                t.Q[ee] = static_cast<float>((static_cast<double>(best_q) * best_n - 1) / static_cast<double>(best_n + 1));
-            t.N[ee] = best_n + 1;
-            t.vl[ee] = static_cast<uint8_t>(best_vl + 1);
-        }
-        if (ARA_LANE == 0) {
-            t.st->sum_select_k += static_cast<unsigned long long>(k);
-            hp->visit_sum = vs_new;
-            hp->cput = cput_new;
-            if (!(h.flags & NF_HAS_D)) hp->flags = h.flags | NF_HAS_D | NF_SORTED;  // prepare_node_for_visits (lazy flag)
-        }
-        return r;
+    const float cput = h.cput;
+    const double sq = h.sqrt_vs;
+    SelectPick r;
+    r.x = pre;
+    int best_i = 0x7fffffff;
+    float best_v = 0.0f;
+    for (int i = ARA_LANE; i < k; i += ARA_WARP_N) {
+        const EdgeRegs x = i == ARA_LANE ? pre : load_edge(t, e + i);
+        const float u = static_cast<float>(static_cast<double>(cput * x.p) * (sq / (static_cast<double>(x.n) + 1.0)));
+        const float v = x.q + u;
+        if (best_i == 0x7fffffff || v > best_v) best_v = v, best_i = i, r.x = x;
     }
-    // single-candidate paths (only one open child / forced win)
-    r.ci = best_i;
-    r.child = best_c;
-    if (ARA_LANE == (r.ci & (ARA_WARP_N - 1))) {
-        const uint32_t ee = e + static_cast<uint32_t>(r.ci);
-        if (virtual_style_of(sp, best_n) == VS_VIRTUAL_LOSS)
-            t.Q[ee] = static_cast<float>((static_cast<double>(best_q) * best_n - 1) / static_cast<double>(best_n + 1));
-        t.N[ee] = best_n + 1;
-        t.vl[ee] = static_cast<uint8_t>(best_vl + 1);
+    const uint32_t img = best_i == 0x7fffffff ? 0u : float_image(best_v);
+    const uint32_t top = ARA_REDUCE_MAX(img);
+    r.ci = static_cast<int>(ARA_REDUCE_MIN(img == top ? static_cast<uint32_t>(best_i) : 0x7fffffffu));
+    r.owner = best_i == r.ci;
+    return r;
+}
+
+// Same decision from fp32 arithmetic with a rigorous error margin.  With U the real value of cput*P*sqrt(N)/(n+1):
+// the reference's u is U(1+d), |d| <= 2^-24 (the double operations contribute < 2^-50); the fp32 value uf below
+// carries at most five roundings (float(sqrt), float(n), +1, *, /), so |uf - u| < 6e-7 uf.  Adding the two roundings
+// of q + u and of the bounds themselves, the exact Q+U of a candidate lies within E = 6e-7 uf + 2.6e-7 |vf| + 1e-30
+// of vf.  If the fp32 winner's lower bound exceeds every other candidate's upper bound it is the reference's strict
+// maximum; otherwise (near-ties, exact ties) `sure` is false and the caller falls back to pick_exact.
+ARA_HD SelectPick pick_fast(const TreeDev& t, const NodeHdr& h, const EdgeRegs& pre, bool* sure) {
+    const int k = h.no_visit_idx;
+    const uint32_t e = h.edge_base;
+    const float cput = h.cput;
+    const float sqf = static_cast<float>(h.sqrt_vs);
+    const float ninf = -3.0e38f;
+    SelectPick r;
+    r.x = pre;
+    int best_i = 0x7fffffff;
+    float best_v = 0.0f, best_hi = ninf, best_lo = 0.0f, oth_hi = ninf;
+    for (int i = ARA_LANE; i < k; i += ARA_WARP_N) {
+        const EdgeRegs x = i == ARA_LANE ? pre : load_edge(t, e + i);
+        const float uf = (cput * x.p) * sqf / (static_cast<float>(x.n) + 1.0f);
+        const float vf = x.q + uf;
+        const float err = uf * 6e-7f + (vf < 0.0f ? -vf : vf) * 2.6e-7f + 1e-30f;
+        const float hi = vf + err;
+        if (best_i == 0x7fffffff || vf > best_v) {
+            if (best_hi > oth_hi) oth_hi = best_hi;
+            best_v = vf, best_hi = hi, best_lo = vf - err, best_i = i, r.x = x;
+        } else if (hi > oth_hi) {
+            oth_hi = hi;
+        }
+    }
+    const uint32_t img = best_i == 0x7fffffff ? 0u : float_image(best_v);
+    const uint32_t top = ARA_REDUCE_MAX(img);
+    r.ci = static_cast<int>(ARA_REDUCE_MIN(img == top ? static_cast<uint32_t>(best_i) : 0x7fffffffu));
+    r.owner = best_i == r.ci;
+    const float others = r.owner ? oth_hi : (best_hi > oth_hi ? best_hi : oth_hi);
+    const uint32_t others_top = ARA_REDUCE_MAX(float_image(others));
+    const uint32_t lo_img = ARA_REDUCE_MAX(r.owner ? float_image(best_lo) : 0u);
+    *sure = lo_img > others_top;
+    return r;
+}
+
+ARA_HD SelectStep select_and_visit(const TreeDev& t, const SearchParams& sp, int nid, const NodeHdr& h,
+                                   const EdgeRegs& pre) {
+    NodeHdr* hp = &t.hdr[nid];
+    const int k = h.no_visit_idx;
+    const uint32_t e = h.edge_base;
+    const bool single = k == 1 || h.checkmate_idx != kNoCheckmate;
+    ARA_FINE_T0(tf);
+    // header refresh values, off the dependent chain
+    const uint32_t vs_new = h.visit_sum + 1;
+    const float cput_new = current_cput(t, sp, vs_new);
+    const double sqrt_new = sqrt(static_cast<double>(vs_new));
+    ARA_FINE(t.st, 4, tf, pre.c ^ static_cast<int>(pre.n) ^ __double2hiint(sqrt_new));
+    SelectPick pk;
+    if (single) {  // only one open child, or a forced win
+        pk.ci = k == 1 ? 0 : h.checkmate_idx;
+        pk.owner = ARA_LANE == (pk.ci & (ARA_WARP_N - 1));
+        pk.x = pre;
+        if (pk.owner && pk.ci != ARA_LANE) pk.x = load_edge(t, e + pk.ci);
+    } else {
+        bool sure = false;
+        pk = pick_fast(t, h, pre, &sure);
+        if (!sure) pk = pick_exact(t, h, pre);
+    }
+    SelectStep r;
+    r.ci = pk.ci;
+    const int owner_lane = pk.ci & (ARA_WARP_N - 1);
+    r.child = ARA_SHFL(pk.x.c, owner_lane);
+    const uint32_t cb = ARA_SHFL(pk.x.cb, owner_lane);
+    ARA_FINE(t.st, 7, tf, r.child);
+    if (r.child >= 0) {  // next level: header and this lane's edge, one round trip, in flight during the stores below
+        load_hdr(&r.ch, &t.hdr[r.child]);
+        r.pre = load_edge(t, cb + ARA_LANE);
+    }
+#if defined(ARA_PROF_FINE)
+    ARA_FINE(t.st, 5, tf, r.child >= 0 ? (r.ch.flags ^ r.pre.c) : 0);
+#endif
+    if (pk.owner) {
+        // apply_virtual_loss_to_child on the owner lane: registers in, stores out
+        const uint32_t ee = e + static_cast<uint32_t>(pk.ci);
+        if (virtual_style_of(sp, pk.x.n) == VS_VIRTUAL_LOSS)
+            t.Q[ee] = static_cast<float>((static_cast<double>(pk.x.q) * pk.x.n - 1) / static_cast<double>(pk.x.n + 1));
+        t.N[ee] = pk.x.n + 1;
+        t.vl[ee] = static_cast<uint8_t>(pk.x.vl + 1);
     }
     if (ARA_LANE == 0) {
+        if (!single) t.st->sum_select_k += static_cast<unsigned long long>(k);
         hp->visit_sum = vs_new;
         hp->cput = cput_new;
-        if (!(h.flags & NF_HAS_D)) hp->flags = h.flags | NF_HAS_D | NF_SORTED;
+        hp->sqrt_vs = sqrt_new;
+        if (!(h.flags & NF_HAS_D)) hp->flags = h.flags | NF_HAS_D | NF_SORTED;  // prepare_node_for_visits (lazy flag)
     }
     return r;
 }
@@ -434,6 +501,7 @@ ARA_HD void revert_virtual_loss(const TreeDev& t, const SearchParams& sp, int ni
     const uint32_t vs = h.visit_sum - 1;
     h.visit_sum = vs;
     h.cput = current_cput(t, sp, vs);
+    h.sqrt_vs = sqrt(static_cast<double>(vs));
     --t.vl[e];
 }
 
@@ -549,7 +617,7 @@ ARA_HD int expand_node_seq(const TreeDev& t, const SearchParams& sp, WarpScratch
             h.node_type = NT_UNSOLVED;
             h.flags = 0;
             h.cput = current_cput(t, sp, 0);
-            h.pad_[0] = h.pad_[1] = 0;
+            h.sqrt_vs = 0.0;
             if (tt != TERM_NONE) {  // check_for_terminal node.cpp:880-904 + mark_as_terminal
                 h.flags = NF_TERMINAL | NF_HAS_D | NF_SORTED;
                 h.no_visit_idx = 0;
@@ -601,6 +669,7 @@ ARA_HD void expand_pending(const TreeDev& t, const SearchParams& sp, WarpScratch
             h.edge_base = static_cast<uint32_t>(e0);
             h.n_moves = static_cast<uint16_t>(n_moves);
             h.n_unsolved = static_cast<uint16_t>(n_moves);
+            if (h.parent >= 0) t.cbase[t.hdr[h.parent].edge_base + h.parent_ci] = static_cast<uint32_t>(e0);
             ws.bcast[0] = e0;
         }
     }
@@ -623,6 +692,7 @@ ARA_HD void expand_pending(const TreeDev& t, const SearchParams& sp, WarpScratch
             t.Q[e + i] = kQInit;
             t.N[e + i] = 0;
             t.child[e + i] = -1;
+            t.cbase[e + i] = 0;
             t.vl[e + i] = 0;
             t.etype[e + i] = NT_UNSOLVED;
         }
@@ -781,20 +851,24 @@ ARA_HD void create_mini_batch_impl(const TreeDev& t, const SearchParams& sp, War
     while (n_new < B && n_coll != B && n_term < 2 * B) {
         int cur = 0, depth = 0, type = -1, leaf = -1;  // type: 0 new, 1 collision, 2 terminal
         long long tq = ARA_CLOCK();
+        NodeHdr h;
+        load_hdr(&h, &t.hdr[0]);
+        EdgeRegs pre = load_edge(t, h.edge_base + ARA_LANE);
         for (;;) {
             if (depth >= kMaxDepth) {
                 if (ARA_LANE == 0) st.error = 3;
                 type = -2;
                 break;
             }
-            const SelectStep step = select_and_visit(t, sp, cur);
+            const SelectStep step = select_and_visit(t, sp, cur, h, pre);
             const int ci = step.ci;
             const int next = step.child;
             if (ARA_LANE == 0) {
                 ws.traj_node[depth] = cur;
                 ws.traj_ci[depth] = static_cast<uint16_t>(ci);
-                ws.path_key[depth] = step.key;
-                ws.path_rep[depth] = step.repetition;
+                ws.traj_edge[depth] = h.edge_base + static_cast<uint32_t>(ci);
+                ws.path_key[depth] = h.key;
+                ws.path_rep[depth] = h.repetition;
             }
             ARA_WARP_SYNC();
             depth++;
@@ -802,9 +876,9 @@ ARA_HD void create_mini_batch_impl(const TreeDev& t, const SearchParams& sp, War
                 ARA_PROF(st, 0, tq);
                 copy_board(&ws.child, &t.board[cur]);
                 if (ARA_LANE == 0) {
-                    do_move(ws.child, t.move[step.edge_base + ci]);
+                    do_move(ws.child, t.move[h.edge_base + ci]);
                     // increment_no_visit_idx: open the next-best sibling (its edge slots are pre-initialised)
-                    if (step.no_visit_idx < step.n_moves) t.hdr[cur].no_visit_idx = static_cast<uint16_t>(step.no_visit_idx + 1);
+                    if (h.no_visit_idx < h.n_moves) t.hdr[cur].no_visit_idx = static_cast<uint16_t>(h.no_visit_idx + 1);
                 }
                 ARA_WARP_SYNC();
                 ARA_PROF(st, 1, tq);
@@ -818,18 +892,19 @@ ARA_HD void create_mini_batch_impl(const TreeDev& t, const SearchParams& sp, War
                 tq = ARA_CLOCK();
                 break;
             }
-            const NodeHdr& nh = t.hdr[next];
-            if (nh.flags & NF_TERMINAL) {
+            if (step.ch.flags & NF_TERMINAL) {
                 type = 2;
                 leaf = next;
                 break;
             }
-            if (!(nh.flags & NF_HAS_NN)) {
+            if (!(step.ch.flags & NF_HAS_NN)) {
                 type = 1;
                 leaf = next;
                 break;
             }
             cur = next;
+            h = step.ch;
+            pre = step.pre;
         }
         if (type == -2) break;
         if (type != 0) ARA_PROF(st, 0, tq);
@@ -844,6 +919,7 @@ ARA_HD void create_mini_batch_impl(const TreeDev& t, const SearchParams& sp, War
             for (int i = ARA_LANE; i < depth; i += ARA_WARP_N) {
                 t.traj_node[row * kMaxDepth + i] = ws.traj_node[i];
                 t.traj_ci[row * kMaxDepth + i] = ws.traj_ci[i];
+                t.traj_edge[row * kMaxDepth + i] = ws.traj_edge[i];
             }
             if (ARA_LANE == 0) {
                 st.sum_depth += static_cast<unsigned long long>(depth);
@@ -883,6 +959,8 @@ ARA_HD void scatter_pending(const TreeDev& t, const SearchParams& sp, WarpScratc
                             const float* probs, int n_labels) {
     const int slot = t.slot_base + b;
     fill_nn_results(t, sp, ws, t.new_node[b], values[slot], probs + static_cast<size_t>(slot) * n_labels);
+    // a fresh leaf has real_visits 1 and value_sum double(v), so its node value is the network value itself
+    if (ARA_LANE == 0) t.new_value[b] = values[slot];
 }
 
 // backup_value_outputs + backup_collisions (searchthread.cpp:312-324): one warp per tree.
@@ -890,17 +968,78 @@ ARA_HD void backup_results(const TreeDev& t, const SearchParams& sp) {
     const TreeState& st = *t.st;
     const int B = sp.batch_size;
     const int n_new = st.n_new, n_coll = st.n_coll;
-    // backup_value (node.h:819-843) without solver: the levels of one trajectory are distinct nodes/edges, so lane i
-    // updates depth i (value sign alternates with the distance to the leaf); consecutive backups that share an edge
-    // share its depth and therefore its lane, which preserves the reference's update order edge by edge.
-    for (int b = 0; b < n_new; ++b) {
-        const float leaf_v = node_value(t.hdr[t.new_node[b]]);
-        const int len = t.traj_len[b];
-        for (int i = ARA_LANE; i < len; i += ARA_WARP_N) {
-            const float v = ((len - i) & 1) ? -leaf_v : leaf_v;
-            revert_virtual_loss_and_update(t, sp, t.traj_node[b * kMaxDepth + i], t.traj_ci[b * kMaxDepth + i], v, false, false);
+    // backup_value (node.h:819-843) without solver: the levels of one trajectory are distinct nodes/edges, so lane d
+    // updates depth d of every trajectory, in trajectory order (value sign alternates with the distance to the leaf).
+    // Backups that share a node or an edge share its depth and therefore its lane, which preserves the reference's
+    // update order node by node and edge by edge.  The node sums and the edge statistics a lane is working on stay in
+    // registers while consecutive trajectories pass through the same node / edge (always true at the root), the
+    // indices of the next trajectory are loaded one iteration ahead and its lines are prefetched, so that the
+    // per-trajectory chain is one L1 access plus the FP64 arithmetic instead of four dependent L2 round trips.
+    int max_len = 0;
+    for (int b = ARA_LANE; b < n_new; b += ARA_WARP_N) max_len = t.traj_len[b] > max_len ? t.traj_len[b] : max_len;
+    max_len = ARA_REDUCE_MAX(max_len);
+    for (int d0 = 0; d0 < max_len; d0 += ARA_WARP_N) {
+        const int d = d0 + ARA_LANE;
+        int c_nid = -1;
+        double c_vsum = 0.0;
+        uint32_t c_rv = 0;
+        uint32_t c_e = 0xffffffffu, c_n = 0;
+        float c_q = 0.0f;
+        uint8_t c_vl = 0;
+        int len_n = n_new > 0 ? t.traj_len[0] : 0;
+        float leaf_n = n_new > 0 ? t.new_value[0] : 0.0f;
+        int nid_n = -1;
+        uint32_t e_n = 0;
+        if (d < len_n) nid_n = t.traj_node[d], e_n = t.traj_edge[d];
+        for (int b = 0; b < n_new; ++b) {
+            const int len = len_n, nid = nid_n;
+            const uint32_t e = e_n;
+            const float leaf_v = leaf_n;
+            if (b + 1 < n_new) {  // indices of the next trajectory + prefetch of its lines
+                len_n = t.traj_len[b + 1];
+                leaf_n = t.new_value[b + 1];
+                if (d < len_n) {
+                    nid_n = t.traj_node[(b + 1) * kMaxDepth + d];
+                    e_n = t.traj_edge[(b + 1) * kMaxDepth + d];
+                    if (nid_n != nid) prefetch_line(&t.hdr[nid_n]);
+                    if (e_n != e) prefetch_line(&t.Q[e_n]), prefetch_line(&t.N[e_n]), prefetch_line(&t.vl[e_n]);
+                }
+            }
+            if (d >= len) continue;
+            const float v = ((len - d) & 1) ? -leaf_v : leaf_v;
+            if (nid != c_nid) {
+                if (c_nid >= 0) t.hdr[c_nid].value_sum = c_vsum, t.hdr[c_nid].real_visits = c_rv;
+                c_nid = nid;
+                c_vsum = t.hdr[nid].value_sum;
+                c_rv = t.hdr[nid].real_visits;
+            }
+            if (e != c_e) {
+                if (c_e != 0xffffffffu) t.Q[c_e] = c_q, t.vl[c_e] = c_vl;
+                c_e = e;
+                c_q = t.Q[e];
+                c_n = t.N[e];
+                c_vl = t.vl[e];
+            }
+            // revert_virtual_loss_and_update (node.h:199-246) on the cached copies
+            c_vsum += v;
+            ++c_rv;
+            if (c_n == 1) {
+                c_q = v;
+            } else {
+                const int style = virtual_style_of(sp, c_n);
+                if (style == VS_VIRTUAL_LOSS) {
+                    c_q = static_cast<float>((static_cast<double>(c_q) * c_n + 1 + v) / c_n);
+                } else if (style == VS_VIRTUAL_VISIT) {
+                    const uint32_t real = c_n - c_vl;
+                    c_q = static_cast<float>((static_cast<double>(c_q) * real + v) / (real + 1));
+                }
+            }
+            --c_vl;
         }
+        if (c_nid >= 0) t.hdr[c_nid].value_sum = c_vsum, t.hdr[c_nid].real_visits = c_rv;
+        if (c_e != 0xffffffffu) t.Q[c_e] = c_q, t.vl[c_e] = c_vl;
     }
+    ARA_WARP_SYNC();
     for (int c = 0; c < n_coll; ++c) {
         const int row = B + c;
         const int len = t.traj_len[row];

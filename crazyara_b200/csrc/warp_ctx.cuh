@@ -19,6 +19,8 @@
 #define ARA_POPC_BELOW(m) __popc((m) & ((1u << ARA_LANE) - 1u))
 #define ARA_SHFL(v, src) __shfl_sync(0xffffffffu, (v), (src))
 #define ARA_SHFL_XOR(v, x) __shfl_xor_sync(0xffffffffu, (v), (x))
+#define ARA_REDUCE_MAX(v) __reduce_max_sync(0xffffffffu, (v))
+#define ARA_REDUCE_MIN(v) __reduce_min_sync(0xffffffffu, (v))
 #else
 #define ARA_LANE 0
 #define ARA_WARP_N 1
@@ -28,4 +30,6 @@
 #define ARA_POPC_BELOW(m) 0
 #define ARA_SHFL(v, src) (v)
 #define ARA_SHFL_XOR(v, x) (v)
+#define ARA_REDUCE_MAX(v) (v)
+#define ARA_REDUCE_MIN(v) (v)
 #endif

@@ -92,6 +92,8 @@ struct HeSearch {
     std::vector<uint8_t> vl, etype;
     std::vector<int32_t> new_node, traj_node, traj_len;
     std::vector<uint16_t> traj_ci;
+    std::vector<uint32_t> traj_edge, cbase;
+    std::vector<float> new_value;
     std::vector<uint64_t> hist_keys;
     std::vector<int16_t> hist_reps;
     std::vector<float> lut;
@@ -114,6 +116,7 @@ HeSearch* he_search_new(const SearchParams* sp, int max_nodes, int max_edges) {
     s->Q.resize(max_edges);
     s->N.resize(max_edges);
     s->child.resize(max_edges);
+    s->cbase.resize(max_edges);
     s->move.resize(max_edges);
     s->vl.resize(max_edges);
     s->etype.resize(max_edges);
@@ -121,6 +124,8 @@ HeSearch* he_search_new(const SearchParams* sp, int max_nodes, int max_edges) {
     s->traj_node.resize(2 * B * kMaxDepth);
     s->traj_ci.resize(2 * B * kMaxDepth);
     s->traj_len.resize(2 * B);
+    s->traj_edge.resize(2 * B * kMaxDepth);
+    s->new_value.resize(B);
     s->channels = planes_channels(sp->mode, sp->input_version);
     s->n_labels = (sp->mode == MODE_CRAZYHOUSE ? 81 : (sp->mode == MODE_CHESS ? 76 : 84)) * 64;
     s->planes.assign(static_cast<size_t>(B) * s->channels * 64, 0.0f);
@@ -135,6 +140,7 @@ HeSearch* he_search_new(const SearchParams* sp, int max_nodes, int max_edges) {
     t.Q = s->Q.data();
     t.N = s->N.data();
     t.child = s->child.data();
+    t.cbase = s->cbase.data();
     t.move = s->move.data();
     t.vl = s->vl.data();
     t.etype = s->etype.data();
@@ -143,6 +149,8 @@ HeSearch* he_search_new(const SearchParams* sp, int max_nodes, int max_edges) {
     t.traj_node = s->traj_node.data();
     t.traj_ci = s->traj_ci.data();
     t.traj_len = s->traj_len.data();
+    t.traj_edge = s->traj_edge.data();
+    t.new_value = s->new_value.data();
     t.hist_keys = nullptr;
     t.hist_reps = nullptr;
     t.hist_len = 0;
@@ -205,4 +213,32 @@ void he_fake_eval(unsigned long long key, int n_labels, float* value, float* pro
     for (int i = 0; i < n_labels; ++i) prob[i] = fake_prob(key, i);
 }
 int he_sizeof_result() { return static_cast<int>(sizeof(SearchResult)); }
+
+// Select-step unit hook: k open children with the given statistics; out = {sure, fast_ci, exact_ci}.
+void he_pick_both(int k, const float* p, const float* q, const unsigned* n, float cput, unsigned visit_sum, int* out) {
+    std::vector<float> P(p, p + k), Q(q, q + k);
+    std::vector<uint32_t> N(n, n + k), cb(k, 0);
+    std::vector<int32_t> child(k, -1);
+    std::vector<uint8_t> vl(k, 0);
+    TreeDev t{};
+    t.P = P.data();
+    t.Q = Q.data();
+    t.N = N.data();
+    t.cbase = cb.data();
+    t.child = child.data();
+    t.vl = vl.data();
+    NodeHdr h{};
+    h.no_visit_idx = static_cast<uint16_t>(k);
+    h.edge_base = 0;
+    h.cput = cput;
+    h.visit_sum = visit_sum;
+    h.sqrt_vs = sqrt(static_cast<double>(visit_sum));
+    const EdgeRegs pre = load_edge(t, 0);
+    bool sure = false;
+    const SelectPick f = pick_fast(t, h, pre, &sure);
+    const SelectPick e = pick_exact(t, h, pre);
+    out[0] = sure ? 1 : 0;
+    out[1] = f.ci;
+    out[2] = e.ci;
+}
 }

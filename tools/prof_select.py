@@ -19,7 +19,10 @@ out = (ctypes.c_ulonglong * 8)()
 lib().ara_search_debug_cycles.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
 lib().ara_search_debug_cycles(agent._h, 0, out)
 names = ["descent", "copy+do_move", "rep+movegen", "node init", "planes", "terminal backup", "bookkeeping", "-"]
-tot = sum(out)
+fine = "fine" in os.environ.get("ARA_B200_LIB", "")
+if fine:  # -DARA_PROF_FINE build: slots 4/7/5 are sub-intervals of the descent
+    names[4], names[7], names[5] = "  descent: edge wait", "  descent: puct+argmax", "  descent: child hdr wait (+term. backup)"
+tot = sum(out) - (out[4] + out[7] + out[5] if fine else 0)
 print("profile", agent.profile(), "go ms", agent.last_go_ms(), "avg depth", r["sum_depth"] / max(1, r["visit_sum"]),
       "sum_k/visit", r["sum_select_k"] / max(1, r["visit_sum"]), "tree nodes", r["tree_nodes"])
 for n, c in zip(names, out):

@@ -27,6 +27,14 @@ build/libara_b200_fine.so: build/search_fine.o $(filter-out build/search.o,$(CU_
 	$(NVCC) $(ARCH) -shared -o $@ $^
 fine: build/libara_b200_fine.so
 
+# profiling build of the trunk kernel: per-role cycle counters (tools/prof_trunk.py with ARA_B200_LIB=build/libara_b200_tprof.so)
+build/rise_trunk_host_prof.o: $(CSRC)/rise_trunk_host.cu $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) $(wildcard include/*.h)
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -DARA_TRUNK_PROF -c $< -o $@
+build/libara_b200_tprof.so: build/rise_trunk_host_prof.o $(filter-out build/rise_trunk_host.o,$(CU_OBJS))
+	$(NVCC) $(ARCH) -shared -o $@ $^
+tprof: build/libara_b200_tprof.so
+
 clean:
 	rm -rf build $(LIB)
 

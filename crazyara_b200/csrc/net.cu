@@ -72,6 +72,7 @@ Net::~Net() {
     for (int k = 0; k < 2; ++k)
         for (auto& g : graphs_[k]) cudaGraphExecDestroy(g.second);
     for (void* p : allocs_) cudaFree(p);
+    rise_trunk_destroy(&trunk_);
     if (stream) cudaStreamDestroy(stream);
 }
 
@@ -92,6 +93,10 @@ int Net::init(const char* blob_path, int dev, int batch_size) {
     {
         const char* f = getenv("ARA_FUSED_BLOCKS");
         use_fused = (f != nullptr && f[0] == '1');  // opt-in until it beats the three-kernel path (profiles/README.md)
+    }
+    {
+        const char* f = getenv("ARA_TRUNK");
+        use_trunk = !(f != nullptr && f[0] == '0') && !use_fused;
     }
     const char* g = getenv("ARA_NO_GRAPH");
     use_graph = !(g != nullptr && g[0] == '1');
@@ -162,9 +167,14 @@ int Net::init(const char* blob_path, int dev, int batch_size) {
             return -1;
     }
     bw_.resize(hdr.n_blocks);
+    std::vector<TrunkBlockHost> trunk_blocks(hdr.n_blocks);
     for (int i = 0; i < hdr.n_blocks; ++i) {
         const BlockDesc& bd = blocks[i];
         BlockW& w = bw_[i];
+        TrunkBlockHost& tb = trunk_blocks[i];
+        tb.c_op = bd.c_op;
+        tb.ksize = bd.kernel;
+        tb.se_type = bd.se_type;
         __half* xin = d_x[i & 1];
         __half* xout = d_x[(i + 1) & 1];
         if (bd.se_type == 1) {
@@ -189,8 +199,10 @@ int Net::init(const char* blob_path, int dev, int batch_size) {
         }
         // conv1 1x1 256 -> c_op (+ReLU)
         if (!rd.tensor(t, static_cast<size_t>(bd.c_op) * C)) return -1;
+        tb.w1 = t;
         if (upload_conv_w(t.data(), bd.c_op, C, 1, &w.w1, &wrows)) return -1;
         if (!rd.tensor(t, bd.c_op)) return -1;
+        tb.b1 = t;
         if (upload_f32(t.data(), bd.c_op, round_up(bd.c_op, 256), &w.b1)) return -1;
         {
             const int bn = conv_layer_choose_bn(batch, bd.c_op);
@@ -201,6 +213,7 @@ int Net::init(const char* blob_path, int dev, int batch_size) {
         // depthwise k x k: blob [c_op][k][k] -> device [k*k][c_op]
         const int kk = bd.kernel * bd.kernel;
         if (!rd.tensor(t, static_cast<size_t>(bd.c_op) * kk)) return -1;
+        tb.wd = t;
         t2.assign(static_cast<size_t>(kk) * bd.c_op, 0.f);
         for (int c = 0; c < bd.c_op; ++c)
             for (int q = 0; q < kk; ++q) t2[static_cast<size_t>(q) * bd.c_op + c] = t[static_cast<size_t>(c) * kk + q];
@@ -213,12 +226,18 @@ int Net::init(const char* blob_path, int dev, int batch_size) {
             if (upload_f32(t3.data(), t3.size(), t3.size(), &w.wd_pad)) return -1;
         }
         if (!rd.tensor(t, bd.c_op)) return -1;
+        tb.bd = t;
         if (upload_f32(t.data(), bd.c_op, cpad64, &w.bd)) return -1;
         // conv2 1x1 c_op -> 256 (+residual)
         if (!rd.tensor(t, static_cast<size_t>(C) * bd.c_op)) return -1;
+        tb.w2 = t;
         if (upload_conv_w(t.data(), C, bd.c_op, 1, &w.w2, &wrows)) return -1;
         if (!rd.tensor(t, C)) return -1;
         if (upload_f32(t.data(), C, 256, &w.b2)) return -1;
+        tb.b2 = w.b2;
+        tb.se_w1t = w.se_w1t;
+        tb.se_w2t = w.se_w2t;
+        tb.se_b = w.se_b;
         {
             const int bn = conv_layer_choose_bn(batch, C);
             if (conv_layer_init(&w.conv2, d_h2, batch_cap, bd.c_op, w.w2, wrows, C, 1, w.b2, 0, xin, C, xout, nullptr, C,
@@ -231,6 +250,10 @@ int Net::init(const char* blob_path, int dev, int batch_size) {
             return -1;
     }
     __half* xfinal = d_x[hdr.n_blocks & 1];
+    // the whole tower as one persistent kernel: stem output d_x[0] -> xfinal
+    if (hdr.n_blocks > kTrunkMaxBlocks) use_trunk = false;
+    if (use_trunk && rise_trunk_init(&trunk_, trunk_blocks, d_x[0], batch_cap, xfinal)) return -1;
+    trunk_blocks.clear();
     // value head
     if (!rd.tensor(t, 8 * 256)) return -1;
     if (upload_f32(t.data(), t.size(), t.size(), &vh_wv)) return -1;
@@ -296,7 +319,11 @@ int Net::enqueue(int n, cudaStream_t s, bool from_f32) {
     }
     if (conv_layer_launch(&stem_conv, n, s)) return -1;
     ++launches;
-    for (int i = 0; i < hdr.n_blocks; ++i) {
+    if (use_trunk) {
+        if (rise_trunk_launch(&trunk_, n, s)) return -1;
+        ++launches;
+    }
+    for (int i = 0; i < hdr.n_blocks && !use_trunk; ++i) {
         const BlockDesc& bd = blocks[i];
         BlockW& w = bw_[i];
         __half* xin = d_x[i & 1];
@@ -381,10 +408,21 @@ int Net::forward_from_f32_device(int n, cudaStream_t s) {
     return 0;
 }
 
+int Net::trunk_cycles(unsigned long long* out32) {
+    if (!use_trunk || trunk_.d_prof == nullptr) return set_error("trunk kernel not in use");
+    ARA_CUDA_OK(cudaSetDevice(device));
+    ARA_CUDA_OK(cudaStreamSynchronize(stream));
+    ARA_CUDA_OK(cudaMemcpy(out32, trunk_.d_prof, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 int Net::kernels_per_forward(bool from_f32) const {
     int k = from_f32 ? 1 : 0;
     k += 1;  // stem
-    for (const auto& b : blocks) k += (use_fused ? 1 : 3) + (b.se_type != 0 ? 1 : 0);
+    if (use_trunk)
+        k += 1;
+    else
+        for (const auto& b : blocks) k += (use_fused ? 1 : 3) + (b.se_type != 0 ? 1 : 0);
     k += 4;  // value head, policy conv x2, softmax
     return k;
 }
@@ -457,3 +495,8 @@ extern "C" int ara_net_forward_device(ara_net_t h, const float* planes_dev, int 
 }
 
 extern "C" long long ara_net_launch_count(ara_net_t h) { return h ? reinterpret_cast<Net*>(h)->launches : 0; }
+
+extern "C" int ara_net_debug_trunk_cycles(ara_net_t h, unsigned long long* out32) {
+    if (h == nullptr || out32 == nullptr) return ara::set_error("ara_net_debug_trunk_cycles: null argument");
+    return reinterpret_cast<Net*>(h)->trunk_cycles(out32);
+}

@@ -8,6 +8,7 @@
 
 #include "conv_gemm_host.h"
 #include "rise_block_host.h"
+#include "rise_trunk_host.h"
 
 namespace ara {
 
@@ -62,6 +63,7 @@ class Net {
     int n_labels() const { return hdr.policy_channels * 64; }
     int n_aux() const { return hdr.wdl_mode ? 4 : 0; }
     int kernels_per_forward(bool from_f32) const;
+    int trunk_cycles(unsigned long long* out32);  // -DARA_TRUNK_PROF builds: per-role cycle counters of CTA 0
     cudaStream_t stream = nullptr;
 
     // device buffers
@@ -78,6 +80,7 @@ class Net {
     long long launches = 0;      // kernels launched so far (bench bookkeeping)
     bool use_graph = true;
     bool use_fused = false;  // ARA_FUSED_BLOCKS=1: one kernel per bottleneck block (rise_block.cuh)
+    bool use_trunk = true;   // the whole residual tower as one persistent kernel (rise_trunk.cuh); ARA_TRUNK=0 disables
 
    private:
     int enqueue(int n, cudaStream_t s, bool from_f32);
@@ -86,6 +89,7 @@ class Net {
     float* stem_b = nullptr;
     ConvLayer stem_conv;
     std::vector<BlockW> bw_;
+    RiseTrunk trunk_;
     float *vh_wv = nullptr, *vh_bv = nullptr, *vh_w1t = nullptr, *vh_b1 = nullptr, *vh_w2 = nullptr, *vh_b2 = nullptr;
     float *vh_wdl_w = nullptr, *vh_wdl_b = nullptr, *vh_plys_w = nullptr, *vh_plys_b = nullptr;
     __half *pol_w1 = nullptr, *pol_w2 = nullptr;

@@ -42,6 +42,9 @@ int ara_net_forward_device(ara_net_t net, const float* planes_dev, int n, float*
 
 /* Number of CUDA kernels this net has launched so far (bench bookkeeping). */
 long long ara_net_launch_count(ara_net_t net);
+/* profiling builds (-DARA_TRUNK_PROF) only: SM-clock cycles of CTA 0 of the last trunk-kernel launch, [0..15] MMA
+ * issuer, [16..31] compute warp; all zero in the product build */
+int ara_net_debug_trunk_cycles(ara_net_t net, unsigned long long* out32);
 
 /* ---- Position seam: replaces State / BoardState for the supported variants (engine/src/state.h:287-509,
  * environments/chess_related/boardstate.{h,cpp}).  A position is one opaque 128-byte line (bitboards, pockets,

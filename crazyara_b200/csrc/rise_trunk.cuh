@@ -3,20 +3,22 @@
 //
 // One CTA owns two boards (128 rows) from the stem output to the tower output: nothing a board needs lives in another
 // CTA (1x1 convolutions are row-local, the depthwise convolution and the SE pooling are board-local), so the
-// 256-channel activation tile X stays in shared memory across ALL blocks and only the weights stream through.
+// 256-channel activation tile X never leaves the SM between blocks: it lives in TENSOR MEMORY (fp16, 128 columns),
+// where the tensor core reads it directly as the A operand and the compute warps read / rewrite it with
+// tcgen05.ld / tcgen05.st.  Only the weights stream through shared memory, as pre-tiled images (the host lays every
+// 64-channel chunk out exactly as its shared-memory bytes, rise_trunk_host.cu) so that a chunk is TWO 1-D bulk copies:
+// the per-SM copy engine handles one operation at a time with ~270 cycles of fixed cost (tools/micro/tma_bw.cu), so
+// few large operations are what reaches its ~30 B/clk.
 // Per block, the operating channels are processed in chunks of 64:
-//     MMA1  D1[128x64]  = X[128x256] . W1_chunk^T        tcgen05, A = resident X tile, B = TMA ring of 16 KB half chunks
+//     MMA1  D1[128x64]  = X[128x256] . W1_chunk^T        tcgen05, A from TMEM, B from the W1 ring
 //     epi1  relu(D1 + b1) -> H1 (smem, fp16, channel-group major)          16 compute warps, tcgen05.ld
 //     dw    depthwise kxk, + bd, relu -> H2 (smem, 128B-swizzled K-major)  CUDA cores: two warps per 8-channel group
 //           (one per board), one lane per (row pair, column): 2 squares x 8 channels in registers, activations and
-//           weights stay packed fp16 and feed the mixed-precision FMA (FHFMA: fp16 x fp16 + fp32), so there is no
-//           conversion instruction and every H1 value is read once per column offset instead of once per tap
-//     MMA2  D2[128x256] += H2[128x64] . W2_chunk^T        tcgen05, two N=128 halves from a second TMA ring,
-//           accumulator stays in TMEM for the whole block
-// then   X <- D2 + b2 + X   written back into the shared-memory tile (and to global after the last block).
-// Warp roles: 0 = TMA producer (X, W1 ring), 1 = MMA issuer + TMEM owner, 2..17 = compute, 18 = TMA producer (W2
-// ring), 19 = producer of the per-chunk vectors (its own warp: it waits on the compute warps, the rings must not).
-// TMEM: D1 double-buffered (2 x 64 columns) + D2 (256 columns).
+//           weights stay packed fp16 and feed the mixed-precision FMA (FHFMA: fp16 x fp16 + fp32)
+//     MMA2  D2[128x256] += H2[128x64] . W2_chunk^T        tcgen05 N=256, accumulator stays in TMEM for the whole block
+// then   X <- D2 + b2 + X   (TMEM -> registers -> TMEM; also to global after the last block).
+// Warp roles: 0 = producer of the W1 ring (weights + per-chunk vectors), 1 = MMA issuer + TMEM owner, 2..17 = compute,
+// 18 = producer of the W2 ring.  TMEM columns: X 0..127, D1 128..255 (2 x 64), D2 256..511.
 #pragma once
 #include "rise_trunk_args.h"
 #include "sm100_prims.cuh"
@@ -25,19 +27,16 @@ namespace ara {
 
 constexpr int kRtComputeWarps = 16;
 constexpr int kRtComputeThreads = kRtComputeWarps * 32;
-constexpr int kRtThreads = (kRtComputeWarps + 4) * 32;
-constexpr int kRtSlot = 16384;       // one ring slot (half a weight chunk)
-constexpr int kRtRing = 3;
-constexpr int kRtAuxSlot = 3712;     // 64 f32 + 64 f32 + 25 * 64 f16
-constexpr int kRtOffW1 = 65536;
-constexpr int kRtOffW2 = kRtOffW1 + kRtRing * kRtSlot;
-constexpr int kRtOffH2 = kRtOffW2 + kRtRing * kRtSlot;
+constexpr int kRtThreads = (kRtComputeWarps + 3) * 32;
+constexpr int kRtW1Ring = 2, kRtW2Ring = 3;
+constexpr int kRtOffW2 = kRtW1Ring * kTrunkW1Image;
+constexpr int kRtOffH2 = kRtOffW2 + kRtW2Ring * kTrunkW2Image;
 constexpr int kRtOffH1 = kRtOffH2 + 2 * 16384;
-constexpr int kRtOffAux = kRtOffH1 + 16384;
-constexpr int kRtOffB2 = kRtOffAux + 2 * kRtAuxSlot;
+constexpr int kRtOffB2 = kRtOffH1 + 16384;
 constexpr int kRtOffBar = kRtOffB2 + 2 * 1024;  // b2 is double-buffered by block parity
 constexpr int kRtSmemBytes = kRtOffBar + 512 + 1024;
 static_assert(kRtSmemBytes <= 232448, "trunk kernel shared memory exceeds the sm_100 limit");
+constexpr uint32_t kRtColX = 0, kRtColD1 = 128, kRtColD2 = 256;
 
 // -DARA_TRUNK_PROF: per-role cycle counters of CTA 0 (args.prof[role * 16 + slot]); see tools/prof_trunk.py
 #if defined(ARA_TRUNK_PROF)
@@ -64,6 +63,11 @@ __device__ __forceinline__ void rt_bar_sync(int id) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kRtComputeThreads) : "memory");
 }
 __device__ __forceinline__ float rt_hard_sigmoid(float x) { return fminf(fmaxf(x * (1.0f / 6.0f) + 0.5f, 0.0f), 1.0f); }
+__device__ __forceinline__ float2 rt_unpack(uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
+__device__ __forceinline__ uint32_t rt_pack(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
 
 // depthwise k x k for 2 vertically adjacent squares (rows y0, y0+1, column x of board db) and the 8 channels of group g.
 // aux: b1[64] f32 | bd[64] f32 | wd[k*k][64] f16
@@ -108,41 +112,34 @@ __device__ __forceinline__ void rt_depthwise(const uint8_t* sH1, const uint8_t* 
     }
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-        __half2* oh = reinterpret_cast<__half2*>(&out[j]);
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-            oh[e] = __floats2half2_rn(fmaxf(acc[j][e * 2], 0.0f), fmaxf(acc[j][e * 2 + 1], 0.0f));
+        out[j].x = rt_pack(fmaxf(acc[j][0], 0.0f), fmaxf(acc[j][1], 0.0f));
+        out[j].y = rt_pack(fmaxf(acc[j][2], 0.0f), fmaxf(acc[j][3], 0.0f));
+        out[j].z = rt_pack(fmaxf(acc[j][4], 0.0f), fmaxf(acc[j][5], 0.0f));
+        out[j].w = rt_pack(fmaxf(acc[j][6], 0.0f), fmaxf(acc[j][7], 0.0f));
     }
 }
 
-__global__ void __launch_bounds__(kRtThreads, 1)
-rise_trunk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w1,
-                  const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ TrunkArgs args) {
+__global__ void __launch_bounds__(kRtThreads, 1) rise_trunk_kernel(const __grid_constant__ TrunkArgs args) {
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sX = smem;
-    uint8_t* sW1 = smem + kRtOffW1;
+    uint8_t* sW1 = smem;
     uint8_t* sW2 = smem + kRtOffW2;
     uint8_t* sH2 = smem + kRtOffH2;
     uint8_t* sH1 = smem + kRtOffH1;
-    uint8_t* sAux = smem + kRtOffAux;
     float* sB2all = reinterpret_cast<float*>(smem + kRtOffB2);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kRtOffBar);
-    uint64_t* x_full = bars + 0;
-    uint64_t* x_ready = bars + 1;
-    uint64_t* w1_full = bars + 2;    // [3]
-    uint64_t* w1_empty = bars + 5;   // [3]
-    uint64_t* w2_full = bars + 8;    // [3]
-    uint64_t* w2_empty = bars + 11;  // [3]
-    uint64_t* aux_full = bars + 14;  // [2]
-    uint64_t* aux_empty = bars + 16; // [2]
-    uint64_t* d1_full = bars + 18;   // [2]
-    uint64_t* d1_empty = bars + 20;  // [2]
-    uint64_t* h2_full = bars + 22;   // [2]
-    uint64_t* h2_empty = bars + 24;  // [2]
-    uint64_t* d2_full = bars + 26;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 27);
+    uint64_t* x_ready = bars + 0;
+    uint64_t* w1_full = bars + 1;    // [2]
+    uint64_t* w1_empty = bars + 3;   // [2]  tensor core done with the tile AND compute warps done with the vectors
+    uint64_t* w2_full = bars + 5;    // [3]
+    uint64_t* w2_empty = bars + 8;   // [3]
+    uint64_t* d1_full = bars + 11;   // [2]
+    uint64_t* d1_empty = bars + 13;  // [2]
+    uint64_t* h2_full = bars + 15;   // [2]
+    uint64_t* h2_empty = bars + 17;  // [2]
+    uint64_t* d2_full = bars + 19;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -150,20 +147,16 @@ rise_trunk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     const int n_blocks = args.n_blocks;
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tm_x);
-        tma_prefetch_desc(&tm_w1);
-        tma_prefetch_desc(&tm_w2);
-        mbar_init(x_full, 1);
         mbar_init(x_ready, kRtComputeWarps);
-        for (int i = 0; i < kRtRing; ++i) {
+        for (int i = 0; i < kRtW1Ring; ++i) {
             mbar_init(&w1_full[i], 1);
-            mbar_init(&w1_empty[i], 1);
+            mbar_init(&w1_empty[i], 1 + kRtComputeWarps);
+        }
+        for (int i = 0; i < kRtW2Ring; ++i) {
             mbar_init(&w2_full[i], 1);
             mbar_init(&w2_empty[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&aux_full[i], 1);
-            mbar_init(&aux_empty[i], kRtComputeWarps);
             mbar_init(&d1_full[i], 1);
             mbar_init(&d1_empty[i], kRtComputeWarps);
             mbar_init(&h2_full[i], kRtComputeWarps);
@@ -181,83 +174,59 @@ rise_trunk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     pdl_launch_dependents();
 
     if (warp == 0) {
-        // ---------------------------------------------------------------- producer: X, W1 half chunks, chunk vectors
-        if (lane == 0) {
-            mbar_arrive_expect_tx(x_full, 65536);
-            for (int p = 0; p < 4; ++p) tma_load_4d(sX + p * 16384, &tm_x, x_full, p * 64, 0, 0, m_tile * 2);
-            uint32_t i1 = 0;
-            for (int b = 0; b < n_blocks; ++b) {
-                const TrunkBlock& B = args.blk[b];
-                for (int j = 0; j < B.n_chunks; ++j) {
-                    for (int h = 0; h < 2; ++h, ++i1) {
-                        const uint32_t slot = i1 % kRtRing;
-                        mbar_wait(&w1_empty[slot], ((i1 / kRtRing) & 1) ^ 1);
-                        mbar_arrive_expect_tx(&w1_full[slot], kRtSlot);
-                        for (int p = 0; p < 2; ++p)
-                            tma_load_2d(sW1 + slot * kRtSlot + p * 8192, &tm_w1, &w1_full[slot], (2 * h + p) * 64,
-                                        B.row0 + j * 64);
-                    }
-                }
-            }
-        }
-    } else if (warp == kRtComputeWarps + 3) {
-        // ---------------------------------------------------------------- producer: per-chunk vectors (b1 | bd | wd)
+        // ---------------------------------------------------------------- producer: W1 images (tile + chunk vectors)
         if (lane == 0) {
             uint32_t gc = 0;
             for (int b = 0; b < n_blocks; ++b) {
                 const TrunkBlock& B = args.blk[b];
                 for (int j = 0; j < B.n_chunks; ++j, ++gc) {
-                    const uint32_t sa = gc & 1;
-                    mbar_wait(&aux_empty[sa], ((gc >> 1) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&aux_full[sa], B.aux_bytes);
-                    bulk_load_1d(sAux + sa * kRtAuxSlot, args.aux + B.aux_off + static_cast<size_t>(j) * B.aux_bytes,
-                                 B.aux_bytes, &aux_full[sa]);
+                    const uint32_t s = gc % kRtW1Ring;
+                    mbar_wait(&w1_empty[s], ((gc / kRtW1Ring) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&w1_full[s], kTrunkW1Image);
+                    bulk_load_1d(sW1 + s * kTrunkW1Image, args.w1_img + static_cast<size_t>(B.chunk0 + j) * kTrunkW1Image,
+                                 kTrunkW1Image, &w1_full[s]);
                 }
             }
         }
     } else if (warp == kRtComputeWarps + 2) {
-        // ---------------------------------------------------------------- producer: W2 half chunks (N halves)
+        // ---------------------------------------------------------------- producer: W2 images
         if (lane == 0) {
-            uint32_t i2 = 0;
+            uint32_t gc = 0;
             for (int b = 0; b < n_blocks; ++b) {
                 const TrunkBlock& B = args.blk[b];
-                for (int j = 0; j < B.n_chunks; ++j)
-                    for (int n = 0; n < 2; ++n, ++i2) {
-                        const uint32_t slot = i2 % kRtRing;
-                        mbar_wait(&w2_empty[slot], ((i2 / kRtRing) & 1) ^ 1);
-                        mbar_arrive_expect_tx(&w2_full[slot], kRtSlot);
-                        tma_load_2d(sW2 + slot * kRtSlot, &tm_w2, &w2_full[slot], B.row0 + j * 64, n * 128);
-                    }
+                for (int j = 0; j < B.n_chunks; ++j, ++gc) {
+                    const uint32_t s = gc % kRtW2Ring;
+                    mbar_wait(&w2_empty[s], ((gc / kRtW2Ring) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&w2_full[s], kTrunkW2Image);
+                    bulk_load_1d(sW2 + s * kTrunkW2Image, args.w2_img + static_cast<size_t>(B.chunk0 + j) * kTrunkW2Image,
+                                 kTrunkW2Image, &w2_full[s]);
+                }
             }
         }
     } else if (warp == 1) {
         // ---------------------------------------------------------------- MMA issuer
         constexpr uint32_t idesc1 = umma_idesc_f16(128, 64, 0);
-        constexpr uint32_t idesc2 = umma_idesc_f16(128, 128, 0);
-        const uint32_t aX = smem_u32(sX), aW1 = smem_u32(sW1), aW2 = smem_u32(sW2), aH2 = smem_u32(sH2);
-        uint32_t i1 = 0, i2 = 0, gc = 0;
+        constexpr uint32_t idesc2 = umma_idesc_f16(128, 256, 0);
+        const uint32_t aW1 = smem_u32(sW1), aW2 = smem_u32(sW2), aH2 = smem_u32(sH2);
+        uint32_t gc = 0;
         RT_PROF_DECL();
         auto mma2 = [&](uint32_t g, bool first) {
-            const uint32_t s = g & 1;
+            const uint32_t s = g & 1, slot = g % kRtW2Ring;
             RT_PROF(0);
             mbar_wait(&h2_full[s], (g >> 1) & 1);
             RT_PROF(1);  // wait for H2 (compute warps)
-            for (int n = 0; n < 2; ++n, ++i2) {
-                const uint32_t slot = i2 % kRtRing;
-                mbar_wait(&w2_full[slot], (i2 / kRtRing) & 1);
-                RT_PROF(2);  // wait for W2 ring
-                tc_fence_after();
-                if (lane == 0) {
+            mbar_wait(&w2_full[slot], (g / kRtW2Ring) & 1);
+            RT_PROF(2);  // wait for W2 ring
+            tc_fence_after();
+            if (lane == 0) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_f16_ss(tmem_base + 128 + n * 128, umma_desc_k_sw128(aH2 + s * 16384 + k * 32, 1024),
-                                    umma_desc_k_sw128(aW2 + slot * kRtSlot + k * 32, 1024), idesc2,
-                                    (first && k == 0) ? 0u : 1u);
-                    umma_commit(&w2_empty[slot]);
-                }
-                __syncwarp();
+                for (int k = 0; k < 4; ++k)
+                    umma_f16_ss(tmem_base + kRtColD2, umma_desc_k_sw128(aH2 + s * 16384 + k * 32, 1024),
+                                umma_desc_k_sw128(aW2 + slot * kTrunkW2Image + k * 32, 1024), idesc2,
+                                (first && k == 0) ? 0u : 1u);
+                umma_commit(&w2_empty[slot]);
+                umma_commit(&h2_empty[s]);
             }
-            if (lane == 0) umma_commit(&h2_empty[s]);
             __syncwarp();
         };
         for (int b = 0; b < n_blocks; ++b) {
@@ -266,28 +235,23 @@ rise_trunk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             mbar_wait(x_ready, b & 1);
             RT_PROF(3);  // wait for the X tile (block boundary)
             for (int j = 0; j < nch; ++j, ++gc) {
-                const uint32_t s = gc & 1;
+                const uint32_t s = gc & 1, slot = gc % kRtW1Ring;
                 mbar_wait(&d1_empty[s], ((gc >> 1) & 1) ^ 1);
                 RT_PROF(4);  // wait for a free D1 buffer
-                for (int h = 0; h < 2; ++h, ++i1) {
-                    const uint32_t slot = i1 % kRtRing;
-                    mbar_wait(&w1_full[slot], (i1 / kRtRing) & 1);
-                    RT_PROF(5);  // wait for W1 ring
-                    tc_fence_after();
-                    if (lane == 0) {
+                mbar_wait(&w1_full[slot], (gc / kRtW1Ring) & 1);
+                RT_PROF(5);  // wait for W1 ring
+                tc_fence_after();
+                if (lane == 0) {
 #pragma unroll
-                        for (int p = 0; p < 2; ++p)
+                    for (int p = 0; p < 4; ++p)
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                umma_f16_ss(tmem_base + s * 64,
-                                            umma_desc_k_sw128(aX + (2 * h + p) * 16384 + k * 32, 1024),
-                                            umma_desc_k_sw128(aW1 + slot * kRtSlot + p * 8192 + k * 32, 1024), idesc1,
-                                            (h > 0 || p > 0 || k > 0) ? 1u : 0u);
-                        umma_commit(&w1_empty[slot]);
-                    }
-                    __syncwarp();
+                        for (int k = 0; k < 4; ++k)
+                            umma_f16_ts(tmem_base + kRtColD1 + s * 64, tmem_base + kRtColX + p * 32 + k * 8,
+                                        umma_desc_k_sw128(aW1 + slot * kTrunkW1Image + p * 8192 + k * 32, 1024), idesc1,
+                                        (p > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(&w1_empty[slot]);
+                    umma_commit(&d1_full[s]);
                 }
-                if (lane == 0) umma_commit(&d1_full[s]);
                 __syncwarp();
                 if (j >= 1) mma2(gc - 1, j == 1);
             }
@@ -301,15 +265,32 @@ rise_trunk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         // ---------------------------------------------------------------- compute warps
         const int cw = warp - 2;        // 0..15
         const int grp = warp & 3;       // TMEM lane group this warp may access
-        const int cq = cw >> 2;         // column quarter handled by this thread in the TMEM read-outs
+        const int cq = cw >> 2;         // column quarter (64 channels) handled by this thread in the TMEM accesses
         const int r = grp * 32 + lane;  // row of the 128-row tile (TMEM lane)
         const int tid = cw * 32 + lane; // 0..511
         const uint32_t lane_addr = static_cast<uint32_t>(grp * 32) << 16;
+        const uint32_t x_addr = tmem_base + lane_addr + kRtColX + cq * 32;
         // depthwise role: two warps per 8-channel group (one per board), lane = (row pair, column)
         const int dg = cw >> 1, db = cw & 1, dy0 = (lane >> 3) * 2, dx = lane & 7;
+        const int m = m_tile * 128 + r;
         uint32_t gc = 0;
         RT_PROF_DECL();
-        mbar_wait(x_full, 0);
+        {   // stem output -> tensor memory (fp16 pairs are already in the packed order the tensor core expects)
+            uint32_t xv[32];
+            if (m < args.M) {
+                const uint4* src = reinterpret_cast<const uint4*>(args.x_in + static_cast<size_t>(m) * 256 + cq * 64);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const uint4 t = __ldg(src + i);
+                    xv[i * 4 + 0] = t.x, xv[i * 4 + 1] = t.y, xv[i * 4 + 2] = t.z, xv[i * 4 + 3] = t.w;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) xv[i] = 0u;
+            }
+            tmem_st_32x32b_x32(x_addr, xv);
+            tmem_st_wait();
+        }
         RT_PROF(0);  // X load
         for (int b = 0; b < n_blocks; ++b) {
             const TrunkBlock& B = args.blk[b];
@@ -318,28 +299,41 @@ rise_trunk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             float* sB2 = sB2all + (b & 1) * 256;  // read in this block's epilogue, behind the chunk loop's barriers
             if (tid < 256) sB2[tid] = __ldg(B.b2 + tid);
             if (B.se_type != 0) {
-                // squeeze-excitation on the block input, in place (se_kernel of net_kernels.cuh, spread over 512 threads)
-                float* sPool = reinterpret_cast<float*>(sH1);  // [2][256]
-                float* sPart = sPool + 512;                     // partial sums: [4][2][128] or [2][2][256]
-                float* sHid = sPart + 1024;                     // [2][128]
-                float* sScale = sHid + 256;                     // [2][256]
+                // squeeze-excitation on the block input, in place (arithmetic of se_kernel, net_kernels.cuh)
+                float* sPoolPart = reinterpret_cast<float*>(sH1);  // [4 row groups][256]
+                float* sPool = sPoolPart + 1024;                    // [2][256]
+                float* sPart = sPool + 512;                         // partial sums: [4][2][128] or [2][2][256]
+                float* sHid = sPart + 1024;                         // [2][128]
+                float* sScale = sHid + 256;                         // [2][256]
                 const int bb = tid >> 8, c = tid & 255;
-                rt_bar_sync(1);  // the tile is complete (epilogue of the previous block) and H1 is no longer read
-                {
-                    const uint8_t* col = sX + (c >> 6) * 16384 + (c & 7) * 2;
-                    const int ch16 = (c & 63) >> 3;
-                    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
-#pragma unroll 4
-                    for (int sq = 0; sq < 64; sq += 4) {
-                        const int rr = bb * 64 + sq;
-                        s0 += __half2float(*reinterpret_cast<const __half*>(col + rr * 128 + ((ch16 ^ (rr & 7)) << 4)));
-                        s1 += __half2float(*reinterpret_cast<const __half*>(col + (rr + 1) * 128 + ((ch16 ^ ((rr + 1) & 7)) << 4)));
-                        s2 += __half2float(*reinterpret_cast<const __half*>(col + (rr + 2) * 128 + ((ch16 ^ ((rr + 2) & 7)) << 4)));
-                        s3 += __half2float(*reinterpret_cast<const __half*>(col + (rr + 3) * 128 + ((ch16 ^ ((rr + 3) & 7)) << 4)));
+                uint32_t xv[32];
+                tmem_ld_32x32b_x32(x_addr, xv);
+                tmem_ld_wait();
+                rt_bar_sync(1);  // H1 (aliased by the scratch above) is no longer read by the previous block
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    // column sums over the warp's 32 rows: butterfly that halves the value count at every step
+                    float vals[32];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float2 f = rt_unpack(xv[hh * 16 + i]);
+                        vals[2 * i] = f.x, vals[2 * i + 1] = f.y;
                     }
-                    sPool[bb * 256 + c] = ((s0 + s1) + (s2 + s3)) * (1.0f / 64.0f);
+#pragma unroll
+                    for (int off = 16, n = 16; off >= 1; off >>= 1, n >>= 1) {
+                        const bool upper = (lane & off) != 0;
+#pragma unroll
+                        for (int i = 0; i < n; ++i) {
+                            const float send = upper ? vals[i] : vals[i + n];
+                            const float keep = upper ? vals[i + n] : vals[i];
+                            vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                        }
+                    }
+                    sPoolPart[grp * 256 + cq * 64 + hh * 32 + lane] = vals[0];
                 }
                 rt_bar_sync(2);
+                sPool[bb * 256 + c] = (sPoolPart[(2 * bb) * 256 + c] + sPoolPart[(2 * bb + 1) * 256 + c]) * (1.0f / 64.0f);
+                rt_bar_sync(1);
                 // every weight is loaded once (fp16) and used for both boards; K is split over the thread groups and
                 // the partial sums meet in shared memory
                 if (B.se_type == 1) {
@@ -360,13 +354,13 @@ rise_trunk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                         sPart[(kq * 2 + 0) * 128 + j] = a0 + c0;
                         sPart[(kq * 2 + 1) * 128 + j] = a1 + c1;
                     }
-                    rt_bar_sync(1);
+                    rt_bar_sync(2);
                     if (tid < 256) {
                         const int b1 = tid >> 7, j = tid & 127;
                         sHid[tid] = fmaxf((sPart[(0 + b1) * 128 + j] + sPart[(2 + b1) * 128 + j]) +
                                               (sPart[(4 + b1) * 128 + j] + sPart[(6 + b1) * 128 + j]), 0.0f);
                     }
-                    rt_bar_sync(2);
+                    rt_bar_sync(1);
                     {   // fc2 (128 -> 256): 2 K-halves x 256 outputs
                         const int jh = tid >> 8;
                         const __half* w = B.se_w2t + (jh * 64) * 256 + c;
@@ -384,7 +378,7 @@ rise_trunk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                         sPart[(jh * 2 + 0) * 256 + c] = a0 + c0;
                         sPart[(jh * 2 + 1) * 256 + c] = a1 + c1;
                     }
-                    rt_bar_sync(1);
+                    rt_bar_sync(2);
                     sScale[bb * 256 + c] = rt_hard_sigmoid(sPart[bb * 256 + c] + sPart[(2 + bb) * 256 + c]);
                 } else {
                     {   // 256 -> 256: 2 K-halves x 256 outputs
@@ -404,47 +398,43 @@ rise_trunk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                         sPart[(kh * 2 + 0) * 256 + c] = a0 + c0;
                         sPart[(kh * 2 + 1) * 256 + c] = a1 + c1;
                     }
-                    rt_bar_sync(1);
+                    rt_bar_sync(2);
                     sScale[bb * 256 + c] =
                         rt_hard_sigmoid(__ldg(B.se_b + c) + (sPart[bb * 256 + c] + sPart[(2 + bb) * 256 + c]));
                 }
                 rt_bar_sync(1);
                 {
                     const float* sc = sScale + (r >> 6) * 256 + cq * 64;
-#pragma unroll 4
-                    for (int ch = 0; ch < 8; ++ch) {
-                        const int cc = cq * 64 + ch * 8;
-                        uint8_t* p = sX + (cc >> 6) * 16384 + r * 128 + ((((cc & 63) >> 3) ^ (r & 7)) << 4);
-                        uint4 xv = *reinterpret_cast<uint4*>(p);
-                        __half* xh = reinterpret_cast<__half*>(&xv);
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) xh[e] = __float2half_rn(__half2float(xh[e]) * sc[ch * 8 + e]);
-                        *reinterpret_cast<uint4*>(p) = xv;
+                    for (int i = 0; i < 32; ++i) {
+                        const float2 f = rt_unpack(xv[i]);
+                        xv[i] = rt_pack(f.x * sc[2 * i], f.y * sc[2 * i + 1]);
                     }
+                    tmem_st_32x32b_x32(x_addr, xv);
+                    tmem_st_wait();
                 }
             }
-            // the tile (TMA-loaded, rewritten by the previous epilogue, or rescaled above) becomes the A operand
-            rt_fence_proxy_async();
+            // the tile (just loaded, rewritten by the previous epilogue, or rescaled above) becomes the A operand
+            tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(x_ready);
             RT_PROF(1);  // squeeze-excitation + hand-over of the tile
 
             for (int j = 0; j < nch; ++j, ++gc) {
-                const uint32_t s = gc & 1;
+                const uint32_t s = gc & 1, slot = gc % kRtW1Ring;
                 // ---- epilogue 1: D1 -> relu(+b1) -> H1
                 mbar_wait(&d1_full[s], (gc >> 1) & 1);
-                RT_PROF(2);  // wait for D1 (tensor core)
+                RT_PROF(2);  // wait for D1 (tensor core); the W1 image (and its vectors) arrived before the MMA ran
                 tc_fence_after();
                 uint32_t v[16];
-                tmem_ld_32x32b_x16(tmem_base + lane_addr + s * 64 + cq * 16, v);
+                tmem_ld_32x32b_x16(tmem_base + lane_addr + kRtColD1 + s * 64 + cq * 16, v);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&d1_empty[s]);
                 RT_PROF(3);  // TMEM read-out
-                mbar_wait(&aux_full[s], (gc >> 1) & 1);
-                RT_PROF(4);  // wait for the chunk vectors
-                const uint8_t* aux = sAux + s * kRtAuxSlot;
+                mbar_wait(&w1_full[slot], (gc / kRtW1Ring) & 1);  // already complete: makes the copied vectors visible here
+                const uint8_t* aux = sW1 + slot * kTrunkW1Image + kTrunkW1Tile;
                 rt_bar_sync(1);  // every thread is done reading the previous chunk's H1
                 RT_PROF(5);
 #pragma unroll
@@ -452,15 +442,11 @@ rise_trunk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                     const float* bp = reinterpret_cast<const float*>(aux) + cq * 16 + q * 8;
                     const float4 ba = *reinterpret_cast<const float4*>(bp);
                     const float4 bb = *reinterpret_cast<const float4*>(bp + 4);
-                    const float bias[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
                     uint4 o;
-                    __half2* oh = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float f0 = fmaxf(__uint_as_float(v[q * 8 + e * 2]) + bias[e * 2], 0.0f);
-                        const float f1 = fmaxf(__uint_as_float(v[q * 8 + e * 2 + 1]) + bias[e * 2 + 1], 0.0f);
-                        oh[e] = __floats2half2_rn(f0, f1);
-                    }
+                    o.x = rt_pack(fmaxf(__uint_as_float(v[q * 8 + 0]) + ba.x, 0.0f), fmaxf(__uint_as_float(v[q * 8 + 1]) + ba.y, 0.0f));
+                    o.y = rt_pack(fmaxf(__uint_as_float(v[q * 8 + 2]) + ba.z, 0.0f), fmaxf(__uint_as_float(v[q * 8 + 3]) + ba.w, 0.0f));
+                    o.z = rt_pack(fmaxf(__uint_as_float(v[q * 8 + 4]) + bb.x, 0.0f), fmaxf(__uint_as_float(v[q * 8 + 5]) + bb.y, 0.0f));
+                    o.w = rt_pack(fmaxf(__uint_as_float(v[q * 8 + 6]) + bb.z, 0.0f), fmaxf(__uint_as_float(v[q * 8 + 7]) + bb.w, 0.0f));
                     *reinterpret_cast<uint4*>(sH1 + (cq * 2 + q) * 2048 + r * 16) = o;
                 }
                 RT_PROF(6);  // H1 write
@@ -473,7 +459,7 @@ rise_trunk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 else
                     rt_depthwise<5>(sH1, aux, dg, db, dy0, dx, o2);
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&aux_empty[s]);
+                if (lane == 0) mbar_arrive(&w1_empty[slot]);  // this warp is done with the chunk vectors
                 RT_PROF(8);  // depthwise
                 // ---- H2 (A operand of MMA2) in the 128B-swizzled K-major layout
                 mbar_wait(&h2_empty[s], ((gc >> 1) & 1) ^ 1);
@@ -488,36 +474,33 @@ rise_trunk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 if (lane == 0) mbar_arrive(&h2_full[s]);
                 RT_PROF(10);  // H2 write
             }
-            // ---- block epilogue: X <- D2 + b2 + X (in place; also to global after the last block)
+            // ---- block epilogue: X <- D2 + b2 + X (tensor memory in place; also to global after the last block)
             mbar_wait(d2_full, b & 1);
             RT_PROF(11);  // wait for D2
             tc_fence_after();
-            const int m = m_tile * 128 + r;
-#pragma unroll 1
-            for (int cc = 0; cc < 2; ++cc) {
-                const int c0 = cq * 64 + cc * 32;
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(tmem_base + lane_addr + 128 + c0, v);
-                tmem_ld_wait();
+            {
+                uint32_t xv[32];
+                tmem_ld_32x32b_x32(x_addr, xv);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int c = c0 + q * 8;
-                    uint8_t* p = sX + (c >> 6) * 16384 + r * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4);
-                    const uint4 xv = *reinterpret_cast<const uint4*>(p);
-                    const __half2* xh = reinterpret_cast<const __half2*>(&xv);
-                    const float4 b0 = *reinterpret_cast<const float4*>(sB2 + c);
-                    const float4 b1 = *reinterpret_cast<const float4*>(sB2 + c + 4);
-                    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                    uint4 o;
-                    __half2* oh = reinterpret_cast<__half2*>(&o);
+                for (int cc = 0; cc < 2; ++cc) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(tmem_base + lane_addr + kRtColD2 + cq * 64 + cc * 32, v);
+                    tmem_ld_wait();
+                    const float* b2p = sB2 + cq * 64 + cc * 32;
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float2 xr = __half22float2(xh[e]);
-                        oh[e] = __floats2half2_rn(__uint_as_float(v[q * 8 + e * 2]) + bb[e * 2] + xr.x,
-                                                  __uint_as_float(v[q * 8 + e * 2 + 1]) + bb[e * 2 + 1] + xr.y);
+                    for (int i = 0; i < 16; ++i) {
+                        const float2 xr = rt_unpack(xv[cc * 16 + i]);
+                        xv[cc * 16 + i] = rt_pack(__uint_as_float(v[2 * i]) + b2p[2 * i] + xr.x,
+                                                  __uint_as_float(v[2 * i + 1]) + b2p[2 * i + 1] + xr.y);
                     }
-                    *reinterpret_cast<uint4*>(p) = o;
-                    if (last && m < args.M) *reinterpret_cast<uint4*>(args.out + static_cast<size_t>(m) * 256 + c) = o;
+                }
+                if (!last) {
+                    tmem_st_32x32b_x32(x_addr, xv);
+                    tmem_st_wait();
+                } else if (m < args.M) {
+                    uint4* dst = reinterpret_cast<uint4*>(args.out + static_cast<size_t>(m) * 256 + cq * 64);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) dst[i] = make_uint4(xv[i * 4], xv[i * 4 + 1], xv[i * 4 + 2], xv[i * 4 + 3]);
                 }
             }
             tc_fence_before();

@@ -6,15 +6,21 @@
 namespace ara {
 
 constexpr int kTrunkMaxBlocks = 24;
+// One 64-channel chunk of a block travels as two pre-tiled images (exact shared-memory byte images, 128B-swizzled
+// K-major, so that each is ONE 1-D bulk copy):
+//   W1 image: [64 rows x 256 K] fp16 as 4 K-panels of 8 KB, then b1[64] f32 | bd[64] f32 | wd[k*k][64] f16
+//   W2 image: [256 rows x 64 K] fp16
+constexpr int kTrunkW1Tile = 32768;
+constexpr int kTrunkAuxBytes = 3712;   // 64 f32 + 64 f32 + 25 * 64 f16
+constexpr int kTrunkW1Image = 36864;   // tile + aux, padded to 1 KB
+constexpr int kTrunkW2Image = 32768;
 
 struct TrunkBlock {
     int n_chunks;     // ceil(Cop / 64)
     int ksize;        // depthwise kernel: 3 or 5
     int se_type;      // 0 none, 1 ca_se, 2 eca_se (applied to the block input, in place)
-    int row0;         // first row of this block in the stacked W1 matrix == first K column in the stacked W2 matrix
-    int aux_off;      // byte offset of the block's first per-chunk record in `aux`
-    int aux_bytes;    // record size: (128 + k*k*64) * 4
-    const float* b2;      // [256]
+    int chunk0;       // index of the block's first chunk in the image arrays
+    const float* b2;       // [256]
     const __half* se_w1t;  // ca_se: [256][128]; eca_se: [256][256] (transposed, fp16 copy owned by the trunk)
     const __half* se_w2t;  // ca_se: [128][256]
     const float* se_b;     // eca_se: [256]
@@ -23,9 +29,11 @@ struct TrunkBlock {
 struct TrunkArgs {
     int M;         // valid rows (= boards * 64)
     int n_blocks;
-    const uint8_t* aux;  // per 64-channel chunk: b1[64] f32 | bd[64] f32 | wd[k*k][64] f32
-    __half* out;         // [M, 256]
-    unsigned long long* prof;  // profiling builds (-DARA_TRUNK_PROF): [2][16] cycle counters of CTA 0, else null
+    const uint8_t* w1_img;  // [chunks][kTrunkW1Image]
+    const uint8_t* w2_img;  // [chunks][kTrunkW2Image]
+    const __half* x_in;     // [M, 256] stem output
+    __half* out;            // [M, 256]
+    unsigned long long* prof;  // profiling builds (-DARA_TRUNK_PROF): [2][16] cycle counters of CTA 0, else unused
     TrunkBlock blk[kTrunkMaxBlocks];
 };
 

@@ -2,17 +2,24 @@
 
 #include <cstring>
 
-#include "rise_block_host.h"  // make_act_tensor_map / make_weight_tensor_map
 #include "rise_trunk.cuh"
 
 namespace ara {
 
+namespace {
+
+// byte offset of element (row, k) inside a K-major tile with 128-byte rows and the 128B swizzle (16-byte chunks XORed
+// with the row index modulo 8): the layout TMA's SWIZZLE_128B produces and the UMMA shared-memory descriptor reads
+inline size_t sw128_offset(int row, int k) { return static_cast<size_t>(row) * 128 + ((((k >> 3) ^ (row & 7)) << 4)) + (k & 7) * 2; }
+
+}  // namespace
+
 int rise_trunk_init(RiseTrunk* T, const std::vector<TrunkBlockHost>& blocks, const __half* x_in, int boards_cap, __half* out) {
+    (void)boards_cap;
     const int nb = static_cast<int>(blocks.size());
     if (nb < 1 || nb > kTrunkMaxBlocks) return set_error("rise_trunk_init: %d blocks unsupported (max %d)", nb, kTrunkMaxBlocks);
     memset(&T->args, 0, sizeof(T->args));
-    int rows = 0;
-    size_t aux_bytes = 0;
+    int chunks = 0;
     for (int i = 0; i < nb; ++i) {
         const TrunkBlockHost& h = blocks[i];
         if (h.ksize != 3 && h.ksize != 5) return set_error("rise_trunk_init: depthwise kernel %d unsupported", h.ksize);
@@ -21,9 +28,7 @@ int rise_trunk_init(RiseTrunk* T, const std::vector<TrunkBlockHost>& blocks, con
         B.n_chunks = (h.c_op + 63) / 64;
         B.ksize = h.ksize;
         B.se_type = h.se_type;
-        B.row0 = rows;
-        B.aux_off = static_cast<int>(aux_bytes);
-        B.aux_bytes = 512 + h.ksize * h.ksize * 128;  // b1[64] f32 | bd[64] f32 | wd[k*k][64] f16
+        B.chunk0 = chunks;
         B.b2 = h.b2;
         B.se_b = h.se_b;
         if (h.se_type != 0) {  // fp16 copies of the squeeze-excitation matrices (the kernel is bound by their traffic)
@@ -40,51 +45,48 @@ int rise_trunk_init(RiseTrunk* T, const std::vector<TrunkBlockHost>& blocks, con
             B.se_w1t = static_cast<const __half*>(d);
             B.se_w2t = n2 ? static_cast<const __half*>(d) + n1 : nullptr;
         }
-        rows += B.n_chunks * 64;
-        aux_bytes += static_cast<size_t>(B.n_chunks) * B.aux_bytes;
+        chunks += B.n_chunks;
     }
     T->args.n_blocks = nb;
+    T->args.x_in = x_in;
     T->args.out = out;
-    // W1 stacked by rows: [rows][256]; W2 stacked along K: [256][rows]; both fp16, zero padded per block to 64
-    std::vector<__half> w1(static_cast<size_t>(rows) * 256, __float2half(0.0f));
-    std::vector<__half> w2(static_cast<size_t>(256) * rows, __float2half(0.0f));
-    std::vector<uint8_t> aux(aux_bytes, 0);
+    // pre-tiled images: every chunk's weights laid out exactly as the bytes the kernel wants in shared memory
+    std::vector<uint8_t> w1(static_cast<size_t>(chunks) * kTrunkW1Image, 0);
+    std::vector<uint8_t> w2(static_cast<size_t>(chunks) * kTrunkW2Image, 0);
     for (int i = 0; i < nb; ++i) {
         const TrunkBlockHost& h = blocks[i];
         const TrunkBlock& B = T->args.blk[i];
         const int kk = h.ksize * h.ksize;
-        for (int c = 0; c < h.c_op; ++c)
-            for (int k = 0; k < 256; ++k)
-                w1[(static_cast<size_t>(B.row0) + c) * 256 + k] = __float2half_rn(h.w1[static_cast<size_t>(c) * 256 + k]);
-        for (int n = 0; n < 256; ++n)
-            for (int c = 0; c < h.c_op; ++c)
-                w2[static_cast<size_t>(n) * rows + B.row0 + c] = __float2half_rn(h.w2[static_cast<size_t>(n) * h.c_op + c]);
         for (int j = 0; j < B.n_chunks; ++j) {
-            uint8_t* rec = aux.data() + B.aux_off + static_cast<size_t>(j) * B.aux_bytes;
-            float* rec_f = reinterpret_cast<float*>(rec);
-            __half* rec_w = reinterpret_cast<__half*>(rec + 512);
+            uint8_t* img1 = w1.data() + static_cast<size_t>(B.chunk0 + j) * kTrunkW1Image;
+            uint8_t* img2 = w2.data() + static_cast<size_t>(B.chunk0 + j) * kTrunkW2Image;
+            float* aux_f = reinterpret_cast<float*>(img1 + kTrunkW1Tile);
+            __half* aux_w = reinterpret_cast<__half*>(img1 + kTrunkW1Tile + 512);
             for (int cc = 0; cc < 64; ++cc) {
                 const int c = j * 64 + cc;
                 if (c >= h.c_op) break;
-                rec_f[cc] = h.b1[c];
-                rec_f[64 + cc] = h.bd[c];
-                for (int q = 0; q < kk; ++q) rec_w[q * 64 + cc] = __float2half_rn(h.wd[static_cast<size_t>(c) * kk + q]);
+                // W1 tile: row = operating channel, K = the 256 trunk channels in 4 panels of 64
+                for (int k = 0; k < 256; ++k)
+                    *reinterpret_cast<__half*>(img1 + (k >> 6) * 8192 + sw128_offset(cc, k & 63)) =
+                        __float2half_rn(h.w1[static_cast<size_t>(c) * 256 + k]);
+                // W2 tile: row = trunk channel, K = the 64 operating channels of this chunk
+                for (int n = 0; n < 256; ++n)
+                    *reinterpret_cast<__half*>(img2 + sw128_offset(n, cc)) = __float2half_rn(h.w2[static_cast<size_t>(n) * h.c_op + c]);
+                aux_f[cc] = h.b1[c];
+                aux_f[64 + cc] = h.bd[c];
+                for (int q = 0; q < kk; ++q) aux_w[q * 64 + cc] = __float2half_rn(h.wd[static_cast<size_t>(c) * kk + q]);
             }
         }
     }
-    ARA_CUDA_OK(cudaMalloc(&T->d_w1, w1.size() * sizeof(__half)));
-    ARA_CUDA_OK(cudaMalloc(&T->d_w2, w2.size() * sizeof(__half)));
-    ARA_CUDA_OK(cudaMalloc(&T->d_aux, aux.size()));
-    ARA_CUDA_OK(cudaMemcpy(T->d_w1, w1.data(), w1.size() * sizeof(__half), cudaMemcpyHostToDevice));
-    ARA_CUDA_OK(cudaMemcpy(T->d_w2, w2.data(), w2.size() * sizeof(__half), cudaMemcpyHostToDevice));
-    ARA_CUDA_OK(cudaMemcpy(T->d_aux, aux.data(), aux.size(), cudaMemcpyHostToDevice));
-    T->args.aux = static_cast<const uint8_t*>(T->d_aux);
+    ARA_CUDA_OK(cudaMalloc(&T->d_w1, w1.size()));
+    ARA_CUDA_OK(cudaMalloc(&T->d_w2, w2.size()));
+    ARA_CUDA_OK(cudaMemcpy(T->d_w1, w1.data(), w1.size(), cudaMemcpyHostToDevice));
+    ARA_CUDA_OK(cudaMemcpy(T->d_w2, w2.data(), w2.size(), cudaMemcpyHostToDevice));
+    T->args.w1_img = static_cast<const uint8_t*>(T->d_w1);
+    T->args.w2_img = static_cast<const uint8_t*>(T->d_w2);
     ARA_CUDA_OK(cudaMalloc(&T->d_prof, 32 * sizeof(unsigned long long)));
     ARA_CUDA_OK(cudaMemset(T->d_prof, 0, 32 * sizeof(unsigned long long)));
     T->args.prof = static_cast<unsigned long long*>(T->d_prof);
-    if (make_act_tensor_map(&T->tm_x, x_in, boards_cap, 256)) return -1;
-    if (make_weight_tensor_map(&T->tm_w1, static_cast<const __half*>(T->d_w1), 256, rows, 64)) return -1;
-    if (make_weight_tensor_map(&T->tm_w2, static_cast<const __half*>(T->d_w2), rows, 256, 128)) return -1;
     ARA_CUDA_OK(cudaFuncSetAttribute(rise_trunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRtSmemBytes));
     return 0;
 }
@@ -92,19 +94,17 @@ int rise_trunk_init(RiseTrunk* T, const std::vector<TrunkBlockHost>& blocks, con
 int rise_trunk_launch(const RiseTrunk* T, int boards, cudaStream_t stream) {
     TrunkArgs a = T->args;
     a.M = boards * 64;
-    ARA_CUDA_OK(launch_pdl(rise_trunk_kernel, dim3((boards + 1) / 2), dim3(kRtThreads), kRtSmemBytes, stream, T->tm_x,
-                           T->tm_w1, T->tm_w2, a));
+    ARA_CUDA_OK(launch_pdl(rise_trunk_kernel, dim3((boards + 1) / 2), dim3(kRtThreads), kRtSmemBytes, stream, a));
     return 0;
 }
 
 void rise_trunk_destroy(RiseTrunk* T) {
     if (T->d_w1) cudaFree(T->d_w1);
     if (T->d_w2) cudaFree(T->d_w2);
-    if (T->d_aux) cudaFree(T->d_aux);
     if (T->d_prof) cudaFree(T->d_prof);
     for (void* p : T->d_se) cudaFree(p);
     T->d_se.clear();
-    T->d_w1 = T->d_w2 = T->d_aux = T->d_prof = nullptr;
+    T->d_w1 = T->d_w2 = T->d_prof = nullptr;
 }
 
 }  // namespace ara

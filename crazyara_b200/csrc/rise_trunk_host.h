@@ -24,11 +24,9 @@ struct TrunkBlockHost {
 };
 
 struct RiseTrunk {
-    CUtensorMap tm_x, tm_w1, tm_w2;
     TrunkArgs args;
     void* d_w1 = nullptr;
     void* d_w2 = nullptr;
-    void* d_aux = nullptr;
     void* d_prof = nullptr;  // [2][16] cycle counters, written only by -DARA_TRUNK_PROF builds
     std::vector<void*> d_se;  // fp16 copies of the squeeze-excitation matrices
 };

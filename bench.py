@@ -136,6 +136,66 @@ def cpu_arm(sims, batch, steps, warmup):
     return nodes / secs, secs / steps * 1e3, cores, nodes
 
 
+def multi_tree_leg(blob, device, trees, batch, sims, flops_pos, reps=3):
+    """T independent searches (each Batch_Size `batch`) advanced together on one GPU: the analysis-server / arena shape.
+    Every iteration one network forward serves all trees, so the conv stack sees T*batch positions."""
+    from crazyara_b200.engine import BoardState, MCTSAgent, default_settings
+    from crazyara_b200.nn import NeuralNetAPI
+    net = NeuralNetAPI("gpu", device, batch * trees, blob)
+    agent = MCTSAgent(net, default_settings("crazyhouse", batch_size=batch, simulations=sims), device, trees)
+    agent.set_profile(True)
+    openings = ["", "e2e4", "d2d4", "g1f3", "e2e4 e7e5", "d2d4 d7d5", "c2c4", "b1c3"]
+    states = []
+    for t in range(trees):
+        s = BoardState().set("", False, 1)
+        if openings[t % len(openings)]:
+            s.do_uci(*openings[t % len(openings)].split())
+        states.append(s)
+    best = None
+    for rep in range(reps + 1):
+        for t, s in enumerate(states):
+            agent.set_position(s, t)
+        agent.evaluate_board_state()
+        if rep == 0:
+            continue
+        ms = agent.last_go_ms()
+        res = agent.results()
+        nodes = sum(r["nodes"] for r in res)
+        evals = sum(r["evals"] for r in res)
+        prof = agent.profile()
+        row = {"trees": trees, "batch_per_tree": batch, "simulations": sims, "nps": nodes / (ms * 1e-3), "ms_per_go": ms,
+               "net_ms": prof["net_ms"], "select_ms": prof["select_ms"], "apply_ms": prof["apply_ms"],
+               "conv_tflops": evals * flops_pos / (prof["net_ms"] * 1e-3) / 1e12}
+        if best is None or row["nps"] > best["nps"]:
+            best = row
+    agent.close()
+    net.close()
+    return best
+
+
+def selfplay_leg(blob, device, n_games, seconds):
+    """Self-play games/hour (second half of BASELINE.json's metric): `n_games` concurrent crazyhouse games per GPU with
+    the reference's RL search settings (rl_config.py:34-65: 800 nodes, Batch_Size 8, Dirichlet 0.25/0.3)."""
+    from crazyara_b200.nn import NeuralNetAPI
+    from crazyara_b200.selfplay import Arena, rl_settings
+    st = rl_settings("crazyhouse")
+    net = NeuralNetAPI("gpu", device, n_games * st.batch_size, blob)
+    arena = Arena(net, st, variant=1, n_games=n_games, device=device, max_plies=160, seed=1)
+    arena.run(max_steps=2)  # warm-up (graph capture, allocations)
+    arena.finished.clear()
+    arena.nodes, arena.search_ms = 0, 0.0
+    res = arena.run(max_seconds=seconds)
+    arena.close()
+    net.close()
+    # random weights do not finish games the way a trained network does, so the rate is quoted per searched move and
+    # converted with a nominal 100-ply game; the games that did finish inside the window are reported beside it
+    return {"concurrent_games": n_games, "settings": "RL defaults: nodes 800, Batch_Size 8, Dirichlet eps 0.25 alpha 0.3, "
+            "temperature 0.8 for 15 plies, games adjudicated at 160 plies (random weights)",
+            "moves_per_s": res["moves_per_s"], "games_per_hour_at_100_plies": res["moves_per_s"] * 36.0,
+            "games_finished_in_window": res["games"], "avg_plies_finished": res["avg_plies"],
+            "search_nps": res["nps"], "wall_s": res["wall_s"]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -146,6 +206,9 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU arm (profiling runs)")
     ap.add_argument("--cpu-sims", type=int, default=1280, help="bounded CPU sample: simulations per CPU search")
+    ap.add_argument("--trees", type=int, default=32, help="extra leg: concurrent searches per GPU (0 = skip)")
+    ap.add_argument("--selfplay-seconds", type=float, default=8.0, help="extra leg: self-play arena window (0 = skip)")
+    ap.add_argument("--selfplay-games", type=int, default=64)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -239,6 +302,24 @@ def main():
     from crazyara_b200.multi import aggregate_counters
     total_nodes, max_dev_ms, max_wall, launches = aggregate_counters(nodes, dev_ms, wall_s, launches, dist, "cuda")
 
+    # secondary legs (outside the timed region of the headline number): many searches per GPU, and self-play
+    agent.close()
+    net.close()
+    extra = {}
+    if args.trees > 0:
+        extra["multi_tree"] = multi_tree_leg(blob, local_rank, args.trees, args.batch, args.sims, flops_pos)
+    if args.selfplay_seconds > 0:
+        extra["selfplay"] = selfplay_leg(blob, local_rank, args.selfplay_games, args.selfplay_seconds)
+    if dist is not None:  # whole-job figures: sums over ranks (independent replicas)
+        sums = torch.tensor([extra.get("multi_tree", {}).get("nps", 0.0), extra.get("selfplay", {}).get("moves_per_s", 0.0)],
+                            device="cuda", dtype=torch.float64)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+        if "multi_tree" in extra:
+            extra["multi_tree"]["nps_all_gpus"] = sums[0].item()
+        if "selfplay" in extra:
+            extra["selfplay"]["moves_per_s_all_gpus"] = sums[1].item()
+            extra["selfplay"]["games_per_hour_at_100_plies_all_gpus"] = sums[1].item() * 36.0
+
     if rank == 0:
         peaks = {}
         try:
@@ -248,6 +329,14 @@ def main():
         peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
         peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained"
         conv_tflops = forwards * args.batch * flops_pos / (net_ms * 1e-3) / 1e12 if net_ms > 0 else 0.0
+        traffic = None  # DRAM bytes per launch of the dominant tensor kernel, from the committed `ncu --set full` capture
+        try:
+            k = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_rise_trunk_kernel.json")))["kernels"][0]
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            traffic = (k["dram__bytes_read.sum"] * scale[k["dram__bytes_read.sum unit"]] +
+                       k["dram__bytes_write.sum"] * scale[k["dram__bytes_write.sum unit"]])
+        except Exception:
+            pass
         value = total_nodes / (max_dev_ms * 1e-3)
         e2e_value = total_nodes / max_wall
         out = {
@@ -265,8 +354,11 @@ def main():
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"bound": "tensor", "achieved": conv_tflops, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": conv_tflops / peak_tf if peak_tf else None, "traffic": None,
-                         "kernel": "RISEv2 conv stack (conv_gemm_kernel tcgen05 GEMMs + depthwise/SE/head kernels), per forward of 64 positions",
+                         "frac": conv_tflops / peak_tf if peak_tf else None, "traffic": traffic,
+                         "traffic_note": "rise_trunk_kernel, one launch of 64 positions, dram__bytes_read+write "
+                                         "(profiles/r01_ncu_rise_trunk_kernel.json; cold L2: the 6.9 MB of weights + the input tile)",
+                         "kernel": "RISEv2 conv stack per forward of 64 positions: rise_trunk_kernel (13 bottleneck blocks, "
+                                   "tcgen05 TS/SS MMAs, one launch) + stem/policy conv_gemm_kernel + head kernels",
                          "flop_per_position": flops_pos, "peak_source": peak_src},
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -274,9 +366,13 @@ def main():
             out["cpu_baseline"] = {"value": nps, "unit": UNIT, "cores": cores, "kind": "port",
                                    "sample": f"2 searches of {args.cpu_sims} simulations (Batch_Size {args.batch}); C oracle "
                                              f"search 1 thread + fp32 torch CPU network {cores} threads"}
+        if "multi_tree" in extra:
+            mt = extra["multi_tree"]
+            mt["conv_frac_of_peak"] = mt["conv_tflops"] / peak_tf if peak_tf else None
+            out["multi_tree"] = mt
+        if "selfplay" in extra:
+            out["selfplay"] = extra["selfplay"]
         print(json.dumps(out))
-    agent.close()
-    net.close()
     if dist is not None:
         dist.destroy_process_group()
 

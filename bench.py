@@ -244,6 +244,9 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # NCCL prints its version banner on stdout at VERSION level; stdout carries exactly one JSON line
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from crazyara_b200.engine import BoardState, MCTSAgent, default_settings

@@ -147,6 +147,7 @@ class Search {
     std::vector<uint64_t*> d_hist_keys_;
     std::vector<int16_t*> d_hist_reps_;
     float* d_lut_ = nullptr;
+    double* d_sqrt_lut_ = nullptr;
     float *d_values_ = nullptr, *d_probs_ = nullptr;  // fake backend buffers
     SearchResult* d_results_ = nullptr;
     int* h_done_ = nullptr;  // pinned
@@ -248,6 +249,11 @@ int Search::init(Net* net, const SearchParams& params, int device, int trees, in
         for (int i = 0; i < len; ++i) lut[i] = logf((static_cast<float>(i) + sp.cpuct_base + 1) / sp.cpuct_base) + sp.cpuct_init;
         if (dalloc(&d_lut_, lut.size())) return -1;
         ARA_CUDA_OK(cudaMemcpy(d_lut_, lut.data(), lut.size() * 4, cudaMemcpyHostToDevice));
+        // sqrt(double(visit_sum)): IEEE-exact on both sides, tabulated only to keep the instruction chain short
+        std::vector<double> sq(len);
+        for (int i = 0; i < len; ++i) sq[i] = sqrt(static_cast<double>(i));
+        if (dalloc(&d_sqrt_lut_, sq.size())) return -1;
+        ARA_CUDA_OK(cudaMemcpy(d_sqrt_lut_, sq.data(), sq.size() * 8, cudaMemcpyHostToDevice));
         h_trees_.resize(n_trees);
         for (auto& t : h_trees_) t.cput_lut_len = len;
     }
@@ -271,6 +277,7 @@ int Search::init(Net* net, const SearchParams& params, int device, int trees, in
         t.hist_reps = d_hist_reps_[i];
         t.hist_len = 0;
         t.cput_lut = d_lut_;
+        t.sqrt_lut = d_sqrt_lut_;
         t.max_nodes = max_nodes_;
         t.max_edges = max_edges_;
         t.slot_base = i * B;

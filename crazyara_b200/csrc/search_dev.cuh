@@ -140,6 +140,7 @@ struct TreeDev {
     int hist_len;
     const float* cput_lut;  // cput for visit_sum < cput_lut_len, computed on the host with the host libm
     int cput_lut_len;
+    const double* sqrt_lut;  // sqrt(double(visit_sum)) for visit_sum < cput_lut_len
     int max_nodes;
     int max_edges;
     int slot_base;  // first row of this tree in the network batch
@@ -174,6 +175,10 @@ ARA_HD void node_set_value(NodeHdr& h, float v) {  // node.cpp:716-720
 ARA_HD float current_cput(const TreeDev& t, const SearchParams& sp, uint32_t visit_sum) {
     if (static_cast<int>(visit_sum) < t.cput_lut_len) return t.cput_lut[visit_sum];
     return logf((static_cast<float>(visit_sum) + sp.cpuct_base + 1) / sp.cpuct_base) + sp.cpuct_init;
+}
+ARA_HD double sqrt_visits(const TreeDev& t, uint32_t visit_sum) {
+    if (static_cast<int>(visit_sum) < t.cput_lut_len) return t.sqrt_lut[visit_sum];
+    return sqrt(static_cast<double>(visit_sum));
 }
 template <typename T>
 ARA_HD T bcast0(T v) {
@@ -307,13 +312,21 @@ ARA_HD SelectPick pick_fast(const TreeDev& t, const NodeHdr& h, const EdgeRegs& 
     r.x = pre;
     int best_i = 0x7fffffff;
     float best_v = 0.0f, best_hi = ninf, best_lo = 0.0f, oth_hi = ninf;
-    for (int i = ARA_LANE; i < k; i += ARA_WARP_N) {
-        const EdgeRegs x = i == ARA_LANE ? pre : load_edge(t, e + i);
+    if (ARA_LANE < k) {  // the usual case: at most one candidate per lane, already in registers
+        const float uf = (cput * pre.p) * sqf / (static_cast<float>(pre.n) + 1.0f);
+        const float err = uf * 6e-7f + fabsf(pre.q + uf) * 2.6e-7f + 1e-30f;
+        best_v = pre.q + uf, best_hi = best_v + err, best_lo = best_v - err, best_i = ARA_LANE;
+    }
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int i = ARA_LANE + ARA_WARP_N; i < k; i += ARA_WARP_N) {  // more open children than lanes
+        const EdgeRegs x = load_edge(t, e + i);
         const float uf = (cput * x.p) * sqf / (static_cast<float>(x.n) + 1.0f);
         const float vf = x.q + uf;
-        const float err = uf * 6e-7f + (vf < 0.0f ? -vf : vf) * 2.6e-7f + 1e-30f;
+        const float err = uf * 6e-7f + fabsf(vf) * 2.6e-7f + 1e-30f;
         const float hi = vf + err;
-        if (best_i == 0x7fffffff || vf > best_v) {
+        if (vf > best_v) {
             if (best_hi > oth_hi) oth_hi = best_hi;
             best_v = vf, best_hi = hi, best_lo = vf - err, best_i = i, r.x = x;
         } else if (hi > oth_hi) {
@@ -324,10 +337,10 @@ ARA_HD SelectPick pick_fast(const TreeDev& t, const NodeHdr& h, const EdgeRegs& 
     const uint32_t top = ARA_REDUCE_MAX(img);
     r.ci = static_cast<int>(ARA_REDUCE_MIN(img == top ? static_cast<uint32_t>(best_i) : 0x7fffffffu));
     r.owner = best_i == r.ci;
+    // the winner's lower bound, broadcast from its lane, against every other candidate's upper bound (one vote)
+    const float lo_w = ARA_SHFL(best_lo, r.ci & (ARA_WARP_N - 1));
     const float others = r.owner ? oth_hi : (best_hi > oth_hi ? best_hi : oth_hi);
-    const uint32_t others_top = ARA_REDUCE_MAX(float_image(others));
-    const uint32_t lo_img = ARA_REDUCE_MAX(r.owner ? float_image(best_lo) : 0u);
-    *sure = lo_img > others_top;
+    *sure = ARA_ALL(others < lo_w);
     return r;
 }
 
@@ -341,7 +354,7 @@ ARA_HD SelectStep select_and_visit(const TreeDev& t, const SearchParams& sp, int
     // header refresh values, off the dependent chain
     const uint32_t vs_new = h.visit_sum + 1;
     const float cput_new = current_cput(t, sp, vs_new);
-    const double sqrt_new = sqrt(static_cast<double>(vs_new));
+    const double sqrt_new = sqrt_visits(t, vs_new);
     ARA_FINE(t.st, 4, tf, pre.c ^ static_cast<int>(pre.n) ^ __double2hiint(sqrt_new));
     SelectPick pk;
     if (single) {  // only one open child, or a forced win
@@ -501,7 +514,7 @@ ARA_HD void revert_virtual_loss(const TreeDev& t, const SearchParams& sp, int ni
     const uint32_t vs = h.visit_sum - 1;
     h.visit_sum = vs;
     h.cput = current_cput(t, sp, vs);
-    h.sqrt_vs = sqrt(static_cast<double>(vs));
+    h.sqrt_vs = sqrt_visits(t, vs);
     --t.vl[e];
 }
 

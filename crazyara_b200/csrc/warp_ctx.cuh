@@ -15,6 +15,7 @@
 #define ARA_WARP_N 32
 #define ARA_WARP_SYNC() __syncwarp()
 #define ARA_BALLOT(p) __ballot_sync(0xffffffffu, (p))
+#define ARA_ALL(p) (__all_sync(0xffffffffu, (p)) != 0)
 #define ARA_POPC(m) __popc(m)
 #define ARA_POPC_BELOW(m) __popc((m) & ((1u << ARA_LANE) - 1u))
 #define ARA_SHFL(v, src) __shfl_sync(0xffffffffu, (v), (src))
@@ -26,6 +27,7 @@
 #define ARA_WARP_N 1
 #define ARA_WARP_SYNC() ((void)0)
 #define ARA_BALLOT(p) ((p) ? 1u : 0u)
+#define ARA_ALL(p) (p)
 #define ARA_POPC(m) __builtin_popcount(m)
 #define ARA_POPC_BELOW(m) 0
 #define ARA_SHFL(v, src) (v)

@@ -97,6 +97,7 @@ struct HeSearch {
     std::vector<uint64_t> hist_keys;
     std::vector<int16_t> hist_reps;
     std::vector<float> lut;
+    std::vector<double> sqrt_lut;
     std::vector<float> planes;
     WarpScratch ws;
     int channels, n_labels;
@@ -155,6 +156,9 @@ HeSearch* he_search_new(const SearchParams* sp, int max_nodes, int max_edges) {
     t.hist_reps = nullptr;
     t.hist_len = 0;
     t.cput_lut = s->lut.data();
+    s->sqrt_lut.resize(lut_len);
+    for (int i = 0; i < lut_len; ++i) s->sqrt_lut[i] = sqrt(static_cast<double>(i));
+    t.sqrt_lut = s->sqrt_lut.data();
     t.cput_lut_len = lut_len;
     t.max_nodes = max_nodes;
     t.max_edges = max_edges;

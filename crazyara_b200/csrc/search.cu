@@ -88,6 +88,14 @@ __global__ void __launch_bounds__(32) backup_kernel(const TreeDev* trees, Search
     if (finalize) finalize_root(t, sp, ws);
 }
 
+// one warp per (tree, item): prepared-child slots of the new leaves and of the nodes expanded in the last mini-batch
+__global__ void __launch_bounds__(32) prepare_kernel(const TreeDev* trees, SearchParams sp, int items) {
+    __shared__ WarpScratch ws;
+    const int tree = blockIdx.x / items, item = blockIdx.x - tree * items;
+    const TreeDev t = trees[tree];
+    prepare_item(t, sp, ws, item);
+}
+
 __global__ void __launch_bounds__(32) result_kernel(const TreeDev* trees, SearchParams sp, SearchResult* out) {
     const TreeDev t = trees[blockIdx.x];
     if (threadIdx.x == 0) collect_result(t, sp, &out[blockIdx.x]);
@@ -272,6 +280,9 @@ int Search::init(Net* net, const SearchParams& params, int device, int trees, in
             dalloc(&t.traj_ci, static_cast<size_t>(2) * B * kMaxDepth) || dalloc(&t.traj_len, 2 * B) ||
             dalloc(&t.traj_edge, static_cast<size_t>(2) * B * kMaxDepth) || dalloc(&t.new_value, B))
             return -1;
+        if (dalloc(&t.prep_board, max_nodes_) || dalloc(&t.prep_ci, max_nodes_) || dalloc(&t.prep_term, max_nodes_) ||
+            dalloc(&t.exp_parent, 3 * B))
+            return -1;
         if (dalloc(&d_hist_keys_[i], hist_cap_) || dalloc(&d_hist_reps_[i], hist_cap_)) return -1;
         t.hist_keys = d_hist_keys_[i];
         t.hist_reps = d_hist_reps_[i];
@@ -329,9 +340,10 @@ int Search::iterate(int count) {
         if (profile) prof_event();
         scatter_kernel<<<n_trees * B, 32, 0, stream_>>>(d_trees_, sp, B, values, probs, n_labels_);
         backup_kernel<<<n_trees, 32, 0, stream_>>>(d_trees_, sp, 0);
+        prepare_kernel<<<n_trees * 4 * B, 32, 0, stream_>>>(d_trees_, sp, 4 * B);
         if (profile) prof_event();
         ++net_forwards;
-        launches += 4;
+        launches += 5;
     }
     ARA_CUDA_OK(cudaGetLastError());
     return 0;
@@ -360,7 +372,8 @@ int Search::go() {
     scatter_kernel<<<n_trees * B, 32, 0, stream_>>>(d_trees_, sp, B, net_ ? net_->d_value : d_values_,
                                                      net_ ? net_->d_prob : d_probs_, n_labels_);
     backup_kernel<<<n_trees, 32, 0, stream_>>>(d_trees_, sp, 1);
-    launches += 4;
+    prepare_kernel<<<n_trees * 4 * B, 32, 0, stream_>>>(d_trees_, sp, 4 * B);
+    launches += 5;
     ARA_CUDA_OK(cudaGetLastError());
     // main loop: enqueue the iterations the visit budget certainly needs, then poll `done` in small chunks
     unsigned budget = sp.simulations ? sp.simulations : sp.nodes;

@@ -78,6 +78,8 @@ struct TreeState {
     int n_edges;
     int n_new;
     int n_coll;
+    int n_exp;     // expansions of the last mini-batch (entries of exp_parent)
+    int n_prep;    // new leaves of the last mini-batch, kept for the prepare step after the backup cleared n_new
     int done;      // search loop condition failed (limits reached / root solved)
     int error;     // 1 node pool, 2 edge pool, 3 depth overflow
     unsigned iterations;
@@ -129,6 +131,14 @@ struct TreeDev {
     uint8_t* vl;
     uint8_t* etype;
     TreeState* st;
+    // "prepared child": at every node exactly one child can be expanded next (index no_visit_idx-1, opened in prior
+    // order); its position, repetition state and terminal verdict depend on the node alone (the tree has no
+    // transpositions), so they are computed ahead of time by parallel warps (prepare_child) and the sequential
+    // select only copies them
+    Board* prep_board;      // [max_nodes]
+    int16_t* prep_ci;       // [max_nodes] child index the slot holds, -1 = none
+    uint8_t* prep_term;     // [max_nodes] its terminal type
+    int32_t* exp_parent;    // [3B] nodes that had a child expanded in the last mini-batch
     int32_t* new_node;      // [B]
     int32_t* traj_node;     // [2B][kMaxDepth]   rows 0..B-1 new leaves, B..2B-1 collisions
     uint16_t* traj_ci;      // [2B][kMaxDepth]
@@ -594,16 +604,24 @@ ARA_HD bool any_legal_move(const Board& b, WarpScratch& ws, bool* checked_out) {
 
 // Creates the node for ws.child (already moved), child `ci` of `parent` (or the root if parent < 0).
 // Returns the new node id (uniform), or -1 on pool exhaustion.  *is_terminal receives the terminal verdict.
-ARA_HD int expand_node_seq(const TreeDev& t, const SearchParams& sp, WarpScratch& ws, int parent, int ci, int depth,
-                           int* is_terminal) {
+// Repetition state and terminal verdict of ws.child (already moved), `depth` plies below the root with the keys of the
+// path in ws.path_key / path_rep.  Warp-collective; writes b.repetition.
+ARA_HD int leaf_verdict(const TreeDev& t, WarpScratch& ws, int depth) {
     Board& b = ws.child;
-    long long tp = ARA_CLOCK();
     const int rep = repetition_on_path(t, ws, depth);
     if (ARA_LANE == 0) b.repetition = static_cast<int16_t>(rep);
     ARA_WARP_SYNC();
     bool checked = false;
     const bool any = any_legal_move(b, ws, &checked);
-    const int tt = terminal_type(b, any ? 1 : 0, checked);
+    return terminal_type(b, any ? 1 : 0, checked);
+}
+
+// tt_known >= 0: ws.child comes from the node's prepared-child slot (repetition already set, verdict known).
+ARA_HD int expand_node_seq(const TreeDev& t, const SearchParams& sp, WarpScratch& ws, int parent, int ci, int depth,
+                           int* is_terminal, int tt_known = -1, uint32_t parent_edge_base = 0) {
+    Board& b = ws.child;
+    long long tp = ARA_CLOCK();
+    const int tt = tt_known >= 0 ? tt_known : leaf_verdict(t, ws, depth);
     ARA_PROF(*t.st, 2, tp);
     int nid = -1;
     if (ARA_LANE == 0) {
@@ -646,7 +664,8 @@ ARA_HD int expand_node_seq(const TreeDev& t, const SearchParams& sp, WarpScratch
                 }
             }
             t.hdr[nid] = h;
-            if (parent >= 0) t.child[t.hdr[parent].edge_base + ci] = nid;
+            t.prep_ci[nid] = -1;
+            if (parent >= 0) t.child[parent_edge_base + ci] = nid;
         }
     }
     nid = bcast0(nid);
@@ -655,6 +674,52 @@ ARA_HD int expand_node_seq(const TreeDev& t, const SearchParams& sp, WarpScratch
     copy_board(&t.board[nid], &b);
     ARA_PROF(*t.st, 3, tp);
     return nid;
+}
+
+// Fills the prepared-child slot of node X (see TreeDev::prep_board).  Warp-collective, one warp per node, any number
+// of nodes of any trees concurrently; runs after the backup of a mini-batch, when nothing else touches the tree.
+ARA_HD void prepare_child(const TreeDev& t, WarpScratch& ws, int X) {
+    const NodeHdr& hx = t.hdr[X];
+    if (!(hx.flags & NF_HAS_NN) || (hx.flags & NF_TERMINAL)) return;
+    const int idx = static_cast<int>(hx.no_visit_idx) - 1;
+    if (idx < 0 || idx >= hx.n_moves) return;
+    if (t.child[hx.edge_base + idx] >= 0 || t.prep_ci[X] == idx) return;  // expanded already / prepared already
+    // keys of the path root..X, in that order (the repetition scan of a leaf below X needs them)
+    int depth = 0;
+    if (ARA_LANE == 0) {
+        for (int n = X; n >= 0; n = t.hdr[n].parent) ++depth;
+        if (depth <= kMaxDepth) {
+            int i = depth;
+            for (int n = X; n >= 0; n = t.hdr[n].parent) {
+                --i;
+                ws.path_key[i] = t.hdr[n].key;
+                ws.path_rep[i] = t.hdr[n].repetition;
+            }
+        }
+    }
+    depth = bcast0(depth);
+    if (depth > kMaxDepth) return;  // the select loop reports the overflow
+    copy_board(&ws.child, &t.board[X]);
+    if (ARA_LANE == 0) do_move(ws.child, t.move[hx.edge_base + idx]);
+    ARA_WARP_SYNC();
+    const int tt = leaf_verdict(t, ws, depth);
+    copy_board(&t.prep_board[X], &ws.child);
+    if (ARA_LANE == 0) {
+        t.prep_term[X] = static_cast<uint8_t>(tt);
+        t.prep_ci[X] = static_cast<int16_t>(idx);
+    }
+    ARA_WARP_SYNC();
+}
+// item < B: the new leaves of the last mini-batch (their first child); item >= B: the nodes expanded in it
+ARA_HD void prepare_item(const TreeDev& t, const SearchParams& sp, WarpScratch& ws, int item) {
+    const TreeState& st = *t.st;
+    if (st.error) return;
+    const int B = sp.batch_size;
+    if (item < B) {
+        if (item < st.n_prep) prepare_child(t, ws, t.new_node[item]);
+    } else if (item - B < st.n_exp) {
+        prepare_child(t, ws, t.exp_parent[item - B]);
+    }
 }
 
 // Second half of the expansion of node `nid` (non-terminal, freshly created by expand_node_seq).  Warp-collective;
@@ -845,6 +910,8 @@ ARA_HD void apply_dirichlet_to_root(const TreeDev& t, const SearchParams& sp, Wa
 // input planes are produced afterwards by expand_pending, one warp per leaf.
 ARA_HD void create_mini_batch_impl(const TreeDev& t, const SearchParams& sp, WarpScratch& ws) {
     TreeState& st = *t.st;
+    if (ARA_LANE == 0) st.n_exp = 0;
+    ARA_WARP_SYNC();
     if (st.done || st.error) {
         if (ARA_LANE == 0) st.n_new = 0, st.n_coll = 0;
         return;
@@ -887,16 +954,40 @@ ARA_HD void create_mini_batch_impl(const TreeDev& t, const SearchParams& sp, War
             depth++;
             if (next < 0) {
                 ARA_PROF(st, 0, tq);
-                copy_board(&ws.child, &t.board[cur]);
+                // the child's position, repetition state and verdict were usually prepared by a parallel warp after
+                // the previous mini-batch (prepare_child); otherwise (second expansion of a node within one
+                // mini-batch) they are computed here
+                // (slot index, verdict and board are fetched together, speculatively: one round trip)
+                const int slot_ci = t.prep_ci[cur];
+                const int slot_tt = t.prep_term[cur];
+#if defined(__CUDA_ARCH__)
+                uint4 slot_b = make_uint4(0u, 0u, 0u, 0u);
+                if (ARA_LANE < 8) slot_b = reinterpret_cast<const uint4*>(&t.prep_board[cur])[ARA_LANE];
+#endif
+                const bool prepared = slot_ci == ci;
+                int tt_known = -1;
+                if (prepared) {
+#if defined(__CUDA_ARCH__)
+                    if (ARA_LANE < 8) reinterpret_cast<uint4*>(&ws.child)[ARA_LANE] = slot_b;
+                    ARA_WARP_SYNC();
+#else
+                    ws.child = t.prep_board[cur];
+#endif
+                    tt_known = slot_tt;
+                } else {
+                    copy_board(&ws.child, &t.board[cur]);
+                    if (ARA_LANE == 0) do_move(ws.child, t.move[h.edge_base + ci]);
+                }
                 if (ARA_LANE == 0) {
-                    do_move(ws.child, t.move[h.edge_base + ci]);
                     // increment_no_visit_idx: open the next-best sibling (its edge slots are pre-initialised)
                     if (h.no_visit_idx < h.n_moves) t.hdr[cur].no_visit_idx = static_cast<uint16_t>(h.no_visit_idx + 1);
+                    if (prepared) t.prep_ci[cur] = -1;
+                    if (st.n_exp < 3 * B) t.exp_parent[st.n_exp++] = cur;
                 }
                 ARA_WARP_SYNC();
                 ARA_PROF(st, 1, tq);
                 int is_term = 0;
-                leaf = expand_node_seq(t, sp, ws, cur, ci, depth, &is_term);
+                leaf = expand_node_seq(t, sp, ws, cur, ci, depth, &is_term, tt_known, h.edge_base);
                 if (leaf < 0) {
                     type = -2;
                     break;
@@ -1061,6 +1152,7 @@ ARA_HD void backup_results(const TreeDev& t, const SearchParams& sp) {
     }
     ARA_WARP_SYNC();
     if (ARA_LANE == 0) {
+        t.st->n_prep = n_new;  // the prepare step that follows still needs the list of new leaves
         t.st->n_new = 0;
         t.st->n_coll = 0;
     }
@@ -1076,6 +1168,8 @@ ARA_HD void create_root(const TreeDev& t, const SearchParams& sp, WarpScratch& w
         st.n_edges = 0;
         st.n_new = 0;
         st.n_coll = 0;
+        st.n_exp = 0;
+        st.n_prep = 0;
         st.done = 0;
         st.error = 0;
         st.iterations = 0;

@@ -94,6 +94,10 @@ struct HeSearch {
     std::vector<uint16_t> traj_ci;
     std::vector<uint32_t> traj_edge, cbase;
     std::vector<float> new_value;
+    std::vector<Board> prep_board;
+    std::vector<int16_t> prep_ci;
+    std::vector<uint8_t> prep_term;
+    std::vector<int32_t> exp_parent;
     std::vector<uint64_t> hist_keys;
     std::vector<int16_t> hist_reps;
     std::vector<float> lut;
@@ -152,6 +156,14 @@ HeSearch* he_search_new(const SearchParams* sp, int max_nodes, int max_edges) {
     t.traj_len = s->traj_len.data();
     t.traj_edge = s->traj_edge.data();
     t.new_value = s->new_value.data();
+    s->prep_board.resize(max_nodes);
+    s->prep_ci.assign(max_nodes, -1);
+    s->prep_term.resize(max_nodes);
+    s->exp_parent.resize(3 * B);
+    t.prep_board = s->prep_board.data();
+    t.prep_ci = s->prep_ci.data();
+    t.prep_term = s->prep_term.data();
+    t.exp_parent = s->exp_parent.data();
     t.hist_keys = nullptr;
     t.hist_reps = nullptr;
     t.hist_len = 0;
@@ -189,6 +201,7 @@ void he_search_root_results(HeSearch* s, const float* values, const float* probs
     for (int b = 0; b < s->st.n_new; ++b) scatter_pending(s->t, s->sp, s->ws, b, values, probs, s->n_labels);
     backup_results(s->t, s->sp);
     finalize_root(s->t, s->sp, s->ws);
+    for (int item = 0; item < 4 * s->sp.batch_size; ++item) prepare_item(s->t, s->sp, s->ws, item);
 }
 int he_search_create_mini_batch(HeSearch* s) {
     create_mini_batch(s->t, s->sp, s->ws);
@@ -202,6 +215,7 @@ int he_search_create_mini_batch(HeSearch* s) {
 void he_search_apply_results(HeSearch* s, const float* values, const float* probs) {
     for (int b = 0; b < s->st.n_new; ++b) scatter_pending(s->t, s->sp, s->ws, b, values, probs, s->n_labels);
     backup_results(s->t, s->sp);
+    for (int item = 0; item < 4 * s->sp.batch_size; ++item) prepare_item(s->t, s->sp, s->ws, item);
 }
 int he_search_done(const HeSearch* s) { return s->st.done || s->st.error; }
 int he_search_error(const HeSearch* s) { return s->st.error; }

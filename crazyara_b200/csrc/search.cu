@@ -280,7 +280,8 @@ int Search::init(Net* net, const SearchParams& params, int device, int trees, in
             dalloc(&t.traj_ci, static_cast<size_t>(2) * B * kMaxDepth) || dalloc(&t.traj_len, 2 * B) ||
             dalloc(&t.traj_edge, static_cast<size_t>(2) * B * kMaxDepth) || dalloc(&t.new_value, B))
             return -1;
-        if (dalloc(&t.prep_board, max_nodes_) || dalloc(&t.prep_ci, max_nodes_) || dalloc(&t.prep_term, max_nodes_) ||
+        const size_t slots = static_cast<size_t>(max_nodes_) * kPrepSlots;
+        if (dalloc(&t.prep_board, slots) || dalloc(&t.prep_ci, slots) || dalloc(&t.prep_term, slots) ||
             dalloc(&t.exp_parent, 3 * B))
             return -1;
         if (dalloc(&d_hist_keys_[i], hist_cap_) || dalloc(&d_hist_reps_[i], hist_cap_)) return -1;

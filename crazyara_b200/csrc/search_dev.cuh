@@ -25,6 +25,7 @@
 namespace ara {
 
 constexpr int kMaxDepth = 256;
+constexpr int kPrepSlots = 2;  // prepared children per node (TreeDev::prep_board)
 constexpr int kNoCheckmate = 65535;
 constexpr float kQInit = -1.0f;
 enum : int { VS_VIRTUAL_LOSS = 0, VS_VIRTUAL_VISIT = 1, VS_VIRTUAL_OFFSET = 2, VS_VIRTUAL_MIX = 3 };
@@ -135,9 +136,9 @@ struct TreeDev {
     // order); its position, repetition state and terminal verdict depend on the node alone (the tree has no
     // transpositions), so they are computed ahead of time by parallel warps (prepare_child) and the sequential
     // select only copies them
-    Board* prep_board;      // [max_nodes]
-    int16_t* prep_ci;       // [max_nodes] child index the slot holds, -1 = none
-    uint8_t* prep_term;     // [max_nodes] its terminal type
+    Board* prep_board;      // [max_nodes][kPrepSlots]
+    int16_t* prep_ci;       // [max_nodes][kPrepSlots] child index the slot holds, -1 = none
+    uint8_t* prep_term;     // [max_nodes][kPrepSlots] its terminal type
     int32_t* exp_parent;    // [3B] nodes that had a child expanded in the last mini-batch
     int32_t* new_node;      // [B]
     int32_t* traj_node;     // [2B][kMaxDepth]   rows 0..B-1 new leaves, B..2B-1 collisions
@@ -664,7 +665,7 @@ ARA_HD int expand_node_seq(const TreeDev& t, const SearchParams& sp, WarpScratch
                 }
             }
             t.hdr[nid] = h;
-            t.prep_ci[nid] = -1;
+            for (int s = 0; s < kPrepSlots; ++s) t.prep_ci[nid * kPrepSlots + s] = -1;
             if (parent >= 0) t.child[parent_edge_base + ci] = nid;
         }
     }
@@ -678,37 +679,45 @@ ARA_HD int expand_node_seq(const TreeDev& t, const SearchParams& sp, WarpScratch
 
 // Fills the prepared-child slot of node X (see TreeDev::prep_board).  Warp-collective, one warp per node, any number
 // of nodes of any trees concurrently; runs after the backup of a mini-batch, when nothing else touches the tree.
+// Children are expanded in index order, so the slots hold the next kPrepSlots unexpanded children (slot = index mod
+// kPrepSlots): a node that is expanded twice within one mini-batch still finds its second child prepared.
 ARA_HD void prepare_child(const TreeDev& t, WarpScratch& ws, int X) {
     const NodeHdr& hx = t.hdr[X];
     if (!(hx.flags & NF_HAS_NN) || (hx.flags & NF_TERMINAL)) return;
-    const int idx = static_cast<int>(hx.no_visit_idx) - 1;
-    if (idx < 0 || idx >= hx.n_moves) return;
-    if (t.child[hx.edge_base + idx] >= 0 || t.prep_ci[X] == idx) return;  // expanded already / prepared already
-    // keys of the path root..X, in that order (the repetition scan of a leaf below X needs them)
-    int depth = 0;
-    if (ARA_LANE == 0) {
-        for (int n = X; n >= 0; n = t.hdr[n].parent) ++depth;
-        if (depth <= kMaxDepth) {
-            int i = depth;
-            for (int n = X; n >= 0; n = t.hdr[n].parent) {
-                --i;
-                ws.path_key[i] = t.hdr[n].key;
-                ws.path_rep[i] = t.hdr[n].repetition;
+    const int first = static_cast<int>(hx.no_visit_idx) - 1;
+    int depth = -1;
+    for (int idx = first; idx < first + kPrepSlots; ++idx) {
+        if (idx < 0 || idx >= hx.n_moves) continue;
+        const int slot = X * kPrepSlots + (idx % kPrepSlots);
+        if (t.child[hx.edge_base + idx] >= 0 || t.prep_ci[slot] == idx) continue;  // expanded / prepared already
+        if (depth < 0) {
+            // keys of the path root..X, in that order (the repetition scan of a leaf below X needs them)
+            depth = 0;
+            if (ARA_LANE == 0) {
+                for (int n = X; n >= 0; n = t.hdr[n].parent) ++depth;
+                if (depth <= kMaxDepth) {
+                    int i = depth;
+                    for (int n = X; n >= 0; n = t.hdr[n].parent) {
+                        --i;
+                        ws.path_key[i] = t.hdr[n].key;
+                        ws.path_rep[i] = t.hdr[n].repetition;
+                    }
+                }
             }
+            depth = bcast0(depth);
+            if (depth > kMaxDepth) return;  // the select loop reports the overflow
         }
+        copy_board(&ws.child, &t.board[X]);
+        if (ARA_LANE == 0) do_move(ws.child, t.move[hx.edge_base + idx]);
+        ARA_WARP_SYNC();
+        const int tt = leaf_verdict(t, ws, depth);
+        copy_board(&t.prep_board[slot], &ws.child);
+        if (ARA_LANE == 0) {
+            t.prep_term[slot] = static_cast<uint8_t>(tt);
+            t.prep_ci[slot] = static_cast<int16_t>(idx);
+        }
+        ARA_WARP_SYNC();
     }
-    depth = bcast0(depth);
-    if (depth > kMaxDepth) return;  // the select loop reports the overflow
-    copy_board(&ws.child, &t.board[X]);
-    if (ARA_LANE == 0) do_move(ws.child, t.move[hx.edge_base + idx]);
-    ARA_WARP_SYNC();
-    const int tt = leaf_verdict(t, ws, depth);
-    copy_board(&t.prep_board[X], &ws.child);
-    if (ARA_LANE == 0) {
-        t.prep_term[X] = static_cast<uint8_t>(tt);
-        t.prep_ci[X] = static_cast<int16_t>(idx);
-    }
-    ARA_WARP_SYNC();
 }
 // item < B: the new leaves of the last mini-batch (their first child); item >= B: the nodes expanded in it
 ARA_HD void prepare_item(const TreeDev& t, const SearchParams& sp, WarpScratch& ws, int item) {
@@ -958,11 +967,12 @@ ARA_HD void create_mini_batch_impl(const TreeDev& t, const SearchParams& sp, War
                 // the previous mini-batch (prepare_child); otherwise (second expansion of a node within one
                 // mini-batch) they are computed here
                 // (slot index, verdict and board are fetched together, speculatively: one round trip)
-                const int slot_ci = t.prep_ci[cur];
-                const int slot_tt = t.prep_term[cur];
+                const int slot = cur * kPrepSlots + (ci % kPrepSlots);
+                const int slot_ci = t.prep_ci[slot];
+                const int slot_tt = t.prep_term[slot];
 #if defined(__CUDA_ARCH__)
                 uint4 slot_b = make_uint4(0u, 0u, 0u, 0u);
-                if (ARA_LANE < 8) slot_b = reinterpret_cast<const uint4*>(&t.prep_board[cur])[ARA_LANE];
+                if (ARA_LANE < 8) slot_b = reinterpret_cast<const uint4*>(&t.prep_board[slot])[ARA_LANE];
 #endif
                 const bool prepared = slot_ci == ci;
                 int tt_known = -1;
@@ -971,7 +981,7 @@ ARA_HD void create_mini_batch_impl(const TreeDev& t, const SearchParams& sp, War
                     if (ARA_LANE < 8) reinterpret_cast<uint4*>(&ws.child)[ARA_LANE] = slot_b;
                     ARA_WARP_SYNC();
 #else
-                    ws.child = t.prep_board[cur];
+                    ws.child = t.prep_board[slot];
 #endif
                     tt_known = slot_tt;
                 } else {
@@ -981,7 +991,7 @@ ARA_HD void create_mini_batch_impl(const TreeDev& t, const SearchParams& sp, War
                 if (ARA_LANE == 0) {
                     // increment_no_visit_idx: open the next-best sibling (its edge slots are pre-initialised)
                     if (h.no_visit_idx < h.n_moves) t.hdr[cur].no_visit_idx = static_cast<uint16_t>(h.no_visit_idx + 1);
-                    if (prepared) t.prep_ci[cur] = -1;
+                    if (prepared) t.prep_ci[slot] = -1;
                     if (st.n_exp < 3 * B) t.exp_parent[st.n_exp++] = cur;
                 }
                 ARA_WARP_SYNC();

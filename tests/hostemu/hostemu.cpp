@@ -156,9 +156,9 @@ HeSearch* he_search_new(const SearchParams* sp, int max_nodes, int max_edges) {
     t.traj_len = s->traj_len.data();
     t.traj_edge = s->traj_edge.data();
     t.new_value = s->new_value.data();
-    s->prep_board.resize(max_nodes);
-    s->prep_ci.assign(max_nodes, -1);
-    s->prep_term.resize(max_nodes);
+    s->prep_board.resize(static_cast<size_t>(max_nodes) * kPrepSlots);
+    s->prep_ci.assign(static_cast<size_t>(max_nodes) * kPrepSlots, -1);
+    s->prep_term.resize(static_cast<size_t>(max_nodes) * kPrepSlots);
     s->exp_parent.resize(3 * B);
     t.prep_board = s->prep_board.data();
     t.prep_ci = s->prep_ci.data();

@@ -51,7 +51,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
     using Cfg = ConvGemmCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1 KB alignment by offset arithmetic on the shared array itself: a pointer -> integer -> pointer round trip would
+    // make every access below a GENERIC load/store (LD.E / ST.E) instead of LDS / STS
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
     uint64_t* empty_bar = full_bar + Cfg::kStages;
     uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;

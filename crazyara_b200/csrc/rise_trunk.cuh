@@ -122,7 +122,9 @@ __device__ __forceinline__ void rt_depthwise(const uint8_t* sH1, const uint8_t* 
 __global__ void __launch_bounds__(kRtThreads, 1) rise_trunk_kernel(const __grid_constant__ TrunkArgs args) {
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1 KB alignment by offset arithmetic on the shared array itself: a pointer -> integer -> pointer round trip would
+    // make every access below a GENERIC load/store (LD.E / ST.E) instead of LDS / STS
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sW1 = smem;
     uint8_t* sW2 = smem + kRtOffW2;
     uint8_t* sH2 = smem + kRtOffH2;

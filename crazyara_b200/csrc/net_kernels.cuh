@@ -180,8 +180,17 @@ __global__ void __launch_bounds__(256) value_head_kernel(const __half* __restric
     __syncthreads();
     const int warp = t >> 5, lane = t & 31;
     if (!w.wdl_mode) {
-        float h = __ldg(w.b1 + t);
-        for (int i = 0; i < 512; ++i) h = fmaf(__ldg(w.w1t + i * 256 + t), s_f[i], h);
+        // 512 L2-resident weight loads per thread: four independent chains, 16 loads in flight
+        float h0 = __ldg(w.b1 + t), h1 = 0.0f, h2 = 0.0f, h3 = 0.0f;
+        const float* wp = w.w1t + t;
+#pragma unroll 4
+        for (int i = 0; i < 512; i += 4) {
+            h0 = fmaf(__ldg(wp + (i + 0) * 256), s_f[i + 0], h0);
+            h1 = fmaf(__ldg(wp + (i + 1) * 256), s_f[i + 1], h1);
+            h2 = fmaf(__ldg(wp + (i + 2) * 256), s_f[i + 2], h2);
+            h3 = fmaf(__ldg(wp + (i + 3) * 256), s_f[i + 3], h3);
+        }
+        float h = (h0 + h1) + (h2 + h3);
         h = fmaxf(h, 0.0f) * __ldg(w.w2 + t);
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) h += __shfl_xor_sync(0xffffffffu, h, off);

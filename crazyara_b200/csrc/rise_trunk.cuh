@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(kRtThreads, 1) rise_trunk_kernel(const __grid_
                 const TrunkBlock& B = args.blk[b];
                 for (int j = 0; j < B.n_chunks; ++j, ++gc) {
                     const uint32_t s = gc % kRtW1Ring;
-                    mbar_wait(&w1_empty[s], ((gc / kRtW1Ring) & 1) ^ 1);
+                    mbar_wait_relaxed(&w1_empty[s], ((gc / kRtW1Ring) & 1) ^ 1);
                     mbar_arrive_expect_tx(&w1_full[s], kTrunkW1Image);
                     bulk_load_1d(sW1 + s * kTrunkW1Image, args.w1_img + static_cast<size_t>(B.chunk0 + j) * kTrunkW1Image,
                                  kTrunkW1Image, &w1_full[s]);
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(kRtThreads, 1) rise_trunk_kernel(const __grid_
                 const TrunkBlock& B = args.blk[b];
                 for (int j = 0; j < B.n_chunks; ++j, ++gc) {
                     const uint32_t s = gc % kRtW2Ring;
-                    mbar_wait(&w2_empty[s], ((gc / kRtW2Ring) & 1) ^ 1);
+                    mbar_wait_relaxed(&w2_empty[s], ((gc / kRtW2Ring) & 1) ^ 1);
                     mbar_arrive_expect_tx(&w2_full[s], kTrunkW2Image);
                     bulk_load_1d(sW2 + s * kTrunkW2Image, args.w2_img + static_cast<size_t>(B.chunk0 + j) * kTrunkW2Image,
                                  kTrunkW2Image, &w2_full[s]);

@@ -8,6 +8,7 @@
 // The host only looks at the per-tree `done` flag once per chunk of iterations.
 // This translation unit is compiled with -fmad=false: the PUCT / Q arithmetic must round exactly like the
 // reference's (and the oracle's) scalar C++ code.
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <memory>
@@ -132,6 +133,7 @@ class Search {
     std::vector<SearchResult> results;
     long long launches = 0;
     double last_go_ms = 0.0;
+    double movetime_ms = 0.0;  // > 0: stop issuing iterations once this much wall time has passed (UCI `go movetime`)
     // per-phase device times of the last go (CUDA events on the search stream), filled when profile is on
     bool profile = false;
     double select_ms = 0.0, net_ms = 0.0, apply_ms = 0.0;
@@ -380,11 +382,19 @@ int Search::go() {
     unsigned budget = sp.simulations ? sp.simulations : sp.nodes;
     int first = budget ? static_cast<int>(budget / (static_cast<unsigned>(B) * 1u)) : 8;
     if (first < 1) first = 1;
+    // movetime (ThreadManager's stop after curMovetime, manager/threadmanager.cpp): iterations go out in small chunks
+    // and the wall clock is read between them
+    const auto t_start = std::chrono::steady_clock::now();
+    const bool timed = movetime_ms > 0.0;
+    if (timed && first > 4) first = 4;
     bool all_done = false;
     int chunk = first;
     int guard = 0;
     bool polled_root = false;
     while (!all_done) {
+        if (timed && polled_root &&
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count() >= movetime_ms)
+            break;
         if (polled_root && iterate(chunk)) return -1;
         for (int i = 0; i < n_trees; ++i)
             ARA_CUDA_OK(cudaMemcpyAsync(&h_done_[i], &d_states_[i]->done, sizeof(int), cudaMemcpyDeviceToHost, stream_));
@@ -401,7 +411,7 @@ int Search::go() {
             }
             if (err) return set_error("ara_search_go: device search error %d (1 node pool, 2 edge pool, 3 depth > %d)", err, kMaxDepth);
         }
-        if (polled_root) chunk = 2;
+        if (polled_root) chunk = timed ? 4 : 2;
         polled_root = true;
         if (++guard > (1 << 22)) return set_error("ara_search_go: search did not terminate");
     }
@@ -484,6 +494,11 @@ extern "C" int ara_search_result(ara_search_t h, int tree, ara_search_result_t* 
     Search* s = reinterpret_cast<Search*>(h);
     if (tree < 0 || tree >= s->n_trees) return ara::set_error("ara_search_result: tree %d out of range", tree);
     memcpy(out, &s->results[tree], sizeof(*out));
+    return 0;
+}
+extern "C" int ara_search_set_movetime(ara_search_t h, double ms) {
+    if (h == nullptr) return ara::set_error("ara_search_set_movetime: null handle");
+    reinterpret_cast<Search*>(h)->movetime_ms = ms > 0.0 ? ms : 0.0;
     return 0;
 }
 extern "C" int ara_search_set_profile(ara_search_t h, int on) {

@@ -930,7 +930,10 @@ ARA_HD void create_mini_batch_impl(const TreeDev& t, const SearchParams& sp, War
         const NodeHdr& r = t.hdr[0];
         const uint32_t node_count = r.visit_sum - r.free_visits;
         const bool limits_ok = (sp.nodes == 0 || node_count < sp.nodes) && (sp.simulations == 0 || r.visit_sum < sp.simulations);
-        if (!(limits_ok && r.node_type == NT_UNSOLVED) || r.n_moves <= 1) {
+        // (a pool sized for a visit budget can never trip the last test before the budget does; it only ends
+        // time-limited searches whose pool is exhausted before their time)
+        const bool pool_ok = st.n_nodes + 3 * sp.batch_size + 8 <= t.max_nodes;
+        if (!(limits_ok && r.node_type == NT_UNSOLVED) || r.n_moves <= 1 || !pool_ok) {
             if (ARA_LANE == 0) st.done = 1, st.n_new = 0, st.n_coll = 0;
             return;
         }

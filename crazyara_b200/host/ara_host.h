@@ -100,6 +100,12 @@ class BoardState {
         return b;
     }
     int side_to_move() const { return ara_state_side_to_move(st_); }
+    // full-move counter of the position (last FEN field), the TimeManager's moveNumber
+    int move_number() const {
+        const std::string f = fen();
+        const size_t p = f.find_last_of(' ');
+        return p == std::string::npos ? 1 : std::max(1, atoi(f.c_str() + p + 1));
+    }
     bool is_chess960() const { return is960_; }
     TerminalType is_terminal() const { return static_cast<TerminalType>(ara_state_is_terminal(st_)); }
     // State::get_state_planes(normalize, inputPlanes, version): GPU plane-encode kernel through host buffers
@@ -181,6 +187,10 @@ class MCTSAgent {
         evalInfo.elapsedMs = ara_search_last_go_ms(search_);
     }
     const ara_search_result_t& last_result() const { return result_; }
+    // SearchLimits::movetime: the following searches also stop after `ms` of wall time (0 = off)
+    void set_movetime(double ms) {
+        if (ara_search_set_movetime(search_, ms) != 0) throw std::runtime_error(ara_last_error());
+    }
 
    private:
     SearchSettings settings_;

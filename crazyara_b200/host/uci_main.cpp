@@ -1,7 +1,9 @@
 // Minimal UCI front-end over the C++ host classes (engine/src/uci/crazyara.cpp:76-143 command loop, option names of
 // uci/optionsuci.cpp:66-220).  Supported: uci, isready, setoption, ucinewgame, position [startpos|fen] [moves ...],
-// go [nodes N] (or the Simulations / Nodes options), root, quit.  Time management (TimeManager / ThreadManager) is not
-// part of the hot path: the search always runs to its Simulations / Nodes limit.
+// go [nodes N | movetime T | wtime W btime B [winc I] [binc I] [movestogo M]] (or the Simulations / Nodes options),
+// root, quit.  The move time follows TimeManager::get_time_for_move (manager/timemanager.cpp:51-100) without its
+// random factor; the search then also stops after that much wall time (ara_search_set_movetime).
+#include <algorithm>
 #include <iomanip>
 #include <iostream>
 #include <map>
@@ -22,7 +24,8 @@ struct Options {
                                              {"Centi_Q_Value_Weight", "100"},  {"Centi_Q_Veto_Delta", "40"},
                                              {"MCTS_Solver", "true"},       {"Virtual_Style", "virtual_mix"},
                                              {"Virtual_Mix_Threshold", "1000"}, {"First_Device_ID", "0"},
-                                             {"UCI_Chess960", "false"},     {"Input_Version", "0"},    {"Dirichlet_Seed", "42"}};
+                                             {"UCI_Chess960", "false"},     {"Input_Version", "0"},    {"Dirichlet_Seed", "42"},
+                                             {"Move_Overhead", "20"},       {"Timed_Search_Nodes", "4000000"}};
     int i(const std::string& k) const { return std::stoi(kv.at(k)); }
     bool b(const std::string& k) const { return kv.at(k) == "true"; }
 };
@@ -35,6 +38,29 @@ int variant_id(const std::string& v) {
 }
 int mode_of_variant(int variant) { return variant == 0 ? 1 : (variant == 1 ? 0 : 2); }
 
+// TimeManager::get_time_for_move with the reference's constants (constants.h:94-98): expected game length 38,
+// proportional system from move 35 with 14 moves to go, increment factor 0.7, safety buffer 30 x overhead
+struct GoLimits {
+    long movetime = 0, time[2] = {0, 0}, inc[2] = {0, 0}, movestogo = 0;
+    bool any() const { return movetime || time[0] || time[1]; }
+};
+long time_for_move(const GoLimits& g, int me, int move_number, long overhead) {
+    const long safe = std::max(g.time[me] - overhead * 30, 1L);
+    auto constant = [&](long moves) { return safe / moves + static_cast<long>(0.7f * g.inc[me]); };
+    long t;
+    if (g.movetime != 0)
+        t = g.movetime;
+    else if (g.movestogo != 0)
+        t = constant(g.movestogo);
+    else if (g.time[me] != 0)
+        t = move_number < 35 ? constant(38 - move_number) : constant(14);
+    else
+        t = 1000;
+    t -= overhead;
+    if (t <= 0) t = overhead * 2;
+    return g.time[me] != 0 ? std::min(safe, t) : t;
+}
+
 }  // namespace
 
 int main() {
@@ -44,6 +70,7 @@ int main() {
     BoardState state;
     EvalInfo info;
     bool ready = false;
+    bool timed = false;  // the current agent was built for time-limited searches
     auto variant = [&]() { return variant_id(opt.kv["UCI_Variant"]); };
     auto new_game = [&]() { state.init(variant(), opt.b("UCI_Chess960")); };
     auto prepare = [&]() {  // CrazyAra::is_ready (crazyara.cpp:597): build net + agent from the options
@@ -69,7 +96,10 @@ int main() {
         net.reset();
         if (!opt.kv["Model_Path"].empty())
             net.reset(new NeuralNetAPI("gpu", opt.i("First_Device_ID"), static_cast<unsigned>(s.batch_size), opt.kv["Model_Path"]));
-        agent.reset(new MCTSAgent(net.get(), s, opt.i("First_Device_ID"), 0));
+        // a time-limited search has no visit budget to size the node pool from
+        const int pool = timed ? opt.i("Timed_Search_Nodes") : 0;
+        if (timed) s.simulations = 0, s.nodes = 0;
+        agent.reset(new MCTSAgent(net.get(), s, opt.i("First_Device_ID"), pool));
         ready = true;
     };
     new_game();
@@ -120,13 +150,39 @@ int main() {
                 }
             } else if (cmd == "go") {
                 std::string tok;
-                while (ss >> tok)
+                GoLimits lim;
+                while (ss >> tok) {
                     if (tok == "nodes") {
                         ss >> tok;
                         opt.kv["Nodes"] = tok;
                         ready = false;
+                    } else if (tok == "movetime") {
+                        ss >> lim.movetime;
+                    } else if (tok == "wtime") {
+                        ss >> lim.time[0];
+                    } else if (tok == "btime") {
+                        ss >> lim.time[1];
+                    } else if (tok == "winc") {
+                        ss >> lim.inc[0];
+                    } else if (tok == "binc") {
+                        ss >> lim.inc[1];
+                    } else if (tok == "movestogo") {
+                        ss >> lim.movestogo;
                     }
+                }
+                if (lim.any() != timed) {
+                    timed = lim.any();
+                    ready = false;
+                }
                 if (!ready) prepare();
+                if (timed) {
+                    const int me = state.side_to_move();
+                    const long ms = time_for_move(lim, me, state.move_number(), opt.i("Move_Overhead"));
+                    agent->set_movetime(static_cast<double>(ms));
+                    std::cout << "info string movetime " << ms << std::endl;
+                } else {
+                    agent->set_movetime(0.0);
+                }
                 agent->evaluate_board_state(state, info);
                 std::cout << "info depth " << info.depth << " nodes " << info.nodes << " nps " << info.calculate_nps() << " score cp "
                           << info.centipawns << " time " << static_cast<long>(info.elapsedMs) << " pv";

@@ -14,7 +14,9 @@ import time
 
 import numpy as np
 
-from .engine import BoardState, MCTSAgent, TERMINAL_NONE, default_settings
+from .engine import (BoardState, MCTSAgent, TERMINAL_DRAW, TERMINAL_LOSS, TERMINAL_NONE, TERMINAL_WIN, default_settings,
+                     encode_planes)
+from .export import BLACK_WIN, DRAWN, WHITE_WIN
 
 
 def rl_settings(mode, **kw):
@@ -27,7 +29,7 @@ def rl_settings(mode, **kw):
 
 class Arena:
     def __init__(self, net, settings, variant, n_games, device=0, is960=False, temperature=0.8, temperature_moves=15,
-                 max_plies=512, seed=0, max_nodes=0):
+                 max_plies=512, seed=0, max_nodes=0, exporter=None):
         self.variant, self.is960 = variant, is960
         self.n_games = n_games
         self.temperature, self.temperature_moves, self.max_plies = temperature, temperature_moves, max_plies
@@ -38,6 +40,10 @@ class Arena:
         self.finished = []  # (plies, terminal type, side to move at the end)
         self.nodes = 0
         self.search_ms = 0.0
+        # training-sample export (crazyara_b200.export.TrainDataExporter): one sample per searched position
+        self.exporter = exporter
+        self.settings = settings
+        self.records = [exporter.new_game() for _ in range(n_games)] if exporter is not None else None
 
     def _new_state(self):
         return BoardState().set("", self.is960, self.variant)
@@ -50,27 +56,45 @@ class Arena:
             return int(self.rng.choice(len(p), p=p))
         return int(res["best_idx"])
 
+    def _game_over(self, t, term, stm_at_end):
+        self.finished.append((self.plies[t], term, stm_at_end))
+        if self.exporter is not None:
+            # the side to move at the end lost (mate, variant loss) or won (variant win); everything else is a draw
+            if term == TERMINAL_LOSS:
+                result = BLACK_WIN if stm_at_end == 0 else WHITE_WIN
+            elif term == TERMINAL_WIN:
+                result = WHITE_WIN if stm_at_end == 0 else BLACK_WIN
+            else:
+                result = DRAWN
+            self.exporter.export_game_samples(self.records[t], result)
+            self.records[t] = self.exporter.new_game()
+        self.states[t], self.plies[t] = self._new_state(), 0
+
     def step(self):
         """One move in every running game."""
         for t, st in enumerate(self.states):
             self.agent.set_position(st, t)
         self.agent.evaluate_board_state()
         self.search_ms += self.agent.last_go_ms()
+        planes = None
+        if self.exporter is not None:  # un-normalised planes of every searched position, one GPU call
+            planes = encode_planes([st.board() for st in self.states], self.settings.mode, self.settings.input_version,
+                                   normalize=False)
         for t, st in enumerate(self.states):
             res = self.agent.result(t)
             self.nodes += int(res["nodes"])
             if len(res["moves"]) == 0:
-                term = st.is_terminal()
-                self.finished.append((self.plies[t], term, st.side_to_move()))
-                self.states[t], self.plies[t] = self._new_state(), 0
+                self._game_over(t, st.is_terminal(), st.side_to_move())
                 continue
             idx = self._pick(res, self.plies[t])
+            if self.exporter is not None:
+                self.exporter.save_sample(self.records[t], planes[t], res["moves"], res["policy"], res["q"][idx],
+                                          st.side_to_move())
             st.do_uci(res["moves"][idx])
             self.plies[t] += 1
             term = st.is_terminal()
             if term != TERMINAL_NONE or self.plies[t] >= self.max_plies:
-                self.finished.append((self.plies[t], term, st.side_to_move()))
-                self.states[t], self.plies[t] = self._new_state(), 0
+                self._game_over(t, term, st.side_to_move())
 
     def run(self, min_games=0, max_steps=1 << 30, max_seconds=1e30):
         t0 = time.perf_counter()

@@ -75,3 +75,54 @@ def export_blob(sd, arch, path, input_version=10):
             f.write(struct.pack("<q", t.size))
             f.write(t.tobytes())
     return path
+
+
+def arch_from_state_dict(sd):
+    """Reads the architecture off a RiseV3 state_dict (rise_mobile_v3.py:81-183): block count, operating channels,
+    depthwise kernel sizes, SE flavour per block, WDL head, input / policy channels."""
+    keys = set(sd.keys())
+    n_blocks = 0
+    while f"body_spatial.{n_blocks + 1}.body.0.weight" in keys:
+        n_blocks += 1
+    if n_blocks == 0:
+        raise ValueError("not a RiseV3 state_dict (no body_spatial.1.body.0.weight)")
+    kernels, se_types, c_ops = [], [], []
+    for i in range(1, n_blocks + 1):
+        p = f"body_spatial.{i}"
+        dw = sd[p + ".body.3.weight"]
+        c_ops.append(int(dw.shape[0]))
+        kernels.append(int(dw.shape[-1]))
+        if p + ".se.fc.0.weight" in keys:
+            se_types.append("ca_se")
+        elif p + ".se.body.0.weight" in keys:
+            se_types.append("eca_se")
+        else:
+            se_types.append(None)
+    stem = sd["body_spatial.0.body.0.weight"]
+    return dict(name=f"rise_{n_blocks}b", in_channels=int(stem.shape[1]), policy_channels=int(sd["policy_head.body.3.weight"].shape[0]),
+                channels=int(stem.shape[0]), kernels=kernels, se_types=se_types, c_ops=c_ops,
+                wdl="value_head.body_wdl.0.weight" in keys, value_channels=int(sd["value_head.body.0.weight"].shape[0]),
+                value_fc=256)
+
+
+def import_checkpoint(checkpoint_path, blob_path, input_version=None):
+    """Reference trainer checkpoint (`torch.save({'model_state_dict': ...})`, trainer_agent_pytorch.py:506-516; a bare
+    state_dict is accepted too) -> ARAB2001 blob.  input_version defaults from the input channel count
+    (34/63 -> 1.0, 51 -> 2.0, 52/64/80 -> 3.0)."""
+    import torch
+    ck = torch.load(checkpoint_path, map_location="cpu", weights_only=False)
+    sd = ck.get("model_state_dict", ck) if isinstance(ck, dict) else ck
+    sd = {k[7:] if k.startswith("module.") else k: v for k, v in sd.items()}  # DataParallel prefix
+    arch = arch_from_state_dict(sd)
+    if input_version is None:
+        input_version = {34: 10, 63: 10, 39: 10, 51: 20, 52: 30, 64: 30, 80: 30}.get(arch["in_channels"], 10)
+    export_blob(sd, arch, blob_path, input_version=input_version)
+    return arch
+
+
+if __name__ == "__main__":
+    import sys
+    if len(sys.argv) < 3:
+        raise SystemExit("usage: python -m crazyara_b200.weights <checkpoint.tar|state_dict.pt> <out.arab> [input_version]")
+    a = import_checkpoint(sys.argv[1], sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else None)
+    print(f"{sys.argv[2]}: {len(a['kernels'])} blocks, {a['in_channels']} -> {a['policy_channels']}x64, wdl={a['wdl']}")

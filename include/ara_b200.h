@@ -157,6 +157,9 @@ int ara_search_set_position(ara_search_t s, int tree, const ara_board_t* root, c
 int ara_search_go(ara_search_t s);
 int ara_search_result(ara_search_t s, int tree, ara_search_result_t* out);
 /* per-phase device times of the last go (CUDA events on the search stream); enable before ara_search_go */
+/* ThreadManager's time stop (manager/threadmanager.cpp, SearchLimits::movetime): ms > 0 makes the following go calls
+ * stop issuing mini-batches once that much wall time has passed (besides the Simulations / Nodes limits); 0 = off */
+int ara_search_set_movetime(ara_search_t s, double ms);
 int ara_search_set_profile(ara_search_t s, int on);
 int ara_search_profile(ara_search_t s, double* select_ms, double* net_ms, double* apply_ms, long long* net_forwards);
 /* SM-clock cycles per phase of the select kernel in the last go (0 descent, 1 do_move, 2 movegen, 3 node init,

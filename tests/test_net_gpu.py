@@ -68,3 +68,45 @@ def test_net_create_fails_loudly_on_bad_blob(tmp_path):
         NeuralNetAPI("gpu", 0, 8, str(p))
     with pytest.raises(AraError):
         NeuralNetAPI("gpu", 0, 8, str(tmp_path / "missing.arab"))
+
+
+@pytest.mark.gpu
+def test_net_output_of_a_position_does_not_depend_on_its_batch(tmp_path):
+    """The search relies on this: a leaf's value / policy are the same bits whichever mini-batch evaluates it."""
+    arch = onet.arch_risev2(34, 81)
+    x = golden_input(arch, n=64, seed=9)
+    net64, _ = _make_net(tmp_path, arch, 64, 10)
+    v64, p64 = np.zeros(64, np.float32), np.zeros((64, 81 * 64), np.float32)
+    net64.predict(x, v64, p64, None, n=64)
+    net64.close()
+    net3, _ = _make_net(tmp_path, arch, 3, 10)
+    for src in (0, 37, 63):
+        xin = np.zeros((3, 34, 8, 8), np.float32)
+        xin[1] = x[src]
+        xin[0] = x[(src + 5) % 64]
+        v, p = np.zeros(3, np.float32), np.zeros((3, 81 * 64), np.float32)
+        net3.predict(xin, v, p, None, n=2)
+        assert v[1] == v64[src] and np.array_equal(p[1], p64[src])
+    net3.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,cin,pch", [("risev2", 34, 81), ("risev33", 52, 76)])
+def test_tower_implementations_agree(tmp_path, monkeypatch, name, cin, pch):
+    """Persistent tower kernel (default) vs one kernel per block vs per-layer launches: same network, fp16 tolerance."""
+    arch = onet.arch_risev2(cin, pch) if name == "risev2" else onet.arch_risev33(cin, pch, True)
+    x = golden_input(arch, n=6, seed=3)
+    outs = []
+    for env in ({}, {"ARA_TRUNK": "0"}, {"ARA_FUSED_BLOCKS": "1"}):
+        for k in ("ARA_TRUNK", "ARA_FUSED_BLOCKS"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        net, _ = _make_net(tmp_path, arch, 6, 10 if name == "risev2" else 30)
+        v, p = np.zeros(6, np.float32), np.zeros((6, pch * 64), np.float32)
+        net.predict(x, v, p, None, n=6)
+        net.close()
+        outs.append((v, p))
+    for v, p in outs[1:]:
+        np.testing.assert_allclose(v, outs[0][0], atol=2 * VALUE_ATOL)
+        np.testing.assert_allclose(p, outs[0][1], rtol=2 * PROB_RTOL, atol=1e-6)

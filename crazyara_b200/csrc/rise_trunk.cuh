@@ -119,7 +119,52 @@ __device__ __forceinline__ void rt_depthwise(const uint8_t* sH1, const uint8_t* 
     }
 }
 
+// the same for the 4 channels `sub` of group g (one-board variant: the work of a chunk is spread over all 16 warps)
+template <int K>
+__device__ __forceinline__ void rt_depthwise4(const uint8_t* sH1, const uint8_t* aux, int g, int sub, int y0, int x,
+                                              uint2 (&out)[2]) {
+    constexpr int R = K / 2, NR = 2 + 2 * R;
+    const float4 b0 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(aux + 256) + g * 8 + sub * 4);
+    const uint8_t* wd = aux + 512 + g * 16 + sub * 8;
+    float acc[2][4];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) acc[j][0] = b0.x, acc[j][1] = b0.y, acc[j][2] = b0.z, acc[j][3] = b0.w;
+    const uint8_t* base = sH1 + g * 1024 + sub * 8;  // 64 rows of 16 bytes per channel group
+#pragma unroll
+    for (int dxi = 0; dxi < K; ++dxi) {
+        const int xx = x + dxi - R;
+        if (xx < 0 || xx > 7) continue;
+        uint2 in[NR];
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            const int yy = y0 - R + i;
+            in[i] = make_uint2(0u, 0u);
+            if (yy >= 0 && yy <= 7) in[i] = *reinterpret_cast<const uint2*>(base + ((yy * 8 + xx) << 4));
+        }
+#pragma unroll
+        for (int dyi = 0; dyi < K; ++dyi) {
+            const uint2 w = *reinterpret_cast<const uint2*>(wd + (dyi * K + dxi) * 128);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                fhfma2(acc[j][0], acc[j][1], in[j + dyi].x, w.x);
+                fhfma2(acc[j][2], acc[j][3], in[j + dyi].y, w.y);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        out[j].x = rt_pack(fmaxf(acc[j][0], 0.0f), fmaxf(acc[j][1], 0.0f));
+        out[j].y = rt_pack(fmaxf(acc[j][2], 0.0f), fmaxf(acc[j][3], 0.0f));
+    }
+}
+
+// kRows = 128: a CTA owns two boards (UMMA M = 128, all 128 TMEM lanes).  kRows = 64: one board per CTA (UMMA M = 64,
+// whose rows live in lanes 0..15 of each 32-lane quadrant: row r <-> lane 32 (r / 16) + r % 16), used while the batch
+// has fewer boards than the GPU has SMs -- twice as many SMs work on the same batch, each CTA's CUDA-core stages
+// handle half the rows.
+template <int kRows>
 __global__ void __launch_bounds__(kRtThreads, 1) rise_trunk_kernel(const __grid_constant__ TrunkArgs args) {
+    constexpr bool kHalf = kRows == 64;
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
     extern __shared__ uint8_t smem_raw[];
     // 1 KB alignment by offset arithmetic on the shared array itself: a pointer -> integer -> pointer round trip would
@@ -207,8 +252,8 @@ __global__ void __launch_bounds__(kRtThreads, 1) rise_trunk_kernel(const __grid_
         }
     } else if (warp == 1) {
         // ---------------------------------------------------------------- MMA issuer
-        constexpr uint32_t idesc1 = umma_idesc_f16(128, 64, 0);
-        constexpr uint32_t idesc2 = umma_idesc_f16(128, 256, 0);
+        constexpr uint32_t idesc1 = umma_idesc_f16(kRows, 64, 0);
+        constexpr uint32_t idesc2 = umma_idesc_f16(kRows, 256, 0);
         const uint32_t aW1 = smem_u32(sW1), aW2 = smem_u32(sW2), aH2 = smem_u32(sH2);
         uint32_t gc = 0;
         RT_PROF_DECL();
@@ -268,18 +313,21 @@ __global__ void __launch_bounds__(kRtThreads, 1) rise_trunk_kernel(const __grid_
         const int cw = warp - 2;        // 0..15
         const int grp = warp & 3;       // TMEM lane group this warp may access
         const int cq = cw >> 2;         // column quarter (64 channels) handled by this thread in the TMEM accesses
-        const int r = grp * 32 + lane;  // row of the 128-row tile (TMEM lane)
+        // row of the tile held by this thread's TMEM lane (one-board variant: only lanes 0..15 of a quadrant hold rows)
+        const bool valid = !kHalf || lane < 16;
+        const int r = kHalf ? grp * 16 + (lane & 15) : grp * 32 + lane;
         const int tid = cw * 32 + lane; // 0..511
         const uint32_t lane_addr = static_cast<uint32_t>(grp * 32) << 16;
         const uint32_t x_addr = tmem_base + lane_addr + kRtColX + cq * 32;
         // depthwise role: two warps per 8-channel group (one per board), lane = (row pair, column)
+        // (one-board variant: two warps per 8-channel group, 4 channels each)
         const int dg = cw >> 1, db = cw & 1, dy0 = (lane >> 3) * 2, dx = lane & 7;
-        const int m = m_tile * 128 + r;
+        const int m = m_tile * kRows + r;
         uint32_t gc = 0;
         RT_PROF_DECL();
         {   // stem output -> tensor memory (fp16 pairs are already in the packed order the tensor core expects)
             uint32_t xv[32];
-            if (m < args.M) {
+            if (valid && m < args.M) {
                 const uint4* src = reinterpret_cast<const uint4*>(args.x_in + static_cast<size_t>(m) * 256 + cq * 64);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -302,39 +350,60 @@ __global__ void __launch_bounds__(kRtThreads, 1) rise_trunk_kernel(const __grid_
             if (tid < 256) sB2[tid] = __ldg(B.b2 + tid);
             if (B.se_type != 0) {
                 // squeeze-excitation on the block input, in place (arithmetic of se_kernel, net_kernels.cuh)
-                float* sPoolPart = reinterpret_cast<float*>(sH1);  // [4 row groups][256]
-                float* sPool = sPoolPart + 1024;                    // [2][256]
-                float* sPart = sPool + 512;                         // partial sums: [4][2][128] or [2][2][256]
-                float* sHid = sPart + 1024;                         // [2][128]
+                // Pooling order (identical in both kernel variants, so that a position's outputs do not depend on which
+                // one evaluates it): 16-row sums by a lane butterfly inside each half warp, then ((s0+s1)+(s2+s3)) over
+                // the four 16-row groups of a board.
+                float* sPoolPart = reinterpret_cast<float*>(sH1);  // [8 groups of 16 rows][256]; dead once sPool exists
+                float* sPart = sPoolPart;                           // partial sums: [4][2][128] or [2][2][256]
+                float* sPool = sPoolPart + 2048;                    // [2][256]
+                float* sHid = sPool + 512;                          // [2][128]
                 float* sScale = sHid + 256;                         // [2][256]
                 const int bb = tid >> 8, c = tid & 255;
                 uint32_t xv[32];
                 tmem_ld_32x32b_x32(x_addr, xv);
                 tmem_ld_wait();
                 rt_bar_sync(1);  // H1 (aliased by the scratch above) is no longer read by the previous block
+                {
+                    // tile rows of this half warp: two-board variant 32 grp + 16 (lane / 16) .., one-board 16 grp ..
+                    const int q16 = kHalf ? grp : 2 * grp + (lane >> 4);
 #pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    // column sums over the warp's 32 rows: butterfly that halves the value count at every step
-                    float vals[32];
+                    for (int hh = 0; hh < 2; ++hh) {
+                        float vals[32];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float2 f = rt_unpack(xv[hh * 16 + i]);
-                        vals[2 * i] = f.x, vals[2 * i + 1] = f.y;
-                    }
+                        for (int i = 0; i < 16; ++i) {
+                            const float2 f = rt_unpack(xv[hh * 16 + i]);
+                            vals[2 * i] = valid ? f.x : 0.0f, vals[2 * i + 1] = valid ? f.y : 0.0f;
+                        }
+                        // butterfly over the 16 lanes of the half warp: the value count halves at every step, lane l
+                        // ends up with the sums of channels 2 (l % 16) and 2 (l % 16) + 1
 #pragma unroll
-                    for (int off = 16, n = 16; off >= 1; off >>= 1, n >>= 1) {
-                        const bool upper = (lane & off) != 0;
+                        for (int off = 8, n = 16; off >= 1; off >>= 1, n >>= 1) {
+                            const bool upper = (lane & off) != 0;
 #pragma unroll
-                        for (int i = 0; i < n; ++i) {
-                            const float send = upper ? vals[i] : vals[i + n];
-                            const float keep = upper ? vals[i + n] : vals[i];
-                            vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                            for (int i = 0; i < n; ++i) {
+                                const float send = upper ? vals[i] : vals[i + n];
+                                const float keep = upper ? vals[i + n] : vals[i];
+                                vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                            }
+                        }
+                        if (valid) {
+                            // channel bits 4..1 come from lane bits 3..0 (bit 3 decided first), bit 0 is the value index
+                            const int l = lane & 15;
+                            const int ch = ((l >> 3) & 1) * 16 + ((l >> 2) & 1) * 8 + ((l >> 1) & 1) * 4 + (l & 1) * 2;
+                            float* dst = sPoolPart + q16 * 256 + cq * 64 + hh * 32 + ch;
+                            dst[0] = vals[0];
+                            dst[1] = vals[1];
                         }
                     }
-                    sPoolPart[grp * 256 + cq * 64 + hh * 32 + lane] = vals[0];
                 }
                 rt_bar_sync(2);
-                sPool[bb * 256 + c] = (sPoolPart[(2 * bb) * 256 + c] + sPoolPart[(2 * bb + 1) * 256 + c]) * (1.0f / 64.0f);
+                {
+                    const float* pp = sPoolPart + (kHalf ? 0 : bb * 1024) + c;
+                    const float sum = (pp[0] + pp[256]) + (pp[512] + pp[768]);
+                    const float pooled = (kHalf && bb) ? 0.0f : sum * (1.0f / 64.0f);  // one-board variant: board 1 is idle
+                    rt_bar_sync(1);  // sPart (the FC scratch) aliases sPoolPart
+                    sPool[bb * 256 + c] = pooled;
+                }
                 rt_bar_sync(1);
                 // every weight is loaded once (fp16) and used for both boards; K is split over the thread groups and
                 // the partial sums meet in shared memory
@@ -406,7 +475,7 @@ __global__ void __launch_bounds__(kRtThreads, 1) rise_trunk_kernel(const __grid_
                 }
                 rt_bar_sync(1);
                 {
-                    const float* sc = sScale + (r >> 6) * 256 + cq * 64;
+                    const float* sc = sScale + (kHalf ? 0 : (r >> 6) * 256) + cq * 64;
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         const float2 f = rt_unpack(xv[i]);
@@ -449,17 +518,25 @@ __global__ void __launch_bounds__(kRtThreads, 1) rise_trunk_kernel(const __grid_
                     o.y = rt_pack(fmaxf(__uint_as_float(v[q * 8 + 2]) + ba.z, 0.0f), fmaxf(__uint_as_float(v[q * 8 + 3]) + ba.w, 0.0f));
                     o.z = rt_pack(fmaxf(__uint_as_float(v[q * 8 + 4]) + bb.x, 0.0f), fmaxf(__uint_as_float(v[q * 8 + 5]) + bb.y, 0.0f));
                     o.w = rt_pack(fmaxf(__uint_as_float(v[q * 8 + 6]) + bb.z, 0.0f), fmaxf(__uint_as_float(v[q * 8 + 7]) + bb.w, 0.0f));
-                    *reinterpret_cast<uint4*>(sH1 + (cq * 2 + q) * 2048 + r * 16) = o;
+                    if (valid) *reinterpret_cast<uint4*>(sH1 + (cq * 2 + q) * (kRows * 16) + r * 16) = o;
                 }
                 RT_PROF(6);  // H1 write
                 rt_bar_sync(2);  // H1 complete
                 RT_PROF(7);
                 // ---- depthwise k x k
                 uint4 o2[2];
-                if (B.ksize == 3)
-                    rt_depthwise<3>(sH1, aux, dg, db, dy0, dx, o2);
-                else
-                    rt_depthwise<5>(sH1, aux, dg, db, dy0, dx, o2);
+                uint2 o2h[2];
+                if (kHalf) {
+                    if (B.ksize == 3)
+                        rt_depthwise4<3>(sH1, aux, dg, db, dy0, dx, o2h);
+                    else
+                        rt_depthwise4<5>(sH1, aux, dg, db, dy0, dx, o2h);
+                } else {
+                    if (B.ksize == 3)
+                        rt_depthwise<3>(sH1, aux, dg, db, dy0, dx, o2);
+                    else
+                        rt_depthwise<5>(sH1, aux, dg, db, dy0, dx, o2);
+                }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&w1_empty[slot]);  // this warp is done with the chunk vectors
                 RT_PROF(8);  // depthwise
@@ -468,8 +545,13 @@ __global__ void __launch_bounds__(kRtThreads, 1) rise_trunk_kernel(const __grid_
                 RT_PROF(9);  // wait for a free H2 buffer
 #pragma unroll
                 for (int jj = 0; jj < 2; ++jj) {
-                    const int rr = db * 64 + (dy0 + jj) * 8 + dx;
-                    *reinterpret_cast<uint4*>(sH2 + s * 16384 + rr * 128 + ((dg ^ (rr & 7)) << 4)) = o2[jj];
+                    if (kHalf) {
+                        const int rr = (dy0 + jj) * 8 + dx;
+                        *reinterpret_cast<uint2*>(sH2 + s * 16384 + rr * 128 + ((dg ^ (rr & 7)) << 4) + db * 8) = o2h[jj];
+                    } else {
+                        const int rr = db * 64 + (dy0 + jj) * 8 + dx;
+                        *reinterpret_cast<uint4*>(sH2 + s * 16384 + rr * 128 + ((dg ^ (rr & 7)) << 4)) = o2[jj];
+                    }
                 }
                 rt_fence_proxy_async();
                 __syncwarp();
@@ -499,7 +581,7 @@ __global__ void __launch_bounds__(kRtThreads, 1) rise_trunk_kernel(const __grid_
                 if (!last) {
                     tmem_st_32x32b_x32(x_addr, xv);
                     tmem_st_wait();
-                } else if (m < args.M) {
+                } else if (valid && m < args.M) {
                     uint4* dst = reinterpret_cast<uint4*>(args.out + static_cast<size_t>(m) * 256 + cq * 64);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) dst[i] = make_uint4(xv[i * 4], xv[i * 4 + 1], xv[i * 4 + 2], xv[i * 4 + 3]);

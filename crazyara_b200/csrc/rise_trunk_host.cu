@@ -1,5 +1,6 @@
 #include "rise_trunk_host.h"
 
+#include <cstdlib>
 #include <cstring>
 
 #include "rise_trunk.cuh"
@@ -87,14 +88,28 @@ int rise_trunk_init(RiseTrunk* T, const std::vector<TrunkBlockHost>& blocks, con
     ARA_CUDA_OK(cudaMalloc(&T->d_prof, 32 * sizeof(unsigned long long)));
     ARA_CUDA_OK(cudaMemset(T->d_prof, 0, 32 * sizeof(unsigned long long)));
     T->args.prof = static_cast<unsigned long long*>(T->d_prof);
-    ARA_CUDA_OK(cudaFuncSetAttribute(rise_trunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRtSmemBytes));
+    ARA_CUDA_OK(cudaFuncSetAttribute(rise_trunk_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRtSmemBytes));
+    ARA_CUDA_OK(cudaFuncSetAttribute(rise_trunk_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRtSmemBytes));
+    {
+        int dev = 0;
+        cudaDeviceProp prop;
+        ARA_CUDA_OK(cudaGetDevice(&dev));
+        ARA_CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+        T->sm_count = prop.multiProcessorCount;
+    }
     return 0;
 }
 
 int rise_trunk_launch(const RiseTrunk* T, int boards, cudaStream_t stream) {
     TrunkArgs a = T->args;
     a.M = boards * 64;
-    ARA_CUDA_OK(launch_pdl(rise_trunk_kernel, dim3((boards + 1) / 2), dim3(kRtThreads), kRtSmemBytes, stream, a));
+    // one board per CTA while that still fits the GPU in one wave (twice the SMs on a small batch), else two
+    const char* force = getenv("ARA_TRUNK_ROWS");
+    const bool one_board = force ? atoi(force) == 64 : boards <= T->sm_count;
+    if (one_board)
+        ARA_CUDA_OK(launch_pdl(rise_trunk_kernel<64>, dim3(boards), dim3(kRtThreads), kRtSmemBytes, stream, a));
+    else
+        ARA_CUDA_OK(launch_pdl(rise_trunk_kernel<128>, dim3((boards + 1) / 2), dim3(kRtThreads), kRtSmemBytes, stream, a));
     return 0;
 }
 

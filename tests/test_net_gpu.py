@@ -97,8 +97,9 @@ def test_tower_implementations_agree(tmp_path, monkeypatch, name, cin, pch):
     arch = onet.arch_risev2(cin, pch) if name == "risev2" else onet.arch_risev33(cin, pch, True)
     x = golden_input(arch, n=6, seed=3)
     outs = []
-    for env in ({}, {"ARA_TRUNK": "0"}, {"ARA_FUSED_BLOCKS": "1"}):
-        for k in ("ARA_TRUNK", "ARA_FUSED_BLOCKS"):
+    # default = tower kernel, one board per CTA at this batch size; then two boards per CTA; then the older forms
+    for env in ({}, {"ARA_TRUNK_ROWS": "128"}, {"ARA_TRUNK": "0"}, {"ARA_FUSED_BLOCKS": "1"}):
+        for k in ("ARA_TRUNK", "ARA_FUSED_BLOCKS", "ARA_TRUNK_ROWS"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -110,3 +111,21 @@ def test_tower_implementations_agree(tmp_path, monkeypatch, name, cin, pch):
     for v, p in outs[1:]:
         np.testing.assert_allclose(v, outs[0][0], atol=2 * VALUE_ATOL)
         np.testing.assert_allclose(p, outs[0][1], rtol=2 * PROB_RTOL, atol=1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,cin,pch", [("risev2", 34, 81), ("risev33", 52, 76)])
+def test_tower_variants_are_bit_identical(tmp_path, monkeypatch, name, cin, pch):
+    """One board per CTA (small batches) and two boards per CTA (large batches) must give the same bits: a search with
+    many trees evaluates the same positions in bigger batches than a single-tree search."""
+    arch = onet.arch_risev2(cin, pch) if name == "risev2" else onet.arch_risev33(cin, pch, True)
+    x = golden_input(arch, n=5, seed=11)
+    outs = []
+    for rows in ("64", "128"):
+        monkeypatch.setenv("ARA_TRUNK_ROWS", rows)
+        net, _ = _make_net(tmp_path, arch, 5, 10 if name == "risev2" else 30)
+        v, p = np.zeros(5, np.float32), np.zeros((5, pch * 64), np.float32)
+        net.predict(x, v, p, None, n=5)
+        net.close()
+        outs.append((v, p))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])

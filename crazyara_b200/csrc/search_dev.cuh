@@ -1103,24 +1103,28 @@ ARA_HD void backup_results(const TreeDev& t, const SearchParams& sp) {
         uint32_t c_e = 0xffffffffu, c_n = 0;
         float c_q = 0.0f;
         uint8_t c_vl = 0;
-        int len_n = n_new > 0 ? t.traj_len[0] : 0;
-        float leaf_n = n_new > 0 ? t.new_value[0] : 0.0f;
-        int nid_n = -1;
-        uint32_t e_n = 0;
-        if (d < len_n) nid_n = t.traj_node[d], e_n = t.traj_edge[d];
+        // two-deep pipeline: the indices of trajectory b+2 are requested while b is processed (unconditionally: the
+        // trajectory arrays are dense, entries beyond a trajectory's length are simply not used), the lines of b+1 are
+        // prefetched with indices that arrived an iteration ago
+        const int dd = d < kMaxDepth ? d : kMaxDepth - 1;
+        int len_n = n_new > 0 ? t.traj_len[0] : 0, len_nn = n_new > 1 ? t.traj_len[1] : 0;
+        float leaf_n = n_new > 0 ? t.new_value[0] : 0.0f, leaf_nn = n_new > 1 ? t.new_value[1] : 0.0f;
+        int nid_n = n_new > 0 ? t.traj_node[dd] : -1, nid_nn = n_new > 1 ? t.traj_node[kMaxDepth + dd] : -1;
+        uint32_t e_n = n_new > 0 ? t.traj_edge[dd] : 0, e_nn = n_new > 1 ? t.traj_edge[kMaxDepth + dd] : 0;
         for (int b = 0; b < n_new; ++b) {
             const int len = len_n, nid = nid_n;
             const uint32_t e = e_n;
             const float leaf_v = leaf_n;
-            if (b + 1 < n_new) {  // indices of the next trajectory + prefetch of its lines
-                len_n = t.traj_len[b + 1];
-                leaf_n = t.new_value[b + 1];
-                if (d < len_n) {
-                    nid_n = t.traj_node[(b + 1) * kMaxDepth + d];
-                    e_n = t.traj_edge[(b + 1) * kMaxDepth + d];
-                    if (nid_n != nid) prefetch_line(&t.hdr[nid_n]);
-                    if (e_n != e) prefetch_line(&t.Q[e_n]), prefetch_line(&t.N[e_n]), prefetch_line(&t.vl[e_n]);
-                }
+            len_n = len_nn, leaf_n = leaf_nn, nid_n = nid_nn, e_n = e_nn;
+            if (b + 2 < n_new) {
+                len_nn = t.traj_len[b + 2];
+                leaf_nn = t.new_value[b + 2];
+                nid_nn = t.traj_node[(b + 2) * kMaxDepth + dd];
+                e_nn = t.traj_edge[(b + 2) * kMaxDepth + dd];
+            }
+            if (b + 1 < n_new && d < len_n) {
+                if (nid_n != nid) prefetch_line(&t.hdr[nid_n]);
+                if (e_n != e) prefetch_line(&t.Q[e_n]), prefetch_line(&t.N[e_n]), prefetch_line(&t.vl[e_n]);
             }
             if (d >= len) continue;
             const float v = ((len - d) & 1) ? -leaf_v : leaf_v;

@@ -407,71 +407,82 @@ __global__ void __launch_bounds__(kRtThreads, 1) rise_trunk_kernel(const __grid_
                 rt_bar_sync(1);
                 // every weight is loaded once (fp16) and used for both boards; K is split over the thread groups and
                 // the partial sums meet in shared memory
+                // (half2 loads: two adjacent outputs per thread, 128 contiguous bytes per warp request)
                 if (B.se_type == 1) {
-                    {   // fc1 (256 -> 128): 4 K-quarters x 128 outputs
-                        const int kq = tid >> 7, j = tid & 127;
-                        const __half* w = B.se_w1t + (kq * 64) * 128 + j;
-                        const float* p0 = sPool + kq * 64;
-                        const float* p1 = sPool + 256 + kq * 64;
-                        float a0 = 0.0f, a1 = 0.0f, c0 = 0.0f, c1 = 0.0f;
+                    {   // fc1 (256 -> 128): 8 K-groups of 32 x 64 output pairs
+                        const int kg = tid >> 6, jp = tid & 63;
+                        const __half2* w = reinterpret_cast<const __half2*>(B.se_w1t + (kg * 32) * 128) + jp;
+                        const float* p0 = sPool + kg * 32;
+                        const float* p1 = sPool + 256 + kg * 32;
+                        float a0 = 0.0f, a1 = 0.0f, c0 = 0.0f, c1 = 0.0f;  // (output 2jp, 2jp+1) x (board 0, 1)
 #pragma unroll 8
-                        for (int k = 0; k < 64; k += 2) {
-                            const float w0 = __half2float(__ldg(w + k * 128)), w1 = __half2float(__ldg(w + (k + 1) * 128));
-                            a0 = fmaf(w0, p0[k], a0);
-                            a1 = fmaf(w0, p1[k], a1);
-                            c0 = fmaf(w1, p0[k + 1], c0);
-                            c1 = fmaf(w1, p1[k + 1], c1);
+                        for (int k = 0; k < 32; ++k) {
+                            const float2 wf = __half22float2(__ldg(w + k * 64));
+                            a0 = fmaf(wf.x, p0[k], a0);
+                            a1 = fmaf(wf.x, p1[k], a1);
+                            c0 = fmaf(wf.y, p0[k], c0);
+                            c1 = fmaf(wf.y, p1[k], c1);
                         }
-                        sPart[(kq * 2 + 0) * 128 + j] = a0 + c0;
-                        sPart[(kq * 2 + 1) * 128 + j] = a1 + c1;
+                        sPart[(kg * 2 + 0) * 128 + 2 * jp] = a0;
+                        sPart[(kg * 2 + 1) * 128 + 2 * jp] = a1;
+                        sPart[(kg * 2 + 0) * 128 + 2 * jp + 1] = c0;
+                        sPart[(kg * 2 + 1) * 128 + 2 * jp + 1] = c1;
                     }
                     rt_bar_sync(2);
                     if (tid < 256) {
-                        const int b1 = tid >> 7, j = tid & 127;
-                        sHid[tid] = fmaxf((sPart[(0 + b1) * 128 + j] + sPart[(2 + b1) * 128 + j]) +
-                                              (sPart[(4 + b1) * 128 + j] + sPart[(6 + b1) * 128 + j]), 0.0f);
+                        const float* q = sPart + (tid >> 7) * 128 + (tid & 127);
+                        sHid[tid] = fmaxf(((q[0] + q[256]) + (q[512] + q[768])) + ((q[1024] + q[1280]) + (q[1536] + q[1792])), 0.0f);
                     }
                     rt_bar_sync(1);
-                    {   // fc2 (128 -> 256): 2 K-halves x 256 outputs
-                        const int jh = tid >> 8;
-                        const __half* w = B.se_w2t + (jh * 64) * 256 + c;
-                        const float* h0 = sHid + jh * 64;
-                        const float* h1 = sHid + 128 + jh * 64;
+                    {   // fc2 (128 -> 256): 4 K-groups of 32 x 128 output pairs
+                        const int kg = tid >> 7, cp = tid & 127;
+                        const __half2* w = reinterpret_cast<const __half2*>(B.se_w2t + (kg * 32) * 256) + cp;
+                        const float* h0 = sHid + kg * 32;
+                        const float* h1 = sHid + 128 + kg * 32;
                         float a0 = 0.0f, a1 = 0.0f, c0 = 0.0f, c1 = 0.0f;
 #pragma unroll 8
-                        for (int j = 0; j < 64; j += 2) {
-                            const float w0 = __half2float(__ldg(w + j * 256)), w1 = __half2float(__ldg(w + (j + 1) * 256));
-                            a0 = fmaf(w0, h0[j], a0);
-                            a1 = fmaf(w0, h1[j], a1);
-                            c0 = fmaf(w1, h0[j + 1], c0);
-                            c1 = fmaf(w1, h1[j + 1], c1);
+                        for (int j = 0; j < 32; ++j) {
+                            const float2 wf = __half22float2(__ldg(w + j * 128));
+                            a0 = fmaf(wf.x, h0[j], a0);
+                            a1 = fmaf(wf.x, h1[j], a1);
+                            c0 = fmaf(wf.y, h0[j], c0);
+                            c1 = fmaf(wf.y, h1[j], c1);
                         }
-                        sPart[(jh * 2 + 0) * 256 + c] = a0 + c0;
-                        sPart[(jh * 2 + 1) * 256 + c] = a1 + c1;
+                        sPart[(kg * 2 + 0) * 256 + 2 * cp] = a0;
+                        sPart[(kg * 2 + 1) * 256 + 2 * cp] = a1;
+                        sPart[(kg * 2 + 0) * 256 + 2 * cp + 1] = c0;
+                        sPart[(kg * 2 + 1) * 256 + 2 * cp + 1] = c1;
                     }
                     rt_bar_sync(2);
-                    sScale[bb * 256 + c] = rt_hard_sigmoid(sPart[bb * 256 + c] + sPart[(2 + bb) * 256 + c]);
+                    {
+                        const float* q = sPart + bb * 256 + c;
+                        sScale[bb * 256 + c] = rt_hard_sigmoid((q[0] + q[512]) + (q[1024] + q[1536]));
+                    }
                 } else {
-                    {   // 256 -> 256: 2 K-halves x 256 outputs
-                        const int kh = tid >> 8;
-                        const __half* w = B.se_w1t + (kh * 128) * 256 + c;
-                        const float* p0 = sPool + kh * 128;
-                        const float* p1 = sPool + 256 + kh * 128;
+                    {   // 256 -> 256: 4 K-groups of 64 x 128 output pairs
+                        const int kg = tid >> 7, cp = tid & 127;
+                        const __half2* w = reinterpret_cast<const __half2*>(B.se_w1t + (kg * 64) * 256) + cp;
+                        const float* p0 = sPool + kg * 64;
+                        const float* p1 = sPool + 256 + kg * 64;
                         float a0 = 0.0f, a1 = 0.0f, c0 = 0.0f, c1 = 0.0f;
 #pragma unroll 8
-                        for (int k = 0; k < 128; k += 2) {
-                            const float w0 = __half2float(__ldg(w + k * 256)), w1 = __half2float(__ldg(w + (k + 1) * 256));
-                            a0 = fmaf(w0, p0[k], a0);
-                            a1 = fmaf(w0, p1[k], a1);
-                            c0 = fmaf(w1, p0[k + 1], c0);
-                            c1 = fmaf(w1, p1[k + 1], c1);
+                        for (int k = 0; k < 64; ++k) {
+                            const float2 wf = __half22float2(__ldg(w + k * 128));
+                            a0 = fmaf(wf.x, p0[k], a0);
+                            a1 = fmaf(wf.x, p1[k], a1);
+                            c0 = fmaf(wf.y, p0[k], c0);
+                            c1 = fmaf(wf.y, p1[k], c1);
                         }
-                        sPart[(kh * 2 + 0) * 256 + c] = a0 + c0;
-                        sPart[(kh * 2 + 1) * 256 + c] = a1 + c1;
+                        sPart[(kg * 2 + 0) * 256 + 2 * cp] = a0;
+                        sPart[(kg * 2 + 1) * 256 + 2 * cp] = a1;
+                        sPart[(kg * 2 + 0) * 256 + 2 * cp + 1] = c0;
+                        sPart[(kg * 2 + 1) * 256 + 2 * cp + 1] = c1;
                     }
                     rt_bar_sync(2);
-                    sScale[bb * 256 + c] =
-                        rt_hard_sigmoid(__ldg(B.se_b + c) + (sPart[bb * 256 + c] + sPart[(2 + bb) * 256 + c]));
+                    {
+                        const float* q = sPart + bb * 256 + c;
+                        sScale[bb * 256 + c] = rt_hard_sigmoid(__ldg(B.se_b + c) + ((q[0] + q[512]) + (q[1024] + q[1536])));
+                    }
                 }
                 rt_bar_sync(1);
                 {

@@ -25,7 +25,7 @@ struct Options {
                                              {"MCTS_Solver", "true"},       {"Virtual_Style", "virtual_mix"},
                                              {"Virtual_Mix_Threshold", "1000"}, {"First_Device_ID", "0"},
                                              {"UCI_Chess960", "false"},     {"Input_Version", "0"},    {"Dirichlet_Seed", "42"},
-                                             {"Move_Overhead", "20"},       {"Timed_Search_Nodes", "4000000"}};
+                                             {"Move_Overhead", "20"},       {"Timed_Search_Nodes", "1000000"}};
     int i(const std::string& k) const { return std::stoi(kv.at(k)); }
     bool b(const std::string& k) const { return kv.at(k) == "true"; }
 };

@@ -43,6 +43,18 @@ def test_gpu_search_equals_oracle_fake_backend(case):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(32))
+def test_gpu_search_equals_oracle_random_cases(seed):
+    """The randomised cases of tests/test_search_fuzz_hostemu.py on the real device search."""
+    from tests.test_search_fuzz_hostemu import _random_case
+    pos, _, st, (vid, played) = _random_case(seed)
+    S = osr.Search(st)
+    ro = S.run(pos, osr.fake_net(S.n_labels), with_keys=True)
+    rg = _gpu_search(vid, None, False, played, st)[0]
+    assert_same_search(ro, rg)
+
+
+@pytest.mark.gpu
 def test_gpu_multi_tree_search_matches_single_tree():
     st = osr.default_settings("crazyhouse", batch_size=8, simulations=300, node_policy_temperature=1.0)
     pos = Position(variant="crazyhouse")

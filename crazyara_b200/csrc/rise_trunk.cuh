@@ -162,9 +162,17 @@ __device__ __forceinline__ void rt_depthwise4(const uint8_t* sH1, const uint8_t*
 // whose rows live in lanes 0..15 of each 32-lane quadrant: row r <-> lane 32 (r / 16) + r % 16), used while the batch
 // has fewer boards than the GPU has SMs -- twice as many SMs work on the same batch, each CTA's CUDA-core stages
 // handle half the rows.
-template <int kRows>
+//
+// kSplit = 2 (one-board variant only, launched as clusters of two CTAs): the two CTAs of a cluster hold the same board
+// and take alternate chunks of every block, so that a batch of 64 boards occupies 128 SMs.  Each ends a block with a
+// partial accumulator; they exchange halves through distributed shared memory (the CTA that owns a column half adds
+// the partner's partial sums, finishes X for those columns and sends the fp16 result back), synchronised by
+// cluster-scope mbarriers.  The SE of a block is computed redundantly by both.
+template <int kRows, int kSplit = 1>
 __global__ void __launch_bounds__(kRtThreads, 1) rise_trunk_kernel(const __grid_constant__ TrunkArgs args) {
     constexpr bool kHalf = kRows == 64;
+    static_assert(kSplit == 1 || (kSplit == 2 && kHalf), "the chunk split exists for the one-board variant only");
+    constexpr int kW2Ring = kSplit == 2 ? 2 : kRtW2Ring;  // the third W2 slot holds the exchange buffer when splitting
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
     extern __shared__ uint8_t smem_raw[];
     // 1 KB alignment by offset arithmetic on the shared array itself: a pointer -> integer -> pointer round trip would
@@ -187,10 +195,14 @@ __global__ void __launch_bounds__(kRtThreads, 1) rise_trunk_kernel(const __grid_
     uint64_t* h2_empty = bars + 17;  // [2]
     uint64_t* d2_full = bars + 19;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+    uint64_t* ex1_full = bars + 21;  // split: the partner's partial sums for my columns have arrived
+    uint64_t* ex2_full = bars + 22;  // split: the partner's finished X columns have arrived
+    float* sEx = reinterpret_cast<float*>(sW2 + 2 * kTrunkW2Image);  // split: [64 rows][128 cols] fp32 partials
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int m_tile = blockIdx.x;
+    const int crank = kSplit == 2 ? static_cast<int>(blockIdx.x & 1) : 0;  // rank inside the CTA pair
+    const int m_tile = kSplit == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
     const int n_blocks = args.n_blocks;
 
     if (warp == 0 && lane == 0) {
@@ -199,10 +211,12 @@ __global__ void __launch_bounds__(kRtThreads, 1) rise_trunk_kernel(const __grid_
             mbar_init(&w1_full[i], 1);
             mbar_init(&w1_empty[i], 1 + kRtComputeWarps);
         }
-        for (int i = 0; i < kRtW2Ring; ++i) {
+        for (int i = 0; i < kW2Ring; ++i) {
             mbar_init(&w2_full[i], 1);
             mbar_init(&w2_empty[i], 1);
         }
+        mbar_init(ex1_full, kRtComputeWarps / 2);
+        mbar_init(ex2_full, kRtComputeWarps / 2);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&d1_full[i], 1);
             mbar_init(&d1_empty[i], kRtComputeWarps);
@@ -217,6 +231,7 @@ __global__ void __launch_bounds__(kRtThreads, 1) rise_trunk_kernel(const __grid_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (kSplit == 2) cluster_sync_all();  // the partner's barriers exist before anything arrives on them
     pdl_wait();
     pdl_launch_dependents();
 
@@ -226,7 +241,7 @@ __global__ void __launch_bounds__(kRtThreads, 1) rise_trunk_kernel(const __grid_
             uint32_t gc = 0;
             for (int b = 0; b < n_blocks; ++b) {
                 const TrunkBlock& B = args.blk[b];
-                for (int j = 0; j < B.n_chunks; ++j, ++gc) {
+                for (int j = crank; j < B.n_chunks; j += kSplit, ++gc) {
                     const uint32_t s = gc % kRtW1Ring;
                     mbar_wait_relaxed(&w1_empty[s], ((gc / kRtW1Ring) & 1) ^ 1);
                     mbar_arrive_expect_tx(&w1_full[s], kTrunkW1Image);
@@ -241,9 +256,9 @@ __global__ void __launch_bounds__(kRtThreads, 1) rise_trunk_kernel(const __grid_
             uint32_t gc = 0;
             for (int b = 0; b < n_blocks; ++b) {
                 const TrunkBlock& B = args.blk[b];
-                for (int j = 0; j < B.n_chunks; ++j, ++gc) {
-                    const uint32_t s = gc % kRtW2Ring;
-                    mbar_wait_relaxed(&w2_empty[s], ((gc / kRtW2Ring) & 1) ^ 1);
+                for (int j = crank; j < B.n_chunks; j += kSplit, ++gc) {
+                    const uint32_t s = gc % kW2Ring;
+                    mbar_wait_relaxed(&w2_empty[s], ((gc / kW2Ring) & 1) ^ 1);
                     mbar_arrive_expect_tx(&w2_full[s], kTrunkW2Image);
                     bulk_load_1d(sW2 + s * kTrunkW2Image, args.w2_img + static_cast<size_t>(B.chunk0 + j) * kTrunkW2Image,
                                  kTrunkW2Image, &w2_full[s]);
@@ -258,11 +273,11 @@ __global__ void __launch_bounds__(kRtThreads, 1) rise_trunk_kernel(const __grid_
         uint32_t gc = 0;
         RT_PROF_DECL();
         auto mma2 = [&](uint32_t g, bool first) {
-            const uint32_t s = g & 1, slot = g % kRtW2Ring;
+            const uint32_t s = g & 1, slot = g % kW2Ring;
             RT_PROF(0);
             mbar_wait(&h2_full[s], (g >> 1) & 1);
             RT_PROF(1);  // wait for H2 (compute warps)
-            mbar_wait(&w2_full[slot], (g / kRtW2Ring) & 1);
+            mbar_wait(&w2_full[slot], (g / kW2Ring) & 1);
             RT_PROF(2);  // wait for W2 ring
             tc_fence_after();
             if (lane == 0) {
@@ -281,7 +296,8 @@ __global__ void __launch_bounds__(kRtThreads, 1) rise_trunk_kernel(const __grid_
             RT_PROF(0);
             mbar_wait(x_ready, b & 1);
             RT_PROF(3);  // wait for the X tile (block boundary)
-            for (int j = 0; j < nch; ++j, ++gc) {
+            int own = 0;  // index among this CTA's chunks of the block
+            for (int j = crank; j < nch; j += kSplit, ++gc, ++own) {
                 const uint32_t s = gc & 1, slot = gc % kRtW1Ring;
                 mbar_wait(&d1_empty[s], ((gc >> 1) & 1) ^ 1);
                 RT_PROF(4);  // wait for a free D1 buffer
@@ -300,9 +316,9 @@ __global__ void __launch_bounds__(kRtThreads, 1) rise_trunk_kernel(const __grid_
                     umma_commit(&d1_full[s]);
                 }
                 __syncwarp();
-                if (j >= 1) mma2(gc - 1, j == 1);
+                if (own >= 1) mma2(gc - 1, own == 1);
             }
-            mma2(gc - 1, nch == 1);
+            mma2(gc - 1, own == 1);
             if (lane == 0) umma_commit(d2_full);
             __syncwarp();
         }
@@ -502,7 +518,7 @@ __global__ void __launch_bounds__(kRtThreads, 1) rise_trunk_kernel(const __grid_
             if (lane == 0) mbar_arrive(x_ready);
             RT_PROF(1);  // squeeze-excitation + hand-over of the tile
 
-            for (int j = 0; j < nch; ++j, ++gc) {
+            for (int j = crank; j < nch; j += kSplit, ++gc) {
                 const uint32_t s = gc & 1, slot = gc % kRtW1Ring;
                 // ---- epilogue 1: D1 -> relu(+b1) -> H1
                 mbar_wait(&d1_full[s], (gc >> 1) & 1);
@@ -573,7 +589,79 @@ __global__ void __launch_bounds__(kRtThreads, 1) rise_trunk_kernel(const __grid_
             mbar_wait(d2_full, b & 1);
             RT_PROF(11);  // wait for D2
             tc_fence_after();
-            {
+            if (kSplit == 2) {
+                // This CTA's D2 holds the sum over ITS chunks only.  Column half `crank` is finished here: the partner
+                // sends its partial sums for those columns, this CTA adds them, applies bias + residual, keeps the new
+                // X columns and sends them back; for the other half the roles are swapped.
+                const bool mine = (cq >> 1) == crank;
+                const uint32_t partner = static_cast<uint32_t>(crank ^ 1);
+                uint32_t* sXh = reinterpret_cast<uint32_t*>(sH2 + (cq & 1) * 16384 + 8192);  // [64 rows][32] packed fp16 pairs
+                if (!mine) {
+                    const uint32_t rex = cluster_map(sEx + r * 128 + (cq & 1) * 64, partner);
+#pragma unroll
+                    for (int cc = 0; cc < 2; ++cc) {
+                        uint32_t v[32];
+                        tmem_ld_32x32b_x32(tmem_base + lane_addr + kRtColD2 + cq * 64 + cc * 32, v);
+                        tmem_ld_wait();
+                        if (valid) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                st_cluster_v4(rex + (cc * 32 + i * 4) * 4, v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
+                        }
+                    }
+                    asm volatile("fence.acq_rel.cluster;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(cluster_map(ex1_full, partner));
+                    if (!last) {  // the finished X columns come back from the partner
+                        mbar_wait_cluster(ex2_full, b & 1);
+                        uint32_t xv[32];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const uint4 t = *reinterpret_cast<const uint4*>(sXh + r * 32 + i * 4);
+                            xv[i * 4] = t.x, xv[i * 4 + 1] = t.y, xv[i * 4 + 2] = t.z, xv[i * 4 + 3] = t.w;
+                        }
+                        tmem_st_32x32b_x32(x_addr, xv);
+                        tmem_st_wait();
+                    }
+                } else {
+                    mbar_wait_cluster(ex1_full, b & 1);
+                    uint32_t xv[32];
+                    tmem_ld_32x32b_x32(x_addr, xv);
+#pragma unroll
+                    for (int cc = 0; cc < 2; ++cc) {
+                        uint32_t v[32];
+                        tmem_ld_32x32b_x32(tmem_base + lane_addr + kRtColD2 + cq * 64 + cc * 32, v);
+                        tmem_ld_wait();
+                        const float* b2p = sB2 + cq * 64 + cc * 32;
+                        const float* pp = sEx + r * 128 + (cq & 1) * 64 + cc * 32;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float2 xr = rt_unpack(xv[cc * 16 + i]);
+                            const float2 pr = valid ? *reinterpret_cast<const float2*>(pp + 2 * i) : make_float2(0.0f, 0.0f);
+                            // chunk order of the unsplit kernel is even, odd, even, ...: rank 0's partial first
+                            const float s0 = crank == 0 ? __uint_as_float(v[2 * i]) + pr.x : pr.x + __uint_as_float(v[2 * i]);
+                            const float s1 = crank == 0 ? __uint_as_float(v[2 * i + 1]) + pr.y : pr.y + __uint_as_float(v[2 * i + 1]);
+                            xv[cc * 16 + i] = rt_pack(s0 + b2p[2 * i] + xr.x, s1 + b2p[2 * i + 1] + xr.y);
+                        }
+                    }
+                    if (!last) {
+                        tmem_st_32x32b_x32(x_addr, xv);
+                        if (valid) {
+                            const uint32_t rxh = cluster_map(sXh + r * 32, partner);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) st_cluster_v4(rxh + i * 16, xv[i * 4], xv[i * 4 + 1], xv[i * 4 + 2], xv[i * 4 + 3]);
+                        }
+                        tmem_st_wait();
+                        asm volatile("fence.acq_rel.cluster;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(cluster_map(ex2_full, partner));
+                    } else if (valid && m < args.M) {
+                        uint4* dst = reinterpret_cast<uint4*>(args.out + static_cast<size_t>(m) * 256 + cq * 64);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) dst[i] = make_uint4(xv[i * 4], xv[i * 4 + 1], xv[i * 4 + 2], xv[i * 4 + 3]);
+                    }
+                }
+            } else {
                 uint32_t xv[32];
                 tmem_ld_32x32b_x32(x_addr, xv);
 #pragma unroll
@@ -605,6 +693,7 @@ __global__ void __launch_bounds__(kRtThreads, 1) rise_trunk_kernel(const __grid_
     }
     tc_fence_before();
     __syncthreads();
+    if (kSplit == 2) cluster_sync_all();  // no CTA leaves while its partner may still write into its shared memory
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc<512>(tmem_base);

@@ -98,8 +98,10 @@ def test_tower_implementations_agree(tmp_path, monkeypatch, name, cin, pch):
     x = golden_input(arch, n=6, seed=3)
     outs = []
     # default = tower kernel, one board per CTA at this batch size; then two boards per CTA; then the older forms
-    for env in ({}, {"ARA_TRUNK_ROWS": "128"}, {"ARA_TRUNK": "0"}, {"ARA_FUSED_BLOCKS": "1"}):
-        for k in ("ARA_TRUNK", "ARA_FUSED_BLOCKS", "ARA_TRUNK_ROWS"):
+    # default = tower kernel, one CTA per board at this batch size; CTA pair per board (opt-in experiment); two boards
+    # per CTA; then the older forms
+    for env in ({}, {"ARA_TRUNK_SPLIT": "2"}, {"ARA_TRUNK_ROWS": "128"}, {"ARA_TRUNK": "0"}, {"ARA_FUSED_BLOCKS": "1"}):
+        for k in ("ARA_TRUNK", "ARA_FUSED_BLOCKS", "ARA_TRUNK_ROWS", "ARA_TRUNK_SPLIT"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -121,7 +123,7 @@ def test_tower_variants_are_bit_identical(tmp_path, monkeypatch, name, cin, pch)
     arch = onet.arch_risev2(cin, pch) if name == "risev2" else onet.arch_risev33(cin, pch, True)
     x = golden_input(arch, n=5, seed=11)
     outs = []
-    for rows in ("64", "128"):
+    for rows in ("64", "128"):  # (forcing the row count also switches the CTA-pair chunk split off)
         monkeypatch.setenv("ARA_TRUNK_ROWS", rows)
         net, _ = _make_net(tmp_path, arch, 5, 10 if name == "risev2" else 30)
         v, p = np.zeros(5, np.float32), np.zeros((5, pch * 64), np.float32)

@@ -45,7 +45,14 @@ struct NullWriterFactory {  // fake backend: no planes needed
 __global__ void __launch_bounds__(32) root_kernel(const TreeDev* trees, SearchParams sp, const Board* roots) {
     __shared__ WarpScratch ws;
     const TreeDev t = trees[blockIdx.x];
-    create_root(t, sp, ws, &roots[blockIdx.x]);
+    // the subtree kept by ara_search_apply_move is searched on if it is this position, else a new tree starts
+    if (!reuse_root(t, sp, &roots[blockIdx.x])) create_root(t, sp, ws, &roots[blockIdx.x]);
+}
+
+// MCTSAgent::apply_move_to_tree for one tree
+__global__ void __launch_bounds__(32) advance_kernel(const TreeDev* trees, int tree, Move move) {
+    const TreeDev t = trees[tree];
+    if (threadIdx.x == 0) advance_root(t, move);
 }
 
 // one warp per tree: the sequential part of SearchThread::create_mini_batch
@@ -121,6 +128,7 @@ class Search {
     int init(Net* net, const SearchParams& sp, int device, int n_trees, int max_nodes);
     int set_position(int tree, const Board& root, const uint64_t* hist_keys, const int16_t* hist_reps, int hist_len);
     int go();
+    int apply_move(int tree, unsigned short move);
     int fetch_results();
     int debug_cycles(int tree, unsigned long long* out8) {
         TreeState st;
@@ -144,6 +152,7 @@ class Search {
     int dalloc(T** p, size_t count);
     int iterate(int count);
     Net* net_ = nullptr;
+    bool searched_ = false;  // a go has run: the device holds trees that apply_move may keep
     int device_ = 0;
     cudaStream_t stream_ = nullptr;
     bool own_stream_ = false;
@@ -356,6 +365,7 @@ int Search::go() {
     ARA_CUDA_OK(cudaSetDevice(device_));
     prof_used_ = 0;
     net_forwards = 0;
+    searched_ = true;
     ARA_CUDA_OK(cudaEventRecord(ev0_, stream_));
     ARA_CUDA_OK(cudaMemcpyAsync(d_trees_, h_trees_.data(), sizeof(TreeDev) * n_trees, cudaMemcpyHostToDevice, stream_));
     ARA_CUDA_OK(cudaMemcpyAsync(d_roots_, h_roots_.data(), sizeof(Board) * n_trees, cudaMemcpyHostToDevice, stream_));
@@ -421,6 +431,17 @@ int Search::go() {
     ARA_CUDA_OK(cudaEventElapsedTime(&ms, ev0_, ev1_));
     last_go_ms = ms;
     if (profile && prof_collect()) return -1;
+    return 0;
+}
+
+int Search::apply_move(int tree, unsigned short move) {
+    if (tree < 0 || tree >= n_trees) return set_error("ara_search_apply_move: tree %d out of range", tree);
+    ARA_CUDA_OK(cudaSetDevice(device_));
+    if (!searched_) return 0;  // nothing to keep before the first search
+    // d_trees_ still holds the descriptors of the last go (pool pointers never change)
+    advance_kernel<<<1, 32, 0, stream_>>>(d_trees_, tree, static_cast<Move>(move));
+    ++launches;
+    ARA_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
@@ -495,6 +516,10 @@ extern "C" int ara_search_result(ara_search_t h, int tree, ara_search_result_t* 
     if (tree < 0 || tree >= s->n_trees) return ara::set_error("ara_search_result: tree %d out of range", tree);
     memcpy(out, &s->results[tree], sizeof(*out));
     return 0;
+}
+extern "C" int ara_search_apply_move(ara_search_t h, int tree, unsigned short move) {
+    if (h == nullptr) return ara::set_error("ara_search_apply_move: null handle");
+    return reinterpret_cast<Search*>(h)->apply_move(tree, move);
 }
 extern "C" int ara_search_set_movetime(ara_search_t h, double ms) {
     if (h == nullptr) return ara::set_error("ara_search_set_movetime: null handle");

@@ -79,12 +79,17 @@ struct TreeState {
     int n_edges;
     int n_new;
     int n_coll;
+    int root;        // node id of the current root (0 for a new tree, the re-rooted child when the tree is reused)
+    int next_root;   // candidate root after ara_search_apply_move (MCTSAgent::ownNextRoot / opponentsNextRoot), -1 none
+    int next_valid;  // apply_move has been called since the last search: only next_root may be reused
     int n_exp;     // expansions of the last mini-batch (entries of exp_parent)
     int n_prep;    // new leaves of the last mini-batch, kept for the prepare step after the backup cleared n_new
     int done;      // search loop condition failed (limits reached / root solved)
     int error;     // 1 node pool, 2 edge pool, 3 depth overflow
     unsigned iterations;
     unsigned evals;
+    unsigned pre_nodes;  // EvalInfo::nodesPreSearch: node count of the root when the search began (0 for a new tree)
+    unsigned pad_;
     unsigned long long sum_select_k;
     unsigned long long sum_depth;
     // SM-clock cycles spent per phase of create_mini_batch (lane 0): 0 descent, 1 board copy + do_move, 2 repetition +
@@ -898,7 +903,7 @@ ARA_HD float gamma_f(MinStd& g, float alpha) {
 }
 // MCTSAgent::evaluate_board_state :311-316: noise on the (sorted) root priors, then open all children.  Lane 0.
 ARA_HD void apply_dirichlet_to_root(const TreeDev& t, const SearchParams& sp, WarpScratch& ws) {
-    NodeHdr& h = t.hdr[0];
+    NodeHdr& h = t.hdr[t.st->root];
     const int n = h.n_moves;
     MinStd g;
     g.x = static_cast<uint32_t>(sp.seed % 2147483647ULL);
@@ -929,7 +934,7 @@ ARA_HD void create_mini_batch_impl(const TreeDev& t, const SearchParams& sp, War
     }
     // run_search_thread loop condition (searchthread.cpp:326-340, :418-426), checked before every iteration
     {
-        const NodeHdr& r = t.hdr[0];
+        const NodeHdr& r = t.hdr[st.root];
         const uint32_t node_count = r.visit_sum - r.free_visits;
         const bool limits_ok = (sp.nodes == 0 || node_count < sp.nodes) && (sp.simulations == 0 || r.visit_sum < sp.simulations);
         // (a pool sized for a visit budget can never trip the last test before the budget does; it only ends
@@ -943,10 +948,10 @@ ARA_HD void create_mini_batch_impl(const TreeDev& t, const SearchParams& sp, War
     const int B = sp.batch_size;
     int n_new = 0, n_coll = 0, n_term = 0;
     while (n_new < B && n_coll != B && n_term < 2 * B) {
-        int cur = 0, depth = 0, type = -1, leaf = -1;  // type: 0 new, 1 collision, 2 terminal
+        int cur = st.root, depth = 0, type = -1, leaf = -1;  // type: 0 new, 1 collision, 2 terminal
         long long tq = ARA_CLOCK();
         NodeHdr h;
-        load_hdr(&h, &t.hdr[0]);
+        load_hdr(&h, &t.hdr[cur]);
         EdgeRegs pre = load_edge(t, h.edge_base + ARA_LANE);
         for (;;) {
             if (depth >= kMaxDepth) {
@@ -1183,6 +1188,9 @@ ARA_HD void create_root(const TreeDev& t, const SearchParams& sp, WarpScratch& w
     copy_board(&ws.child, root_board);
     if (ARA_LANE == 0) {
         TreeState& st = *t.st;
+        st.root = 0;
+        st.next_root = -1;
+        st.next_valid = 0;
         st.n_nodes = 0;
         st.n_edges = 0;
         st.n_new = 0;
@@ -1193,6 +1201,7 @@ ARA_HD void create_root(const TreeDev& t, const SearchParams& sp, WarpScratch& w
         st.error = 0;
         st.iterations = 0;
         st.evals = 0;
+        st.pre_nodes = 0;
         st.sum_select_k = 0;
         st.sum_depth = 0;
         for (int i = 0; i < 8; ++i) st.prof[i] = 0;
@@ -1214,10 +1223,65 @@ ARA_HD void create_root(const TreeDev& t, const SearchParams& sp, WarpScratch& w
     }
     ARA_WARP_SYNC();
 }
+// MCTSAgent::apply_move_to_tree + pick_next_node (mctsagent.cpp:230-247): the child behind `move` becomes the candidate
+// root of the next search; a second call (the opponent's reply) descends once more.  Lane 0.
+ARA_HD void advance_root(const TreeDev& t, Move move) {
+    TreeState& st = *t.st;
+    const int base = st.next_valid ? st.next_root : (st.n_nodes > 0 ? st.root : -1);
+    st.next_root = -1;
+    st.next_valid = 1;
+    if (base < 0) return;
+    const NodeHdr& h = t.hdr[base];
+    if (!(h.flags & NF_HAS_D) || !(h.flags & NF_HAS_NN)) return;  // is_playout_node
+    for (int i = 0; i < h.n_moves; ++i)
+        if (t.move[h.edge_base + i] == move) {
+            st.next_root = t.child[h.edge_base + i];
+            break;
+        }
+}
+
+// MCTSAgent::init_root_node / get_root_node_from_tree (mctsagent.cpp:113-160): if the candidate root is the searched
+// position, is a playout node with visits of its own and the pools have room for another search, the subtree is kept
+// (make_to_root) and the search continues on its statistics.  Returns 1 if the tree is reused.  Warp-uniform.
+ARA_HD int reuse_root(const TreeDev& t, const SearchParams& sp, const Board* root_board) {
+    TreeState& st = *t.st;
+    const int cand = (st.next_valid && st.n_nodes > 0 && !st.error) ? st.next_root : -1;
+    int ok = 0;
+    if (cand >= 0) {
+        const NodeHdr& h = t.hdr[cand];
+        // a time-limited search has no visit budget: it keeps the tree only while half of the pool is still free
+        const unsigned limit = sp.simulations ? sp.simulations : sp.nodes;
+        const unsigned budget = limit ? limit : static_cast<unsigned>(t.max_nodes / 2);
+        const bool room = st.n_nodes + static_cast<int>(budget) + 4 * sp.batch_size + 64 <= t.max_nodes &&
+                          st.n_edges + (static_cast<long long>(budget) + 4 * sp.batch_size + 64) * (sp.mode == 1 ? 128 : 320) <= t.max_edges;
+        ok = h.key == root_board->key && (h.flags & NF_HAS_D) && (h.flags & NF_HAS_NN) && h.visit_sum - h.free_visits > 0 && room;
+    }
+    ARA_WARP_SYNC();
+    if (ARA_LANE == 0) {
+        st.next_root = -1;
+        st.next_valid = 0;
+        if (ok) {
+            NodeHdr& h = t.hdr[cand];
+            st.root = cand;
+            h.parent = -1;  // make_to_root: the path walks of prepare_child stop here
+            st.n_new = st.n_coll = st.n_exp = st.n_prep = 0;
+            st.done = ((h.flags & NF_TERMINAL) || h.n_moves == 0) ? 1 : 0;
+            st.iterations = 0;
+            st.evals = 0;
+            st.pre_nodes = h.visit_sum - h.free_visits;
+            st.sum_select_k = 0;
+            st.sum_depth = 0;
+            for (int i = 0; i < 8; ++i) st.prof[i] = 0;
+        }
+    }
+    ARA_WARP_SYNC();
+    return ok;
+}
+
 // second half: after expand_pending + network + scatter_pending + backup_results (root trajectory is empty)
 ARA_HD void finalize_root(const TreeDev& t, const SearchParams& sp, WarpScratch& ws) {
     if (ARA_LANE == 0 && !t.st->done && !t.st->error) {
-        NodeHdr& h = t.hdr[0];
+        NodeHdr& h = t.hdr[t.st->root];
         h.flags |= NF_HAS_D | NF_SORTED;  // prepare_node_for_visits
         if (sp.dirichlet_epsilon > 0.009f && h.n_moves > 1) apply_dirichlet_to_root(t, sp, ws);
     }
@@ -1239,6 +1303,7 @@ struct SearchResult {
     unsigned evals;
     int tree_nodes;
     int error;
+    unsigned nodes_pre_search;
     unsigned long long sum_select_k;
     unsigned long long sum_depth;
     Move moves[kMaxMoves];
@@ -1336,9 +1401,10 @@ ARA_HD float value_display(const NodeHdr& h) {
 }
 ARA_HD void collect_result(const TreeDev& t, const SearchParams& sp, SearchResult* r) {  // lane 0
     const TreeState& st = *t.st;
-    const NodeHdr& h = t.hdr[0];
+    const NodeHdr& h = t.hdr[t.st->root];
     r->error = st.error;
     r->tree_nodes = st.n_nodes;
+    r->nodes_pre_search = st.pre_nodes;
     r->iterations = st.iterations;
     r->evals = st.evals;
     r->sum_select_k = st.sum_select_k;

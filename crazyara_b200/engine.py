@@ -37,7 +37,7 @@ class SearchResult(ctypes.Structure):
                 ("node_type", ctypes.c_int), ("pv_len", ctypes.c_int), ("root_value", ctypes.c_float),
                 ("best_move_q", ctypes.c_float), ("visit_sum", ctypes.c_uint), ("free_visits", ctypes.c_uint),
                 ("iterations", ctypes.c_uint), ("evals", ctypes.c_uint), ("tree_nodes", ctypes.c_int),
-                ("error", ctypes.c_int), ("sum_select_k", ctypes.c_ulonglong), ("sum_depth", ctypes.c_ulonglong),
+                ("error", ctypes.c_int), ("nodes_pre_search", ctypes.c_uint), ("sum_select_k", ctypes.c_ulonglong), ("sum_depth", ctypes.c_ulonglong),
                 ("moves", ctypes.c_uint16 * 512), ("visits", ctypes.c_uint32 * 512), ("q", ctypes.c_float * 512),
                 ("prior", ctypes.c_float * 512), ("policy", ctypes.c_double * 512), ("pv", ctypes.c_uint16 * 256)]
 
@@ -75,6 +75,8 @@ def _L():
         L.ara_search_go.argtypes = [vp]
         L.ara_search_result.argtypes = [vp, ci, vp]
         L.ara_search_set_profile.argtypes = [vp, ci]
+        L.ara_search_apply_move.argtypes = [vp, ci, ctypes.c_ushort]
+        L.ara_search_set_movetime.argtypes = [vp, ctypes.c_double]
         L.ara_search_profile.argtypes = [vp] + [vp] * 4
         L.ara_search_last_go_ms.restype = ctypes.c_double
         L.ara_search_last_go_ms.argtypes = [vp]
@@ -215,7 +217,7 @@ def _result_to_dict(r, is960):
              policy=np.array(r.policy[:k], np.float64), root_value=r.root_value, visit_sum=r.visit_sum,
              free_visits=r.free_visits, nodes=r.visit_sum - r.free_visits, best_idx=r.best_idx,
              best_move_q=r.best_move_q, node_type=r.node_type, pv_len=r.pv_len, iterations=r.iterations, evals=r.evals,
-             tree_nodes=r.tree_nodes, sum_select_k=r.sum_select_k, sum_depth=r.sum_depth, error=r.error,
+             tree_nodes=r.tree_nodes, sum_select_k=r.sum_select_k, sum_depth=r.sum_depth, nodes_pre_search=r.nodes_pre_search, error=r.error,
              pv=[move_to_uci(m, is960) for m in r.pv[:r.pv_len]])
     if k > 0 and r.best_idx >= 0:
         d["best_move"] = d["moves"][r.best_idx]
@@ -259,11 +261,22 @@ class MCTSAgent:
         ms = _L().ara_search_last_go_ms(self._h)
         d["elapsed_ms"] = ms
         # EvalInfo::calculate_nps (evalinfo.cpp:73-85): (nodes - nodesPreSearch) / elapsed
-        d["nps"] = d["nodes"] / (ms / 1000.0) if ms > 0 else 0.0
+        d["nps"] = (d["nodes"] - d["nodes_pre_search"]) / (ms / 1000.0) if ms > 0 else 0.0
         return d
 
     def results(self):
         return [self.result(t) for t in range(self.n_trees)]
+
+    def apply_move_to_tree(self, move, tree=0):
+        """MCTSAgent::apply_move_to_tree: tell the tree which move was played (UCI string of the position last searched,
+        or the 16-bit move code); the next search on the resulting position continues on the kept subtree."""
+        if isinstance(move, str):
+            move = self._states[tree].uci_to_action(move)
+        check(_L().ara_search_apply_move(self._h, tree, int(move)))
+
+    def set_movetime(self, ms):
+        """SearchLimits::movetime: following searches also stop after `ms` of wall time (0 = off)."""
+        check(_L().ara_search_set_movetime(self._h, float(ms)))
 
     def set_profile(self, on=True):
         check(_L().ara_search_set_profile(self._h, int(on)))

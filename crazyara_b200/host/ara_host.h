@@ -182,11 +182,15 @@ class MCTSAgent {
         evalInfo.rootValue = r.root_value;
         evalInfo.centipawns = value_to_centipawn(r.best_move_q, settings_.mode == 1 ? 1.4f : 1.2f);
         evalInfo.nodes = r.visit_sum - r.free_visits;
-        evalInfo.nodesPreSearch = 0;
+        evalInfo.nodesPreSearch = r.nodes_pre_search;
         evalInfo.depth = static_cast<size_t>(r.pv_len);
         evalInfo.elapsedMs = ara_search_last_go_ms(search_);
     }
     const ara_search_result_t& last_result() const { return result_; }
+    // MCTSAgent::apply_move_to_tree: the subtree behind `move` is kept for the next search
+    void apply_move_to_tree(Action move) {
+        if (ara_search_apply_move(search_, 0, move) != 0) throw std::runtime_error(ara_last_error());
+    }
     // SearchLimits::movetime: the following searches also stop after `ms` of wall time (0 = off)
     void set_movetime(double ms) {
         if (ara_search_set_movetime(search_, ms) != 0) throw std::runtime_error(ara_last_error());

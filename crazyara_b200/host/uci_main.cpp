@@ -9,6 +9,7 @@
 #include <map>
 #include <memory>
 #include <sstream>
+#include <vector>
 
 #include "ara_host.h"
 
@@ -25,7 +26,8 @@ struct Options {
                                              {"MCTS_Solver", "true"},       {"Virtual_Style", "virtual_mix"},
                                              {"Virtual_Mix_Threshold", "1000"}, {"First_Device_ID", "0"},
                                              {"UCI_Chess960", "false"},     {"Input_Version", "0"},    {"Dirichlet_Seed", "42"},
-                                             {"Move_Overhead", "20"},       {"Timed_Search_Nodes", "1000000"}};
+                                             {"Move_Overhead", "20"},       {"Timed_Search_Nodes", "1000000"},
+                                             {"Reuse_Tree", "true"}};
     int i(const std::string& k) const { return std::stoi(kv.at(k)); }
     bool b(const std::string& k) const { return kv.at(k) == "true"; }
 };
@@ -71,6 +73,11 @@ int main() {
     EvalInfo info;
     bool ready = false;
     bool timed = false;  // the current agent was built for time-limited searches
+    // game of the last searched position (base + moves): a `position` that extends it walks the kept tree
+    // (MCTSAgent::apply_move_to_tree, mctsagent.cpp:230) instead of discarding it
+    std::string searchedBase, gameBase;
+    std::vector<std::string> searchedMoves, gameMoves;
+    bool searched = false;
     auto variant = [&]() { return variant_id(opt.kv["UCI_Variant"]); };
     auto new_game = [&]() { state.init(variant(), opt.b("UCI_Chess960")); };
     auto prepare = [&]() {  // CrazyAra::is_ready (crazyara.cpp:597): build net + agent from the options
@@ -97,8 +104,12 @@ int main() {
         if (!opt.kv["Model_Path"].empty())
             net.reset(new NeuralNetAPI("gpu", opt.i("First_Device_ID"), static_cast<unsigned>(s.batch_size), opt.kv["Model_Path"]));
         // a time-limited search has no visit budget to size the node pool from
-        const int pool = timed ? opt.i("Timed_Search_Nodes") : 0;
+        // a kept subtree lives in the same pools as the next search: room for a few searches before a fresh tree
+        const long budget = s.simulations ? s.simulations : s.nodes;
+        const int pool = timed ? opt.i("Timed_Search_Nodes")
+                               : (opt.b("Reuse_Tree") ? static_cast<int>(std::min(8 * budget + 4L * s.batch_size + 64, 1L << 24)) : 0);
         if (timed) s.simulations = 0, s.nodes = 0;
+        searched = false;
         agent.reset(new MCTSAgent(net.get(), s, opt.i("First_Device_ID"), pool));
         ready = true;
     };
@@ -130,6 +141,7 @@ int main() {
                 }
             } else if (cmd == "ucinewgame") {
                 new_game();
+                searched = false;
             } else if (cmd == "position") {
                 std::string tok, fen;
                 ss >> tok;
@@ -140,12 +152,20 @@ int main() {
                     while (ss >> tok && tok != "moves") fen += (fen.empty() ? "" : " ") + tok;
                     state.set(fen, opt.b("UCI_Chess960"), variant());
                 }
-                while (ss >> tok) {
-                    const Action a = state.uci_to_action(tok);
+                gameBase = fen.empty() ? "startpos" : fen;
+                gameMoves.clear();
+                while (ss >> tok) gameMoves.push_back(tok);
+                const bool extends = searched && ready && agent && opt.b("Reuse_Tree") && gameBase == searchedBase &&
+                                     gameMoves.size() > searchedMoves.size() &&
+                                     std::equal(searchedMoves.begin(), searchedMoves.end(), gameMoves.begin());
+                for (size_t i = 0; i < gameMoves.size(); ++i) {
+                    const Action a = state.uci_to_action(gameMoves[i]);
                     if (a == 0) {
-                        std::cout << "info string illegal move " << tok << std::endl;
+                        std::cout << "info string illegal move " << gameMoves[i] << std::endl;
+                        gameMoves.resize(i);
                         break;
                     }
+                    if (extends && i >= searchedMoves.size()) agent->apply_move_to_tree(a);
                     state.do_action(a);
                 }
             } else if (cmd == "go") {
@@ -154,8 +174,8 @@ int main() {
                 while (ss >> tok) {
                     if (tok == "nodes") {
                         ss >> tok;
+                        if (opt.kv["Nodes"] != tok) ready = false;
                         opt.kv["Nodes"] = tok;
-                        ready = false;
                     } else if (tok == "movetime") {
                         ss >> lim.movetime;
                     } else if (tok == "wtime") {
@@ -184,6 +204,10 @@ int main() {
                     agent->set_movetime(0.0);
                 }
                 agent->evaluate_board_state(state, info);
+                searched = true;
+                searchedBase = gameBase;
+                searchedMoves = gameMoves;
+                if (info.nodesPreSearch) std::cout << "info string reused " << info.nodesPreSearch << " nodes" << std::endl;
                 std::cout << "info depth " << info.depth << " nodes " << info.nodes << " nps " << info.calculate_nps() << " score cp "
                           << info.centipawns << " time " << static_cast<long>(info.elapsedMs) << " pv";
                 for (Action a : info.pv) std::cout << " " << state.action_to_uci(a);

@@ -29,19 +29,24 @@ def rl_settings(mode, **kw):
 
 class Arena:
     def __init__(self, net, settings, variant, n_games, device=0, is960=False, temperature=0.8, temperature_moves=15,
-                 max_plies=512, seed=0, max_nodes=0, exporter=None):
+                 max_plies=512, seed=0, max_nodes=0, exporter=None, reuse_tree=False):
         self.variant, self.is960 = variant, is960
         self.n_games = n_games
         self.temperature, self.temperature_moves, self.max_plies = temperature, temperature_moves, max_plies
         self.rng = np.random.default_rng(seed)
+        if reuse_tree and max_nodes == 0:  # room for the kept subtrees of several moves before a tree starts over
+            max_nodes = 8 * int(settings.simulations or settings.nodes) + 4 * int(settings.batch_size) + 64
         self.agent = MCTSAgent(net, settings, device, n_games, max_nodes)
         self.states = [self._new_state() for _ in range(n_games)]
         self.plies = [0] * n_games
         self.finished = []  # (plies, terminal type, side to move at the end)
         self.nodes = 0
+        self.reused_nodes = 0  # visits inherited from kept subtrees (EvalInfo::nodesPreSearch summed)
         self.search_ms = 0.0
         # training-sample export (crazyara_b200.export.TrainDataExporter): one sample per searched position
         self.exporter = exporter
+        # Reuse_Tree (off in the reference's RL configuration, rl_config.py:56): keep the subtree of the played move
+        self.reuse_tree = reuse_tree
         self.settings = settings
         self.records = [exporter.new_game() for _ in range(n_games)] if exporter is not None else None
 
@@ -82,7 +87,8 @@ class Arena:
                                    normalize=False)
         for t, st in enumerate(self.states):
             res = self.agent.result(t)
-            self.nodes += int(res["nodes"])
+            self.nodes += int(res["nodes"]) - int(res["nodes_pre_search"])
+            self.reused_nodes += int(res["nodes_pre_search"])
             if len(res["moves"]) == 0:
                 self._game_over(t, st.is_terminal(), st.side_to_move())
                 continue
@@ -90,6 +96,8 @@ class Arena:
             if self.exporter is not None:
                 self.exporter.save_sample(self.records[t], planes[t], res["moves"], res["policy"], res["q"][idx],
                                           st.side_to_move())
+            if self.reuse_tree:
+                self.agent.apply_move_to_tree(res["moves"][idx], t)
             st.do_uci(res["moves"][idx])
             self.plies[t] += 1
             term = st.is_terminal()
@@ -108,7 +116,7 @@ class Arena:
         moves = steps * self.n_games
         return dict(games=len(self.finished), steps=steps, moves=moves, wall_s=wall,
                     games_per_hour=len(self.finished) / wall * 3600.0 if wall > 0 else 0.0,
-                    moves_per_s=moves / wall if wall > 0 else 0.0, nodes=self.nodes,
+                    moves_per_s=moves / wall if wall > 0 else 0.0, nodes=self.nodes, reused_nodes=self.reused_nodes,
                     nps=self.nodes / (self.search_ms / 1000.0) if self.search_ms > 0 else 0.0,
                     avg_plies=float(np.mean([g[0] for g in self.finished])) if self.finished else 0.0)
 

@@ -134,6 +134,7 @@ typedef struct ara_search_result_s {
     unsigned evals;
     int tree_nodes;
     int error;
+    unsigned nodes_pre_search; /* EvalInfo::nodesPreSearch: nodes of the kept subtree when the search began, 0 for a new tree */
     unsigned long long sum_select_k; /* sum over selections of the number of open children read (HBM accounting) */
     unsigned long long sum_depth;
     unsigned short moves[512];
@@ -157,6 +158,12 @@ int ara_search_set_position(ara_search_t s, int tree, const ara_board_t* root, c
 int ara_search_go(ara_search_t s);
 int ara_search_result(ara_search_t s, int tree, ara_search_result_t* out);
 /* per-phase device times of the last go (CUDA events on the search stream); enable before ara_search_go */
+/* MCTSAgent::apply_move_to_tree (agents/mctsagent.cpp:230-247): tells the tree which move was played.  The next go
+ * on the position after that move (after both moves, when called twice) continues on the subtree behind it
+ * (init_root_node / get_root_node_from_tree, :113-160) instead of starting a new tree -- provided the subtree's root is
+ * that position, has been visited, and the node pool (ara_search_create max_nodes) has room for another search.
+ * `move` is the engine's 16-bit move code (ara_search_result_t.moves). */
+int ara_search_apply_move(ara_search_t s, int tree, unsigned short move);
 /* ThreadManager's time stop (manager/threadmanager.cpp, SearchLimits::movetime): ms > 0 makes the following go calls
  * stop issuing mini-batches once that much wall time has passed (besides the Simulations / Nodes limits); 0 = off */
 int ara_search_set_movetime(ara_search_t s, double ms);

@@ -67,6 +67,8 @@ struct OSearch {
     int channels, n_labels;
     OPos root_state;
     ONode* root;
+    ONode* next_root; /* ownNextRoot / opponentsNextRoot of MCTSAgent (mctsagent.h): candidate root after applied moves */
+    int next_root_valid;
     /* batch state (SearchThread members) */
     ONode** new_nodes;
     int* new_stm;
@@ -484,6 +486,8 @@ static void free_tree(OSearch* s) {
     for (size_t i = 0; i < s->n_all; ++i) node_free(s->all_nodes[i]);
     s->n_all = 0;
     s->root = NULL;
+    s->next_root = NULL;
+    s->next_root_valid = 0;
 }
 void osearch_free(OSearch* s) {
     free_tree(s);
@@ -512,10 +516,40 @@ void osearch_batch_keys(const OSearch* s, unsigned long long* out) {
     for (int i = 0; i < s->n_new; ++i) out[i] = s->new_nodes[i]->key;
 }
 
-int osearch_set_root(OSearch* s, const OPos* pos) { /* MCTSAgent::evaluate_board_state :292-296, create_new_root_node */
-    free_tree(s);
-    s->num_nodes = s->sum_select_k = s->sum_depth = 0;
+/* MCTSAgent::apply_move_to_tree + pick_next_node (mctsagent.cpp:230-247): the child behind `move` becomes the
+ * candidate root of the next search; applying a second move (the opponent's reply) descends once more.  Returns 1 if a
+ * candidate exists afterwards. */
+int osearch_apply_move(OSearch* s, uint32_t move) {
+    ONode* base = s->next_root_valid ? s->next_root : s->root;
+    s->next_root = NULL;
+    s->next_root_valid = 1; /* from now on only next_root counts (NULL = the tree is dropped at the next search) */
+    if (base == NULL || !base->has_d) return 0; /* is_playout_node */
+    for (int i = 0; i < base->n_actions; ++i)
+        if (base->actions[i] == move) {
+            s->next_root = base->child[i];
+            break;
+        }
+    return s->next_root != NULL;
+}
+
+/* MCTSAgent::evaluate_board_state :292-296 with init_root_node / get_root_node_from_tree (:113-160): 0 = nothing to
+ * search, 1 = new tree (the root needs its network evaluation), 2 = the candidate root of the former tree is reused. */
+int osearch_set_root(OSearch* s, const OPos* pos) {
+    ONode* cand = s->next_root_valid ? s->next_root : NULL;
+    s->next_root = NULL;
+    s->next_root_valid = 0;
+    s->sum_select_k = s->sum_depth = 0;
     s->n_new = s->n_coll = 0;
+    if (cand != NULL && cand->key == pos->key && cand->has_d && cand->visit_sum - cand->free_visits > 0) {
+        /* the rest of the old tree is only garbage-collected by the reference; here it stays allocated */
+        s->root = cand;
+        opos_copy(&s->root_state, pos);
+        s->root->number_parents = 0; /* make_to_root */
+        if (s->root->is_terminal || s->root->n_actions == 0) return 0;
+        return 2;
+    }
+    free_tree(s);
+    s->num_nodes = 0;
     opos_copy(&s->root_state, pos);
     s->root = node_new(s, pos);
     s->root->number_parents = 0; /* make_to_root */
@@ -524,9 +558,7 @@ int osearch_set_root(OSearch* s, const OPos* pos) { /* MCTSAgent::evaluate_board
     return 1;
 }
 
-void osearch_root_results(OSearch* s, const float* value, const float* prob) {
-    fill_nn_results(s, s->root, value[0], prob);
-    prepare_node_for_visits(s->root);
+static void root_noise_and_open(OSearch* s) {
     if (s->st.dirichlet_epsilon > 0.009f) { /* mctsagent.cpp:311-316 */
         float* noise = (float*)malloc(sizeof(float) * (size_t)s->root->n_actions);
         odirichlet_noise(s->st.seed, s->root->n_actions, s->st.dirichlet_alpha, noise);
@@ -536,6 +568,13 @@ void osearch_root_results(OSearch* s, const float* value, const float* prob) {
         fully_expand_node(s->root);
     }
 }
+void osearch_root_results(OSearch* s, const float* value, const float* prob) {
+    fill_nn_results(s, s->root, value[0], prob);
+    prepare_node_for_visits(s->root);
+    root_noise_and_open(s);
+}
+/* reused root: it already has its network results and NodeData; the noise is applied to it like to a new root */
+void osearch_root_reused(OSearch* s) { root_noise_and_open(s); }
 
 static ONode* get_new_child_to_evaluate(OSearch* s, int* type) { /* searchthread.cpp:164-271 (eps features off) */
     ONode* cur = s->root;

@@ -40,7 +40,9 @@ void osearch_free(OSearch* s);
 int osearch_channels(const OSearch* s);
 int osearch_nb_labels(const OSearch* s); /* policy-map length P*64 */
 /* MCTSAgent::evaluate_board_state, first half: new root for `pos`; root planes are placed in slot 0 of planes() */
-int osearch_set_root(OSearch* s, const OPos* pos);
+int osearch_set_root(OSearch* s, const OPos* pos); /* 0 nothing to search, 1 new tree, 2 reused subtree */
+int osearch_apply_move(OSearch* s, uint32_t move);  /* MCTSAgent::apply_move_to_tree */
+void osearch_root_reused(OSearch* s);
 /* set_root_node_predictions second half + prepare_node_for_visits + optional Dirichlet noise */
 void osearch_root_results(OSearch* s, const float* value, const float* prob);
 /* SearchThread::create_mini_batch: returns the number of new leaves whose planes sit in planes() */

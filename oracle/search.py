@@ -47,6 +47,8 @@ def _lib():
                      "osearch_root_node_type"):
             getattr(L, name).argtypes = [ctypes.c_void_p]
         L.osearch_set_root.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.osearch_apply_move.argtypes = [ctypes.c_void_p, ctypes.c_uint]
+        L.osearch_root_reused.argtypes = [ctypes.c_void_p]
         L.osearch_root_results.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.osearch_apply_results.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.osearch_planes.restype = ctypes.c_void_p
@@ -100,12 +102,19 @@ class Search:
         self.pos = pos
         iters = 0
         evals = 0
-        if L.osearch_set_root(h, pos._buf):
-            v, p = net_fn(self._planes(1).copy(), self._keys(1)) if with_keys else net_fn(self._planes(1).copy())
-            v = np.ascontiguousarray(v, np.float32)
-            p = np.ascontiguousarray(p, np.float32)
-            L.osearch_root_results(h, v.ctypes.data, p.ctypes.data)
-            evals += 1
+        rc = L.osearch_set_root(h, pos._buf)
+        self.reused = rc == 2
+        self.nodes_pre_search = 0
+        if rc:
+            if rc == 1:
+                v, p = net_fn(self._planes(1).copy(), self._keys(1)) if with_keys else net_fn(self._planes(1).copy())
+                v = np.ascontiguousarray(v, np.float32)
+                p = np.ascontiguousarray(p, np.float32)
+                L.osearch_root_results(h, v.ctypes.data, p.ctypes.data)
+                evals += 1
+            else:
+                self.nodes_pre_search = L.osearch_root_visits(h) - L.osearch_root_free_visits(h)
+                L.osearch_root_reused(h)
             if L.osearch_root_num_children(h) > 1:
                 while L.osearch_continue(h) and iters < max_iterations:
                     n = L.osearch_create_mini_batch(h)
@@ -121,6 +130,10 @@ class Search:
                     L.osearch_apply_results(h, v.ctypes.data, p.ctypes.data)
                     iters += 1
         return self.result(iters, evals)
+
+    def apply_move(self, move):
+        """MCTSAgent::apply_move_to_tree: keep the subtree behind `move` (oracle move code) for the next run()."""
+        return bool(self.L.osearch_apply_move(self.h, int(move)))
 
     def result(self, iters=0, evals=0):
         L, h = self.L, self.h

@@ -112,7 +112,7 @@ class SearchResult(ctypes.Structure):
                 ("node_type", ctypes.c_int), ("pv_len", ctypes.c_int), ("root_value", ctypes.c_float),
                 ("best_move_q", ctypes.c_float), ("visit_sum", ctypes.c_uint), ("free_visits", ctypes.c_uint),
                 ("iterations", ctypes.c_uint), ("evals", ctypes.c_uint), ("tree_nodes", ctypes.c_int),
-                ("error", ctypes.c_int), ("sum_select_k", ctypes.c_ulonglong), ("sum_depth", ctypes.c_ulonglong),
+                ("error", ctypes.c_int), ("nodes_pre_search", ctypes.c_uint), ("sum_select_k", ctypes.c_ulonglong), ("sum_depth", ctypes.c_ulonglong),
                 ("moves", ctypes.c_uint16 * 512), ("visits", ctypes.c_uint32 * 512), ("q", ctypes.c_float * 512),
                 ("prior", ctypes.c_float * 512), ("policy", ctypes.c_double * 512), ("pv", ctypes.c_uint16 * 256)]
 
@@ -125,7 +125,7 @@ def result_to_dict(r, uci_fn):
              policy=np.array(r.policy[:k], np.float64), root_value=r.root_value, visit_sum=r.visit_sum,
              free_visits=r.free_visits, nodes=r.visit_sum - r.free_visits, best_idx=r.best_idx,
              best_move_q=r.best_move_q, node_type=r.node_type, pv_len=r.pv_len, iterations=r.iterations,
-             evals=r.evals, tree_nodes=r.tree_nodes, sum_select_k=r.sum_select_k, sum_depth=r.sum_depth,
+             evals=r.evals, tree_nodes=r.tree_nodes, sum_select_k=r.sum_select_k, sum_depth=r.sum_depth, nodes_pre_search=r.nodes_pre_search,
              error=r.error, pv=[uci_fn(m) for m in r.pv[:r.pv_len]])
     if k > 0 and r.best_idx >= 0:
         d["best_move"] = d["moves"][r.best_idx]
@@ -176,12 +176,21 @@ class HeSearch:
         self.L.he_search_batch_keys(self.h, k.ctypes.data)
         return k[:n]
 
+    def apply_move(self, move):
+        """MCTSAgent::apply_move_to_tree (16-bit move code of the device rules)."""
+        self.L.he_search_apply_move.argtypes = [ctypes.c_void_p, ctypes.c_uint16]
+        self.L.he_search_apply_move(self.h, int(move))
+
     def run(self, he_state, net_fn, with_keys=False):
         L, h, np = self.L, self.h, self.np
         n = L.he_search_set_root(h, he_state.h)
+        self.reused = n == 2
         if n:
-            v, p = net_fn(self._planes(1), self._keys(1)) if with_keys else net_fn(self._planes(1))
-            v, p = np.ascontiguousarray(v, np.float32), np.ascontiguousarray(p, np.float32)
+            if n == 2:  # kept subtree: no root evaluation, only the noise / opening step
+                v, p = np.zeros(1, np.float32), np.zeros(1, np.float32)
+            else:
+                v, p = net_fn(self._planes(1), self._keys(1)) if with_keys else net_fn(self._planes(1))
+                v, p = np.ascontiguousarray(v, np.float32), np.ascontiguousarray(p, np.float32)
             L.he_search_root_results(h, v.ctypes.data, p.ctypes.data)
             while True:
                 n = L.he_search_create_mini_batch(h)

@@ -189,6 +189,7 @@ int he_search_set_root(HeSearch* s, const HeState* root) {
     s->t.hist_keys = s->hist_keys.data();
     s->t.hist_reps = s->hist_reps.data();
     s->t.hist_len = static_cast<int>(s->hist_keys.size());
+    if (reuse_root(s->t, s->sp, &s->root)) return s->st.done ? 0 : 2;  // 2: the kept subtree is searched on
     create_root(s->t, s->sp, s->ws, &s->root);
     HostWriterFactory wf{s->planes.data(), s->channels};
     for (int b = 0; b < s->st.n_new; ++b) {
@@ -197,6 +198,7 @@ int he_search_set_root(HeSearch* s, const HeState* root) {
     }
     return s->st.n_new;
 }
+void he_search_apply_move(HeSearch* s, unsigned short move) { advance_root(s->t, move); }
 void he_search_root_results(HeSearch* s, const float* values, const float* probs) {
     for (int b = 0; b < s->st.n_new; ++b) scatter_pending(s->t, s->sp, s->ws, b, values, probs, s->n_labels);
     backup_results(s->t, s->sp);

@@ -129,3 +129,40 @@ def test_gpu_search_dirichlet_close_to_oracle():
     assert ro["moves"] == rg["moves"]
     np.testing.assert_allclose(rg["prior"], ro["prior"], rtol=1e-4, atol=1e-7)
     assert rg["visit_sum"] == ro["visit_sum"] and (rg["visits"] > 0).sum() == (ro["visits"] > 0).sum() or True
+
+
+REUSE_CASES = [("crazyhouse", 1, "crazyhouse", 8, 300, {}), ("chess", 0, "chess", 16, 400, {}),
+               ("crazyhouse", 1, "crazyhouse", 8, 0, dict(nodes=250, dirichlet_epsilon=0.25, dirichlet_alpha=0.3)),
+               ("3check", 3, "lichess", 4, 200, {})]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant,vid,mode,batch,sims,extra", REUSE_CASES)
+def test_gpu_tree_reuse_equals_oracle(variant, vid, mode, batch, sims, extra):
+    """MCTSAgent::apply_move_to_tree / init_root_node (agents/mctsagent.cpp:113-160, 230-247) on the device: a game of
+    searched and played moves, every search continuing on the kept subtree, bit-exact with the oracle."""
+    from crazyara_b200.engine import BoardState, MCTSAgent, SearchSettings
+    st = osr.default_settings(mode, batch_size=batch, simulations=sims, node_policy_temperature=1.0, **extra)
+    s = SearchSettings()
+    for f, _ in s._fields_:
+        setattr(s, f, getattr(st, f))
+    pos = Position(None, variant, False)
+    bs = BoardState().set("", False, vid)
+    S = osr.Search(st)
+    agent = MCTSAgent(None, s, 0, 1, 1 << 15)
+    for ply in range(6):
+        ro = S.run(pos, osr.fake_net(S.n_labels), with_keys=True)
+        rg = agent.evaluate_board_state(bs)
+        assert_same_search(ro, rg)
+        assert S.reused == (ply > 0) and rg["nodes_pre_search"] == S.nodes_pre_search
+        order = np.argsort(-ro["visits"].astype(np.int64), kind="stable")
+        pick = int(order[1 if (ply % 3 == 2 and len(order) > 1 and ro["visits"][order[1]] > 0) else 0])
+        uci = ro["moves"][pick]
+        assert S.apply_move(pos.move_from_uci(uci))
+        agent.apply_move_to_tree(uci)
+        pos.push_uci(uci)
+        bs.do_uci(uci)
+    # a position that is not the kept one starts a new tree
+    other = BoardState().set("", False, vid)
+    assert agent.evaluate_board_state(other)["nodes_pre_search"] == 0
+    agent.close()

@@ -29,3 +29,14 @@ def test_arena_real_net_chess960(tmp_path):
     assert res["games"] >= 8 and res["nps"] > 0
     arena.close()
     net.close()
+
+
+@pytest.mark.gpu
+def test_arena_with_tree_reuse():
+    """Reuse_Tree in self-play: the subtree of the played move carries its visits into the next search."""
+    from crazyara_b200.selfplay import Arena, rl_settings
+    st = rl_settings("crazyhouse", batch_size=8, nodes=80, simulations=320)
+    arena = Arena(None, st, variant=1, n_games=4, temperature_moves=6, max_plies=30, seed=5, reuse_tree=True)
+    res = arena.run(min_games=4, max_steps=40)
+    assert res["games"] >= 4 and res["reused_nodes"] > 0 and res["nodes"] > 0
+    arena.close()

@@ -50,3 +50,34 @@ def test_uci_time_managed_go():
     assert 150 <= times[0] <= 450 and 500 <= times[1] <= 900 and nodes[1] > nodes[0] > 1000
     assert nodes[2] >= 300 and nodes[2] < 400   # back to a visit budget: the time limit is off again
     assert wall < 60
+
+
+@pytest.mark.gpu
+def test_uci_position_extension_reuses_the_tree():
+    """`position ... moves` that extends the searched game walks the kept tree (Reuse_Tree, apply_move_to_tree for our
+    move and the reply); the second search equals the Python agent doing the same, and reports the reused nodes."""
+    from crazyara_b200.engine import BoardState, MCTSAgent, default_settings
+    st = BoardState().set("", False, 1)
+    agent = MCTSAgent(None, default_settings("crazyhouse", batch_size=8, simulations=300, node_policy_temperature=1.0), 0, 1, 4096)
+    r0 = agent.evaluate_board_state(st)
+    best, reply = r0["pv"][0], r0["pv"][1]
+    for m in (best, reply):
+        agent.apply_move_to_tree(m)
+        st.do_uci(m)
+    r1 = agent.evaluate_board_state(st)
+    assert r1["nodes_pre_search"] > 0
+    exe = os.path.join(ROOT, "crazyara_b200", "ara_uci")
+    head = ["uci", "setoption name UCI_Variant value crazyhouse", "setoption name Batch_Size value 8",
+            "setoption name Simulations value 300", "setoption name Centi_Node_Temperature value 100", "isready"]
+    game = ["position startpos", "go", f"position startpos moves {best} {reply}", "go", "quit"]
+    out = subprocess.run([exe], input="\n".join(head + game) + "\n", capture_output=True, text=True, timeout=120).stdout
+    lines = out.splitlines()
+    assert [l for l in lines if l.startswith("info string reused")] == [f"info string reused {r1['nodes_pre_search']} nodes"]
+    bests = [l.split()[1] for l in lines if l.startswith("bestmove")]
+    nodes = [int(l.split(" nodes ")[1].split()[0]) for l in lines if l.startswith("info depth")]
+    assert bests == [best, r1["best_move"]] and nodes == [r0["nodes"], r1["nodes"]]
+    # with the option off the second search starts from scratch
+    off = head[:-1] + ["setoption name Reuse_Tree value false", "isready"] + game
+    out = subprocess.run([exe], input="\n".join(off) + "\n", capture_output=True, text=True, timeout=120).stdout
+    assert "info string reused" not in out
+    agent.close()

@@ -74,6 +74,9 @@ Net::~Net() {
     for (void* p : allocs_) cudaFree(p);
     rise_trunk_destroy(&trunk_);
     if (stream) cudaStreamDestroy(stream);
+    if (head_stream) cudaStreamDestroy(head_stream);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
 }
 
 int Net::init(const char* blob_path, int dev, int batch_size) {
@@ -90,6 +93,10 @@ int Net::init(const char* blob_path, int dev, int batch_size) {
                              prop.major, prop.minor);
     }
     ARA_CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    ARA_CUDA_OK(cudaStreamCreateWithFlags(&head_stream, cudaStreamNonBlocking));
+    ARA_CUDA_OK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    ARA_CUDA_OK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    if (const char* e = getenv("ARA_NET_FORK_HEADS")) fork_heads = atoi(e) != 0;
     {
         const char* f = getenv("ARA_FUSED_BLOCKS");
         use_fused = (f != nullptr && f[0] == '1');  // opt-in until it beats the three-kernel path (profiles/README.md)
@@ -348,10 +355,18 @@ int Net::enqueue(int n, cudaStream_t s, bool from_f32) {
     }
     __half* xfinal = d_x[hdr.n_blocks & 1];
     ValueHeadW vw{vh_wv, vh_bv, vh_w1t, vh_b1, vh_w2, vh_b2, vh_wdl_w, vh_wdl_b, vh_plys_w, vh_plys_b, hdr.wdl_mode};
-    ARA_CUDA_OK(launch_pdl(value_head_kernel, dim3(n), dim3(256), 0, s, xfinal, vw, d_value, d_aux));
+    if (fork_heads) {  // value head on the side stream (a second branch of the captured graph), policy head on s
+        ARA_CUDA_OK(cudaEventRecord(ev_fork, s));
+        ARA_CUDA_OK(cudaStreamWaitEvent(head_stream, ev_fork, 0));
+        value_head_kernel<<<dim3(n), dim3(256), 0, head_stream>>>(xfinal, vw, d_value, d_aux);
+        ARA_CUDA_OK(cudaEventRecord(ev_join, head_stream));
+    } else {
+        ARA_CUDA_OK(launch_pdl(value_head_kernel, dim3(n), dim3(256), 0, s, xfinal, vw, d_value, d_aux));
+    }
     if (conv_layer_launch(&pol_conv1, n, s)) return -1;
     if (conv_layer_launch(&pol_conv2, n, s)) return -1;
     ARA_CUDA_OK(launch_pdl(policy_softmax_kernel, dim3(n), dim3(256), n_labels() * 4, s, d_logits, d_prob, hdr.policy_channels, ldp));
+    if (fork_heads) ARA_CUDA_OK(cudaStreamWaitEvent(s, ev_join, 0));
     launches += 4;
     ARA_CUDA_OK(cudaGetLastError());
     return 0;

@@ -65,6 +65,10 @@ class Net {
     int kernels_per_forward(bool from_f32) const;
     int trunk_cycles(unsigned long long* out32);  // -DARA_TRUNK_PROF builds: per-role cycle counters of CTA 0
     cudaStream_t stream = nullptr;
+    // the value head runs beside the policy head: forked side stream, joined before the forward ends
+    cudaStream_t head_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool fork_heads = true;  // ARA_NET_FORK_HEADS=0: both heads in sequence on one stream
 
     // device buffers
     float* d_in_f32 = nullptr;   // [batch, C, 64]

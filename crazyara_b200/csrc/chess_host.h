@@ -222,4 +222,47 @@ inline Move uci_to_move(const Board& b, const std::string& uci) {
     return 0;
 }
 
+// pgn_move / is_pgn_move_ambiguous (environments/chess_related/board.cpp:277-385): the SAN spelling the reference
+// writes into its PGN files -- promotions without '=', the origin file on pawn captures, disambiguation by file unless
+// another candidate shares the file (then the rank; both: the whole square), '+' / '#' from gives_check.
+inline std::string move_to_san(const Board& b, Move m, const std::vector<Move>& legal, bool leads_to_win) {
+    static const char* kW = "PNBRQK";
+    if (m == 0) return "(none)";
+    const int from = mv_from(m), to = mv_to(m), flag = mv_flag(m);
+    auto square = [](int s) { return std::string{static_cast<char>('a' + (s & 7)), static_cast<char>('1' + (s >> 3))}; };
+    std::string out;
+    if (flag >= MF_DROP) {
+        out = std::string{kW[flag - MF_DROP], '@'} + square(to);
+    } else if (flag == MF_CASTLE) {
+        out = (from & 7) < (to & 7) ? "O-O" : "O-O-O";
+    } else {
+        const int pt = piece_type_on(b, from);
+        bool ambiguous = false, same_file = false, same_rank = false;
+        for (Move o : legal) {
+            if (mv_flag(o) >= MF_DROP) continue;
+            const int of = mv_from(o);
+            if (mv_to(o) == to && of != from && piece_type_on(b, of) == pt) {
+                ambiguous = true;
+                if ((of & 7) == (from & 7)) same_file = true;
+                if ((of >> 3) == (from >> 3)) same_rank = true;
+            }
+        }
+        std::string origin;
+        if (ambiguous)
+            origin = same_file && same_rank ? square(from)
+                                            : (same_file ? std::string{static_cast<char>('1' + (from >> 3))}
+                                                         : std::string{static_cast<char>('a' + (from & 7))});
+        const bool capture = flag == MF_EP || ((b.by_color[0] | b.by_color[1]) & bit(to)) != 0;
+        if (pt == PT_PAWN)
+            out = capture ? std::string{static_cast<char>('a' + (from & 7)), 'x'} + square(to) : square(to);
+        else
+            out = std::string{kW[pt]} + origin + (capture ? "x" : "") + square(to);
+        if (flag >= MF_PROMO_N && flag <= MF_PROMO_Q) out += kW[flag];
+    }
+    Board after = b;
+    do_move(after, m);
+    if (in_check(after)) out += leads_to_win ? "#" : "+";
+    return out;
+}
+
 }  // namespace ara

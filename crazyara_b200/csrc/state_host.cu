@@ -85,6 +85,21 @@ extern "C" int ara_state_legal_moves(ara_state_t h, unsigned short* moves_out) {
     return static_cast<int>(mv.size());
 }
 extern "C" int ara_state_side_to_move(ara_state_t h) { return h ? reinterpret_cast<HostState*>(h)->b.stm : -1; }
+extern "C" int ara_state_in_check(ara_state_t h) {
+    if (h == nullptr) return set_error("ara_state_in_check: null state");
+    return in_check(reinterpret_cast<HostState*>(h)->b) ? 1 : 0;
+}
+extern "C" int ara_state_move_to_san(ara_state_t h, unsigned short move, int leads_to_win, char* buf16) {
+    if (h == nullptr || buf16 == nullptr) return set_error("ara_state_move_to_san: null argument");
+    const Board& b = reinterpret_cast<HostState*>(h)->b;
+    const std::vector<Move> legal = legal_moves_host(b);
+    bool found = false;
+    for (Move m : legal) found = found || m == move;
+    if (!found) return set_error("ara_state_move_to_san: move 0x%04x is not legal here", move);
+    const std::string s = move_to_san(b, move, legal, leads_to_win != 0);
+    memcpy(buf16, s.c_str(), s.size() + 1);
+    return 0;
+}
 extern "C" int ara_state_is_terminal(ara_state_t h) {
     if (h == nullptr) return set_error("ara_state_is_terminal: null state");
     const Board& b = reinterpret_cast<HostState*>(h)->b;

@@ -63,6 +63,8 @@ def _L():
         L.ara_state_legal_moves.argtypes = [vp, vp]
         L.ara_state_side_to_move.argtypes = [vp]
         L.ara_state_is_terminal.argtypes = [vp]
+        L.ara_state_in_check.argtypes = [vp]
+        L.ara_state_move_to_san.argtypes = [vp, ctypes.c_ushort, ci, ctypes.c_char_p]
         L.ara_move_to_uci.argtypes = [ctypes.c_ushort, ci, cs]
         L.ara_board_from_fen.argtypes = [cs, ci, ci, vp]
         L.ara_encode_planes.argtypes = [vp, ci, ci, ci, ci, vp]
@@ -160,6 +162,17 @@ class BoardState:
 
     def do_action(self, action):
         check(_L().ara_state_do_move(self._h, int(action)))
+
+    def in_check(self):
+        return bool(_L().ara_state_in_check(self._h))
+
+    def action_to_san(self, action, leads_to_win=False):
+        """State::action_to_san -> pgn_move (board.cpp:277-359); `action` may be the 16-bit code or a UCI string."""
+        if isinstance(action, str):
+            action = self.uci_to_action(action)
+        b = ctypes.create_string_buffer(16)
+        check(_L().ara_state_move_to_san(self._h, int(action), int(leads_to_win), b))
+        return b.value.decode()
 
     def do_uci(self, *moves):
         for u in moves:

@@ -8,7 +8,8 @@ so multi-GPU scaling is N independent processes -- no collective.
 
 Move selection follows Agent::set_best_move / MCTSAgent play settings (agents/agent.cpp:38-53): argmax of the MCTS
 posterior, or a sample from posterior^(1/T) during the first `temperature_moves` plies (RL defaults:
-DeepCrazyhouse/configs/rl_config.py:34-65).  Training-sample export (zarr) is out of scope.
+DeepCrazyhouse/configs/rl_config.py:34-65).  Optional outputs: training samples (`exporter=`, crazyara_b200.export) and
+the games as PGN (`pgn_path=`, crazyara_b200.pgn).
 """
 import time
 
@@ -17,6 +18,7 @@ import numpy as np
 from .engine import (BoardState, MCTSAgent, TERMINAL_DRAW, TERMINAL_LOSS, TERMINAL_NONE, TERMINAL_WIN, default_settings,
                      encode_planes)
 from .export import BLACK_WIN, DRAWN, WHITE_WIN
+from .pgn import GamePGN, result_string
 
 
 def rl_settings(mode, **kw):
@@ -29,7 +31,7 @@ def rl_settings(mode, **kw):
 
 class Arena:
     def __init__(self, net, settings, variant, n_games, device=0, is960=False, temperature=0.8, temperature_moves=15,
-                 max_plies=512, seed=0, max_nodes=0, exporter=None, reuse_tree=False):
+                 max_plies=512, seed=0, max_nodes=0, exporter=None, reuse_tree=False, pgn_path=None):
         self.variant, self.is960 = variant, is960
         self.n_games = n_games
         self.temperature, self.temperature_moves, self.max_plies = temperature, temperature_moves, max_plies
@@ -49,6 +51,13 @@ class Arena:
         self.reuse_tree = reuse_tree
         self.settings = settings
         self.records = [exporter.new_game() for _ in range(n_games)] if exporter is not None else None
+        # games.pgn of the reference's self-play (selfplay.cpp:315-324): one GamePGN per running game
+        self.pgn_path = pgn_path
+        self.pgns = None
+        if pgn_path is not None:
+            self.pgns = [GamePGN(variant, is960, "CrazyAra-B200", "CrazyAra-B200") for _ in range(n_games)]
+            for g, st in zip(self.pgns, self.states):
+                g.fen = st.fen()
 
     def _new_state(self):
         return BoardState().set("", self.is960, self.variant)
@@ -63,17 +72,22 @@ class Arena:
 
     def _game_over(self, t, term, stm_at_end):
         self.finished.append((self.plies[t], term, stm_at_end))
+        # the side to move at the end lost (mate, variant loss) or won (variant win); everything else is a draw
+        if term == TERMINAL_LOSS:
+            result = BLACK_WIN if stm_at_end == 0 else WHITE_WIN
+        elif term == TERMINAL_WIN:
+            result = WHITE_WIN if stm_at_end == 0 else BLACK_WIN
+        else:
+            result = DRAWN
         if self.exporter is not None:
-            # the side to move at the end lost (mate, variant loss) or won (variant win); everything else is a draw
-            if term == TERMINAL_LOSS:
-                result = BLACK_WIN if stm_at_end == 0 else WHITE_WIN
-            elif term == TERMINAL_WIN:
-                result = WHITE_WIN if stm_at_end == 0 else BLACK_WIN
-            else:
-                result = DRAWN
             self.exporter.export_game_samples(self.records[t], result)
             self.records[t] = self.exporter.new_game()
         self.states[t], self.plies[t] = self._new_state(), 0
+        if self.pgns is not None:
+            self.pgns[t].result = result_string(result)
+            self.pgns[t].write(self.pgn_path)
+            self.pgns[t].new_game()
+            self.pgns[t].fen = self.states[t].fen()
 
     def step(self):
         """One move in every running game."""
@@ -98,7 +112,10 @@ class Arena:
                                           st.side_to_move())
             if self.reuse_tree:
                 self.agent.apply_move_to_tree(res["moves"][idx], t)
-            st.do_uci(res["moves"][idx])
+            if self.pgns is not None:
+                self.pgns[t].play_move(st, res["moves"][idx])
+            else:
+                st.do_uci(res["moves"][idx])
             self.plies[t] += 1
             term = st.is_terminal()
             if term != TERMINAL_NONE or self.plies[t] >= self.max_plies:

@@ -92,6 +92,10 @@ int ara_state_fen(ara_state_t s, char* buf, int buf_len);                      /
 int ara_state_legal_moves(ara_state_t s, unsigned short* moves_out);           /* returns the count */
 int ara_state_side_to_move(ara_state_t s);
 int ara_state_is_terminal(ara_state_t s);                                      /* TerminalType */
+int ara_state_in_check(ara_state_t s);                                         /* 1 if the side to move is in check */
+/* State::action_to_san -> pgn_move (environments/chess_related/board.cpp:277-359): SAN as the reference's PGN files
+   spell it (promotion without '=', "O-O", drops "N@f3"); leads_to_win turns a trailing '+' into '#'.  buf16: >= 16 B */
+int ara_state_move_to_san(ara_state_t s, unsigned short move, int leads_to_win, char* buf16);
 
 /* ---- Search seam: replaces MCTSAgent::evaluate_board_state + SearchThread::thread_iteration + Node
  * (agents/mctsagent.cpp:292-337, searchthread.cpp:403-426, node.{h,cpp}) with a device-resident tree.

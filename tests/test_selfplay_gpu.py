@@ -40,3 +40,23 @@ def test_arena_with_tree_reuse():
     res = arena.run(min_games=4, max_steps=40)
     assert res["games"] >= 4 and res["reused_nodes"] > 0 and res["nodes"] > 0
     arena.close()
+
+
+@pytest.mark.gpu
+def test_arena_writes_pgn(tmp_path):
+    """games.pgn of the reference's self-play: every finished game is appended with its result and SAN moves."""
+    from crazyara_b200.selfplay import Arena, rl_settings
+    st = rl_settings("crazyhouse", batch_size=8, nodes=60, simulations=240)
+    path = str(tmp_path / "games.pgn")
+    arena = Arena(None, st, variant=1, n_games=4, temperature_moves=8, max_plies=24, seed=11, pgn_path=path)
+    res = arena.run(min_games=4, max_steps=40)
+    arena.close()
+    text = open(path).read()
+    games = text.count('[Variant "crazyhouse"]')
+    assert games == res["games"] >= 4
+    assert text.count("[Result ") == games and '[PlyCount "0"]' not in text
+    for block in text.strip().split("\n\n\n"):
+        header, body = block.split("\n\n", 1)
+        plies = int(header.split('[PlyCount "')[1].split('"')[0])
+        tokens = [t for t in body.split() if not t.endswith(".")]
+        assert len(tokens) == plies + 1 and tokens[-1] in ("1-0", "0-1", "1/2-1/2")

@@ -18,6 +18,7 @@
 #include "ara_b200.h"
 #include "net.h"
 #include "search_dev.cuh"
+#include "time_manager.h"
 
 namespace ara {
 
@@ -109,6 +110,11 @@ __global__ void __launch_bounds__(32) result_kernel(const TreeDev* trees, Search
     if (threadIdx.x == 0) collect_result(t, sp, &out[blockIdx.x]);
 }
 
+__global__ void __launch_bounds__(32) time_stats_kernel(const TreeDev* trees, RootTimeStats* out) {
+    const TreeDev t = trees[blockIdx.x];
+    if (threadIdx.x == 0) collect_time_stats(t, &out[blockIdx.x]);
+}
+
 // Fake backend: value/prob rows of the pending new nodes from their Zobrist keys (oracle/fake.c definition).
 __global__ void fake_eval_kernel(const TreeDev* trees, int n_trees, int batch, float* values, float* probs, int n_labels) {
     const int slot = blockIdx.x;  // tree * batch + b
@@ -142,6 +148,13 @@ class Search {
     long long launches = 0;
     double last_go_ms = 0.0;
     double movetime_ms = 0.0;  // > 0: stop issuing iterations once this much wall time has passed (UCI `go movetime`)
+    // ThreadManager heuristics (time_manager.h): parameters, and what happened in the last go
+    bool use_tc = false;
+    ara_time_control_t tc{};
+    ara_time_report_t tr{};
+    RootTimeStats* d_tstats_ = nullptr;
+    RootTimeStats* h_tstats_ = nullptr;  // pinned
+    int read_time_stats(RootStatsHost* out);
     // per-phase device times of the last go (CUDA events on the search stream), filled when profile is on
     bool profile = false;
     double select_ms = 0.0, net_ms = 0.0, apply_ms = 0.0;
@@ -216,6 +229,8 @@ Search::~Search() {
     if (stream_) cudaStreamSynchronize(stream_);
     for (void* p : allocs_) cudaFree(p);
     if (h_done_) cudaFreeHost(h_done_);
+    if (h_tstats_) cudaFreeHost(h_tstats_);
+    if (d_tstats_) cudaFree(d_tstats_);
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
     for (cudaEvent_t e : prof_events_) cudaEventDestroy(e);
@@ -310,6 +325,8 @@ int Search::init(Net* net, const SearchParams& params, int device, int trees, in
     h_roots_.resize(n_trees);
     results.resize(n_trees);
     ARA_CUDA_OK(cudaMallocHost(&h_done_, sizeof(int) * n_trees));
+    ARA_CUDA_OK(cudaMallocHost(&h_tstats_, sizeof(RootTimeStats)));
+    ARA_CUDA_OK(cudaMalloc(&d_tstats_, sizeof(RootTimeStats)));
     ARA_CUDA_OK(cudaEventCreate(&ev0_));
     ARA_CUDA_OK(cudaEventCreate(&ev1_));
     return 0;
@@ -395,16 +412,57 @@ int Search::go() {
     // movetime (ThreadManager's stop after curMovetime, manager/threadmanager.cpp): iterations go out in small chunks
     // and the wall clock is read between them
     const auto t_start = std::chrono::steady_clock::now();
-    const bool timed = movetime_ms > 0.0;
+    auto elapsed_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
+    const bool managed = use_tc && n_trees == 1 && tc.movetime_ms > 0.0;
+    const double move_ms = managed ? tc.movetime_ms : movetime_ms;
+    const bool timed = move_ms > 0.0;
     if (timed && first > 4) first = 4;
     bool all_done = false;
     int chunk = first;
     int guard = 0;
     bool polled_root = false;
+    // ThreadManager::stop_search_based_on_limits: the move time is spent in update intervals; after each one the early
+    // stopping rule is consulted, and when a period of move time is over the search may be prolonged by another one
+    double period_end = move_ms;
+    double next_check = managed ? tc.update_interval_ms : 0.0;
+    int checked = 0;
+    float last_eval = tc.last_value_eval;
+    tr = ara_time_report_t{};
     while (!all_done) {
-        if (timed && polled_root &&
-            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count() >= movetime_ms)
-            break;
+        if (timed && polled_root) {
+            const double now = elapsed_ms();
+            if (managed && now >= next_check && now < period_end) {
+                RootStatsHost rs;
+                if (read_time_stats(&rs)) return -1;
+                const double remaining = period_end - next_check;  // remainingMoveTimeMS after this interval
+                next_check += tc.update_interval_ms;
+                tr.value_eval = rs.value_eval;
+                if (checked == 0) {
+                    const int rule = tm_early_stopping(tc, remaining, rs);
+                    if (rule != 0 && !tm_continue_search(tc, remaining, rs, &checked, &last_eval)) {
+                        tr.early_stopped = rule;
+                        tr.saved_ms = remaining;
+                        break;
+                    }
+                }
+            }
+            if (now >= period_end) {
+                // `while (continue_search())` of the reference: what is left of the period by then is the division
+                // remainder of move time by update interval, below the interval, so the literal rule cannot extend
+                // the search here -- evaluated all the same, with the same arguments
+                bool more = false;
+                if (managed) {
+                    RootStatsHost rs;
+                    if (read_time_stats(&rs)) return -1;
+                    tr.value_eval = rs.value_eval;
+                    const double left = move_ms - std::floor(move_ms / tc.update_interval_ms) * tc.update_interval_ms;
+                    more = tm_continue_search(tc, left, rs, &checked, &last_eval);
+                }
+                if (!more) break;
+                period_end += move_ms;  // "Increase search time"
+                next_check = now + tc.update_interval_ms;
+            }
+        }
         if (polled_root && iterate(chunk)) return -1;
         for (int i = 0; i < n_trees; ++i)
             ARA_CUDA_OK(cudaMemcpyAsync(&h_done_[i], &d_states_[i]->done, sizeof(int), cudaMemcpyDeviceToHost, stream_));
@@ -425,12 +483,24 @@ int Search::go() {
         polled_root = true;
         if (++guard > (1 << 22)) return set_error("ara_search_go: search did not terminate");
     }
+    tr.prolonged = checked;
+    tr.elapsed_ms = elapsed_ms();
     ARA_CUDA_OK(cudaEventRecord(ev1_, stream_));
     ARA_CUDA_OK(cudaEventSynchronize(ev1_));
     float ms = 0.0f;
     ARA_CUDA_OK(cudaEventElapsedTime(&ms, ev0_, ev1_));
     last_go_ms = ms;
     if (profile && prof_collect()) return -1;
+    return 0;
+}
+
+int Search::read_time_stats(RootStatsHost* out) {
+    time_stats_kernel<<<1, 32, 0, stream_>>>(d_trees_, d_tstats_);
+    ++launches;
+    ARA_CUDA_OK(cudaMemcpyAsync(h_tstats_, d_tstats_, sizeof(RootTimeStats), cudaMemcpyDeviceToHost, stream_));
+    ARA_CUDA_OK(cudaStreamSynchronize(stream_));
+    static_assert(sizeof(RootStatsHost) == sizeof(RootTimeStats), "root statistics layout");
+    memcpy(out, h_tstats_, sizeof(*out));
     return 0;
 }
 
@@ -525,6 +595,42 @@ extern "C" int ara_search_set_movetime(ara_search_t h, double ms) {
     if (h == nullptr) return ara::set_error("ara_search_set_movetime: null handle");
     reinterpret_cast<Search*>(h)->movetime_ms = ms > 0.0 ? ms : 0.0;
     return 0;
+}
+extern "C" int ara_search_set_time_control(ara_search_t h, const ara_time_control_t* tc) {
+    if (h == nullptr) return ara::set_error("ara_search_set_time_control: null handle");
+    Search* s = reinterpret_cast<Search*>(h);
+    if (tc == nullptr) {
+        s->use_tc = false;
+        return 0;
+    }
+    if (!(tc->movetime_ms > 0.0) || !(tc->update_interval_ms > 0.0))
+        return ara::set_error("ara_search_set_time_control: movetime %.1f ms / update interval %.1f ms must be positive",
+                              tc->movetime_ms, tc->update_interval_ms);
+    if (s->n_trees != 1) return ara::set_error("ara_search_set_time_control: the time manager drives single-tree searches");
+    s->tc = *tc;
+    s->use_tc = true;
+    return 0;
+}
+extern "C" int ara_search_time_report(ara_search_t h, ara_time_report_t* out) {
+    if (h == nullptr || out == nullptr) return ara::set_error("ara_search_time_report: null argument");
+    *out = reinterpret_cast<Search*>(h)->tr;
+    return 0;
+}
+extern "C" int ara_time_early_stopping(const ara_time_control_t* tc, double remaining_ms, unsigned node_count,
+                                       int max_q_is_max_visits, unsigned first_visits, unsigned second_visits, float q_first,
+                                       float q_second) {
+    if (tc == nullptr) return ara::set_error("ara_time_early_stopping: null argument");
+    const ara::RootStatsHost r{node_count, first_visits, second_visits, q_first, q_second, max_q_is_max_visits, 0.0f, 1};
+    return ara::tm_early_stopping(*tc, remaining_ms, r);
+}
+extern "C" int ara_time_continue_search(const ara_time_control_t* tc, double remaining_ms, float value_eval, int* checked,
+                                        float* last_value_eval) {
+    if (tc == nullptr || checked == nullptr || last_value_eval == nullptr)
+        return ara::set_error("ara_time_continue_search: null argument");
+    ara::RootStatsHost r{};
+    r.value_eval = value_eval;
+    r.valid = 1;
+    return ara::tm_continue_search(*tc, remaining_ms, r, checked, last_value_eval) ? 1 : 0;
 }
 extern "C" int ara_search_set_profile(ara_search_t h, int on) {
     if (h == nullptr) return ara::set_error("ara_search_set_profile: null handle");

@@ -388,6 +388,7 @@ ARA_HD SelectStep select_and_visit(const TreeDev& t, const SearchParams& sp, int
     SelectStep r;
     r.ci = pk.ci;
     const int owner_lane = pk.ci & (ARA_WARP_N - 1);
+    (void)owner_lane;  // the 1-lane host build has no shuffles
     r.child = ARA_SHFL(pk.x.c, owner_lane);
     const uint32_t cb = ARA_SHFL(pk.x.cb, owner_lane);
     ARA_FINE(t.st, 7, tf, r.child);
@@ -561,6 +562,7 @@ ARA_HD int repetition_on_path(const TreeDev& t, const WarpScratch& ws, int depth
             const int src = __ffs(m) - 1;
 #else
             const int src = 0;
+            (void)src;
 #endif
             const int ri = ARA_SHFL(rep, src);
             const int ii = ARA_SHFL(i, src);
@@ -1286,6 +1288,60 @@ ARA_HD void finalize_root(const TreeDev& t, const SearchParams& sp, WarpScratch&
         if (sp.dirichlet_epsilon > 0.009f && h.n_moves > 1) apply_dirichlet_to_root(t, sp, ws);
     }
     ARA_WARP_SYNC();
+}
+
+// ------------------------------------------------------------------ root statistics for the ThreadManager heuristics
+// What ThreadManager::early_stopping / continue_search (manager/threadmanager.cpp:114-178) read off the root while the
+// search runs.  Lane 0.
+struct RootTimeStats {
+    unsigned node_count;      // Node::get_node_count(): visits - free visits of the root
+    unsigned first_visits;    // first_and_second_max over the open children, each less its child's free visits
+    unsigned second_visits;
+    float q_first, q_second;  // Node::get_q_value of those two
+    int max_q_is_max_visits;  // max_q_child() == max_visits_child()
+    float value_eval;         // Node::updated_value_eval (node.cpp:784-810)
+    int valid;                // the root has at least one open child
+};
+ARA_HD void collect_time_stats(const TreeDev& t, RootTimeStats* r) {
+    const TreeState& st = *t.st;
+    const NodeHdr& h = t.hdr[st.root];
+    r->node_count = h.visit_sum - h.free_visits;
+    r->first_visits = r->second_visits = 0;
+    r->q_first = r->q_second = 0.0f;
+    r->max_q_is_max_visits = 0;
+    r->value_eval = h.real_visits ? node_value(h) : 0.0f;
+    r->valid = 0;
+    const int k = h.no_visit_idx;
+    if (st.n_nodes <= 0 || k <= 0 || !(h.flags & NF_HAS_D)) return;
+    r->valid = 1;
+    const uint32_t e = h.edge_base;
+    // first_and_second_max (util/blazeutil.h:149-177): strict '>' scans, so the first maximum wins
+    uint32_t first = t.N[e], second = 0;
+    int a1 = 0, a2 = 0, best_q = 0;
+    for (int i = 1; i < k; ++i) {
+        const uint32_t n = t.N[e + i];
+        if (n > first) {
+            second = first, a2 = a1;
+            first = n, a1 = i;
+        } else if (n > second) {
+            second = n, a2 = i;
+        }
+        if (t.Q[e + i] > t.Q[e + best_q]) best_q = i;
+    }
+    r->max_q_is_max_visits = best_q == a1;
+    r->q_first = t.Q[e + a1];
+    r->q_second = t.Q[e + a2];
+    const int c1 = t.child[e + a1], c2 = t.child[e + a2];
+    if (c1 >= 0 && (t.hdr[c1].flags & NF_HAS_D)) first -= t.hdr[c1].free_visits;
+    if (c2 >= 0 && (t.hdr[c2].flags & NF_HAS_D)) second -= t.hdr[c2].free_visits;
+    r->first_visits = first;
+    r->second_visits = second;
+    if ((h.flags & NF_SORTED) && h.visit_sum != 1) {
+        if (h.node_type == NT_WIN) r->value_eval = 1.0f;
+        else if (h.node_type == NT_DRAW) r->value_eval = 0.0f;
+        else if (h.node_type == NT_LOSS) r->value_eval = -1.0f;
+        else r->value_eval = t.Q[e + a1];
+    }
 }
 
 // ------------------------------------------------------------------ results (lane 0): update_eval_info

@@ -32,6 +32,31 @@ class SearchSettings(ctypes.Structure):
                 ("mode", ctypes.c_int), ("input_version", ctypes.c_int)]
 
 
+class TimeControl(ctypes.Structure):
+    """ara_time_control_t: what MCTSAgent::run_mcts_search hands to the ThreadManager (agents/mctsagent.cpp:350-352)."""
+    _fields_ = [("movetime_ms", ctypes.c_double), ("update_interval_ms", ctypes.c_double), ("overall_nps", ctypes.c_double),
+                ("safe_remaining_ms", ctypes.c_double), ("move_overhead_ms", ctypes.c_double),
+                ("last_value_eval", ctypes.c_float), ("in_game", ctypes.c_int), ("can_prolong", ctypes.c_int)]
+
+
+class TimeReport(ctypes.Structure):
+    _fields_ = [("early_stopped", ctypes.c_int), ("prolonged", ctypes.c_int), ("saved_ms", ctypes.c_double),
+                ("elapsed_ms", ctypes.c_double), ("value_eval", ctypes.c_float)]
+
+
+def early_stopping(tc, remaining_ms, node_count, max_q_is_max_visits, first_visits, second_visits, q_first, q_second):
+    """ThreadManager::early_stopping as a pure function: 0 keep searching, 1 'max nodes' rule, 2 'cannot catch up' rule."""
+    return _L().ara_time_early_stopping(ctypes.byref(tc), float(remaining_ms), int(node_count), int(max_q_is_max_visits),
+                                        int(first_visits), int(second_visits), float(q_first), float(q_second))
+
+
+def continue_search(tc, remaining_ms, value_eval, checked, last_value_eval):
+    """ThreadManager::continue_search as a pure function; returns (prolong?, checked', last_value_eval')."""
+    c, l = ctypes.c_int(checked), ctypes.c_float(last_value_eval)
+    r = _L().ara_time_continue_search(ctypes.byref(tc), float(remaining_ms), float(value_eval), ctypes.byref(c), ctypes.byref(l))
+    return bool(r), c.value, l.value
+
+
 class SearchResult(ctypes.Structure):
     _fields_ = [("n_moves", ctypes.c_int), ("no_visit_idx", ctypes.c_int), ("best_idx", ctypes.c_int),
                 ("node_type", ctypes.c_int), ("pv_len", ctypes.c_int), ("root_value", ctypes.c_float),
@@ -78,6 +103,11 @@ def _L():
         L.ara_search_result.argtypes = [vp, ci, vp]
         L.ara_search_set_profile.argtypes = [vp, ci]
         L.ara_search_apply_move.argtypes = [vp, ci, ctypes.c_ushort]
+        L.ara_search_set_time_control.argtypes = [vp, vp]
+        L.ara_search_time_report.argtypes = [vp, vp]
+        L.ara_time_early_stopping.argtypes = [vp, ctypes.c_double, ctypes.c_uint, ci, ctypes.c_uint, ctypes.c_uint,
+                                              ctypes.c_float, ctypes.c_float]
+        L.ara_time_continue_search.argtypes = [vp, ctypes.c_double, ctypes.c_float, vp, vp]
         L.ara_search_set_movetime.argtypes = [vp, ctypes.c_double]
         L.ara_search_profile.argtypes = [vp] + [vp] * 4
         L.ara_search_last_go_ms.restype = ctypes.c_double
@@ -286,6 +316,16 @@ class MCTSAgent:
         if isinstance(move, str):
             move = self._states[tree].uci_to_action(move)
         check(_L().ara_search_apply_move(self._h, tree, int(move)))
+
+    def set_time_control(self, tc):
+        """ThreadManager heuristics for the following searches (TimeControl), None = off."""
+        check(_L().ara_search_set_time_control(self._h, ctypes.byref(tc) if tc is not None else None))
+
+    def time_report(self):
+        r = TimeReport()
+        check(_L().ara_search_time_report(self._h, ctypes.byref(r)))
+        return dict(early_stopped=r.early_stopped, prolonged=r.prolonged, saved_ms=r.saved_ms, elapsed_ms=r.elapsed_ms,
+                    value_eval=r.value_eval)
 
     def set_movetime(self, ms):
         """SearchLimits::movetime: following searches also stop after `ms` of wall time (0 = off)."""

@@ -185,7 +185,39 @@ class MCTSAgent {
         evalInfo.nodesPreSearch = r.nodes_pre_search;
         evalInfo.depth = static_cast<size_t>(r.pv_len);
         evalInfo.elapsedMs = ara_search_last_go_ms(search_);
+        lastValueEval_ = evalInfo.bestMoveQ;                                       // mctsagent.cpp:331
+        if (useNPSTimemanager && evalInfo.elapsedMs > 0) {                         // update_nps_measurement, :222-228
+            ++nbNPSentries_;
+            overallNPS_ += 1.0f / nbNPSentries_ * (static_cast<float>(evalInfo.calculate_nps()) - overallNPS_);
+        }
     }
+    // MCTSAgent::clear_game_history (mctsagent.cpp:249-258): the per-game measurements start over
+    void clear_game_history() {
+        lastValueEval_ = -1.0f;
+        nbNPSentries_ = 0;
+        overallNPS_ = 0.0f;
+    }
+    // run_mcts_search (mctsagent.cpp:350-352): the next searches run under the ThreadManager's heuristics with this
+    // move time; inGame = is_game_sceneario(limits), canProlong = can_prolong_search(move number, thresh move)
+    void set_time_control(double movetimeMs, bool inGame, bool canProlong, double safeRemainingMs, double moveOverheadMs) {
+        ara_time_control_t tc{};
+        tc.movetime_ms = movetimeMs;
+        tc.update_interval_ms = 250;
+        tc.overall_nps = overallNPS_;
+        tc.safe_remaining_ms = safeRemainingMs;
+        tc.move_overhead_ms = moveOverheadMs;
+        tc.last_value_eval = lastValueEval_;
+        tc.in_game = inGame ? 1 : 0;
+        tc.can_prolong = canProlong ? 1 : 0;
+        if (ara_search_set_time_control(search_, &tc) != 0) throw std::runtime_error(ara_last_error());
+    }
+    void clear_time_control() { ara_search_set_time_control(search_, nullptr); }
+    ara_time_report_t time_report() const {
+        ara_time_report_t r{};
+        ara_search_time_report(search_, &r);
+        return r;
+    }
+    bool useNPSTimemanager = true;  // UCI option Use_NPS_Time_Manager
     const ara_search_result_t& last_result() const { return result_; }
     // MCTSAgent::apply_move_to_tree: the subtree behind `move` is kept for the next search
     void apply_move_to_tree(Action move) {
@@ -200,6 +232,8 @@ class MCTSAgent {
     SearchSettings settings_;
     ara_search_t search_ = nullptr;
     ara_search_result_t result_{};
+    float lastValueEval_ = -1.0f, overallNPS_ = 0.0f;
+    size_t nbNPSentries_ = 0;
 };
 
 }  // namespace crazyara

@@ -2,7 +2,8 @@
 // uci/optionsuci.cpp:66-220).  Supported: uci, isready, setoption, ucinewgame, position [startpos|fen] [moves ...],
 // go [nodes N | movetime T | wtime W btime B [winc I] [binc I] [movestogo M]] (or the Simulations / Nodes options),
 // root, quit.  The move time follows TimeManager::get_time_for_move (manager/timemanager.cpp:51-100) without its
-// random factor; the search then also stops after that much wall time (ara_search_set_movetime).
+// random factor; the search then also stops after that much wall time (ara_search_set_movetime), and in clock games
+// the ThreadManager's early stopping / prolongation rules run on top (ara_search_set_time_control).
 #include <algorithm>
 #include <iomanip>
 #include <iostream>
@@ -27,7 +28,7 @@ struct Options {
                                              {"Virtual_Mix_Threshold", "1000"}, {"First_Device_ID", "0"},
                                              {"UCI_Chess960", "false"},     {"Input_Version", "0"},    {"Dirichlet_Seed", "42"},
                                              {"Move_Overhead", "20"},       {"Timed_Search_Nodes", "1000000"},
-                                             {"Reuse_Tree", "true"}};
+                                             {"Reuse_Tree", "true"},           {"Use_NPS_Time_Manager", "true"}};
     int i(const std::string& k) const { return std::stoi(kv.at(k)); }
     bool b(const std::string& k) const { return kv.at(k) == "true"; }
 };
@@ -142,6 +143,7 @@ int main() {
             } else if (cmd == "ucinewgame") {
                 new_game();
                 searched = false;
+                if (agent) agent->clear_game_history();
             } else if (cmd == "position") {
                 std::string tok, fen;
                 ss >> tok;
@@ -195,15 +197,31 @@ int main() {
                     ready = false;
                 }
                 if (!ready) prepare();
+                const bool inGame = lim.time[0] != 0 || lim.time[1] != 0 || lim.movestogo != 0;  // is_game_sceneario
+                agent->clear_time_control();
                 if (timed) {
                     const int me = state.side_to_move();
-                    const long ms = time_for_move(lim, me, state.move_number(), opt.i("Move_Overhead"));
+                    const long overhead = opt.i("Move_Overhead");
+                    const long ms = time_for_move(lim, me, state.move_number(), overhead);
                     agent->set_movetime(static_cast<double>(ms));
+                    // the ThreadManager's early stopping / prolongation applies to clock games only
+                    if (inGame)
+                        agent->set_time_control(static_cast<double>(ms), true, state.move_number() < 35,
+                                                static_cast<double>(std::max(lim.time[me] - overhead * 30, 1L)),
+                                                static_cast<double>(overhead));
                     std::cout << "info string movetime " << ms << std::endl;
                 } else {
                     agent->set_movetime(0.0);
                 }
+                agent->useNPSTimemanager = opt.b("Use_NPS_Time_Manager");
                 agent->evaluate_board_state(state, info);
+                if (timed && inGame) {
+                    const ara_time_report_t tr = agent->time_report();
+                    if (tr.early_stopped)
+                        std::cout << "info string Early stopping" << (tr.early_stopped == 1 ? " (max nodes)" : "")
+                                  << ", saved time: " << static_cast<long>(tr.saved_ms) << std::endl;
+                    if (tr.prolonged) std::cout << "info string Increase search time" << std::endl;
+                }
                 searched = true;
                 searchedBase = gameBase;
                 searchedMoves = gameMoves;

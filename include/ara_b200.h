@@ -171,6 +171,35 @@ int ara_search_apply_move(ara_search_t s, int tree, unsigned short move);
 /* ThreadManager's time stop (manager/threadmanager.cpp, SearchLimits::movetime): ms > 0 makes the following go calls
  * stop issuing mini-batches once that much wall time has passed (besides the Simulations / Nodes limits); 0 = off */
 int ara_search_set_movetime(ara_search_t s, double ms);
+/* ThreadManager's in-game heuristics (manager/threadmanager.cpp:68-178), evaluated every update interval on the root's
+ * statistics: early stopping once the move is decided, one or two prolongations when the evaluation dropped.  The
+ * parameters are what MCTSAgent::run_mcts_search hands to the ThreadManager (agents/mctsagent.cpp:350-352). */
+typedef struct {
+    double movetime_ms;        /* TimeManager::get_time_for_move; > 0 */
+    double update_interval_ms; /* ThreadManagerParams::updateIntervalMS (250) */
+    double overall_nps;        /* MCTSAgent::overallNPS, running mean over the game's searches; 0 = heuristics off */
+    double safe_remaining_ms;  /* SearchLimits::get_safe_remaining_time(side to move) */
+    double move_overhead_ms;   /* SearchLimits::moveOverhead */
+    float last_value_eval;     /* MCTSAgent::lastValueEval: best-move Q of the previous search, -1 after ucinewgame */
+    int in_game;               /* is_game_sceneario: wtime / btime / movestogo given */
+    int can_prolong;           /* can_prolong_search(move number, TimeManager thresh move) */
+} ara_time_control_t;
+typedef struct {
+    int early_stopped; /* 0 no, 1 "max nodes" rule, 2 "second move cannot catch up" rule */
+    int prolonged;     /* number of times the search time was extended (checkedContinueSearch) */
+    double saved_ms;   /* remaining move time when the search stopped early */
+    double elapsed_ms; /* wall time of the go loop */
+    float value_eval;  /* Node::updated_value_eval of the root at the last check */
+} ara_time_report_t;
+/* tc != NULL: the following go calls run under these limits (tc->movetime_ms replaces ara_search_set_movetime);
+ * NULL switches the manager off again.  Single-tree searches only. */
+int ara_search_set_time_control(ara_search_t s, const ara_time_control_t* tc);
+int ara_search_time_report(ara_search_t s, ara_time_report_t* out);
+/* the two decisions as pure functions (no device): root statistics in, verdict out -- for tests and host-side reuse */
+int ara_time_early_stopping(const ara_time_control_t* tc, double remaining_ms, unsigned node_count, int max_q_is_max_visits,
+                            unsigned first_visits, unsigned second_visits, float q_first, float q_second);
+int ara_time_continue_search(const ara_time_control_t* tc, double remaining_ms, float value_eval, int* checked,
+                             float* last_value_eval);
 int ara_search_set_profile(ara_search_t s, int on);
 int ara_search_profile(ara_search_t s, double* select_ms, double* net_ms, double* apply_ms, long long* net_forwards);
 /* SM-clock cycles per phase of the select kernel in the last go (0 descent, 1 do_move, 2 movegen, 3 node init,

@@ -181,6 +181,14 @@ class HeSearch:
         self.L.he_search_apply_move.argtypes = [ctypes.c_void_p, ctypes.c_uint16]
         self.L.he_search_apply_move(self.h, int(move))
 
+    def time_stats(self):
+        """collect_time_stats of the current tree (what the ThreadManager rules read)."""
+        i, f = (ctypes.c_uint * 5)(), (ctypes.c_float * 3)()
+        self.L.he_search_time_stats.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        self.L.he_search_time_stats(self.h, i, f)
+        return dict(node_count=i[0], first_visits=i[1], second_visits=i[2], max_q_is_max_visits=int(i[3]), valid=int(i[4]),
+                    q_first=f[0], q_second=f[1], value_eval=f[2])
+
     def run(self, he_state, net_fn, with_keys=False):
         L, h, np = self.L, self.h, self.np
         n = L.he_search_set_root(h, he_state.h)

@@ -233,6 +233,14 @@ void he_fake_eval(unsigned long long key, int n_labels, float* value, float* pro
     for (int i = 0; i < n_labels; ++i) prob[i] = fake_prob(key, i);
 }
 int he_sizeof_result() { return static_cast<int>(sizeof(SearchResult)); }
+// root statistics of the ThreadManager heuristics: {node_count, first, second, max_q_is_max_visits, valid}, {q1, q2, eval}
+void he_search_time_stats(HeSearch* s, unsigned* iout, float* fout) {
+    RootTimeStats r;
+    collect_time_stats(s->t, &r);
+    iout[0] = r.node_count, iout[1] = r.first_visits, iout[2] = r.second_visits;
+    iout[3] = static_cast<unsigned>(r.max_q_is_max_visits), iout[4] = static_cast<unsigned>(r.valid);
+    fout[0] = r.q_first, fout[1] = r.q_second, fout[2] = r.value_eval;
+}
 
 // Select-step unit hook: k open children with the given statistics; out = {sure, fast_ci, exact_ci}.
 void he_pick_both(int k, const float* p, const float* q, const unsigned* n, float cput, unsigned visit_sum, int* out) {

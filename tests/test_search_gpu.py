@@ -166,3 +166,33 @@ def test_gpu_tree_reuse_equals_oracle(variant, vid, mode, batch, sims, extra):
     other = BoardState().set("", False, vid)
     assert agent.evaluate_board_state(other)["nodes_pre_search"] == 0
     agent.close()
+
+
+@pytest.mark.gpu
+def test_gpu_time_manager_early_stop_and_veto():
+    """ThreadManager on the device search: with a (deliberately tiny) NPS estimate the early-stopping rules fire at the
+    first update interval at which the most visited move also looks best; a dropped evaluation vetoes the stop once
+    (continue_search) and the search then runs its whole move time."""
+    from crazyara_b200.engine import BoardState, MCTSAgent, TimeControl, default_settings
+    # (1.d4 d5 with the hash-derived fake network: the rules hold at > 99 % of the iterations of a host-emulated
+    # search, so one of the first update intervals triggers; at the start position they hold at < 10 %)
+    s = default_settings("chess", batch_size=16, simulations=0, nodes=0, node_policy_temperature=1.0)
+    agent = MCTSAgent(None, s, 0, 1, 150000)
+    st = BoardState().set("", False, 0).do_uci("d2d4", "d7d5")
+    base = dict(movetime_ms=400.0, update_interval_ms=20.0, overall_nps=1.0, safe_remaining_ms=60000.0, move_overhead_ms=20.0,
+                in_game=1, can_prolong=1)
+    agent.set_movetime(400.0)
+    agent.set_time_control(TimeControl(last_value_eval=-1.0, **base))   # evaluation cannot have dropped below -1
+    r = agent.evaluate_board_state(st)
+    rep = agent.time_report()
+    assert rep["early_stopped"] in (1, 2) and rep["prolonged"] == 0
+    assert rep["elapsed_ms"] < 300.0 and rep["saved_ms"] > 0 and r["nodes"] > 100
+    agent.set_time_control(TimeControl(last_value_eval=0.999, **base))  # every evaluation is a drop: veto, search on
+    r2 = agent.evaluate_board_state(st)
+    rep2 = agent.time_report()
+    assert rep2["early_stopped"] == 0 and rep2["prolonged"] == 1
+    assert 380.0 <= rep2["elapsed_ms"] < 700.0 and r2["nodes"] > r["nodes"]
+    agent.set_time_control(None)                                        # manager off: plain move time
+    agent.evaluate_board_state(st)
+    assert agent.time_report()["early_stopped"] == 0 and agent.time_report()["prolonged"] == 0
+    agent.close()

@@ -29,12 +29,13 @@ def test_uci_binary_matches_python_agent():
 
 @pytest.mark.gpu
 def test_uci_time_managed_go():
-    """`go movetime` / `go wtime btime`: TimeManager's move time (overhead 20 ms subtracted) bounds the search."""
+    """`go movetime` / `go wtime btime`: TimeManager's move time (overhead 20 ms subtracted) bounds the search.
+    (`ucinewgame` clears the game's NPS estimate, so the clock search runs its whole move time: no early stop.)"""
     import time
     exe = os.path.join(ROOT, "crazyara_b200", "ara_uci")
     script = "\n".join(["uci", "setoption name UCI_Variant value crazyhouse", "setoption name Batch_Size value 16",
                         "setoption name Timed_Search_Nodes value 120000", "isready", "position startpos",
-                        "go movetime 220", "go wtime 20000 btime 20000 winc 100 binc 100",
+                        "go movetime 220", "ucinewgame", "go wtime 20000 btime 20000 winc 100 binc 100",
                         "go nodes 300", "quit"]) + "\n"
     t0 = time.time()
     out = subprocess.run([exe], input=script, capture_output=True, text=True, timeout=180).stdout

@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(kRtThreads, 1) rise_trunk_kernel(const __grid_
                         const float* p0 = sPool + kg * 32;
                         const float* p1 = sPool + 256 + kg * 32;
                         float a0 = 0.0f, a1 = 0.0f, c0 = 0.0f, c1 = 0.0f;  // (output 2jp, 2jp+1) x (board 0, 1)
-#pragma unroll 8
+#pragma unroll 32
                         for (int k = 0; k < 32; ++k) {
                             const float2 wf = __half22float2(__ldg(w + k * 64));
                             a0 = fmaf(wf.x, p0[k], a0);
@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(kRtThreads, 1) rise_trunk_kernel(const __grid_
                         const float* h0 = sHid + kg * 32;
                         const float* h1 = sHid + 128 + kg * 32;
                         float a0 = 0.0f, a1 = 0.0f, c0 = 0.0f, c1 = 0.0f;
-#pragma unroll 8
+#pragma unroll 32
                         for (int j = 0; j < 32; ++j) {
                             const float2 wf = __half22float2(__ldg(w + j * 128));
                             a0 = fmaf(wf.x, h0[j], a0);
@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(kRtThreads, 1) rise_trunk_kernel(const __grid_
                         const float* p0 = sPool + kg * 64;
                         const float* p1 = sPool + 256 + kg * 64;
                         float a0 = 0.0f, a1 = 0.0f, c0 = 0.0f, c1 = 0.0f;
-#pragma unroll 8
+#pragma unroll 32
                         for (int k = 0; k < 64; ++k) {
                             const float2 wf = __half22float2(__ldg(w + k * 128));
                             a0 = fmaf(wf.x, p0[k], a0);

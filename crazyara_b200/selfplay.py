@@ -29,6 +29,25 @@ def rl_settings(mode, **kw):
     return default_settings(mode, **base)
 
 
+def chess960_fen(rng):
+    """chess960fen() of the reference (environments/chess_related/chess960position.h:36-80): bishops on opposite
+    colours, then queen and knights on random free files, then rook - king - rook on the free files left to right.
+    The reference draws from the unseeded C `rand()`; here the draws come from the arena's seeded generator."""
+    p = [None] * 8
+    p[2 * int(rng.integers(4))] = "B"
+    p[2 * int(rng.integers(4)) + 1] = "B"
+    for c in "QNN":
+        while True:
+            loc = int(rng.integers(8))
+            if p[loc] is None:
+                p[loc] = c
+                break
+    for c in "RKR":
+        p[p.index(None)] = c
+    first = "".join(p)
+    return f"{first.lower()}/pppppppp/8/8/8/8/PPPPPPPP/{first} w KQkq - 0 1"
+
+
 class Arena:
     def __init__(self, net, settings, variant, n_games, device=0, is960=False, temperature=0.8, temperature_moves=15,
                  max_plies=512, seed=0, max_nodes=0, exporter=None, reuse_tree=False, pgn_path=None):
@@ -60,6 +79,9 @@ class Arena:
                 g.fen = st.fen()
 
     def _new_state(self):
+        # BoardState::init (boardstate.cpp:260-270): chess960 games start from a random chess960 position
+        if self.is960 and self.variant == 0:
+            return BoardState().set(chess960_fen(self.rng), True, 0)
         return BoardState().set("", self.is960, self.variant)
 
     def _pick(self, res, ply):

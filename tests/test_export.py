@@ -101,3 +101,26 @@ def test_arena_exports_samples(tmp_path):
     assert np.allclose(pol.sum(1), 1.0, atol=1e-5)
     plys = read_dataset(path, "plys_to_end")
     assert plys[starts[1] - 1] == 1 and plys[0] == starts[1]
+
+
+def test_chess960_start_positions():
+    """chess960fen (chess960position.h:36-80): all 960 arrangements are reachable, each is a legal chess960 set-up that
+    the state code accepts with both castling rights per side."""
+    import numpy as np
+    from crazyara_b200.engine import BoardState
+    from crazyara_b200.selfplay import chess960_fen
+    rng = np.random.default_rng(7)
+    seen = set()
+    for _ in range(20000):
+        fen = chess960_fen(rng)
+        rank = fen.split("/")[7].split(" ")[0]
+        seen.add(rank)
+    assert len(seen) == 960 and "RNBQKBNR" in seen
+    for rank in sorted(seen)[::37]:
+        b = [i for i, c in enumerate(rank) if c == "B"]
+        r = [i for i, c in enumerate(rank) if c == "R"]
+        assert sorted(rank) == sorted("RNBQKBNR") and (b[0] + b[1]) % 2 == 1 and r[0] < rank.index("K") < r[1]
+        st = BoardState().set(f"{rank.lower()}/pppppppp/8/8/8/8/PPPPPPPP/{rank} w KQkq - 0 1", True, 0)
+        back = st.fen().split(" ")
+        assert back[0].split("/")[7] == rank and len(back[2]) == 4      # four castling rights (Shredder letters)
+        assert len(st.legal_actions()) >= 16                             # 16 pawn moves + knight moves

@@ -24,7 +24,9 @@ def test_arena_real_net_chess960(tmp_path):
     n_games, B = 8, 8
     net = NeuralNetAPI("gpu", 0, n_games * B, blob)
     st = rl_settings("chess", batch_size=B, nodes=100, simulations=400, input_version=3)
-    arena = Arena(net, st, variant=0, n_games=n_games, max_plies=12, seed=1)
+    arena = Arena(net, st, variant=0, n_games=n_games, is960=True, max_plies=12, seed=1)
+    starts = {s.fen().split(" ")[0].split("/")[7] for s in arena.states}
+    assert len(starts) > 1 and all(sorted(r) == sorted("RNBQKBNR") for r in starts)   # random chess960 set-ups
     res = arena.run(min_games=8, max_steps=14)
     assert res["games"] >= 8 and res["nps"] > 0
     arena.close()

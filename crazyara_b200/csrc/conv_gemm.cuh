@@ -29,6 +29,9 @@ struct ConvGemmArgs {
     __half* out_h;  // [M, ldo] fp16 output (or nullptr)
     float* out_f;   // [M, ldo] fp32 output (or nullptr)
     int ldo;        // multiple of 32
+    // device-side batch size (or nullptr): number of boards that really hold input; M tiles beyond it leave at once, so
+    // a launch sized for the largest batch costs only what the rows in use cost
+    const int* boards_dev;
 };
 
 constexpr int kGemmThreads = 192;  // warp0: TMA producer, warp1: MMA issuer (+TMEM alloc), warps2-5: epilogue
@@ -63,6 +66,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int lane = threadIdx.x & 31;
     const int m_tile = blockIdx.x;
     const int n_tile = blockIdx.y;
+    if (args.boards_dev != nullptr && m_tile * (kBlockM / 64) >= *args.boards_dev) return;  // written >= 2 launches upstream
     const int taps = args.ksize * args.ksize;
     const int num_kb = taps * args.c_chunks;
 

@@ -135,9 +135,10 @@ static int launch_bn(const ConvLayer* L, const ConvGemmArgs& a, dim3 grid, cudaS
     return 0;
 }
 
-int conv_layer_launch(const ConvLayer* L, int boards, cudaStream_t stream) {
+int conv_layer_launch(const ConvLayer* L, int boards, cudaStream_t stream, const int* boards_dev) {
     ConvGemmArgs a = L->args;
     a.M = boards * 64;
+    a.boards_dev = boards_dev;
     dim3 grid((boards + 1) / 2, (L->n_out + L->bn - 1) / L->bn, 1);
     switch (L->bn) {
         case 64: return launch_bn<64>(L, a, grid, stream);

@@ -22,6 +22,7 @@ int conv_layer_init(ConvLayer* L, const __half* act, int boards_cap, int cin, co
                     int ksize, const float* bias, int relu, const __half* residual, int ldr, __half* out_h,
                     float* out_f, int ldo, int bn);
 
-int conv_layer_launch(const ConvLayer* L, int boards, cudaStream_t stream);
+// boards_dev (optional): device-side count of the boards in use, <= boards (see ConvGemmArgs::boards_dev)
+int conv_layer_launch(const ConvLayer* L, int boards, cudaStream_t stream, const int* boards_dev = nullptr);
 
 }  // namespace ara

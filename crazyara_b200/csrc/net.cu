@@ -69,7 +69,7 @@ int Net::upload_conv_w(const float* w, int n_out, int cin, int ksize, __half** d
 
 Net::~Net() {
     cudaSetDevice(device);
-    for (int k = 0; k < 2; ++k)
+    for (int k = 0; k < 3; ++k)
         for (auto& g : graphs_[k]) cudaGraphExecDestroy(g.second);
     for (void* p : allocs_) cudaFree(p);
     rise_trunk_destroy(&trunk_);
@@ -319,15 +319,15 @@ int Net::init(const char* blob_path, int dev, int batch_size) {
     return 0;
 }
 
-int Net::enqueue(int n, cudaStream_t s, bool from_f32) {
+int Net::enqueue(int n, cudaStream_t s, bool from_f32, const int* cnt) {
     if (from_f32) {
         ARA_CUDA_OK(launch_pdl(nchw_f32_to_nhwc_f16_kernel, dim3(n), dim3(256), hdr.in_channels * 65 * 4, s, d_in_f32, d_in_h, hdr.in_channels, cin_pad));
         ++launches;
     }
-    if (conv_layer_launch(&stem_conv, n, s)) return -1;
+    if (conv_layer_launch(&stem_conv, n, s, cnt)) return -1;
     ++launches;
     if (use_trunk) {
-        if (rise_trunk_launch(&trunk_, n, s)) return -1;
+        if (rise_trunk_launch(&trunk_, n, s, cnt)) return -1;
         ++launches;
     }
     for (int i = 0; i < hdr.n_blocks && !use_trunk; ++i) {
@@ -358,32 +358,39 @@ int Net::enqueue(int n, cudaStream_t s, bool from_f32) {
     if (fork_heads) {  // value head on the side stream (a second branch of the captured graph), policy head on s
         ARA_CUDA_OK(cudaEventRecord(ev_fork, s));
         ARA_CUDA_OK(cudaStreamWaitEvent(head_stream, ev_fork, 0));
-        value_head_kernel<<<dim3(n), dim3(256), 0, head_stream>>>(xfinal, vw, d_value, d_aux);
+        value_head_kernel<<<dim3(n), dim3(256), 0, head_stream>>>(xfinal, vw, d_value, d_aux, cnt);
         ARA_CUDA_OK(cudaEventRecord(ev_join, head_stream));
     } else {
-        ARA_CUDA_OK(launch_pdl(value_head_kernel, dim3(n), dim3(256), 0, s, xfinal, vw, d_value, d_aux));
+        ARA_CUDA_OK(launch_pdl(value_head_kernel, dim3(n), dim3(256), 0, s, xfinal, vw, d_value, d_aux, cnt));
     }
-    if (conv_layer_launch(&pol_conv1, n, s)) return -1;
-    if (conv_layer_launch(&pol_conv2, n, s)) return -1;
-    ARA_CUDA_OK(launch_pdl(policy_softmax_kernel, dim3(n), dim3(256), n_labels() * 4, s, d_logits, d_prob, hdr.policy_channels, ldp));
+    if (conv_layer_launch(&pol_conv1, n, s, cnt)) return -1;
+    if (conv_layer_launch(&pol_conv2, n, s, cnt)) return -1;
+    ARA_CUDA_OK(launch_pdl(policy_softmax_kernel, dim3(n), dim3(256), n_labels() * 4, s, d_logits, d_prob, hdr.policy_channels, ldp, cnt));
     if (fork_heads) ARA_CUDA_OK(cudaStreamWaitEvent(s, ev_join, 0));
     launches += 4;
     ARA_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-int Net::forward_device(int n, cudaStream_t s) {
+int Net::forward_device(int n, cudaStream_t s, const int* cnt) {
     if (n < 1 || n > batch) return set_error("forward: n=%d outside [1,%d]", n, batch);
-    if (!use_graph) return enqueue(n, s, false);
-    auto it = graphs_[0].find(n);
-    if (it == graphs_[0].end()) {
+    if (!use_graph) return enqueue(n, s, false, cnt);
+    const int gk = cnt != nullptr ? 2 : 0;
+    if (cnt != nullptr && cnt != count_ptr_) {  // graphs captured with another counter are of no use
+        for (auto& g : graphs_[2]) cudaGraphExecDestroy(g.second);
+        graphs_[2].clear();
+        count_ptr_ = cnt;
+    }
+    auto& graphs = graphs_[gk];
+    auto it = graphs.find(n);
+    if (it == graphs.end()) {
         // warm-up launch outside capture (sets function attributes), then capture
-        if (enqueue(n, s, false)) return -1;
+        if (enqueue(n, s, false, cnt)) return -1;
         ARA_CUDA_OK(cudaStreamSynchronize(s));
         const long long before = launches;
         cudaGraph_t g;
         ARA_CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-        int rc = enqueue(n, s, false);
+        int rc = enqueue(n, s, false, cnt);
         cudaError_t e = cudaStreamEndCapture(s, &g);
         launches = before;
         if (rc) return -1;
@@ -391,7 +398,7 @@ int Net::forward_device(int n, cudaStream_t s) {
         cudaGraphExec_t ge;
         ARA_CUDA_OK(cudaGraphInstantiate(&ge, g, 0));
         cudaGraphDestroy(g);
-        it = graphs_[0].emplace(n, ge).first;
+        it = graphs.emplace(n, ge).first;
     }
     ARA_CUDA_OK(cudaGraphLaunch(it->second, s));
     launches += kernels_per_forward(false);

@@ -50,7 +50,9 @@ class Net {
     // host-buffer API (reference NeuralNetAPI::predict semantics, synchronous)
     int predict(const float* planes_host, int n, float* value_host, float* prob_host, float* aux_host);
     // device-resident API: input already in in_h (NHWC fp16), outputs stay in d_value / d_prob
-    int forward_device(int n, cudaStream_t stream);
+    // boards_dev (optional): device-side count (<= n) of the input rows that really hold positions -- the launch is
+    // sized for n, thread blocks of the rows beyond the count leave at once; the pointer is baked into the CUDA graph
+    int forward_device(int n, cudaStream_t stream, const int* boards_dev = nullptr);
     int forward_from_f32_device(int n, cudaStream_t stream);  // converts d_in_f32 -> in_h first
 
     NetHeader hdr{};
@@ -87,7 +89,7 @@ class Net {
     bool use_trunk = true;   // the whole residual tower as one persistent kernel (rise_trunk.cuh); ARA_TRUNK=0 disables
 
    private:
-    int enqueue(int n, cudaStream_t s, bool from_f32);
+    int enqueue(int n, cudaStream_t s, bool from_f32, const int* boards_dev = nullptr);
     std::vector<void*> allocs_;
     __half* stem_w = nullptr;
     float* stem_b = nullptr;
@@ -99,7 +101,8 @@ class Net {
     __half *pol_w1 = nullptr, *pol_w2 = nullptr;
     float* pol_b1 = nullptr;
     ConvLayer pol_conv1, pol_conv2;
-    std::map<int, cudaGraphExec_t> graphs_[2];
+    std::map<int, cudaGraphExec_t> graphs_[3];  // plain, from fp32 input, with a device-side count
+    const int* count_ptr_ = nullptr;            // the pointer the graphs_[2] entries were captured with
     template <typename T>
     int dalloc(T** p, size_t count);
     int upload_conv_w(const float* w, int n_out, int cin, int ksize, __half** dst, int* rows);

@@ -152,7 +152,9 @@ struct ValueHeadW {
 };
 
 __global__ void __launch_bounds__(256) value_head_kernel(const __half* __restrict__ x, ValueHeadW w,
-                                                           float* __restrict__ value, float* __restrict__ aux) {
+                                                           float* __restrict__ value, float* __restrict__ aux,
+                                                           const int* __restrict__ boards_dev) {
+    if (boards_dev != nullptr && static_cast<int>(blockIdx.x) >= *boards_dev) return;  // row without input
     __shared__ __half s_x[64 * 264];  // padded rows
     __shared__ float s_wv[8 * 256];
     __shared__ float s_f[512];
@@ -233,10 +235,11 @@ __global__ void __launch_bounds__(256) value_head_kernel(const __half* __restric
 // logits: [boards*64, ldp] fp32 (NHWC, channel = policy plane), prob: [boards, P*64] fp32 with index ch*64+sq
 // (the reference's NCHW flatten, builder_util.py:229).  One CTA (256 threads) per board.
 __global__ void __launch_bounds__(256) policy_softmax_kernel(const float* __restrict__ logits, float* __restrict__ prob,
-                                                               int P, int ldp) {
+                                                               int P, int ldp, const int* __restrict__ boards_dev) {
     extern __shared__ float s_l[];  // [P*64] in output order
     __shared__ float s_red[8];
     __shared__ float s_bcast;
+    if (boards_dev != nullptr && static_cast<int>(blockIdx.x) >= *boards_dev) return;  // row without input
     pdl_wait();
     pdl_launch_dependents();
     const int b = blockIdx.x;

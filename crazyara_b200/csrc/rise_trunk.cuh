@@ -204,6 +204,8 @@ __global__ void __launch_bounds__(kRtThreads, 1) rise_trunk_kernel(const __grid_
     const int crank = kSplit == 2 ? static_cast<int>(blockIdx.x & 1) : 0;  // rank inside the CTA pair
     const int m_tile = kSplit == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
     const int n_blocks = args.n_blocks;
+    // device-side batch size: a CTA (pair) whose boards hold no input leaves before it allocates anything
+    if (args.boards_dev != nullptr && m_tile * (kRows / 64) >= *args.boards_dev) return;
 
     if (warp == 0 && lane == 0) {
         mbar_init(x_ready, kRtComputeWarps);

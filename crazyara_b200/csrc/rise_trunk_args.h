@@ -33,6 +33,7 @@ struct TrunkArgs {
     const uint8_t* w2_img;  // [chunks][kTrunkW2Image]
     const __half* x_in;     // [M, 256] stem output
     __half* out;            // [M, 256]
+    const int* boards_dev;     // device-side count of the boards in use (or nullptr): CTAs beyond it leave at once
     unsigned long long* prof;  // profiling builds (-DARA_TRUNK_PROF): [2][16] cycle counters of CTA 0, else unused
     TrunkBlock blk[kTrunkMaxBlocks];
 };

@@ -101,9 +101,10 @@ int rise_trunk_init(RiseTrunk* T, const std::vector<TrunkBlockHost>& blocks, con
     return 0;
 }
 
-int rise_trunk_launch(const RiseTrunk* T, int boards, cudaStream_t stream) {
+int rise_trunk_launch(const RiseTrunk* T, int boards, cudaStream_t stream, const int* boards_dev) {
     TrunkArgs a = T->args;
     a.M = boards * 64;
+    a.boards_dev = boards_dev;
     // one board per CTA while that still fits the GPU in one wave (twice the SMs on a small batch), else two
     const char* force = getenv("ARA_TRUNK_ROWS");
     const bool one_board = force ? atoi(force) == 64 : boards <= T->sm_count;

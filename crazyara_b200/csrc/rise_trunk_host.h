@@ -35,7 +35,7 @@ struct RiseTrunk {
 // x_in: [boards_cap, 8, 8, 256] fp16 (stem output); out: [boards*64, 256] fp16 (may alias x_in: every CTA reads its
 // own rows before it writes them)
 int rise_trunk_init(RiseTrunk* T, const std::vector<TrunkBlockHost>& blocks, const __half* x_in, int boards_cap, __half* out);
-int rise_trunk_launch(const RiseTrunk* T, int boards, cudaStream_t stream);
+int rise_trunk_launch(const RiseTrunk* T, int boards, cudaStream_t stream, const int* boards_dev = nullptr);
 void rise_trunk_destroy(RiseTrunk* T);
 
 }  // namespace ara

@@ -63,6 +63,27 @@ __global__ void __launch_bounds__(32) select_kernel(const TreeDev* trees, Search
     create_mini_batch(t, sp, ws);
 }
 
+// Multi-tree searches: the new leaves of all trees are packed into consecutive rows of the network batch (tree i gets
+// the rows after those of trees 0..i-1) and their total goes to `count`, which the network kernels read to skip the
+// unused rows: a search of many small mini-batches (self-play: Batch_Size 8, often 2-3 new leaves per tree) then
+// costs what its leaves cost, not what the widest possible batch costs.  One warp.
+__global__ void __launch_bounds__(32) pack_kernel(TreeDev* trees, int n_trees, int* count) {
+    int base = 0;
+    for (int i0 = 0; i0 < n_trees; i0 += 32) {
+        const int i = i0 + static_cast<int>(threadIdx.x);
+        const int n = i < n_trees ? (trees[i].st->error ? 0 : trees[i].st->n_new) : 0;
+        int incl = n;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, off);
+            if (static_cast<int>(threadIdx.x) >= off) incl += v;
+        }
+        if (i < n_trees) trees[i].slot_base = base + incl - n;
+        base += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (threadIdx.x == 0) *count = base;
+}
+
 // one warp per (tree, new leaf): move lists, edges, policy indices, input planes of all new leaves in parallel
 __global__ void __launch_bounds__(32) expand_kernel(const TreeDev* trees, SearchParams sp, int batch, __half* in_h, int cpad) {
     __shared__ WarpScratch ws;
@@ -117,11 +138,11 @@ __global__ void __launch_bounds__(32) time_stats_kernel(const TreeDev* trees, Ro
 
 // Fake backend: value/prob rows of the pending new nodes from their Zobrist keys (oracle/fake.c definition).
 __global__ void fake_eval_kernel(const TreeDev* trees, int n_trees, int batch, float* values, float* probs, int n_labels) {
-    const int slot = blockIdx.x;  // tree * batch + b
-    const int tree = slot / batch, b = slot - tree * batch;
+    const int tree = blockIdx.x / batch, b = blockIdx.x - tree * batch;
     if (tree >= n_trees) return;
     const TreeDev t = trees[tree];
     if (b >= t.st->n_new) return;
+    const int slot = t.slot_base + b;  // row of this leaf in the (possibly packed) batch
     const uint64_t key = t.hdr[t.new_node[b]].key;
     if (threadIdx.x == 0) values[slot] = fake_value(key);
     for (int i = threadIdx.x; i < n_labels; i += blockDim.x) probs[static_cast<size_t>(slot) * n_labels + i] = fake_prob(key, i);
@@ -152,6 +173,7 @@ class Search {
     bool use_tc = false;
     ara_time_control_t tc{};
     ara_time_report_t tr{};
+    int* d_count_ = nullptr;  // multi-tree searches: rows of the network batch in use (written by pack_kernel)
     RootTimeStats* d_tstats_ = nullptr;
     RootTimeStats* h_tstats_ = nullptr;  // pinned
     int read_time_stats(RootStatsHost* out);
@@ -231,6 +253,7 @@ Search::~Search() {
     if (h_done_) cudaFreeHost(h_done_);
     if (h_tstats_) cudaFreeHost(h_tstats_);
     if (d_tstats_) cudaFree(d_tstats_);
+    if (d_count_) cudaFree(d_count_);
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
     for (cudaEvent_t e : prof_events_) cudaEventDestroy(e);
@@ -327,6 +350,7 @@ int Search::init(Net* net, const SearchParams& params, int device, int trees, in
     ARA_CUDA_OK(cudaMallocHost(&h_done_, sizeof(int) * n_trees));
     ARA_CUDA_OK(cudaMallocHost(&h_tstats_, sizeof(RootTimeStats)));
     ARA_CUDA_OK(cudaMalloc(&d_tstats_, sizeof(RootTimeStats)));
+    ARA_CUDA_OK(cudaMalloc(&d_count_, sizeof(int)));
     ARA_CUDA_OK(cudaEventCreate(&ev0_));
     ARA_CUDA_OK(cudaEventCreate(&ev1_));
     return 0;
@@ -358,10 +382,14 @@ int Search::iterate(int count) {
     for (int it = 0; it < count; ++it) {
         if (profile) prof_event();
         select_kernel<<<n_trees, 32, 0, stream_>>>(d_trees_, sp);
+        if (n_trees > 1) {
+            pack_kernel<<<1, 32, 0, stream_>>>(d_trees_, n_trees, d_count_);
+            ++launches;
+        }
         expand_kernel<<<n_trees * B, 32, 0, stream_>>>(d_trees_, sp, B, in_h, cpad);
         if (profile) prof_event();
         if (net_) {
-            if (net_->forward_device(n_trees * B, stream_)) return -1;
+            if (net_->forward_device(n_trees * B, stream_, n_trees > 1 ? d_count_ : nullptr)) return -1;
         } else {
             fake_eval_kernel<<<n_trees * B, 128, 0, stream_>>>(d_trees_, n_trees, B, d_values_, d_probs_, n_labels_);
             ++launches;
@@ -391,10 +419,14 @@ int Search::go() {
     const int B = sp.batch_size;
     // root: create, expand, evaluate (set_root_node_predictions), scatter, prepare_node_for_visits (+ Dirichlet)
     root_kernel<<<n_trees, 32, 0, stream_>>>(d_trees_, sp, d_roots_);
+    if (n_trees > 1) {
+        pack_kernel<<<1, 32, 0, stream_>>>(d_trees_, n_trees, d_count_);
+        ++launches;
+    }
     expand_kernel<<<n_trees * B, 32, 0, stream_>>>(d_trees_, sp, B, in_h, cpad);
     if (net_) {
-        // the root of tree i sits in batch row i * B; a single-tree search only needs row 0
-        if (net_->forward_device(n_trees == 1 ? 1 : n_trees * B, stream_)) return -1;
+        // a single-tree search only needs row 0; the new roots of a multi-tree search are packed into the first rows
+        if (net_->forward_device(n_trees == 1 ? 1 : n_trees * B, stream_, n_trees > 1 ? d_count_ : nullptr)) return -1;
     } else {
         fake_eval_kernel<<<n_trees * B, 128, 0, stream_>>>(d_trees_, n_trees, B, d_values_, d_probs_, n_labels_);
         ++launches;

@@ -196,3 +196,32 @@ def test_gpu_time_manager_early_stop_and_veto():
     agent.evaluate_board_state(st)
     assert agent.time_report()["early_stopped"] == 0 and agent.time_report()["prolonged"] == 0
     agent.close()
+
+
+@pytest.mark.gpu
+def test_gpu_packed_multi_tree_batches_equal_single_tree_searches(tmp_path):
+    """Several trees share each network batch; their new leaves are packed into consecutive rows and the network skips
+    the unused rows (device-side count).  Every tree must come out exactly as when it is searched alone."""
+    from crazyara_b200.engine import BoardState, MCTSAgent, SearchSettings
+    from oracle import net as onet
+    B, sims = 8, 240
+    lines = [[], ["e2e4"], ["e2e4", "e7e5"], ["d2d4", "g8f6", "c2c4"], ["g1f3", "d7d5"]]
+    net = _make_net(tmp_path, onet.arch_risev2(34, 81), len(lines) * B, 10)
+    st = osr.default_settings("crazyhouse", batch_size=B, simulations=sims, node_policy_temperature=1.0,
+                              dirichlet_epsilon=0.25, dirichlet_alpha=0.3, seed=3)
+    s = SearchSettings()
+    for f, _ in s._fields_:
+        setattr(s, f, getattr(st, f))
+    multi = MCTSAgent(net, s, 0, len(lines))
+    for t, moves in enumerate(lines):
+        multi.set_position(BoardState().set("", False, 1).do_uci(*moves), t)
+    multi.evaluate_board_state()
+    together = multi.results()
+    multi.close()
+    for t, moves in enumerate(lines):
+        alone = MCTSAgent(net, s, 0, 1)
+        r = alone.evaluate_board_state(BoardState().set("", False, 1).do_uci(*moves))
+        alone.close()
+        assert_same_search(r, together[t])   # (every tree draws its Dirichlet noise from the same seed)
+        assert together[t]["evals"] > 0
+    net.close()

@@ -179,17 +179,21 @@ def selfplay_leg(blob, device, n_games, seconds):
     from crazyara_b200.nn import NeuralNetAPI
     from crazyara_b200.selfplay import Arena, rl_settings
     st = rl_settings("crazyhouse")
-    net = NeuralNetAPI("gpu", device, n_games * st.batch_size, blob)
-    arena = Arena(net, st, variant=1, n_games=n_games, device=device, max_plies=160, seed=1)
+    # two groups of games, each with its own agent and network buffers, searched from two host threads: one group's
+    # tree kernels overlap the other's network forward
+    groups = 2 if n_games % 2 == 0 else 1
+    nets = [NeuralNetAPI("gpu", device, n_games // groups * st.batch_size, blob) for _ in range(groups)]
+    arena = Arena(nets, st, variant=1, n_games=n_games, device=device, max_plies=160, seed=1)
     arena.run(max_steps=2)  # warm-up (graph capture, allocations)
     arena.finished.clear()
     arena.nodes, arena.search_ms = 0, 0.0
     res = arena.run(max_seconds=seconds)
     arena.close()
-    net.close()
+    for net in nets:
+        net.close()
     # random weights do not finish games the way a trained network does, so the rate is quoted per searched move and
     # converted with a nominal 100-ply game; the games that did finish inside the window are reported beside it
-    return {"concurrent_games": n_games, "settings": "RL defaults: nodes 800, Batch_Size 8, Dirichlet eps 0.25 alpha 0.3, "
+    return {"concurrent_games": n_games, "game_groups": groups, "settings": "RL defaults: nodes 800, Batch_Size 8, Dirichlet eps 0.25 alpha 0.3, "
             "temperature 0.8 for 15 plies, games adjudicated at 160 plies (random weights)",
             "moves_per_s": res["moves_per_s"], "games_per_hour_at_100_plies": res["moves_per_s"] * 36.0,
             "games_finished_in_window": res["games"], "avg_plies_finished": res["avg_plies"],

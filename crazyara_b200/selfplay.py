@@ -11,6 +11,7 @@ posterior, or a sample from posterior^(1/T) during the first `temperature_moves`
 DeepCrazyhouse/configs/rl_config.py:34-65).  Optional outputs: training samples (`exporter=`, crazyara_b200.export) and
 the games as PGN (`pgn_path=`, crazyara_b200.pgn).
 """
+import threading
 import time
 
 import numpy as np
@@ -57,7 +58,15 @@ class Arena:
         self.rng = np.random.default_rng(seed)
         if reuse_tree and max_nodes == 0:  # room for the kept subtrees of several moves before a tree starts over
             max_nodes = 8 * int(settings.simulations or settings.nodes) + 4 * int(settings.batch_size) + 64
-        self.agent = MCTSAgent(net, settings, device, n_games, max_nodes)
+        # `net` may be a list of networks: the games are then split into that many groups, each with its own agent
+        # (own stream, own network buffers) searched from its own host thread, so that one group's tree kernels run
+        # while another group's network forward does.  Trees never interact, so nothing else changes.
+        nets = list(net) if isinstance(net, (list, tuple)) else [net]
+        if n_games % len(nets) != 0:
+            raise ValueError("n_games must be a multiple of the number of networks (game groups)")
+        self.per_group = n_games // len(nets)
+        self.agents = [MCTSAgent(n, settings, device, self.per_group, max_nodes) for n in nets]
+        self.agent = self.agents[0]
         self.states = [self._new_state() for _ in range(n_games)]
         self.plies = [0] * n_games
         self.finished = []  # (plies, terminal type, side to move at the end)
@@ -113,16 +122,36 @@ class Arena:
 
     def step(self):
         """One move in every running game."""
+        G = self.per_group
         for t, st in enumerate(self.states):
-            self.agent.set_position(st, t)
-        self.agent.evaluate_board_state()
-        self.search_ms += self.agent.last_go_ms()
+            self.agents[t // G].set_position(st, t % G)
+        t_search = time.perf_counter()
+        if len(self.agents) == 1:
+            self.agent.evaluate_board_state()
+            self.search_ms += self.agent.last_go_ms()
+        else:  # the C call releases the GIL: the groups' searches overlap on the device
+            errors = []
+
+            def go(a):
+                try:
+                    a.evaluate_board_state()
+                except Exception as e:  # noqa: BLE001 -- re-raised below on the calling thread
+                    errors.append(e)
+            threads = [threading.Thread(target=go, args=(a,)) for a in self.agents]
+            for th in threads:
+                th.start()
+            for th in threads:
+                th.join()
+            if errors:
+                raise errors[0]
+            self.search_ms += (time.perf_counter() - t_search) * 1e3
         planes = None
         if self.exporter is not None:  # un-normalised planes of every searched position, one GPU call
             planes = encode_planes([st.board() for st in self.states], self.settings.mode, self.settings.input_version,
                                    normalize=False)
         for t, st in enumerate(self.states):
-            res = self.agent.result(t)
+            agent, lt = self.agents[t // G], t % G
+            res = agent.result(lt)
             self.nodes += int(res["nodes"]) - int(res["nodes_pre_search"])
             self.reused_nodes += int(res["nodes_pre_search"])
             if len(res["moves"]) == 0:
@@ -133,7 +162,7 @@ class Arena:
                 self.exporter.save_sample(self.records[t], planes[t], res["moves"], res["policy"], res["q"][idx],
                                           st.side_to_move())
             if self.reuse_tree:
-                self.agent.apply_move_to_tree(res["moves"][idx], t)
+                agent.apply_move_to_tree(res["moves"][idx], lt)
             if self.pgns is not None:
                 self.pgns[t].play_move(st, res["moves"][idx])
             else:
@@ -160,4 +189,5 @@ class Arena:
                     avg_plies=float(np.mean([g[0] for g in self.finished])) if self.finished else 0.0)
 
     def close(self):
-        self.agent.close()
+        for a in self.agents:
+            a.close()

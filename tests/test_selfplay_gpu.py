@@ -62,3 +62,20 @@ def test_arena_writes_pgn(tmp_path):
         plies = int(header.split('[PlyCount "')[1].split('"')[0])
         tokens = [t for t in body.split() if not t.endswith(".")]
         assert len(tokens) == plies + 1 and tokens[-1] in ("1-0", "0-1", "1/2-1/2")
+
+
+@pytest.mark.gpu
+def test_arena_game_groups_on_separate_threads():
+    """Two groups of games with an agent each, searched concurrently from two host threads: the games are the ones a
+    single-group arena with the same seed plays (trees never interact; every tree draws the same Dirichlet seed)."""
+    from crazyara_b200.selfplay import Arena, rl_settings
+    st = rl_settings("crazyhouse", batch_size=8, nodes=60, simulations=240)
+    a1 = Arena(None, st, variant=1, n_games=4, temperature_moves=0, max_plies=20, seed=2)
+    a2 = Arena([None, None], st, variant=1, n_games=4, temperature_moves=0, max_plies=20, seed=2)
+    for _ in range(6):
+        a1.step()
+        a2.step()
+        assert [s.fen() for s in a1.states] == [s.fen() for s in a2.states]
+    assert a2.nodes == a1.nodes > 0
+    a1.close()
+    a2.close()

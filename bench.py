@@ -9,9 +9,10 @@ all device-resident.  NPS is computed exactly like the reference: (root.visitSum
   value  : device-resident NPS -- CUDA events on the search stream around each go (root board already uploaded)
   e2e    : the same searches through the public host API (BoardState -> MCTSAgent.evaluate_board_state -> EvalInfo),
            wall clock, host<->device copies inside
-  roofline: conv stack (the dominant kernels): algorithmic FLOPs of the network forwards issued during the timed
-           searches / their device time (CUDA events around every forward on the search stream) vs the measured
-           sustained bf16 tensor peak of MEASURED_PEAKS.json
+  roofline: conv stack (the dominant kernels): algorithmic FLOPs of the network forwards of a search / their device
+           time (CUDA events around every forward on the search stream, taken live on three extra searches right after
+           the timed ones -- the timed searches launch each iteration as one graph, without events in between) vs the
+           measured sustained bf16 tensor peak of MEASURED_PEAKS.json
   cpu_baseline: the CPU oracle search (oracle/mcts.c, 1 thread, the reference's cost structure) with the fp32 torch
            CPU network on all host cores, on a bounded sample of the same workload (rank 0, N = 1 only)
 
@@ -265,7 +266,6 @@ def main():
     net = NeuralNetAPI("gpu", local_rank, args.batch, blob)
     settings = default_settings("crazyhouse", batch_size=args.batch, simulations=args.sims)
     agent = MCTSAgent(net, settings, local_rank, 1)
-    agent.set_profile(True)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     def step():
@@ -275,7 +275,7 @@ def main():
         state = BoardState().set("", False, 1)
         r = agent.evaluate_board_state(state)
         wall = time.perf_counter() - t0
-        return r, wall, agent.last_go_ms(), agent.profile()
+        return r, wall, agent.last_go_ms()
 
     for _ in range(args.warmup):
         step()
@@ -290,14 +290,10 @@ def main():
     forwards = 0
     last = None
     for _ in range(args.steps):
-        r, wall, ms, prof = step()
+        r, wall, ms = step()
         nodes += int(r["nodes"])
         dev_ms += ms
         wall_s += wall
-        net_ms += prof["net_ms"]
-        sel_ms += prof["select_ms"]
-        app_ms += prof["apply_ms"]
-        forwards += prof["net_forwards"]
         last = r
     torch.cuda.synchronize()
     if dist is not None:
@@ -305,6 +301,18 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
     launches = agent.launch_count() + net.launch_count() - launches0
+    # phase split (select / network / apply): CUDA events between the kernels of every iteration, which the timed
+    # searches above do without (an iteration is one graph launch there) -- measured on extra searches, scaled to K
+    agent.set_profile(True)
+    n_prof = 3
+    for _ in range(n_prof):
+        step()
+        prof = agent.profile()
+        net_ms += prof["net_ms"] * args.steps / n_prof
+        sel_ms += prof["select_ms"] * args.steps / n_prof
+        app_ms += prof["apply_ms"] * args.steps / n_prof
+        forwards += prof["net_forwards"] * args.steps / n_prof
+    agent.set_profile(False)
 
     from crazyara_b200.multi import aggregate_counters
     total_nodes, max_dev_ms, max_wall, launches = aggregate_counters(nodes, dev_ms, wall_s, launches, dist, "cuda")

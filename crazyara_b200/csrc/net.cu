@@ -375,6 +375,11 @@ int Net::enqueue(int n, cudaStream_t s, bool from_f32, const int* cnt) {
 int Net::forward_device(int n, cudaStream_t s, const int* cnt) {
     if (n < 1 || n > batch) return set_error("forward: n=%d outside [1,%d]", n, batch);
     if (!use_graph) return enqueue(n, s, false, cnt);
+    {   // inside somebody else's capture (the search's iteration graph) the kernels go in directly
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        ARA_CUDA_OK(cudaStreamIsCapturing(s, &cs));
+        if (cs == cudaStreamCaptureStatusActive) return enqueue(n, s, false, cnt);
+    }
     const int gk = cnt != nullptr ? 2 : 0;
     if (cnt != nullptr && cnt != count_ptr_) {  // graphs captured with another counter are of no use
         for (auto& g : graphs_[2]) cudaGraphExecDestroy(g.second);

@@ -173,6 +173,10 @@ class Search {
     bool use_tc = false;
     ara_time_control_t tc{};
     ara_time_report_t tr{};
+    // one iteration as a CUDA graph (ARA_ITER_GRAPH=0 switches it off)
+    bool use_iter_graph_ = true, iter_warm_ = false;
+    cudaGraphExec_t iter_graph_ = nullptr;
+    int enqueue_iteration(bool with_events);
     int* d_count_ = nullptr;  // multi-tree searches: rows of the network batch in use (written by pack_kernel)
     RootTimeStats* d_tstats_ = nullptr;
     RootTimeStats* h_tstats_ = nullptr;  // pinned
@@ -254,6 +258,7 @@ Search::~Search() {
     if (h_tstats_) cudaFreeHost(h_tstats_);
     if (d_tstats_) cudaFree(d_tstats_);
     if (d_count_) cudaFree(d_count_);
+    if (iter_graph_) cudaGraphExecDestroy(iter_graph_);
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
     for (cudaEvent_t e : prof_events_) cudaEventDestroy(e);
@@ -351,6 +356,7 @@ int Search::init(Net* net, const SearchParams& params, int device, int trees, in
     ARA_CUDA_OK(cudaMallocHost(&h_tstats_, sizeof(RootTimeStats)));
     ARA_CUDA_OK(cudaMalloc(&d_tstats_, sizeof(RootTimeStats)));
     ARA_CUDA_OK(cudaMalloc(&d_count_, sizeof(int)));
+    if (const char* e = getenv("ARA_ITER_GRAPH")) use_iter_graph_ = atoi(e) != 0;
     ARA_CUDA_OK(cudaEventCreate(&ev0_));
     ARA_CUDA_OK(cudaEventCreate(&ev1_));
     return 0;
@@ -373,34 +379,61 @@ int Search::set_position(int tree, const Board& root, const uint64_t* hist_keys,
     return 0;
 }
 
-int Search::iterate(int count) {
+// One search iteration on the stream: select -> (pack) -> expand -> network -> scatter -> backup -> prepare.
+int Search::enqueue_iteration(bool with_events) {
     __half* in_h = net_ ? net_->d_in_h : nullptr;
     const int cpad = net_ ? net_->cin_pad : 0;
     const int B = sp.batch_size;
     const float* values = net_ ? net_->d_value : d_values_;
     const float* probs = net_ ? net_->d_prob : d_probs_;
+    if (with_events) prof_event();
+    select_kernel<<<n_trees, 32, 0, stream_>>>(d_trees_, sp);
+    if (n_trees > 1) pack_kernel<<<1, 32, 0, stream_>>>(d_trees_, n_trees, d_count_);
+    expand_kernel<<<n_trees * B, 32, 0, stream_>>>(d_trees_, sp, B, in_h, cpad);
+    if (with_events) prof_event();
+    if (net_) {
+        if (net_->forward_device(n_trees * B, stream_, n_trees > 1 ? d_count_ : nullptr)) return -1;
+    } else {
+        fake_eval_kernel<<<n_trees * B, 128, 0, stream_>>>(d_trees_, n_trees, B, d_values_, d_probs_, n_labels_);
+    }
+    if (with_events) prof_event();
+    scatter_kernel<<<n_trees * B, 32, 0, stream_>>>(d_trees_, sp, B, values, probs, n_labels_);
+    backup_kernel<<<n_trees, 32, 0, stream_>>>(d_trees_, sp, 0);
+    prepare_kernel<<<n_trees * 4 * B, 32, 0, stream_>>>(d_trees_, sp, 4 * B);
+    if (with_events) prof_event();
+    return 0;
+}
+
+// `count` iterations.  Outside profiling runs an iteration is ONE graph launch: the kernels of an iteration never
+// change (same pointers, same grids), so the sequence is captured once per handle -- the network's own graph becomes a
+// child node -- and the dependent-launch gaps between the seven search kernels shrink to graph-edge latency.
+int Search::iterate(int count) {
+    const int search_kernels = 5 + (n_trees > 1 ? 1 : 0) + (net_ ? 0 : 1);
+    const bool graphed = use_iter_graph_ && !profile;
     for (int it = 0; it < count; ++it) {
-        if (profile) prof_event();
-        select_kernel<<<n_trees, 32, 0, stream_>>>(d_trees_, sp);
-        if (n_trees > 1) {
-            pack_kernel<<<1, 32, 0, stream_>>>(d_trees_, n_trees, d_count_);
-            ++launches;
-        }
-        expand_kernel<<<n_trees * B, 32, 0, stream_>>>(d_trees_, sp, B, in_h, cpad);
-        if (profile) prof_event();
-        if (net_) {
-            if (net_->forward_device(n_trees * B, stream_, n_trees > 1 ? d_count_ : nullptr)) return -1;
+        if (graphed && iter_graph_ != nullptr) {
+            ARA_CUDA_OK(cudaGraphLaunch(iter_graph_, stream_));
+            if (net_) net_->launches += net_->kernels_per_forward(false);
+        } else if (graphed && iter_warm_) {
+            // second iteration of the handle's life (the first one ran eagerly and warmed the network's graph up)
+            const long long net_before = net_ ? net_->launches : 0;
+            cudaGraph_t g;
+            ARA_CUDA_OK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+            const int rc = enqueue_iteration(false);
+            const cudaError_t e = cudaStreamEndCapture(stream_, &g);
+            if (net_) net_->launches = net_before;
+            if (rc) return -1;
+            ARA_CUDA_OK(e);
+            ARA_CUDA_OK(cudaGraphInstantiate(&iter_graph_, g, 0));
+            cudaGraphDestroy(g);
+            --it;  // nothing ran yet: launch the graph in the next pass
+            continue;
         } else {
-            fake_eval_kernel<<<n_trees * B, 128, 0, stream_>>>(d_trees_, n_trees, B, d_values_, d_probs_, n_labels_);
-            ++launches;
+            if (enqueue_iteration(profile)) return -1;
+            iter_warm_ = true;
         }
-        if (profile) prof_event();
-        scatter_kernel<<<n_trees * B, 32, 0, stream_>>>(d_trees_, sp, B, values, probs, n_labels_);
-        backup_kernel<<<n_trees, 32, 0, stream_>>>(d_trees_, sp, 0);
-        prepare_kernel<<<n_trees * 4 * B, 32, 0, stream_>>>(d_trees_, sp, 4 * B);
-        if (profile) prof_event();
         ++net_forwards;
-        launches += 5;
+        launches += search_kernels;
     }
     ARA_CUDA_OK(cudaGetLastError());
     return 0;

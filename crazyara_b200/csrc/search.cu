@@ -111,10 +111,10 @@ __global__ void __launch_bounds__(32) scatter_kernel(const TreeDev* trees, Searc
 }
 
 // one warp per tree: value backups along the stored trajectories, collision reverts
-__global__ void __launch_bounds__(32) backup_kernel(const TreeDev* trees, SearchParams sp, int finalize) {
+__global__ void __launch_bounds__(32) backup_kernel(const TreeDev* trees, SearchParams sp, int finalize, const float* values) {
     __shared__ WarpScratch ws;
     const TreeDev t = trees[blockIdx.x];
-    backup_results(t, sp);
+    backup_results(t, sp, values);
     if (finalize) finalize_root(t, sp, ws);
 }
 
@@ -176,6 +176,8 @@ class Search {
     // one iteration as a CUDA graph (ARA_ITER_GRAPH=0 switches it off)
     bool use_iter_graph_ = true, iter_warm_ = false;
     cudaGraphExec_t iter_graph_ = nullptr;
+    cudaStream_t side_stream_ = nullptr;  // second branch of an iteration (value backups)
+    cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr;
     int enqueue_iteration(bool with_events);
     int* d_count_ = nullptr;  // multi-tree searches: rows of the network batch in use (written by pack_kernel)
     RootTimeStats* d_tstats_ = nullptr;
@@ -259,6 +261,9 @@ Search::~Search() {
     if (d_tstats_) cudaFree(d_tstats_);
     if (d_count_) cudaFree(d_count_);
     if (iter_graph_) cudaGraphExecDestroy(iter_graph_);
+    if (side_stream_) cudaStreamDestroy(side_stream_);
+    if (ev_fork_) cudaEventDestroy(ev_fork_);
+    if (ev_join_) cudaEventDestroy(ev_join_);
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
     for (cudaEvent_t e : prof_events_) cudaEventDestroy(e);
@@ -357,6 +362,9 @@ int Search::init(Net* net, const SearchParams& params, int device, int trees, in
     ARA_CUDA_OK(cudaMalloc(&d_tstats_, sizeof(RootTimeStats)));
     ARA_CUDA_OK(cudaMalloc(&d_count_, sizeof(int)));
     if (const char* e = getenv("ARA_ITER_GRAPH")) use_iter_graph_ = atoi(e) != 0;
+    ARA_CUDA_OK(cudaStreamCreateWithFlags(&side_stream_, cudaStreamNonBlocking));
+    ARA_CUDA_OK(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
+    ARA_CUDA_OK(cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming));
     ARA_CUDA_OK(cudaEventCreate(&ev0_));
     ARA_CUDA_OK(cudaEventCreate(&ev1_));
     return 0;
@@ -397,9 +405,15 @@ int Search::enqueue_iteration(bool with_events) {
         fake_eval_kernel<<<n_trees * B, 128, 0, stream_>>>(d_trees_, n_trees, B, d_values_, d_probs_, n_labels_);
     }
     if (with_events) prof_event();
+    // the value backups (one warp per tree, a latency chain) run beside scatter -> prepare: neither reads what the
+    // other writes (backup_results); a second branch of the iteration graph
+    ARA_CUDA_OK(cudaEventRecord(ev_fork_, stream_));
+    ARA_CUDA_OK(cudaStreamWaitEvent(side_stream_, ev_fork_, 0));
+    backup_kernel<<<n_trees, 32, 0, side_stream_>>>(d_trees_, sp, 0, values);
+    ARA_CUDA_OK(cudaEventRecord(ev_join_, side_stream_));
     scatter_kernel<<<n_trees * B, 32, 0, stream_>>>(d_trees_, sp, B, values, probs, n_labels_);
-    backup_kernel<<<n_trees, 32, 0, stream_>>>(d_trees_, sp, 0);
     prepare_kernel<<<n_trees * 4 * B, 32, 0, stream_>>>(d_trees_, sp, 4 * B);
+    ARA_CUDA_OK(cudaStreamWaitEvent(stream_, ev_join_, 0));
     if (with_events) prof_event();
     return 0;
 }
@@ -466,7 +480,7 @@ int Search::go() {
     }
     scatter_kernel<<<n_trees * B, 32, 0, stream_>>>(d_trees_, sp, B, net_ ? net_->d_value : d_values_,
                                                      net_ ? net_->d_prob : d_probs_, n_labels_);
-    backup_kernel<<<n_trees, 32, 0, stream_>>>(d_trees_, sp, 1);
+    backup_kernel<<<n_trees, 32, 0, stream_>>>(d_trees_, sp, 1, net_ ? net_->d_value : d_values_);
     prepare_kernel<<<n_trees * 4 * B, 32, 0, stream_>>>(d_trees_, sp, 4 * B);
     launches += 5;
     ARA_CUDA_OK(cudaGetLastError());

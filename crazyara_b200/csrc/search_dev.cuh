@@ -83,7 +83,7 @@ struct TreeState {
     int next_root;   // candidate root after ara_search_apply_move (MCTSAgent::ownNextRoot / opponentsNextRoot), -1 none
     int next_valid;  // apply_move has been called since the last search: only next_root may be reused
     int n_exp;     // expansions of the last mini-batch (entries of exp_parent)
-    int n_prep;    // new leaves of the last mini-batch, kept for the prepare step after the backup cleared n_new
+    int n_prep;    // (unused; kept for the layout)
     int done;      // search loop condition failed (limits reached / root solved)
     int error;     // 1 node pool, 2 edge pool, 3 depth overflow
     unsigned iterations;
@@ -734,7 +734,7 @@ ARA_HD void prepare_item(const TreeDev& t, const SearchParams& sp, WarpScratch& 
     if (st.error) return;
     const int B = sp.batch_size;
     if (item < B) {
-        if (item < st.n_prep) prepare_child(t, ws, t.new_node[item]);
+        if (item < st.n_new) prepare_child(t, ws, t.new_node[item]);
     } else if (item - B < st.n_exp) {
         prepare_child(t, ws, t.exp_parent[item - B]);
     }
@@ -1085,12 +1085,13 @@ ARA_HD void scatter_pending(const TreeDev& t, const SearchParams& sp, WarpScratc
                             const float* probs, int n_labels) {
     const int slot = t.slot_base + b;
     fill_nn_results(t, sp, ws, t.new_node[b], values[slot], probs + static_cast<size_t>(slot) * n_labels);
-    // a fresh leaf has real_visits 1 and value_sum double(v), so its node value is the network value itself
-    if (ARA_LANE == 0) t.new_value[b] = values[slot];
 }
 
 // backup_value_outputs + backup_collisions (searchthread.cpp:312-324): one warp per tree.
-ARA_HD void backup_results(const TreeDev& t, const SearchParams& sp) {
+// `values`: the network's value output; the new leaf b of this tree sits in row slot_base + b (a fresh leaf has
+// real_visits 1 and value_sum double(v), so its node value is the network value itself).  Reads nothing the scatter
+// step writes and writes nothing the scatter / prepare steps read, so it may run beside them.
+ARA_HD void backup_results(const TreeDev& t, const SearchParams& sp, const float* values) {
     const TreeState& st = *t.st;
     const int B = sp.batch_size;
     const int n_new = st.n_new, n_coll = st.n_coll;
@@ -1117,7 +1118,8 @@ ARA_HD void backup_results(const TreeDev& t, const SearchParams& sp) {
         // prefetched with indices that arrived an iteration ago
         const int dd = d < kMaxDepth ? d : kMaxDepth - 1;
         int len_n = n_new > 0 ? t.traj_len[0] : 0, len_nn = n_new > 1 ? t.traj_len[1] : 0;
-        float leaf_n = n_new > 0 ? t.new_value[0] : 0.0f, leaf_nn = n_new > 1 ? t.new_value[1] : 0.0f;
+        const float* leaf_values = values + t.slot_base;
+        float leaf_n = n_new > 0 ? leaf_values[0] : 0.0f, leaf_nn = n_new > 1 ? leaf_values[1] : 0.0f;
         int nid_n = n_new > 0 ? t.traj_node[dd] : -1, nid_nn = n_new > 1 ? t.traj_node[kMaxDepth + dd] : -1;
         uint32_t e_n = n_new > 0 ? t.traj_edge[dd] : 0, e_nn = n_new > 1 ? t.traj_edge[kMaxDepth + dd] : 0;
         for (int b = 0; b < n_new; ++b) {
@@ -1127,7 +1129,7 @@ ARA_HD void backup_results(const TreeDev& t, const SearchParams& sp) {
             len_n = len_nn, leaf_n = leaf_nn, nid_n = nid_nn, e_n = e_nn;
             if (b + 2 < n_new) {
                 len_nn = t.traj_len[b + 2];
-                leaf_nn = t.new_value[b + 2];
+                leaf_nn = leaf_values[b + 2];
                 nid_nn = t.traj_node[(b + 2) * kMaxDepth + dd];
                 e_nn = t.traj_edge[(b + 2) * kMaxDepth + dd];
             }
@@ -1177,12 +1179,8 @@ ARA_HD void backup_results(const TreeDev& t, const SearchParams& sp) {
             revert_virtual_loss(t, sp, t.traj_node[row * kMaxDepth + i], t.traj_ci[row * kMaxDepth + i]);
     }
     ARA_WARP_SYNC();
-    if (ARA_LANE == 0) {
-        t.st->n_prep = n_new;  // the prepare step that follows still needs the list of new leaves
-        t.st->n_new = 0;
-        t.st->n_coll = 0;
-    }
-    ARA_WARP_SYNC();
+    // (n_new / n_coll stay as the select step left them: the scatter and prepare steps, which may run concurrently,
+    // read n_new; the next select step overwrites both)
 }
 
 // Root creation: MCTSAgent::create_new_root_node (mctsagent.cpp:180-196), first half (before the network call).

@@ -200,8 +200,8 @@ int he_search_set_root(HeSearch* s, const HeState* root) {
 }
 void he_search_apply_move(HeSearch* s, unsigned short move) { advance_root(s->t, move); }
 void he_search_root_results(HeSearch* s, const float* values, const float* probs) {
+    backup_results(s->t, s->sp, values);  // (independent of the scatter step: the device runs them side by side)
     for (int b = 0; b < s->st.n_new; ++b) scatter_pending(s->t, s->sp, s->ws, b, values, probs, s->n_labels);
-    backup_results(s->t, s->sp);
     finalize_root(s->t, s->sp, s->ws);
     for (int item = 0; item < 4 * s->sp.batch_size; ++item) prepare_item(s->t, s->sp, s->ws, item);
 }
@@ -215,8 +215,8 @@ int he_search_create_mini_batch(HeSearch* s) {
     return s->st.n_new;
 }
 void he_search_apply_results(HeSearch* s, const float* values, const float* probs) {
+    backup_results(s->t, s->sp, values);
     for (int b = 0; b < s->st.n_new; ++b) scatter_pending(s->t, s->sp, s->ws, b, values, probs, s->n_labels);
-    backup_results(s->t, s->sp);
     for (int item = 0; item < 4 * s->sp.batch_size; ++item) prepare_item(s->t, s->sp, s->ws, item);
 }
 int he_search_done(const HeSearch* s) { return s->st.done || s->st.error; }

@@ -354,7 +354,7 @@ int Search::init(Net* net, const SearchParams& params, int device, int trees, in
         if (dalloc(&t.st, 1)) return -1;
         if (dalloc(&t.new_node, B) || dalloc(&t.traj_node, static_cast<size_t>(2) * B * kMaxDepth) ||
             dalloc(&t.traj_ci, static_cast<size_t>(2) * B * kMaxDepth) || dalloc(&t.traj_len, 2 * B) ||
-            dalloc(&t.traj_edge, static_cast<size_t>(2) * B * kMaxDepth) || dalloc(&t.new_value, B))
+            dalloc(&t.traj_edge, static_cast<size_t>(2) * B * kMaxDepth))
             return -1;
         const size_t slots = static_cast<size_t>(max_nodes_) * kPrepSlots;
         if (dalloc(&t.prep_board, slots) || dalloc(&t.prep_ci, slots) || dalloc(&t.prep_term, slots) ||

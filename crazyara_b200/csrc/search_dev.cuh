@@ -83,7 +83,6 @@ struct TreeState {
     int next_root;   // candidate root after ara_search_apply_move (MCTSAgent::ownNextRoot / opponentsNextRoot), -1 none
     int next_valid;  // apply_move has been called since the last search: only next_root may be reused
     int n_exp;     // expansions of the last mini-batch (entries of exp_parent)
-    int n_prep;    // (unused; kept for the layout)
     int done;      // search loop condition failed (limits reached / root solved)
     int error;     // 1 node pool, 2 edge pool, 3 depth overflow
     unsigned iterations;
@@ -150,7 +149,6 @@ struct TreeDev {
     uint16_t* traj_ci;      // [2B][kMaxDepth]
     uint32_t* traj_edge;    // [2B][kMaxDepth]   absolute edge index (edge_base + ci) of every step
     int32_t* traj_len;      // [2B]
-    float* new_value;       // [B] network value of every new leaf (written by the scatter step)
     const uint64_t* hist_keys;  // positions before the root, oldest first
     const int16_t* hist_reps;
     int hist_len;
@@ -1196,7 +1194,6 @@ ARA_HD void create_root(const TreeDev& t, const SearchParams& sp, WarpScratch& w
         st.n_new = 0;
         st.n_coll = 0;
         st.n_exp = 0;
-        st.n_prep = 0;
         st.done = 0;
         st.error = 0;
         st.iterations = 0;
@@ -1264,7 +1261,7 @@ ARA_HD int reuse_root(const TreeDev& t, const SearchParams& sp, const Board* roo
             NodeHdr& h = t.hdr[cand];
             st.root = cand;
             h.parent = -1;  // make_to_root: the path walks of prepare_child stop here
-            st.n_new = st.n_coll = st.n_exp = st.n_prep = 0;
+            st.n_new = st.n_coll = st.n_exp = 0;
             st.done = ((h.flags & NF_TERMINAL) || h.n_moves == 0) ? 1 : 0;
             st.iterations = 0;
             st.evals = 0;

@@ -93,7 +93,6 @@ struct HeSearch {
     std::vector<int32_t> new_node, traj_node, traj_len;
     std::vector<uint16_t> traj_ci;
     std::vector<uint32_t> traj_edge, cbase;
-    std::vector<float> new_value;
     std::vector<Board> prep_board;
     std::vector<int16_t> prep_ci;
     std::vector<uint8_t> prep_term;
@@ -130,7 +129,6 @@ HeSearch* he_search_new(const SearchParams* sp, int max_nodes, int max_edges) {
     s->traj_ci.resize(2 * B * kMaxDepth);
     s->traj_len.resize(2 * B);
     s->traj_edge.resize(2 * B * kMaxDepth);
-    s->new_value.resize(B);
     s->channels = planes_channels(sp->mode, sp->input_version);
     s->n_labels = (sp->mode == MODE_CRAZYHOUSE ? 81 : (sp->mode == MODE_CHESS ? 76 : 84)) * 64;
     s->planes.assign(static_cast<size_t>(B) * s->channels * 64, 0.0f);
@@ -155,7 +153,6 @@ HeSearch* he_search_new(const SearchParams* sp, int max_nodes, int max_edges) {
     t.traj_ci = s->traj_ci.data();
     t.traj_len = s->traj_len.data();
     t.traj_edge = s->traj_edge.data();
-    t.new_value = s->new_value.data();
     s->prep_board.resize(static_cast<size_t>(max_nodes) * kPrepSlots);
     s->prep_ci.assign(static_cast<size_t>(max_nodes) * kPrepSlots, -1);
     s->prep_term.resize(static_cast<size_t>(max_nodes) * kPrepSlots);

@@ -1097,9 +1097,9 @@ ARA_HD void backup_results(const TreeDev& t, const SearchParams& sp, const float
     // updates depth d of every trajectory, in trajectory order (value sign alternates with the distance to the leaf).
     // Backups that share a node or an edge share its depth and therefore its lane, which preserves the reference's
     // update order node by node and edge by edge.  The node sums and the edge statistics a lane is working on stay in
-    // registers while consecutive trajectories pass through the same node / edge (always true at the root), the
-    // indices of the next trajectory are loaded one iteration ahead and its lines are prefetched, so that the
-    // per-trajectory chain is one L1 access plus the FP64 arithmetic instead of four dependent L2 round trips.
+    // registers while consecutive trajectories pass through the same node / edge (always true at the root); indices
+    // are loaded two trajectories ahead and the statistics one trajectory ahead, so that the per-trajectory chain is
+    // the FP64 arithmetic alone instead of four dependent L2 round trips.
     int max_len = 0;
     for (int b = ARA_LANE; b < n_new; b += ARA_WARP_N) max_len = t.traj_len[b] > max_len ? t.traj_len[b] : max_len;
     max_len = ARA_REDUCE_MAX(max_len);
@@ -1111,19 +1111,34 @@ ARA_HD void backup_results(const TreeDev& t, const SearchParams& sp, const float
         uint32_t c_e = 0xffffffffu, c_n = 0;
         float c_q = 0.0f;
         uint8_t c_vl = 0;
-        // two-deep pipeline: the indices of trajectory b+2 are requested while b is processed (unconditionally: the
-        // trajectory arrays are dense, entries beyond a trajectory's length are simply not used), the lines of b+1 are
-        // prefetched with indices that arrived an iteration ago
+        // software pipeline: the indices of trajectory b+2 are requested while b is processed (unconditionally: the
+        // trajectory arrays are dense, entries beyond a trajectory's length are simply not used), and the node sums
+        // and edge statistics of trajectory b+1 are LOADED (p_*) while b's FP64 chain runs.  A pre-loaded value is
+        // current when it is used: this lane is the only writer of its depth's nodes and edges, it writes them only
+        // when its register copy moves on to another node / edge, and that store is issued before the pre-load of the
+        // same iteration; if b+1 stays on b's node / edge the register copy is used and the pre-load is ignored.
         const int dd = d < kMaxDepth ? d : kMaxDepth - 1;
-        int len_n = n_new > 0 ? t.traj_len[0] : 0, len_nn = n_new > 1 ? t.traj_len[1] : 0;
         const float* leaf_values = values + t.slot_base;
+        int len_n = n_new > 0 ? t.traj_len[0] : 0, len_nn = n_new > 1 ? t.traj_len[1] : 0;
         float leaf_n = n_new > 0 ? leaf_values[0] : 0.0f, leaf_nn = n_new > 1 ? leaf_values[1] : 0.0f;
         int nid_n = n_new > 0 ? t.traj_node[dd] : -1, nid_nn = n_new > 1 ? t.traj_node[kMaxDepth + dd] : -1;
         uint32_t e_n = n_new > 0 ? t.traj_edge[dd] : 0, e_nn = n_new > 1 ? t.traj_edge[kMaxDepth + dd] : 0;
+        double p_vsum = 0.0;
+        uint32_t p_rv = 0, p_n = 0;
+        float p_q = 0.0f;
+        uint8_t p_vl = 0;
+        if (n_new > 0 && d < len_n) {  // pre-load of trajectory 0
+            p_vsum = t.hdr[nid_n].value_sum, p_rv = t.hdr[nid_n].real_visits;
+            p_q = t.Q[e_n], p_n = t.N[e_n], p_vl = t.vl[e_n];
+        }
         for (int b = 0; b < n_new; ++b) {
             const int len = len_n, nid = nid_n;
             const uint32_t e = e_n;
             const float leaf_v = leaf_n;
+            const double l_vsum = p_vsum;
+            const uint32_t l_rv = p_rv, l_n = p_n;
+            const float l_q = p_q;
+            const uint8_t l_vl = p_vl;
             len_n = len_nn, leaf_n = leaf_nn, nid_n = nid_nn, e_n = e_nn;
             if (b + 2 < n_new) {
                 len_nn = t.traj_len[b + 2];
@@ -1131,26 +1146,29 @@ ARA_HD void backup_results(const TreeDev& t, const SearchParams& sp, const float
                 nid_nn = t.traj_node[(b + 2) * kMaxDepth + dd];
                 e_nn = t.traj_edge[(b + 2) * kMaxDepth + dd];
             }
-            if (b + 1 < n_new && d < len_n) {
-                if (nid_n != nid) prefetch_line(&t.hdr[nid_n]);
-                if (e_n != e) prefetch_line(&t.Q[e_n]), prefetch_line(&t.N[e_n]), prefetch_line(&t.vl[e_n]);
+            const bool active = d < len;
+            if (active) {  // move the register copies on to this trajectory's node / edge (stores first)
+                if (nid != c_nid) {
+                    if (c_nid >= 0) t.hdr[c_nid].value_sum = c_vsum, t.hdr[c_nid].real_visits = c_rv;
+                    c_nid = nid;
+                    c_vsum = l_vsum;
+                    c_rv = l_rv;
+                }
+                if (e != c_e) {
+                    if (c_e != 0xffffffffu) t.Q[c_e] = c_q, t.vl[c_e] = c_vl;
+                    c_e = e;
+                    c_q = l_q;
+                    c_n = l_n;
+                    c_vl = l_vl;
+                }
             }
-            if (d >= len) continue;
+            if (b + 1 < n_new && d < len_n) {  // pre-load of trajectory b+1, in flight during the arithmetic below
+                p_vsum = t.hdr[nid_n].value_sum, p_rv = t.hdr[nid_n].real_visits;
+                p_q = t.Q[e_n], p_n = t.N[e_n], p_vl = t.vl[e_n];
+            }
+            if (!active) continue;
             const float v = ((len - d) & 1) ? -leaf_v : leaf_v;
-            if (nid != c_nid) {
-                if (c_nid >= 0) t.hdr[c_nid].value_sum = c_vsum, t.hdr[c_nid].real_visits = c_rv;
-                c_nid = nid;
-                c_vsum = t.hdr[nid].value_sum;
-                c_rv = t.hdr[nid].real_visits;
-            }
-            if (e != c_e) {
-                if (c_e != 0xffffffffu) t.Q[c_e] = c_q, t.vl[c_e] = c_vl;
-                c_e = e;
-                c_q = t.Q[e];
-                c_n = t.N[e];
-                c_vl = t.vl[e];
-            }
-            // revert_virtual_loss_and_update (node.h:199-246) on the cached copies
+            // revert_virtual_loss_and_update (node.h:199-246) on the register copies
             c_vsum += v;
             ++c_rv;
             if (c_n == 1) {

@@ -111,8 +111,9 @@ def cpu_arm(sims, batch, steps, warmup):
         pass
     cores = max(1, min(avail, int(os.environ.get("ARA_CPU_THREADS", "16"))))
     torch.set_num_threads(cores)
-    arch = onet.arch_risev2(34, 81)
-    sd = onet.make_state_dict(arch, 0)
+    from crazyara_b200 import synthetic
+    arch = synthetic.risev2(34, 81)              # the same random network the GPU arm runs
+    sd = synthetic.random_state_dict(arch, 0)
     st = osr.default_settings("crazyhouse", batch_size=batch, simulations=sims)
 
     def net_fn(planes):
@@ -260,12 +261,12 @@ def main():
     from crazyara_b200.engine import BoardState, MCTSAgent, default_settings
     from crazyara_b200.nn import NeuralNetAPI
     from crazyara_b200.weights import export_blob
-    from oracle import net as onet  # seeded synthetic weights (no trained weights ship with the reference)
+    from crazyara_b200 import synthetic  # seeded random weights (no trained weights ship with the reference)
 
-    arch = onet.arch_risev2(34, 81)
+    arch = synthetic.risev2(34, 81)
     flops_pos = net_flops_per_position(arch)
     tmp = tempfile.mkdtemp(prefix="ara_bench_")
-    blob = export_blob(onet.make_state_dict(arch, 0), arch, os.path.join(tmp, f"risev2_{rank}.arab"), input_version=10)
+    blob = export_blob(synthetic.random_state_dict(arch, 0), arch, os.path.join(tmp, f"risev2_{rank}.arab"), input_version=10)
     net = NeuralNetAPI("gpu", local_rank, args.batch, blob)
     settings = default_settings("crazyhouse", batch_size=args.batch, simulations=args.sims)
     agent = MCTSAgent(net, settings, local_rank, 1)

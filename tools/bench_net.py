@@ -9,14 +9,14 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from crazyara_b200.nn import NeuralNetAPI  # noqa: E402
 from crazyara_b200.weights import export_blob  # noqa: E402
-from oracle import net as onet  # noqa: E402  (seeded weights only)
+from crazyara_b200 import synthetic
 
 
 def main():
     import torch
     iters = int(os.environ.get("ITERS", "200"))
-    for name, arch, ver in (("risev2", onet.arch_risev2(34, 81), 10), ("risev33", onet.arch_risev33(52, 76, True), 30)):
-        sd = onet.make_state_dict(arch, 0)
+    for name, arch, ver in (("risev2", synthetic.risev2(34, 81), 10), ("risev33", synthetic.risev33(52, 76, True), 30)):
+        sd = synthetic.random_state_dict(arch, 0)
         with tempfile.TemporaryDirectory() as d:
             blob = export_blob(sd, arch, os.path.join(d, "w.arab"), input_version=ver)
             for batch in (1, 8, 64, 128):

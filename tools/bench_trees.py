@@ -10,7 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from crazyara_b200.engine import BoardState, MCTSAgent, default_settings
 from crazyara_b200.nn import NeuralNetAPI
 from crazyara_b200.weights import export_blob
-from oracle import net as onet
+from crazyara_b200 import synthetic
 
 FLOP_POS = None
 
@@ -20,11 +20,11 @@ def main():
     sims = int(os.environ.get("SIMS", "3200"))
     batch = int(os.environ.get("BATCH", "64"))
     reps = int(os.environ.get("REPS", "5"))
-    arch = onet.arch_risev2(34, 81)
+    arch = synthetic.risev2(34, 81)
     import bench
     flops = bench.net_flops_per_position(arch)
     d = tempfile.mkdtemp()
-    blob = export_blob(onet.make_state_dict(arch, 0), arch, os.path.join(d, "w.arab"), input_version=10)
+    blob = export_blob(synthetic.random_state_dict(arch, 0), arch, os.path.join(d, "w.arab"), input_version=10)
     openings = ["", "e2e4", "d2d4", "g1f3", "e2e4 e7e5", "d2d4 d7d5", "c2c4", "b1c3"]
     for T in trees:
         net = NeuralNetAPI("gpu", 0, batch * T, blob)

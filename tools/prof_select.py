@@ -5,11 +5,11 @@ from crazyara_b200 import lib
 from crazyara_b200.engine import BoardState, MCTSAgent, default_settings
 from crazyara_b200.nn import NeuralNetAPI
 from crazyara_b200.weights import export_blob
-from oracle import net as onet
+from crazyara_b200 import synthetic
 
-arch = onet.arch_risev2(34, 81)
+arch = synthetic.risev2(34, 81)
 d = tempfile.mkdtemp()
-blob = export_blob(onet.make_state_dict(arch, 0), arch, os.path.join(d, "w.arab"), input_version=10)
+blob = export_blob(synthetic.random_state_dict(arch, 0), arch, os.path.join(d, "w.arab"), input_version=10)
 net = NeuralNetAPI("gpu", 0, 64, blob)
 agent = MCTSAgent(net, default_settings("crazyhouse", batch_size=64, simulations=3200), 0, 1)
 agent.set_profile(True)

@@ -5,13 +5,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from crazyara_b200.nn import NeuralNetAPI
 from crazyara_b200.selfplay import Arena, rl_settings
 from crazyara_b200.weights import export_blob
-from oracle import net as onet
+from crazyara_b200 import synthetic
 
 n_games = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 12
 groups = int(sys.argv[3]) if len(sys.argv) > 3 else 1
-arch = onet.arch_risev2(34, 81)
-blob = export_blob(onet.make_state_dict(arch, 0), arch, os.path.join(tempfile.mkdtemp(), "w.arab"), input_version=10)
+arch = synthetic.risev2(34, 81)
+blob = export_blob(synthetic.random_state_dict(arch, 0), arch, os.path.join(tempfile.mkdtemp(), "w.arab"), input_version=10)
 st = rl_settings("crazyhouse")
 nets = [NeuralNetAPI("gpu", 0, n_games // groups * st.batch_size, blob) for _ in range(groups)]
 arena = Arena(nets if groups > 1 else nets[0], st, variant=1, n_games=n_games, max_plies=160, seed=1)

@@ -11,13 +11,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from crazyara_b200 import lib
 from crazyara_b200.nn import NeuralNetAPI
 from crazyara_b200.weights import export_blob
-from oracle import net as onet
+from crazyara_b200 import synthetic
 
 arch_name = sys.argv[1] if len(sys.argv) > 1 else "risev2"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 64
-arch = onet.arch_risev2(34, 81) if arch_name == "risev2" else onet.arch_risev33(52, 76)
+arch = synthetic.risev2(34, 81) if arch_name == "risev2" else synthetic.risev33(52, 76)
 d = tempfile.mkdtemp()
-blob = export_blob(onet.make_state_dict(arch, 0), arch, os.path.join(d, "w.arab"), input_version=10 if arch_name == "risev2" else 30)
+blob = export_blob(synthetic.random_state_dict(arch, 0), arch, os.path.join(d, "w.arab"), input_version=10 if arch_name == "risev2" else 30)
 net = NeuralNetAPI("gpu", 0, B, blob)
 x = np.random.default_rng(0).random((B, arch["in_channels"], 8, 8), dtype=np.float32)
 val = np.zeros(B, np.float32)

@@ -1,10 +1,11 @@
 // Minimal UCI front-end over the C++ host classes (engine/src/uci/crazyara.cpp:76-143 command loop, option names of
 // uci/optionsuci.cpp:66-220).  Supported: uci, isready, setoption, ucinewgame, position [startpos|fen] [moves ...],
 // go [nodes N | movetime T | wtime W btime B [winc I] [binc I] [movestogo M]] (or the Simulations / Nodes options),
-// root, quit.  The move time follows TimeManager::get_time_for_move (manager/timemanager.cpp:51-100) without its
+// benchmark <movetime>, inference [warmup N] [iterations N], root, quit.  The move time follows TimeManager::get_time_for_move (manager/timemanager.cpp:51-100) without its
 // random factor; the search then also stops after that much wall time (ara_search_set_movetime), and in clock games
 // the ThreadManager's early stopping / prolongation rules run on top (ara_search_set_time_control).
 #include <algorithm>
+#include <chrono>
 #include <iomanip>
 #include <iostream>
 #include <map>
@@ -13,6 +14,7 @@
 #include <vector>
 
 #include "ara_host.h"
+#include "benchmark_positions.h"
 
 using namespace crazyara;
 
@@ -230,6 +232,72 @@ int main() {
                           << info.centipawns << " time " << static_cast<long>(info.elapsedMs) << " pv";
                 for (Action a : info.pv) std::cout << " " << state.action_to_uci(a);
                 std::cout << "\nbestmove " << (info.bestMove ? state.action_to_uci(info.bestMove) : std::string("(none)")) << std::endl;
+            } else if (cmd == "benchmark") {  // CrazyAra::benchmark (crazyara.cpp:287-330): `benchmark <movetime ms>`
+                long moveTime = 3000;
+                ss >> moveTime;
+                if (variant() != 1) {
+                    std::cout << "info string the benchmark positions are crazyhouse positions (set UCI_Variant)" << std::endl;
+                    continue;
+                }
+                if (!timed) {
+                    timed = true;
+                    ready = false;
+                }
+                if (!ready) prepare();
+                agent->clear_time_control();
+                agent->set_movetime(static_cast<double>(moveTime));
+                searched = false;  // every position is searched on a tree of its own
+                int passed = 0;
+                long totalNPS = 0, totalDepth = 0;
+                std::vector<long> nps;
+                const size_t n = sizeof(kBenchmarkPositions) / sizeof(kBenchmarkPositions[0]);
+                for (const TestPosition& tp : kBenchmarkPositions) {
+                    BoardState bs;
+                    bs.set(tp.fen, false, 1);
+                    EvalInfo ei;
+                    agent->evaluate_board_state(bs, ei);
+                    const std::string uciMove = ei.bestMove ? bs.action_to_uci(ei.bestMove) : std::string("(none)");
+                    if (uciMove != tp.blunderMove) {
+                        std::cout << "passed      -- " << uciMove << " != " << tp.blunderMove << std::endl;
+                        ++passed;
+                    } else {
+                        std::cout << "failed      -- " << uciMove << " == " << tp.blunderMove << std::endl;
+                    }
+                    std::cout << "alternative -- " << uciMove << (uciMove == tp.alternativeMove ? " == " : " != ") << tp.alternativeMove
+                              << std::endl;
+                    const long cur = static_cast<long>(ei.calculate_nps());
+                    totalNPS += cur;
+                    totalDepth += static_cast<long>(ei.depth);
+                    nps.push_back(cur);
+                }
+                std::sort(nps.begin(), nps.end());
+                std::cout << "\nSummary\n----------------------\nPassed:\t\t" << passed << "/" << n << "\nNPS (avg):\t" << totalNPS / static_cast<long>(n)
+                          << "\nNPS (median):\t" << nps[nps.size() / 2] << "\nPV-Depth:\t" << totalDepth / static_cast<long>(n) << std::endl;
+            } else if (cmd == "inference") {  // CrazyAra::inference (crazyara.cpp:156-181): `inference [warmup N] [iterations N]`
+                size_t warmupIterations = 100, iterations = 3000;
+                std::string tok;
+                while (ss >> tok) {
+                    if (tok == "warmup") ss >> warmupIterations;
+                    if (tok == "iterations") ss >> iterations;
+                }
+                if (!ready) prepare();
+                if (!net) {
+                    std::cout << "info string inference needs a network (setoption name Model_Path)" << std::endl;
+                    continue;
+                }
+                const unsigned B = net->get_batch_size();
+                std::cout << "info string running " << warmupIterations << " warmup iteration...\ninfo string running " << iterations
+                          << " iterations...\ninfo string batch-size: " << B << std::endl;
+                // NeuralNetAPIUser::run_inference (neuralnetapiuser.cpp:104-110): predict() on the caller's host buffers
+                std::vector<float> planes(static_cast<size_t>(B) * net->get_nb_input_values_total(), 0.0f), value(B),
+                    prob(static_cast<size_t>(B) * net->get_nb_policy_values()),
+                    aux(static_cast<size_t>(B) * std::max(1u, net->get_nb_auxiliary_outputs()));
+                for (size_t i = 0; i < warmupIterations; ++i) net->predict(planes.data(), value.data(), prob.data(), aux.data());
+                const auto t0 = std::chrono::steady_clock::now();
+                for (size_t i = 0; i < iterations; ++i) net->predict(planes.data(), value.data(), prob.data(), aux.data());
+                const double elapsedMS = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+                std::cout << "info string Inference results\ninfo string -----------------\ninfo string Elapsed time: " << elapsedMS / 1000.0
+                          << " s\ninfo string Evaluations per second: " << (iterations / elapsedMS) * 1000.0 * B << " nps" << std::endl;
             } else if (cmd == "root") {  // Node::print_node_statistics (node.cpp:1248-1301): the parity dump format
                 std::cout << "  #  | Move  |    Visits    |  Policy   |  Q-values  |  CP   \n";
                 std::cout << std::fixed << std::setprecision(7);

@@ -82,3 +82,29 @@ def test_uci_position_extension_reuses_the_tree():
     out = subprocess.run([exe], input="\n".join(off) + "\n", capture_output=True, text=True, timeout=120).stdout
     assert "info string reused" not in out
     agent.close()
+
+
+@pytest.mark.gpu
+def test_uci_benchmark_and_inference_commands(tmp_path):
+    """`benchmark <movetime>` (crazyara.cpp:287-330: the 15 tactical positions, pass count, NPS mean / median) and
+    `inference` (crazyara.cpp:156-181: evaluations per second of the loaded network)."""
+    from crazyara_b200 import synthetic
+    from crazyara_b200.weights import export_blob
+    exe = os.path.join(ROOT, "crazyara_b200", "ara_uci")
+    head = ["uci", "setoption name UCI_Variant value crazyhouse", "setoption name Batch_Size value 16",
+            "setoption name Timed_Search_Nodes value 60000"]
+    out = subprocess.run([exe], input="\n".join(head + ["benchmark 60", "quit"]) + "\n", capture_output=True, text=True,
+                         timeout=180).stdout
+    lines = out.splitlines()
+    verdicts = [l for l in lines if l.startswith(("passed      -- ", "failed      -- "))]
+    assert len(verdicts) == 15 and len([l for l in lines if l.startswith("alternative -- ")]) == 15
+    assert any(l.startswith("Passed:") and l.endswith("/15") for l in lines)
+    nps = [int(l.split()[-1]) for l in lines if l.startswith(("NPS (avg):", "NPS (median):"))]
+    assert len(nps) == 2 and min(nps) > 1000
+    arch = synthetic.risev2(34, 81)
+    blob = export_blob(synthetic.random_state_dict(arch, 0), arch, str(tmp_path / "risev2.arab"), input_version=10)
+    script = head + [f"setoption name Model_Path value {blob}", "isready", "inference warmup 2 iterations 6", "quit"]
+    out = subprocess.run([exe], input="\n".join(script) + "\n", capture_output=True, text=True, timeout=180).stdout
+    assert "info string batch-size: 16" in out
+    rate = [float(l.split()[-2]) for l in out.splitlines() if l.startswith("info string Evaluations per second:")]
+    assert len(rate) == 1 and rate[0] > 100.0

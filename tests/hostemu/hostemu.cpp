@@ -239,6 +239,35 @@ void he_search_time_stats(HeSearch* s, unsigned* iout, float* fout) {
     fout[0] = r.q_first, fout[1] = r.q_second, fout[2] = r.value_eval;
 }
 
+// first_and_second_max as collect_time_stats applies it: a root with k open, childless edges of the given visit counts
+// and Q values; iout = {first, second, max_q_is_max_visits}, fout = {q_first, q_second, value_eval}.
+void he_time_stats_of(int k, const unsigned* n, const float* q, unsigned* iout, float* fout) {
+    std::vector<uint32_t> N(n, n + k);
+    std::vector<float> Q(q, q + k);
+    std::vector<int32_t> child(k, -1);
+    NodeHdr root{};
+    root.no_visit_idx = static_cast<uint16_t>(k);
+    root.n_moves = static_cast<uint16_t>(k);
+    root.edge_base = 0;
+    root.flags = NF_HAS_D | NF_SORTED | NF_HAS_NN;
+    root.node_type = NT_UNSOLVED;
+    for (int i = 0; i < k; ++i) root.visit_sum += N[i];
+    root.real_visits = root.visit_sum;
+    TreeState st{};
+    st.n_nodes = 1;
+    st.root = 0;
+    TreeDev t{};
+    t.hdr = &root;
+    t.N = N.data();
+    t.Q = Q.data();
+    t.child = child.data();
+    t.st = &st;
+    RootTimeStats r;
+    collect_time_stats(t, &r);
+    iout[0] = r.first_visits, iout[1] = r.second_visits, iout[2] = static_cast<unsigned>(r.max_q_is_max_visits);
+    fout[0] = r.q_first, fout[1] = r.q_second, fout[2] = r.value_eval;
+}
+
 // Select-step unit hook: k open children with the given statistics; out = {sure, fast_ci, exact_ci}.
 void he_pick_both(int k, const float* p, const float* q, const unsigned* n, float cput, unsigned visit_sum, int* out) {
     std::vector<float> P(p, p + k), Q(q, q + k);

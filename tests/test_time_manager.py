@@ -78,3 +78,28 @@ def test_root_statistics_match_the_oracle_tree():
         assert ts["q_first"] == q[a1] and ts["q_second"] == q[a2]
         assert ts["max_q_is_max_visits"] == int(int(np.argmax(q)) == a1)
         assert ts["value_eval"] == q[a1]                       # updated_value_eval of an unsolved root
+
+
+def test_first_and_second_max_reference_vectors():
+    """The reference's own known-answer test of first_and_second_max (tests.cpp:626-646), through the device code that
+    applies it to the root's visit counts (collect_time_stats); the Q values tell which children were picked."""
+    import ctypes
+    import numpy as np
+    from tests.hostemu import lib
+    L = lib()
+    L.he_time_stats_of.argtypes = [ctypes.c_int] + [ctypes.c_void_p] * 4
+
+    def stats(visits):
+        n = np.array(visits, np.uint32)
+        q = (np.arange(len(visits)) * 0.01 - 0.5).astype(np.float32)      # q[i] identifies child i
+        i, f = np.zeros(3, np.uint32), np.zeros(3, np.float32)
+        L.he_time_stats_of(len(visits), n.ctypes.data, q.ctypes.data, i.ctypes.data, f.ctypes.data)
+        return int(i[0]), int(i[1]), int(round((f[0] + 0.5) * 100)), int(round((f[1] + 0.5) * 100)), float(f[2]), q
+
+    first, second, a1, a2, eval_, q = stats([3, 42, 1, 3, 99, 8, 7])
+    assert (first, second, a1, a2) == (99, 42, 4, 1) and eval_ == q[4]
+    first, second, a1, a2, eval_, q = stats([99, 3, 1, 3, 42, 8, 7])
+    assert (first, second, a1, a2) == (99, 42, 0, 4) and eval_ == q[0]
+    # ties: the first maximum wins both ranks (strict comparisons)
+    assert stats([5, 5, 5])[:4] == (5, 5, 0, 1)
+    assert stats([7])[:4] == (7, 0, 0, 0)

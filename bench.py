@@ -380,6 +380,19 @@ def main():
                                    "tcgen05 TS/SS MMAs, one launch) + stem/policy conv_gemm_kernel + head kernels",
                          "flop_per_position": flops_pos, "peak_source": peak_src},
         }
+        try:
+            # the other big kernel, against ITS roofline: select reads 32 B of header + 13 B per open child
+            # (Q, n, P, vl) at every tree level -- a dependent pointer chase, so far below the HBM peak by nature
+            sel_bytes = 32.0 * float(last.get("sum_depth", 0)) + 13.0 * float(last.get("sum_select_k", 0))
+            hbm_peak = float(peaks.get("hbm_gbs", 6500.0))
+            sel_gbs = sel_bytes / (sel_ms / args.steps * 1e-3) / 1e9 if sel_ms > 0 else 0.0
+            out["roofline_select"] = {"bound": "hbm", "achieved": sel_gbs, "peak": hbm_peak, "unit": "GB/s",
+                                      "frac": sel_gbs / hbm_peak if hbm_peak else None,
+                                      "algorithmic_bytes_per_search": sel_bytes,
+                                      "note": "select_kernel: one warp per tree, one dependent L2/HBM round trip per tree "
+                                              "level; latency-bound (profiles/r01_ncu_select_kernel.json)"}
+        except Exception:
+            pass
         if world == 1 and not args.no_cpu_baseline:
             nps, ms, cores, _ = cpu_arm(args.cpu_sims, args.batch, 2, 1)
             out["cpu_baseline"] = {"value": nps, "unit": UNIT, "cores": cores, "kind": "port",

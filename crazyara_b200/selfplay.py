@@ -11,6 +11,7 @@ posterior, or a sample from posterior^(1/T) during the first `temperature_moves`
 DeepCrazyhouse/configs/rl_config.py:34-65).  Optional outputs: training samples (`exporter=`, crazyara_b200.export) and
 the games as PGN (`pgn_path=`, crazyara_b200.pgn).
 """
+import os
 import threading
 import time
 
@@ -191,3 +192,80 @@ class Arena:
     def close(self):
         for a in self.agents:
             a.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Launcher: one process per GPU, like the reference's `python rl_loop.py --device-id N` per device
+# (engine/src/rl/README.md:84-97): games never interact, so the processes share nothing and need no collective.
+
+def plan_workers(total_games, devices, out_dir):
+    """What every worker process does: its GPU, its share of the concurrent games (crazyara_b200.multi.shard_range) and
+    its output files, named like the reference's (selfplay.cpp:116-127: data_<device>.zarr, games_<device>.pgn with
+    device = gpu_<id>)."""
+    from .multi import shard_range
+    plan = []
+    for rank, dev in enumerate(devices):
+        lo, hi = shard_range(total_games, rank, len(devices))
+        if hi > lo:
+            name = f"gpu_{dev}"
+            plan.append(dict(rank=rank, device=int(dev), n_games=hi - lo, seed_offset=lo,
+                             zarr=os.path.join(out_dir, f"data_{name}.zarr"), pgn=os.path.join(out_dir, f"games_{name}.pgn")))
+    return plan
+
+
+def _worker(job, args):
+    from .export import TrainDataExporter
+    from .nn import NeuralNetAPI
+    st = rl_settings(args.mode, batch_size=args.batch_size, nodes=args.nodes, simulations=4 * args.nodes,
+                     input_version=args.input_version)
+    groups = 2 if job["n_games"] % 2 == 0 and job["n_games"] >= 4 else 1
+    nets = [NeuralNetAPI("gpu", job["device"], job["n_games"] // groups * args.batch_size, args.model) for _ in range(groups)]
+    channels = nets[0].get_nb_input_values_total() // 64
+    exporter = TrainDataExporter(job["zarr"], args.mode, channels, number_chunks=args.chunks) if args.export else None
+    arena = Arena(nets if groups > 1 else nets[0], st, variant=args.variant, n_games=job["n_games"], device=job["device"],
+                  is960=args.chess960, max_plies=args.max_plies, seed=args.seed + job["seed_offset"], exporter=exporter,
+                  pgn_path=job["pgn"] if args.pgn else None)
+    res = arena.run(min_games=args.games_per_worker, max_seconds=args.seconds)
+    arena.close()
+    for n in nets:
+        n.close()
+    print(f"[{os.path.basename(job['zarr'])}] {res['games']} games, {res['moves_per_s']:.0f} moves/s, "
+          f"{res['games_per_hour']:.0f} games/h, search {res['nps']:.0f} nps", flush=True)
+
+
+def main(argv=None):
+    import argparse
+    import multiprocessing as mp
+    ap = argparse.ArgumentParser(description="self-play on several GPUs: one process per GPU, independent games")
+    ap.add_argument("model", help="weight blob (.arab, see crazyara_b200.weights)")
+    ap.add_argument("--devices", default="0", help="comma-separated GPU ids")
+    ap.add_argument("--games", type=int, default=64, help="concurrent games over all GPUs")
+    ap.add_argument("--games-per-worker", type=int, default=0, help="stop a worker after this many finished games (0 = no limit)")
+    ap.add_argument("--seconds", type=float, default=1e30, help="stop after this much wall time")
+    ap.add_argument("--mode", default="crazyhouse", choices=["crazyhouse", "chess", "lichess"])
+    ap.add_argument("--variant", type=int, default=1, help="0 chess, 1 crazyhouse, 2 king of the hill, 3 three-check")
+    ap.add_argument("--chess960", action="store_true")
+    ap.add_argument("--input-version", type=int, default=1)
+    ap.add_argument("--batch-size", type=int, default=8)
+    ap.add_argument("--nodes", type=int, default=800)
+    ap.add_argument("--max-plies", type=int, default=512)
+    ap.add_argument("--chunks", type=int, default=200, help="zarr chunks of 128 samples per data file")
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--out", default=".", help="directory of data_gpu_<id>.zarr / games_gpu_<id>.pgn")
+    ap.add_argument("--no-export", dest="export", action="store_false")
+    ap.add_argument("--no-pgn", dest="pgn", action="store_false")
+    args = ap.parse_args(argv)
+    os.makedirs(args.out, exist_ok=True)
+    plan = plan_workers(args.games, [int(d) for d in args.devices.split(",")], args.out)
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_worker, args=(job, args)) for job in plan]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join()
+    return max((p.exitcode or 0) for p in procs) if procs else 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())
+

@@ -124,3 +124,16 @@ def test_chess960_start_positions():
         back = st.fen().split(" ")
         assert back[0].split("/")[7] == rank and len(back[2]) == 4      # four castling rights (Shredder letters)
         assert len(st.legal_actions()) >= 16                             # 16 pawn moves + knight moves
+
+
+def test_selfplay_launcher_plan():
+    """One worker per GPU: the concurrent games are split evenly, every worker writes the reference's file names
+    (selfplay.cpp:116-127) and draws from its own seed range."""
+    from crazyara_b200.selfplay import plan_workers
+    plan = plan_workers(64, [0, 1, 2, 3, 4, 5, 6, 7], "/data/rl")
+    assert [j["n_games"] for j in plan] == [8] * 8 and [j["device"] for j in plan] == list(range(8))
+    assert plan[3]["zarr"] == "/data/rl/data_gpu_3.zarr" and plan[3]["pgn"] == "/data/rl/games_gpu_3.pgn"
+    assert [j["seed_offset"] for j in plan] == list(range(0, 64, 8))
+    uneven = plan_workers(10, [4, 5, 6], "o")
+    assert [j["n_games"] for j in uneven] == [4, 3, 3] and sum(j["n_games"] for j in uneven) == 10
+    assert [j["device"] for j in plan_workers(2, [0, 1, 2], "o")] == [0, 1]          # no idle worker is started

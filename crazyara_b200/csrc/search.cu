@@ -711,6 +711,10 @@ extern "C" int ara_search_time_report(ara_search_t h, ara_time_report_t* out) {
     *out = reinterpret_cast<Search*>(h)->tr;
     return 0;
 }
+extern "C" int ara_time_for_move(long movetime_ms, int time_me_ms, int inc_me_ms, int movestogo, int move_overhead_ms,
+                                 int move_number) {
+    return ara::tm_time_for_move(movetime_ms, time_me_ms, inc_me_ms, movestogo, move_overhead_ms, move_number);
+}
 extern "C" int ara_time_early_stopping(const ara_time_control_t* tc, double remaining_ms, unsigned node_count,
                                        int max_q_is_max_visits, unsigned first_visits, unsigned second_visits, float q_first,
                                        float q_second) {

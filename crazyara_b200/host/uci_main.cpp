@@ -50,20 +50,8 @@ struct GoLimits {
     bool any() const { return movetime || time[0] || time[1]; }
 };
 long time_for_move(const GoLimits& g, int me, int move_number, long overhead) {
-    const long safe = std::max(g.time[me] - overhead * 30, 1L);
-    auto constant = [&](long moves) { return safe / moves + static_cast<long>(0.7f * g.inc[me]); };
-    long t;
-    if (g.movetime != 0)
-        t = g.movetime;
-    else if (g.movestogo != 0)
-        t = constant(g.movestogo);
-    else if (g.time[me] != 0)
-        t = move_number < 35 ? constant(38 - move_number) : constant(14);
-    else
-        t = 1000;
-    t -= overhead;
-    if (t <= 0) t = overhead * 2;
-    return g.time[me] != 0 ? std::min(safe, t) : t;
+    return ara_time_for_move(g.movetime, static_cast<int>(g.time[me]), static_cast<int>(g.inc[me]), static_cast<int>(g.movestogo),
+                             static_cast<int>(overhead), move_number);
 }
 
 }  // namespace

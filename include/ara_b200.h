@@ -195,6 +195,9 @@ typedef struct {
  * NULL switches the manager off again.  Single-tree searches only. */
 int ara_search_set_time_control(ara_search_t s, const ara_time_control_t* tc);
 int ara_search_time_report(ara_search_t s, ara_time_report_t* out);
+/* TimeManager::get_time_for_move (manager/timemanager.cpp:51-98; constants.h:94-98; random factor off): the move time
+ * in ms from `go movetime` / the mover's clock and increment / movestogo, less the move overhead.  Pure function. */
+int ara_time_for_move(long movetime_ms, int time_me_ms, int inc_me_ms, int movestogo, int move_overhead_ms, int move_number);
 /* the two decisions as pure functions (no device): root statistics in, verdict out -- for tests and host-side reuse */
 int ara_time_early_stopping(const ara_time_control_t* tc, double remaining_ms, unsigned node_count, int max_q_is_max_visits,
                             unsigned first_visits, unsigned second_visits, float q_first, float q_second);

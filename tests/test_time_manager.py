@@ -103,3 +103,48 @@ def test_first_and_second_max_reference_vectors():
     # ties: the first maximum wins both ranks (strict comparisons)
     assert stats([5, 5, 5])[:4] == (5, 5, 0, 1)
     assert stats([7])[:4] == (7, 0, 0, 0)
+
+
+def _ara_time_for_move(row):
+    import ctypes
+    from crazyara_b200 import lib
+    L = lib()
+    L.ara_time_for_move.argtypes = [ctypes.c_long] + [ctypes.c_int] * 5
+    movetime, wtime, btime, winc, binc, movestogo, overhead, me, move_number = row[:9]
+    return L.ara_time_for_move(movetime, (wtime, btime)[me], (winc, binc)[me], movestogo, overhead, move_number)
+
+
+def test_time_for_move_equals_the_reference_golden():
+    """ara_time_for_move against outputs of the UNMODIFIED reference TimeManager (tests/golden/timeman.json, generated
+    by tests/golden/gen_timeman_golden.py from oracle/_ref)."""
+    import json
+    import os
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "timeman.json")))
+    assert len(g["rows"]) > 2000
+    bad = [r for r in g["rows"] if _ara_time_for_move(r) != r[9]]
+    assert bad == []
+
+
+def test_time_for_move_equals_the_compiled_reference_live():
+    """The same against oracle/_ref/libref_timeman.so itself on fresh random inputs, where the reference sources exist
+    (the build container); skipped on boxes without them."""
+    import ctypes
+    import os
+    import random
+    import subprocess
+    import pytest
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = os.path.join(root, "oracle", "_ref", "libref_timeman.so")
+    if not os.path.exists(so):
+        if not os.path.isdir("/root/reference/engine/src"):
+            pytest.skip("no reference sources on this box")
+        subprocess.run(["make", "-s", "-C", os.path.join(root, "oracle"), "ref"], check=True)
+    R = ctypes.CDLL(so)
+    R.ref_time_for_move.argtypes = [ctypes.c_long] + [ctypes.c_int] * 8
+    rng = random.Random(11)
+    for _ in range(5000):
+        clock = rng.random() < 0.8
+        row = (0 if clock else rng.choice((0, 1, 30, 250, 4000)), rng.randrange(0, 3000000) if clock else 0,
+               rng.randrange(0, 3000000) if clock else 0, rng.randrange(0, 30000), rng.randrange(0, 30000),
+               rng.choice((0, 0, 0, 1, 7, 40)), rng.choice((0, 20, 100, 500)), rng.randrange(2), rng.randrange(1, 120))
+        assert _ara_time_for_move(row) == R.ref_time_for_move(*row), row

@@ -1,4 +1,4 @@
-"""Generates tests/golden/timeman.json from the UNMODIFIED reference TimeManager (oracle/_ref/libref_timeman.so, built by
+"""Generates tests/golden/timeman.json from the UNMODIFIED reference TimeManager (oracle/_ref/libref_parts.so, built by
 `make -C oracle ref` from /root/reference/engine/src/manager/timemanager.cpp + agents/config/searchlimits.cpp).
 Run in the build container (the GPU box has no /root/reference):  python tests/golden/gen_timeman_golden.py"""
 import ctypes
@@ -22,7 +22,7 @@ def cases():
 
 
 def main():
-    L = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref_timeman.so"))
+    L = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref_parts.so"))
     L.ref_time_for_move.argtypes = [ctypes.c_long] + [ctypes.c_int] * 8
     rows = [list(c) + [L.ref_time_for_move(*c)] for c in cases()]
     json.dump({"columns": ["movetime", "wtime", "btime", "winc", "binc", "movestogo", "move_overhead", "me", "move_number",

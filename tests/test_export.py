@@ -137,3 +137,21 @@ def test_selfplay_launcher_plan():
     uneven = plan_workers(10, [4, 5, 6], "o")
     assert [j["n_games"] for j in uneven] == [4, 3, 3] and sum(j["n_games"] for j in uneven) == 10
     assert [j["device"] for j in plan_workers(2, [0, 1, 2], "o")] == [0, 1]          # no idle worker is started
+
+
+def test_chess960_generator_covers_the_reference_set():
+    """The reference's chess960fen() (compiled from chess960position.h into oracle/_ref) reaches exactly 960 set-ups over
+    30 000 seeds (tests/golden/ref_misc.json); ours must reach the same set, in the same FEN shape."""
+    import json
+    import os
+    import numpy as np
+    from crazyara_b200.selfplay import chess960_fen
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ref_misc.json")))
+    ref = g["chess960_back_ranks"]
+    assert len(ref) == 960
+    rng = np.random.default_rng(99)
+    fens = {chess960_fen(rng) for _ in range(30000)}
+    assert sorted(f.split("/")[7].split(" ")[0] for f in fens) == ref
+    shape = sorted({f.split("/", 1)[1].split("/", 6)[0] + "|" + f.split(" ", 1)[1] for f in fens})
+    assert shape == g["chess960_fen_shape"] == ["pppppppp|w KQkq - 0 1"]
+    assert all(f.split("/")[0] == f.split("/")[7].split(" ")[0].lower() for f in fens)

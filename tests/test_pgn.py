@@ -76,3 +76,41 @@ def test_line_break_every_eight_plies():
     g = GamePGN("chess", date="d")
     g.game_moves = ["a"] * 9
     assert str(g).split("\n\n", 1)[1] == "1. a a 2. a a 3. a a 4. a a \n5. a ?\n\n"
+
+
+def _game_from(case):
+    g = GamePGN("chess", date=case["header"][2])
+    (g.variant, g.event, g.date, g.site, g.round, g.fen, g.white, g.black, g.result, g.time_control) = case["header"]
+    g.game_moves = list(case["moves"])
+    return g
+
+
+def test_pgn_text_equals_the_reference_writer_golden():
+    """str(GamePGN) against the text the UNMODIFIED reference `operator<<(ostream&, GamePGN)` wrote for the same record
+    (tests/golden/ref_misc.json, generated from oracle/_ref by tests/golden/gen_ref_misc_golden.py)."""
+    import json
+    import os
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ref_misc.json")))
+    assert len(g["pgn"]) >= 4
+    for case in g["pgn"]:
+        assert str(_game_from(case)) == case["text"]
+
+
+def test_pgn_text_equals_the_compiled_reference_live():
+    import ctypes
+    import os
+    import random
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libref_parts.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref not built on this box (no reference sources)")
+    L = ctypes.CDLL(so)
+    rng = random.Random(5)
+    for n in (0, 1, 2, 7, 8, 9, 16, 33, 120):
+        moves = [rng.choice(["e4", "Nf3", "O-O", "exd5", "Q@h5+", "a8Q", "Rad1", "N@f7#"]) for _ in range(n)]
+        header = ["crazyhouse960", "SelfPlay", "2026.09.24 10:00:00", "Darmstadt, GER", "?", "some fen", "x", "y",
+                  rng.choice(["1-0", "0-1", "1/2-1/2"]), "?"]
+        hdr = (ctypes.c_char_p * 10)(*[h.encode() for h in header])
+        mv = (ctypes.c_char_p * max(n, 1))(*[m.encode() for m in moves] or [b""])
+        out = ctypes.create_string_buffer(1 << 16)
+        assert L.ref_pgn_render(hdr, mv, n, out, 1 << 16) >= 0
+        assert str(_game_from(dict(header=header, moves=moves))) == out.value.decode()

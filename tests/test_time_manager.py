@@ -126,7 +126,7 @@ def test_time_for_move_equals_the_reference_golden():
 
 
 def test_time_for_move_equals_the_compiled_reference_live():
-    """The same against oracle/_ref/libref_timeman.so itself on fresh random inputs, where the reference sources exist
+    """The same against oracle/_ref/libref_parts.so itself on fresh random inputs, where the reference sources exist
     (the build container); skipped on boxes without them."""
     import ctypes
     import os
@@ -134,7 +134,7 @@ def test_time_for_move_equals_the_compiled_reference_live():
     import subprocess
     import pytest
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    so = os.path.join(root, "oracle", "_ref", "libref_timeman.so")
+    so = os.path.join(root, "oracle", "_ref", "libref_parts.so")
     if not os.path.exists(so):
         if not os.path.isdir("/root/reference/engine/src"):
             pytest.skip("no reference sources on this box")

@@ -181,6 +181,8 @@ class Arena:
             steps += 1
             if min_games and len(self.finished) >= min_games:
                 break
+            if self.exporter is not None and self.exporter.is_file_full():
+                break  # SelfPlay::go (selfplay.cpp:367-385): generate games until the data file is full
         wall = time.perf_counter() - t0
         moves = steps * self.n_games
         return dict(games=len(self.finished), steps=steps, moves=moves, wall_s=wall,

@@ -155,3 +155,36 @@ def test_chess960_generator_covers_the_reference_set():
     shape = sorted({f.split("/", 1)[1].split("/", 6)[0] + "|" + f.split(" ", 1)[1] for f in fens})
     assert shape == g["chess960_fen_shape"] == ["pppppppp|w KQkq - 0 1"]
     assert all(f.split("/")[0] == f.split("/")[7].split(" ")[0].lower() for f in fens)
+
+
+def test_rl_settings_follow_the_reference_rl_config():
+    """rl_settings / Arena defaults against the reference's own UCIConfig dataclass (DeepCrazyhouse/configs/rl_config.py),
+    imported where the reference tree exists, else the values recorded from it (tests/golden/rl_config.json)."""
+    import importlib.util
+    import json
+    import os
+    golden = os.path.join(os.path.dirname(__file__), "golden", "rl_config.json")
+    src = "/root/reference/DeepCrazyhouse/configs/rl_config.py"
+    if os.path.exists(src):
+        spec = importlib.util.spec_from_file_location("ref_rl_config", src)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        cfg = {k: v for k, v in vars(mod.UCIConfig()).items()}
+        recorded = json.load(open(golden)) if os.path.exists(golden) else None
+        if recorded != cfg:                       # (re)record for boxes without the reference tree
+            json.dump(cfg, open(golden, "w"), indent=1, sort_keys=True)
+    else:
+        cfg = json.load(open(golden))
+    import inspect
+    from crazyara_b200.selfplay import Arena, rl_settings
+    s = rl_settings("crazyhouse")
+    assert s.batch_size == cfg["Batch_Size"] and s.nodes == cfg["Nodes"] and s.simulations == cfg["Simulations"]
+    assert round(s.dirichlet_alpha * 100) == cfg["Centi_Dirichlet_Alpha"]
+    assert round(s.dirichlet_epsilon * 100) == cfg["Centi_Dirichlet_Epsilon"]
+    assert round(s.node_policy_temperature * 100) == cfg["Centi_Node_Temperature"]
+    assert round(s.q_value_weight * 100) == cfg["Centi_Q_Value_Weight"] and bool(s.mcts_solver) == cfg["MCTS_Solver"]
+    defaults = {k: v.default for k, v in inspect.signature(Arena.__init__).parameters.items()}
+    assert round(defaults["temperature"] * 100) == cfg["Centi_Temperature"]
+    assert defaults["temperature_moves"] == cfg["Temperature_Moves"] and defaults["reuse_tree"] == bool(cfg["Reuse_Tree"])
+    from crazyara_b200.export import TrainDataExporter
+    assert inspect.signature(TrainDataExporter.__init__).parameters["chunk_size"].default == cfg["Selfplay_Chunk_Size"]

@@ -73,3 +73,16 @@ def test_fake_backends_identical():
         HeSearch(osr.default_settings("crazyhouse"))  # sets argtypes
         helib().he_fake_eval(key, 5184, vh.ctypes.data, ph.ctypes.data)
         assert vo[0] == vh[0] and np.array_equal(po, ph)
+
+
+def test_oracle_search_reproduces_its_recorded_results():
+    """tests/golden/search_oracle.json: the oracle's own results for the cases above, bit patterns included.  A change of
+    the oracle that moves any of them has to be made visibly (by regenerating the file)."""
+    import json
+    import os
+    from tests.golden.gen_search_golden import run_case
+    recorded = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "search_oracle.json")))
+    assert len(recorded) == len(CASES)
+    for rec, case in zip(recorded, CASES):
+        assert rec["case"][:8] == [list(x) if isinstance(x, (list, tuple)) else x for x in case[:8]] and rec["case"][8] == case[8]
+        assert run_case(case) == rec["result"], case[:8]

@@ -68,3 +68,14 @@ def test_search_create_fails_loudly_without_gpu():
     from crazyara_b200.engine import MCTSAgent, default_settings
     with pytest.raises(AraError):
         MCTSAgent(None, default_settings("crazyhouse", simulations=10), 0, 1)
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/ara_b200.h is the boundary other languages bind: it must compile as strict C99 on its own."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "h.c"
+    src.write_text('#include "ara_b200.h"\nint main(void) { ara_time_control_t t; ara_search_result_t r; (void)t; (void)r; return 0; }\n')
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(root, "include"), "-c",
+                    str(src), "-o", str(tmp_path / "h.o")], check=True)

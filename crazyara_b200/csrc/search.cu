@@ -8,6 +8,7 @@
 // The host only looks at the per-tree `done` flag once per chunk of iterations.
 // This translation unit is compiled with -fmad=false: the PUCT / Q arithmetic must round exactly like the
 // reference's (and the oracle's) scalar C++ code.
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstring>
@@ -173,6 +174,7 @@ class Search {
     int set_position(int tree, const Board& root, const uint64_t* hist_keys, const int16_t* hist_reps, int hist_len);
     int go();
     int apply_move(int tree, unsigned short move);
+    void request_stop() { stop_requested_.store(true, std::memory_order_relaxed); }
     int fetch_results();
     int debug_cycles(int tree, unsigned long long* out8) {
         TreeState st;
@@ -211,6 +213,8 @@ class Search {
     int iterate(int count);
     Net* net_ = nullptr;
     bool searched_ = false;  // a go has run: the device holds trees that apply_move may keep
+    // UCI `stop` (SearchThread::stop): set from another host thread while go() runs; go() leaves its loop at the next poll
+    std::atomic<bool> stop_requested_{false};
     int device_ = 0;
     cudaStream_t stream_ = nullptr;
     bool own_stream_ = false;
@@ -474,6 +478,7 @@ int Search::go() {
     prof_used_ = 0;
     net_forwards = 0;
     searched_ = true;
+    stop_requested_.store(false, std::memory_order_relaxed);
     ARA_CUDA_OK(cudaEventRecord(ev0_, stream_));
     ARA_CUDA_OK(cudaMemcpyAsync(d_trees_, h_trees_.data(), sizeof(TreeDev) * n_trees, cudaMemcpyHostToDevice, stream_));
     ARA_CUDA_OK(cudaMemcpyAsync(d_roots_, h_roots_.data(), sizeof(Board) * n_trees, cudaMemcpyHostToDevice, stream_));
@@ -524,6 +529,7 @@ int Search::go() {
     float last_eval = tc.last_value_eval;
     tr = ara_time_report_t{};
     while (!all_done) {
+        if (polled_root && stop_requested_.load(std::memory_order_relaxed)) break;
         if (timed && polled_root) {
             const double now = elapsed_ms();
             if (managed && now >= next_check && now < period_end) {
@@ -685,6 +691,11 @@ extern "C" int ara_search_result(ara_search_t h, int tree, ara_search_result_t* 
 extern "C" int ara_search_apply_move(ara_search_t h, int tree, unsigned short move) {
     if (h == nullptr) return ara::set_error("ara_search_apply_move: null handle");
     return reinterpret_cast<Search*>(h)->apply_move(tree, move);
+}
+extern "C" int ara_search_stop(ara_search_t h) {
+    if (h == nullptr) return ara::set_error("ara_search_stop: null handle");
+    reinterpret_cast<Search*>(h)->request_stop();
+    return 0;
 }
 extern "C" int ara_search_set_movetime(ara_search_t h, double ms) {
     if (h == nullptr) return ara::set_error("ara_search_set_movetime: null handle");

@@ -104,6 +104,7 @@ def _L():
         L.ara_search_set_profile.argtypes = [vp, ci]
         L.ara_search_apply_move.argtypes = [vp, ci, ctypes.c_ushort]
         L.ara_search_set_time_control.argtypes = [vp, vp]
+        L.ara_search_stop.argtypes = [vp]
         L.ara_search_time_report.argtypes = [vp, vp]
         L.ara_time_early_stopping.argtypes = [vp, ctypes.c_double, ctypes.c_uint, ci, ctypes.c_uint, ctypes.c_uint,
                                               ctypes.c_float, ctypes.c_float]
@@ -326,6 +327,10 @@ class MCTSAgent:
         check(_L().ara_search_time_report(self._h, ctypes.byref(r)))
         return dict(early_stopped=r.early_stopped, prolonged=r.prolonged, saved_ms=r.saved_ms, elapsed_ms=r.elapsed_ms,
                     value_eval=r.value_eval)
+
+    def stop(self):
+        """UCI `stop`: may be called from another thread while evaluate_board_state runs on this agent."""
+        check(_L().ara_search_stop(self._h))
 
     def set_movetime(self, ms):
         """SearchLimits::movetime: following searches also stop after `ms` of wall time (0 = off)."""

@@ -223,6 +223,8 @@ class MCTSAgent {
     void apply_move_to_tree(Action move) {
         if (ara_search_apply_move(search_, 0, move) != 0) throw std::runtime_error(ara_last_error());
     }
+    // MCTSAgent::stop (UCI `stop`): callable from another thread while evaluate_board_state runs
+    void stop() { ara_search_stop(search_); }
     // SearchLimits::movetime: the following searches also stop after `ms` of wall time (0 = off)
     void set_movetime(double ms) {
         if (ara_search_set_movetime(search_, ms) != 0) throw std::runtime_error(ara_last_error());

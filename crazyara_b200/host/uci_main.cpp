@@ -1,11 +1,13 @@
 // Minimal UCI front-end over the C++ host classes (engine/src/uci/crazyara.cpp:76-143 command loop, option names of
 // uci/optionsuci.cpp:66-220).  Supported: uci, isready, setoption, ucinewgame, position [startpos|fen] [moves ...],
 // go [nodes N | movetime T | wtime W btime B [winc I] [binc I] [movestogo M]] (or the Simulations / Nodes options),
-// benchmark <movetime>, inference [warmup N] [iterations N], root, quit.  The move time follows TimeManager::get_time_for_move (manager/timemanager.cpp:51-100) without its
+// go infinite + stop, benchmark <movetime>, inference [warmup N] [iterations N], root, quit.  The move time follows TimeManager::get_time_for_move (manager/timemanager.cpp:51-100) without its
 // random factor; the search then also stops after that much wall time (ara_search_set_movetime), and in clock games
 // the ThreadManager's early stopping / prolongation rules run on top (ara_search_set_time_control).
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <thread>
 #include <iomanip>
 #include <iostream>
 #include <map>
@@ -47,7 +49,8 @@ int mode_of_variant(int variant) { return variant == 0 ? 1 : (variant == 1 ? 0 :
 // proportional system from move 35 with 14 moves to go, increment factor 0.7, safety buffer 30 x overhead
 struct GoLimits {
     long movetime = 0, time[2] = {0, 0}, inc[2] = {0, 0}, movestogo = 0;
-    bool any() const { return movetime || time[0] || time[1]; }
+    bool infinite = false;  // `go infinite`: search until `stop` (or until the node pool is full)
+    bool any() const { return movetime || time[0] || time[1] || infinite; }
 };
 long time_for_move(const GoLimits& g, int me, int move_number, long overhead) {
     return ara_time_for_move(g.movetime, static_cast<int>(g.time[me]), static_cast<int>(g.inc[me]), static_cast<int>(g.movestogo),
@@ -105,11 +108,40 @@ int main() {
         ready = true;
     };
     new_game();
+    // `go infinite` runs on a worker thread so that `stop` can be read meanwhile (the reference's search threads +
+    // CrazyAra::stop_search, crazyara.cpp); every other search is synchronous as before
+    std::thread worker;
+    std::atomic<bool> searching{false};
+    auto print_result = [&]() {
+        if (info.nodesPreSearch) std::cout << "info string reused " << info.nodesPreSearch << " nodes" << std::endl;
+        std::cout << "info depth " << info.depth << " nodes " << info.nodes << " nps " << info.calculate_nps() << " score cp "
+                  << info.centipawns << " time " << static_cast<long>(info.elapsedMs) << " pv";
+        for (Action a : info.pv) std::cout << " " << state.action_to_uci(a);
+        std::cout << "\nbestmove " << (info.bestMove ? state.action_to_uci(info.bestMove) : std::string("(none)")) << std::endl;
+    };
+    auto stop_and_join = [&]() {
+        if (!worker.joinable()) return;
+        while (searching.load()) {  // a stop that arrives before the search loop has started would be reset by it
+            agent->stop();
+            std::this_thread::sleep_for(std::chrono::milliseconds(2));
+        }
+        worker.join();
+    };
     std::string line;
     while (std::getline(std::cin, line)) {
         std::istringstream ss(line);
         std::string cmd;
         ss >> cmd;
+        if (worker.joinable()) {  // an infinite search is (or was) running
+            if (cmd == "isready" && searching.load()) {
+                std::cout << "readyok" << std::endl;
+                continue;
+            }
+            stop_and_join();  // `stop`, or any command that needs the engine: end the search first
+            if (cmd == "stop") continue;
+        } else if (cmd == "stop") {
+            continue;
+        }
         try {
             if (cmd == "uci") {
                 std::cout << "id name CrazyAra-B200\nid author crazyara_b200 (hot path of QueensGambit/CrazyAra on sm_100a)\n";
@@ -180,6 +212,8 @@ int main() {
                         ss >> lim.inc[1];
                     } else if (tok == "movestogo") {
                         ss >> lim.movestogo;
+                    } else if (tok == "infinite") {
+                        lim.infinite = true;
                     }
                 }
                 if (lim.any() != timed) {
@@ -189,6 +223,23 @@ int main() {
                 if (!ready) prepare();
                 const bool inGame = lim.time[0] != 0 || lim.time[1] != 0 || lim.movestogo != 0;  // is_game_sceneario
                 agent->clear_time_control();
+                if (lim.infinite) {
+                    agent->set_movetime(0.0);
+                    searched = true;
+                    searchedBase = gameBase;
+                    searchedMoves = gameMoves;
+                    searching.store(true);
+                    worker = std::thread([&]() {
+                        try {
+                            agent->evaluate_board_state(state, info);
+                            print_result();
+                        } catch (const std::exception& e) {
+                            std::cout << "info string error: " << e.what() << std::endl;
+                        }
+                        searching.store(false);
+                    });
+                    continue;
+                }
                 if (timed) {
                     const int me = state.side_to_move();
                     const long overhead = opt.i("Move_Overhead");
@@ -215,11 +266,7 @@ int main() {
                 searched = true;
                 searchedBase = gameBase;
                 searchedMoves = gameMoves;
-                if (info.nodesPreSearch) std::cout << "info string reused " << info.nodesPreSearch << " nodes" << std::endl;
-                std::cout << "info depth " << info.depth << " nodes " << info.nodes << " nps " << info.calculate_nps() << " score cp "
-                          << info.centipawns << " time " << static_cast<long>(info.elapsedMs) << " pv";
-                for (Action a : info.pv) std::cout << " " << state.action_to_uci(a);
-                std::cout << "\nbestmove " << (info.bestMove ? state.action_to_uci(info.bestMove) : std::string("(none)")) << std::endl;
+                print_result();
             } else if (cmd == "benchmark") {  // CrazyAra::benchmark (crazyara.cpp:287-330): `benchmark <movetime ms>`
                 long moveTime = 3000;
                 ss >> moveTime;
@@ -302,5 +349,6 @@ int main() {
             std::cout << "info string error: " << e.what() << std::endl;
         }
     }
+    stop_and_join();
     return 0;
 }

@@ -171,6 +171,10 @@ int ara_search_apply_move(ara_search_t s, int tree, unsigned short move);
 /* ThreadManager's time stop (manager/threadmanager.cpp, SearchLimits::movetime): ms > 0 makes the following go calls
  * stop issuing mini-batches once that much wall time has passed (besides the Simulations / Nodes limits); 0 = off */
 int ara_search_set_movetime(ara_search_t s, double ms);
+/* UCI `stop` (SearchThread::stop, searchthread.cpp): may be called from another host thread while ara_search_go runs on
+ * this handle; the go call returns after the mini-batches already enqueued (the result is valid as usual).  The only
+ * entry point that may be used concurrently with another call on the same handle. */
+int ara_search_stop(ara_search_t s);
 /* ThreadManager's in-game heuristics (manager/threadmanager.cpp:68-178), evaluated every update interval on the root's
  * statistics: early stopping once the move is decided, one or two prolongations when the evaluation dropped.  The
  * parameters are what MCTSAgent::run_mcts_search hands to the ThreadManager (agents/mctsagent.cpp:350-352). */

@@ -22,4 +22,8 @@ def test_cited_repository_paths_exist():
                 path = os.path.dirname(path) if not path.endswith("/") else path
             if path and not os.path.exists(os.path.join(ROOT, path)):
                 missing.append((doc, token))
+            elif "::" in token and path.endswith(".py"):      # a cited function / class has to be there as well
+                name = token.split("::")[1].split("(")[0].rstrip(".,;)")
+                if name and not re.search(rf"^\s*(def|class)\s+{re.escape(name)}\b", open(os.path.join(ROOT, path)).read(), re.M):
+                    missing.append((doc, token))
     assert missing == []

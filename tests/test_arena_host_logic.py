@@ -1,0 +1,97 @@
+"""The arena's HOST logic (game bookkeeping, result assignment, PGN and sample export, game groups) with the device
+search replaced by a stand-in that plays random legal moves -- so that this logic is covered without a GPU
+(the real search under the same arena is tests/test_selfplay_gpu.py)."""
+import numpy as np
+
+import crazyara_b200.selfplay as sp
+from crazyara_b200.export import BLACK_WIN, DRAWN, WHITE_WIN, read_dataset
+
+
+class FakeAgent:
+    """MCTSAgent's surface as the arena uses it; 'search' = uniform policy over the legal moves, seeded best move."""
+    created = []
+
+    def __init__(self, net, settings, device=0, n_trees=1, max_nodes=0):
+        self.n_trees, self.states, self.applied = n_trees, [None] * n_trees, []
+        self.rng = np.random.default_rng(len(FakeAgent.created))
+        FakeAgent.created.append(self)
+
+    def set_position(self, state, tree=0):
+        self.states[tree] = state
+
+    def evaluate_board_state(self, state=None):
+        self.res = []
+        for st in self.states:
+            moves = [st.action_to_uci(a) for a in st.legal_actions()]
+            k = len(moves)
+            pol = np.full(k, 1.0 / k) if k else np.zeros(0)
+            self.res.append(dict(moves=moves, policy=pol, q=np.zeros(k, np.float32), best_idx=int(self.rng.integers(k)) if k else -1,
+                                 nodes=10, nodes_pre_search=0))
+
+    def result(self, tree=0):
+        return self.res[tree]
+
+    def last_go_ms(self):
+        return 1.0
+
+    def apply_move_to_tree(self, move, tree=0):
+        self.applied.append((tree, move))
+
+    def close(self):
+        pass
+
+
+def _arena(monkeypatch, tmp_path, **kw):
+    FakeAgent.created = []
+    monkeypatch.setattr(sp, "MCTSAgent", FakeAgent)
+    monkeypatch.setattr(sp, "encode_planes", lambda boards, mode, version, normalize=False: np.ones((len(boards), 34, 8, 8), np.float32))
+    st = sp.rl_settings("crazyhouse")
+    return sp.Arena(kw.pop("net", None), st, variant=1, n_games=kw.pop("n_games", 3), temperature_moves=0, max_plies=kw.pop("max_plies", 60),
+                    seed=4, **kw)
+
+
+def test_games_results_pgn_and_samples(monkeypatch, tmp_path):
+    from crazyara_b200.export import TrainDataExporter
+    ex = TrainDataExporter(str(tmp_path / "d.zarr"), "crazyhouse", channels=34, number_chunks=40, chunk_size=16)
+    pgn = str(tmp_path / "games.pgn")
+    arena = _arena(monkeypatch, tmp_path, exporter=ex, pgn_path=pgn, reuse_tree=True)
+    res = arena.run(min_games=6, max_steps=400)
+    assert res["games"] >= 6 and res["nodes"] == 10 * res["moves"]
+    # every played move was announced to the tree first (reuse_tree), one call per game and step
+    assert len(FakeAgent.created[0].applied) == res["moves"]
+    # one PGN record per finished game, result token consistent with the adjudication
+    text = open(pgn).read()
+    blocks = text.strip().split("\n\n\n")
+    assert len(blocks) == res["games"]
+    results = []
+    for block, (plies, term, stm) in zip(blocks, arena.finished):
+        header, body = block.split("\n\n", 1)
+        assert f'[PlyCount "{plies}"]' in header and '[Variant "crazyhouse"]' in header
+        token = body.split()[-1]
+        expect = "1/2-1/2" if term not in (0, 2) else (("0-1" if stm == 0 else "1-0") if term == 0 else ("1-0" if stm == 0 else "0-1"))
+        assert token == expect and f'[Result "{token}"]' in header
+        if term == 0:
+            assert body.split()[-2].endswith("#")          # the game ended by mate (or a variant loss): '#' on the last move
+        results.append({"1-0": WHITE_WIN, "0-1": BLACK_WIN}.get(token, DRAWN))
+    # the exported samples: one per searched position of the finished games, value = result from the mover's view
+    starts = read_dataset(str(tmp_path / "d.zarr"), "start_indices")
+    n_games = ex.game_idx
+    assert n_games == res["games"] and list(starts[1:n_games + 1] - starts[:n_games]) == [p for p, _, _ in arena.finished]
+    values = read_dataset(str(tmp_path / "d.zarr"), "y_value")
+    plys = read_dataset(str(tmp_path / "d.zarr"), "plys_to_end")
+    for g, result in enumerate(results):
+        v = values[starts[g]:starts[g + 1]]
+        white_to_move = (np.arange(len(v)) % 2 == 0)     # games start with white to move
+        want = 0 if result == DRAWN else (1 if result == WHITE_WIN else -1)
+        assert np.array_equal(v, np.where(white_to_move, want, -want))
+        assert list(plys[starts[g]:starts[g + 1]]) == list(range(len(v), 0, -1))
+    pol = read_dataset(str(tmp_path / "d.zarr"), "y_policy")[:starts[n_games]]
+    assert np.allclose(pol.sum(axis=1), 1.0, atol=1e-5)
+
+
+def test_game_groups_split_the_games(monkeypatch, tmp_path):
+    arena = _arena(monkeypatch, tmp_path, net=[None, None], n_games=4, max_plies=12)
+    assert [a.n_trees for a in FakeAgent.created] == [2, 2]
+    res = arena.run(max_steps=30)
+    assert res["moves"] == 4 * 30 and res["games"] >= 4 and all(p <= 12 for p, _, _ in arena.finished)
+    assert all(s is not None for a in FakeAgent.created for s in a.states)

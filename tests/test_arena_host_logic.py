@@ -95,3 +95,34 @@ def test_game_groups_split_the_games(monkeypatch, tmp_path):
     res = arena.run(max_steps=30)
     assert res["moves"] == 4 * 30 and res["games"] >= 4 and all(p <= 12 for p, _, _ in arena.finished)
     assert all(s is not None for a in FakeAgent.created for s in a.states)
+
+
+def test_launcher_worker_end_to_end(monkeypatch, tmp_path, capsys):
+    """python -m crazyara_b200.selfplay: one worker's whole run (network buffers, arena, export, PGN) with the device
+    pieces replaced by stand-ins."""
+    import argparse
+    import crazyara_b200.nn as nn_mod
+
+    class FakeNet:
+        def __init__(self, ctx, device, batch, path):
+            self.batch = batch
+
+        def get_nb_input_values_total(self):
+            return 34 * 64
+
+        def close(self):
+            pass
+
+    FakeAgent.created = []
+    monkeypatch.setattr(sp, "MCTSAgent", FakeAgent)
+    monkeypatch.setattr(sp, "encode_planes", lambda boards, mode, version, normalize=False: np.ones((len(boards), 34, 8, 8), np.float32))
+    monkeypatch.setattr(nn_mod, "NeuralNetAPI", FakeNet)
+    plan = sp.plan_workers(8, [0, 1], str(tmp_path))
+    args = argparse.Namespace(model="m.arab", mode="crazyhouse", variant=1, chess960=False, input_version=1, batch_size=8,
+                              nodes=800, max_plies=16, chunks=4, seed=1, export=True, pgn=True, games_per_worker=4, seconds=30.0)
+    sp._worker(plan[1], args)
+    out = capsys.readouterr().out
+    assert "data_gpu_1.zarr" in out and "games/h" in out
+    assert [a.n_trees for a in FakeAgent.created] == [2, 2]          # 4 games of this worker in two groups
+    assert open(plan[1]["pgn"]).read().count("[Event ") >= 4
+    assert read_dataset(plan[1]["zarr"], "start_indices")[1] > 0

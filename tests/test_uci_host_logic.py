@@ -99,3 +99,43 @@ def test_scripted_session_keeps_the_synchronous_order(env):
     assert kinds[:2] == ["id", "id"] and "uciok" in kinds and "readyok" in kinds
     tail = kinds[kinds.index("readyok") + 1:]
     assert tail[:5] == ["info string", "info depth", "bestmove", "info depth", "bestmove"]
+
+
+def _session(env, tmp_path, commands):
+    log = tmp_path / "calls.log"
+    e = dict(env)
+    e["ARA_STUB_LOG"] = str(log)
+    out = subprocess.run([EXE], input="\n".join(commands + ["quit"]) + "\n", capture_output=True, text=True, timeout=60, env=e).stdout
+    return out.splitlines(), (log.read_text().splitlines() if log.exists() else [])
+
+
+def test_position_extension_walks_the_kept_tree(env, tmp_path):
+    """Reuse_Tree: a `position` that extends the searched game announces exactly the new moves to the tree."""
+    head = ["setoption name UCI_Variant value chess", "isready"]
+    _, calls = _session(env, tmp_path, head + ["position startpos", "go movetime 20",
+                                               "position startpos moves e2e4 e7e5", "go movetime 20",
+                                               "position startpos moves d2d4", "go movetime 20",          # another game: nothing kept
+                                               "ucinewgame", "position startpos moves e2e4", "go movetime 20"])
+    applied = [c for c in calls if c.startswith("apply_move")]
+    assert applied == ["apply_move tree=0 from=12 to=28 flag=0", "apply_move tree=0 from=52 to=36 flag=0"]   # e2e4, e7e5
+    assert len([c for c in calls if c.startswith("go ")]) == 4
+    (tmp_path / "calls.log").unlink()
+    _, calls = _session(env, tmp_path, head[:1] + ["setoption name Reuse_Tree value false", "isready", "position startpos",
+                                                   "go movetime 20", "position startpos moves e2e4 e7e5", "go movetime 20"])
+    assert [c for c in calls if c.startswith("apply_move")] == []
+
+
+def test_clock_games_run_under_the_time_manager(env, tmp_path):
+    """wtime/btime: the move time of ara_time_for_move goes to the search AND to the ThreadManager rules; plain
+    `go movetime` switches them off; the per-game NPS estimate is known from the second clock search on."""
+    lines, calls = _session(env, tmp_path, ["setoption name UCI_Variant value chess", "isready", "position startpos",
+                                            "go wtime 3000 btime 3000 winc 100 binc 100",
+                                            "go wtime 2900 btime 3000 movestogo 40",
+                                            "go movetime 50"])
+    # (3000 - 20*30)/(38-1) + 0.7*100 - 20 = 64 + 70 - 20 = 114;  (2900 - 600)/40 - 20 = 37
+    assert [l for l in lines if l.startswith("info string movetime")] == ["info string movetime 114", "info string movetime 37",
+                                                                          "info string movetime 30"]
+    tc = [c for c in calls if c.startswith("time_control")]
+    assert tc == ["time_control off", "time_control movetime=114 in_game=1 can_prolong=1 nps_known=0",
+                  "time_control off", "time_control movetime=37 in_game=1 can_prolong=1 nps_known=1", "time_control off"]
+    assert [c for c in calls if c.startswith("go ")] == ["go movetime=114", "go movetime=37", "go movetime=30"]

@@ -2,6 +2,8 @@
  * UCI front-end's command loop (threads, `go infinite` / `stop`, ordering of its answers) can be exercised on a box
  * without a GPU.  The "search" just waits until its move time is over or it is told to stop.  Never part of the product. */
 #define _POSIX_C_SOURCE 200809L
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <time.h>
 
@@ -10,6 +12,17 @@
 static volatile int g_stop;
 static double g_movetime_ms, g_elapsed_ms;
 static unsigned g_polls;
+
+/* ARA_STUB_LOG=<file>: one line per call of interest, for the tests to read */
+static void log_call(const char* fmt, double a, double b, double c, double d) {
+    const char* path = getenv("ARA_STUB_LOG");
+    if (!path) return;
+    FILE* f = fopen(path, "a");
+    if (!f) return;
+    fprintf(f, fmt, a, b, c, d);
+    fputc('\n', f);
+    fclose(f);
+}
 
 static double now_ms(void) {
     struct timespec ts;
@@ -38,6 +51,7 @@ int ara_search_go(ara_search_t s) {
         ++g_polls;
     }
     g_elapsed_ms = now_ms() - t0;
+    log_call("go movetime=%.0f%.0s%.0s%.0s", g_movetime_ms, 0, 0, 0);
     return 0;
 }
 int ara_search_stop(ara_search_t s) {
@@ -59,7 +73,17 @@ int ara_search_result(ara_search_t s, int tree, ara_search_result_t* out) {
     return 0;
 }
 double ara_search_last_go_ms(ara_search_t s) { (void)s; return g_elapsed_ms; }
-int ara_search_apply_move(ara_search_t s, int tree, unsigned short move) { (void)s, (void)tree, (void)move; return 0; }
+int ara_search_apply_move(ara_search_t s, int tree, unsigned short move) {
+    (void)s;
+    log_call("apply_move tree=%.0f from=%.0f to=%.0f flag=%.0f", tree, move & 63, (move >> 6) & 63, move >> 12);
+    return 0;
+}
 int ara_search_set_movetime(ara_search_t s, double ms) { (void)s; g_movetime_ms = ms; return 0; }
-int ara_search_set_time_control(ara_search_t s, const ara_time_control_t* tc) { (void)s, (void)tc; return 0; }
+int ara_search_set_time_control(ara_search_t s, const ara_time_control_t* tc) {
+    (void)s;
+    if (tc) log_call("time_control movetime=%.0f in_game=%.0f can_prolong=%.0f nps_known=%.0f", tc->movetime_ms, tc->in_game, tc->can_prolong,
+                     tc->overall_nps > 0 ? 1 : 0);
+    else log_call("time_control off%.0s%.0s%.0s%.0s", 0, 0, 0, 0);
+    return 0;
+}
 int ara_search_time_report(ara_search_t s, ara_time_report_t* out) { (void)s; memset(out, 0, sizeof(*out)); return 0; }

@@ -762,3 +762,28 @@ extern "C" int ara_search_debug_cycles(ara_search_t h, int tree, unsigned long l
 }
 extern "C" double ara_search_last_go_ms(ara_search_t h) { return h ? reinterpret_cast<Search*>(h)->last_go_ms : 0.0; }
 extern "C" long long ara_search_launch_count(ara_search_t h) { return h ? reinterpret_cast<Search*>(h)->launches : 0; }
+
+// ---- debug / unit-test entry: the device build of the glibc powf / logf restatement (glibc_flt32.cuh) on host buffers
+__global__ void glibc_flt32_kernel(const float* x, const float* y, int n, float* pow_out, float* log_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (pow_out) pow_out[i] = ara::glibc::powf_(x[i], y[i]);
+    if (log_out) log_out[i] = ara::glibc::logf_(x[i]);
+}
+extern "C" int ara_debug_powf_logf(const float* x, const float* y, int n, float* pow_out, float* log_out) {
+    if (n <= 0 || !x || !y) return ara::set_error("ara_debug_powf_logf: bad arguments");
+    float *dx = nullptr, *dy = nullptr, *dp = nullptr, *dl = nullptr;
+    const size_t bytes = sizeof(float) * static_cast<size_t>(n);
+    ARA_CUDA_OK(cudaMalloc(&dx, bytes));
+    ARA_CUDA_OK(cudaMalloc(&dy, bytes));
+    ARA_CUDA_OK(cudaMalloc(&dp, bytes));
+    ARA_CUDA_OK(cudaMalloc(&dl, bytes));
+    ARA_CUDA_OK(cudaMemcpy(dx, x, bytes, cudaMemcpyHostToDevice));
+    ARA_CUDA_OK(cudaMemcpy(dy, y, bytes, cudaMemcpyHostToDevice));
+    glibc_flt32_kernel<<<(n + 255) / 256, 256>>>(dx, dy, n, pow_out ? dp : nullptr, log_out ? dl : nullptr);
+    ARA_CUDA_OK(cudaGetLastError());
+    if (pow_out) ARA_CUDA_OK(cudaMemcpy(pow_out, dp, bytes, cudaMemcpyDeviceToHost));
+    if (log_out) ARA_CUDA_OK(cudaMemcpy(log_out, dl, bytes, cudaMemcpyDeviceToHost));
+    cudaFree(dx), cudaFree(dy), cudaFree(dp), cudaFree(dl);
+    return 0;
+}

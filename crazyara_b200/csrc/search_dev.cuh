@@ -20,6 +20,7 @@
 #include <math.h>
 
 #include "chess_dev.cuh"
+#include "glibc_flt32.cuh"
 #include "planes_dev.cuh"
 
 namespace ara {
@@ -73,6 +74,7 @@ struct alignas(16) NodeHdr {  // 64 B: one line per visited node on the select p
     double sqrt_vs;  // sqrt(double(visit_sum)): refreshed by whoever changes visit_sum, which keeps both off the select path
 };
 static_assert(sizeof(NodeHdr) == 64, "NodeHdr must be 64 bytes");
+static_assert(kMaxDepth * sizeof(uint64_t) >= kMaxMoves * sizeof(float), "fill_nn_results borrows path_key as float[kMaxMoves]");
 
 struct TreeState {
     int n_nodes;
@@ -816,21 +818,27 @@ ARA_HD void fill_nn_results(const TreeDev& t, const SearchParams& sp, WarpScratc
         ws.legal[i] = static_cast<Move>(pidx);  // tie-break key (policy indices are < 65536)
     }
     ARA_WARP_SYNC();
-    // apply_temperature (blazeutil.h:78-88): no renormalisation at T == 1
+    // apply_temperature (blazeutil.h:78-88): no renormalisation at T == 1.  The power is glibc's powf restated
+    // (glibc_flt32.cuh); the normalising sum is SEQUENTIAL, in ascending policy-index order: the reference sums in
+    // the order of Stockfish's move generator (through blaze's reduction), which neither this generator nor the
+    // oracle's reproduces, so both sides agree on the generator-independent order instead.
     if (sp.node_policy_temperature != 1.0f) {
         const float inv_t = 1.0f / sp.node_policy_temperature;
-        float part = 0.0f;
+        float* by_index = reinterpret_cast<float*>(ws.path_key);  // kMaxMoves floats; the descent's path is not live here
         for (int i = ARA_LANE; i < n; i += ARA_WARP_N) {
-            const float p = powf(ws.sort_p[i], inv_t);
+            const float p = glibc::powf_(ws.sort_p[i], inv_t);
+            const Move pi = ws.legal[i];
+            int rank = 0;
+            for (int j = 0; j < n; ++j) rank += (ws.legal[j] < pi || (ws.legal[j] == pi && j < i)) ? 1 : 0;
             ws.sort_p[i] = p;
-            part += p;
+            by_index[rank] = p;
         }
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
-#endif
         ARA_WARP_SYNC();
-        for (int i = ARA_LANE; i < n; i += ARA_WARP_N) ws.sort_p[i] = ws.sort_p[i] / part;
+        float sum = 0.0f;
+        if (ARA_LANE == 0)
+            for (int r = 0; r < n; ++r) sum += by_index[r];
+        sum = ARA_SHFL(sum, 0);
+        for (int i = ARA_LANE; i < n; i += ARA_WARP_N) ws.sort_p[i] = ws.sort_p[i] / sum;
         ARA_WARP_SYNC();
     }
     // sort_moves_by_probabilities: descending prior; the reference's std::sort leaves ties unspecified, we order
@@ -886,7 +894,7 @@ ARA_HD float gamma_f(MinStd& g, float alpha) {
                     y = static_cast<float>(2.0f * canonical_f(g) - 1.0);
                     r2 = x * x + y * y;
                 } while (r2 > 1.0 || r2 == 0.0);
-                const float mult = sqrtf(-2 * logf(r2) / r2);
+                const float mult = sqrtf(-2 * glibc::logf_(r2) / r2);
                 saved = x * mult;
                 saved_ok = true;
                 n = y * mult;
@@ -895,11 +903,11 @@ ARA_HD float gamma_f(MinStd& g, float alpha) {
         } while (v <= 0.0);
         v = v * v * v;
         u = canonical_f(g);
-    } while (u > 1.0f - 0.0331 * n * n * n * n && (logf(u) > (0.5 * n * n + a1 * (1.0 - v + logf(v)))));
+    } while (u > 1.0f - 0.0331 * n * n * n * n && (glibc::logf_(u) > (0.5 * n * n + a1 * (1.0 - v + glibc::logf_(v)))));
     if (alpha == malpha) return a1 * v * 1.0f;
     do u = canonical_f(g);
     while (u == 0.0);
-    return powf(u, 1.0f / alpha) * a1 * v * 1.0f;
+    return glibc::powf_(u, 1.0f / alpha) * a1 * v * 1.0f;
 }
 // MCTSAgent::evaluate_board_state :311-316: noise on the (sorted) root priors, then open all children.  Lane 0.
 ARA_HD void apply_dirichlet_to_root(const TreeDev& t, const SearchParams& sp, WarpScratch& ws) {

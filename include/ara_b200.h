@@ -220,6 +220,10 @@ int ara_debug_conv(const void* act_half, int boards_cap, int boards, int cin, co
                    int ksize, const float* bias, int relu, const void* residual, int ldr, void* out_half,
                    float* out_f32, int ldo, int bn, void* stream);
 int ara_debug_choose_bn(int boards, int n_out);
+/* the device build of the glibc powf / logf restatement the search uses for apply_temperature (util/blazeutil.h:78-88)
+ * and the Dirichlet gamma sampler (:113-124): pow_out[i] = powf(x[i], y[i]), log_out[i] = logf(x[i]); host buffers,
+ * either output may be NULL.  tests/test_glibc_flt32.py compares it with the host libm bit for bit. */
+int ara_debug_powf_logf(const float* x, const float* y, int n, float* pow_out, float* log_out);
 
 #ifdef __cplusplus
 }

@@ -448,20 +448,31 @@ static void revert_virtual_loss(ONode* n, int ci, const OSettings* st) { /* node
 }
 
 /* ------------------------------------------------------------------ NN results -> node */
-static void apply_temperature(float* p, int n, float t) { /* util/blazeutil.h:78-88 */
+static void apply_temperature(float* p, const int* pidx, int n, float t) { /* util/blazeutil.h:78-88 */
+    /* dist = pow(dist, 1/T); dist /= sum(dist).  blaze::sum reduces in the order of the vector = the order of
+       Stockfish's move generator (absent); the restatement sums SEQUENTIALLY in ascending policy-index order, the
+       generator-independent order the device uses too (ties cannot occur: an index names one move). */
     if (t == 1) return;
-    float sum = 0.0f;
+    int* order = (int*)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
     for (int i = 0; i < n; ++i) {
         p[i] = powf(p[i], 1.0f / t);
-        sum += p[i];
+        int j = i; /* insertion by (pidx, i) */
+        while (j > 0 && pidx[order[j - 1]] > pidx[i]) {
+            order[j] = order[j - 1];
+            --j;
+        }
+        order[j] = i;
     }
+    float sum = 0.0f;
+    for (int r = 0; r < n; ++r) sum += p[order[r]];
+    free(order);
     for (int i = 0; i < n; ++i) p[i] /= sum;
 }
 
 static void fill_nn_results(OSearch* s, ONode* node, float value, const float* prob) {
     /* searchthread.cpp:290-299; set_probabilities_for_moves node.cpp:961-979 (mirroring inside the index lookup) */
     for (int i = 0; i < node->n_actions; ++i) node->policy[i] = node->pidx[i] >= 0 ? prob[node->pidx[i]] : 0.0f;
-    apply_temperature(node->policy, node->n_actions, s->st.node_policy_temperature); /* node_post_process_policy */
+    apply_temperature(node->policy, node->pidx, node->n_actions, s->st.node_policy_temperature); /* node_post_process_policy */
     node_set_value(node, value);                                                      /* node_assign_value */
     node->has_nn = 1;
 }

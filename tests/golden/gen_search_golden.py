@@ -17,7 +17,8 @@ def run_case(case):
     from oracle import search as osr
     from oracle.chess import Position
     variant, vid, mode, fen, is960, premoves, batch, sims, extra = case
-    st = osr.default_settings(mode, batch_size=batch, simulations=sims, node_policy_temperature=1.0, **extra)
+    from tests.test_search_hostemu import case_settings
+    st = case_settings(mode, batch, sims, extra)
     pos = Position(fen, variant, is960)
     pos.push_uci(*premoves)
     S = osr.Search(st)

@@ -296,3 +296,44 @@ void he_pick_both(int k, const float* p, const float* q, const unsigned* n, floa
     out[2] = e.ci;
 }
 }
+
+// ---------------------------------------------------------------- glibc powf / logf restatement vs the live libm
+#include <math.h>
+
+#include "glibc_flt32.cuh"
+extern "C" {
+float he_powf(float x, float y) { return ara::glibc::powf_(x, y); }
+float he_logf(float x) { return ara::glibc::logf_(x); }
+// bit patterns [lo, hi) step `stride` as x; counts disagreements with libm, first one into *bad
+unsigned long long he_powf_sweep(unsigned lo, unsigned hi, unsigned stride, float y, unsigned* bad) {
+    unsigned long long n = 0;
+    for (unsigned long long u = lo; u < hi; u += stride) {
+        const float x = ara::glibc::u2f(static_cast<uint32_t>(u));
+        const uint32_t a = ara::glibc::f2u(ara::glibc::powf_(x, y)), b = ara::glibc::f2u(powf(x, y));
+        if (a != b && !((a & 0x7fffffffu) > 0x7f800000u && (b & 0x7fffffffu) > 0x7f800000u)) {
+            if (n == 0 && bad) *bad = static_cast<uint32_t>(u);
+            ++n;
+        }
+    }
+    return n;
+}
+unsigned long long he_logf_sweep(unsigned lo, unsigned hi, unsigned stride, unsigned* bad) {
+    unsigned long long n = 0;
+    for (unsigned long long u = lo; u < hi; u += stride) {
+        const float x = ara::glibc::u2f(static_cast<uint32_t>(u));
+        const uint32_t a = ara::glibc::f2u(ara::glibc::logf_(x)), b = ara::glibc::f2u(logf(x));
+        if (a != b) {
+            if (n == 0 && bad) *bad = static_cast<uint32_t>(u);
+            ++n;
+        }
+    }
+    return n;
+}
+// the live libm on arrays (numpy's own float32 pow / log are not glibc's)
+void he_libm_powf_array(const float* x, const float* y, int n, float* out) {
+    for (int i = 0; i < n; ++i) out[i] = powf(x[i], y[i]);
+}
+void he_libm_logf_array(const float* x, int n, float* out) {
+    for (int i = 0; i < n; ++i) out[i] = logf(x[i]);
+}
+}

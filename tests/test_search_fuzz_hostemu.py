@@ -43,9 +43,15 @@ def _random_case(seed):
         extra["mcts_solver"] = 0
     if rng.random() < 0.2:
         extra["nodes"] = int(sims // 2)
-    # node temperature 1: with T != 1 the priors are renormalised by a float sum whose order follows each side's own
-    # move-generation order (open point iii), which is not part of the bit-exact contract
-    st = osr.default_settings(mode, batch_size=batch, simulations=sims, node_policy_temperature=1.0, **extra)
+    # node temperature: 1 (no renormalisation), the UCI default 1.7 and others -- glibc powf restated on the device and a
+    # sequential normalising sum in policy-index order on both sides keep T != 1 inside the bit-exact contract; the same
+    # for Dirichlet noise at the root (libstdc++ gamma sampler over glibc logf / powf)
+    temp = float(rng.choice([1.0, 1.7, 1.7, 1.3, 0.8, 2.5]))
+    if rng.random() < 0.3:
+        extra["dirichlet_epsilon"] = float(rng.choice([0.25, 0.1]))
+        extra["dirichlet_alpha"] = float(rng.choice([0.2, 0.3, 0.6, 1.0, 2.0]))
+        extra["seed"] = int(rng.integers(1, 2**31 - 2))
+    st = osr.default_settings(mode, batch_size=batch, simulations=sims, node_policy_temperature=temp, **extra)
     return pos, he, st, (vid, played)
 
 

@@ -25,11 +25,30 @@ CASES = [
     ("crazyhouse", 1, "crazyhouse", None, False, ["e2e4"], 16, 500, dict(virtual_style=0)),
     ("crazyhouse", 1, "crazyhouse", None, False, ["e2e4"], 16, 0, dict(nodes=300, mcts_solver=0, virtual_mix_threshold=20)),
     ("chess", 0, "chess", None, False, ["d2d4"], 32, 800, dict(q_value_weight=0.0, q_veto_delta=0.0)),
+    # the UCI default node temperature 1.7 (glibc powf + sequential normalising sum on both sides), other temperatures,
+    # and Dirichlet noise at the root (libstdc++ gamma sampler over glibc logf / powf): still bit-exact
+    ("crazyhouse", 1, "crazyhouse", None, False, [], 64, 3200, dict(node_policy_temperature=1.7)),
+    ("crazyhouse", 1, "crazyhouse", None, False, [], 8, 800, dict(node_policy_temperature=1.7)),
+    ("chess", 0, "chess", None, False, [], 64, 1600, dict(node_policy_temperature=1.7)),
+    ("kingofthehill", 2, "lichess", None, False, ["e2e4", "e7e5"], 128, 800, dict(node_policy_temperature=1.7)),
+    ("3check", 3, "lichess", None, False, ["e2e4", "e7e5"], 128, 800, dict(node_policy_temperature=1.7)),
+    ("crazyhouse", 1, "crazyhouse", None, False, ["e2e4", "e7e5"], 16, 500, dict(node_policy_temperature=0.7)),
+    ("crazyhouse", 1, "crazyhouse", None, False, [], 8, 400, dict(dirichlet_epsilon=0.25, dirichlet_alpha=0.3, seed=7)),
+    ("chess", 0, "chess", None, False, ["e2e4"], 8, 0, dict(nodes=800, dirichlet_epsilon=0.25, dirichlet_alpha=0.3, seed=12345,
+                                                          node_policy_temperature=1.7)),
+    ("crazyhouse", 1, "crazyhouse", None, False, [], 16, 400, dict(dirichlet_epsilon=0.25, dirichlet_alpha=1.5, seed=99)),
 ]
 
 
+def case_settings(mode, batch, sims, extra):
+    """Settings of a CASES row: node temperature 1 unless the row sets it."""
+    kw = dict(node_policy_temperature=1.0)
+    kw.update(extra)
+    return osr.default_settings(mode, batch_size=batch, simulations=sims, **kw)
+
+
 def _run_both(variant, vid, mode, fen, is960, premoves, batch, sims, extra):
-    st = osr.default_settings(mode, batch_size=batch, simulations=sims, node_policy_temperature=1.0, **extra)
+    st = case_settings(mode, batch, sims, extra)
     pos = Position(fen, variant, is960)
     he = HeState(pos.fen(), vid, is960)
     for u in premoves:

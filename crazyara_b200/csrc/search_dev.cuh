@@ -288,8 +288,11 @@ struct SelectPick {
     EdgeRegs x;
 };
 
-// Exact arithmetic of the reference (get_current_u_values, node.cpp:1056-1063: float cput*P, then double): first
-// maximum of Q + U over the open children.
+// Exact arithmetic of the reference (get_current_u_values, node.cpp:1056-1063): the blaze expression
+//     cput * subvector(P) * (sqrt(N) / (n + 1.0))
+// is (float scalar * float vector) * double vector; blaze restructures (v*s)*w to (v*w)*s (DVecScalarMultExpr's
+// restructuring operators), so element i is  float( (double(P_i) * (sqrt(N) / (double(n_i) + 1.0))) * double(cput) ).
+// First maximum of Q + U over the open children.
 ARA_HD SelectPick pick_exact(const TreeDev& t, const NodeHdr& h, const EdgeRegs& pre) {
     const int k = h.no_visit_idx;
     const uint32_t e = h.edge_base;
@@ -301,7 +304,7 @@ ARA_HD SelectPick pick_exact(const TreeDev& t, const NodeHdr& h, const EdgeRegs&
     float best_v = 0.0f;
     for (int i = ARA_LANE; i < k; i += ARA_WARP_N) {
         const EdgeRegs x = i == ARA_LANE ? pre : load_edge(t, e + i);
-        const float u = static_cast<float>(static_cast<double>(cput * x.p) * (sq / (static_cast<double>(x.n) + 1.0)));
+        const float u = static_cast<float>((static_cast<double>(x.p) * (sq / (static_cast<double>(x.n) + 1.0))) * static_cast<double>(cput));
         const float v = x.q + u;
         if (best_i == 0x7fffffff || v > best_v) best_v = v, best_i = i, r.x = x;
     }

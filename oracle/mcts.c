@@ -317,13 +317,18 @@ static int select_child_node(OSearch* s, ONode* n) { /* node.cpp:1150-1167 */
     if (!n->sorted) prepare_node_for_visits(n);
     if (n->no_visit_idx == 1) return 0;
     if (n->checkmate_idx != NO_CHECKMATE) return n->checkmate_idx;
-    /* get_current_u_values node.cpp:1056-1063: float cput * float P, times double sqrt(N)/(n+1), narrowed to float */
+    /* get_current_u_values node.cpp:1056-1063:  cput * subvector(P, 0, k) * (sqrt(N) / (n + 1.0))  with cput float,
+       P float, sqrt(N) double (std::sqrt of an integer), n uint32.  Read left to right this is (cput*P) in float times a
+       double vector; blaze, however, restructures (vector*scalar)*vector into (vector*vector)*scalar (the restructuring
+       operators of blaze/math/expressions/DVecScalarMultExpr.h), so element i is evaluated as
+           float( (double(P_i) * (sqrt(N) / (double(n_i) + 1.0))) * double(cput) ).
+       blaze's source is absent here (empty submodule): this is its documented behaviour, not a measured one. */
     const float cput = get_current_cput((float)n->visit_sum, &s->st);
     const double sq = sqrt((double)n->visit_sum);
     int best = 0;
     float best_v = 0;
     for (int i = 0; i < n->no_visit_idx; ++i) {
-        const float u = (float)((double)(cput * n->policy[i]) * (sq / ((double)n->n[i] + 1.0)));
+        const float u = (float)(((double)n->policy[i] * (sq / ((double)n->n[i] + 1.0))) * (double)cput);
         const float v = n->q[i] + u;
         if (i == 0 || v > best_v) best = i, best_v = v;
     }

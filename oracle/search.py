@@ -178,3 +178,30 @@ def fake_net(n_labels):
             L.ofake_eval(int(k), n_labels, v[i:].ctypes.data, p[i].ctypes.data)
         return v, p
     return fn
+
+
+def hash_net(n_labels):
+    """A second hash-derived stand-in network, WITHOUT ties: value as oracle/fake.c, priors (1 + m/2^23) * 2^(-9-t) with
+    23 hashed mantissa bits m and t in 0..7.  oracle/fake.c's priors take only 2048 distinct values, so legal moves tie
+    all the time and the order std::sort leaves tied priors in (node.cpp:464-470: unstable, unspecified) would decide
+    visit orders; comparisons against the reference's compiled search (oracle/refmcts.py) use this one.
+    net_fn(planes, keys) for Search.run(..., with_keys=True)."""
+    m1, m2 = np.uint64(0xBF58476D1CE4E5B9), np.uint64(0x94D049BB133111EB)
+
+    def zmix(z):
+        z = (z ^ (z >> np.uint64(30))) * m1
+        z = (z ^ (z >> np.uint64(27))) * m2
+        return z ^ (z >> np.uint64(31))
+    idx = (np.arange(n_labels, dtype=np.uint64) + np.uint64(1)) * np.uint64(0xD6E8FEB86659FD93)
+
+    def fn(planes, keys):
+        keys = np.asarray(keys, np.uint64)
+        with np.errstate(over="ignore"):
+            h0 = zmix(keys ^ np.uint64(0x9E3779B97F4A7C15))
+            h = zmix(keys[:, None] + idx[None, :])
+        v = (((h0 >> np.uint64(11)) & np.uint64(0xFFFF)).astype(np.int64) - 32768).astype(np.float32) / np.float32(65536)
+        t = (h & np.uint64(7)).astype(np.uint32)
+        m = ((h >> np.uint64(20)) & np.uint64(0x7FFFFF)).astype(np.uint32)
+        p = (((np.uint32(127 - 9) - t) << np.uint32(23)) | m).view(np.float32)
+        return v, np.ascontiguousarray(p)
+    return fn

@@ -21,8 +21,8 @@ def _pick(p, q, n, cput, vs):
 
 
 def _reference_argmax(p, q, n, cput, vs):
-    cp = (np.float32(cput) * p.astype(np.float32)).astype(np.float32)          # float product
-    u = (cp.astype(np.float64) * (np.sqrt(np.float64(vs)) / (n.astype(np.float64) + 1.0))).astype(np.float32)
+    # blaze restructures (cput * P) * w into (P * w) * cput: all double, one final narrowing (oracle/mcts.c select_child_node)
+    u = ((p.astype(np.float64) * (np.sqrt(np.float64(vs)) / (n.astype(np.float64) + 1.0))) * np.float64(np.float32(cput))).astype(np.float32)
     v = (q.astype(np.float32) + u).astype(np.float32)
     return int(np.argmax(v))  # first maximum
 

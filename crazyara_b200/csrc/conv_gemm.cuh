@@ -11,6 +11,12 @@
 // the halo of the 3x3 taps falls outside the tensor and is zero-filled by the TMA unit, so the 3x3
 // convolutions are implicit GEMMs with no im2col buffer.  Both operands land K-major with the 128-byte
 // swizzle; the MMA is issued by one elected thread; four epilogue warps drain TMEM (one row per thread).
+//
+// Precision float32 (the reference's `Precision float32`, uci/optionsuci.cpp:144, nn/tensorrtapi.cpp:334-360) runs on
+// the SAME kernel: an fp32 value x is carried as the fp16 pair hi = fp16(x), lo = fp16(x - hi), activations are stored
+// with their channels tripled [hi | hi | lo] and weights per tap as [hi | lo | hi], so that ONE GEMM over 3*Cin
+// "channels" accumulates  a_hi*w_hi + a_hi*w_lo + a_lo*w_hi  in the fp32 TMEM accumulator (the dropped a_lo*w_lo term
+// is 2^-22 relative); the epilogue adds an fp32 residual and writes fp32 and / or the split form for the next layer.
 #pragma once
 #include "sm100_prims.cuh"
 
@@ -32,6 +38,10 @@ struct ConvGemmArgs {
     // device-side batch size (or nullptr): number of boards that really hold input; M tiles beyond it leave at once, so
     // a launch sized for the largest batch costs only what the rows in use cost
     const int* boards_dev;
+    // ---- Precision float32 (net.cu): fp32 activations between the layers, fp16 hi + lo operand splitting
+    const float* residual_f;  // [M, ldr] fp32 residual (instead of `residual`), or nullptr
+    __half* out_split;        // [M, 3 * split_cs] fp16: the result as hi | hi | lo (x = hi + lo to ~2^-22), or nullptr
+    int split_cs;             // channel pitch of one part (multiple of 64)
 };
 
 constexpr int kGemmThreads = 192;  // warp0: TMA producer, warp1: MMA issuer (+TMEM alloc), warps2-5: epilogue
@@ -177,6 +187,37 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                             f[8 * j + 2 * q] += x.x;
                             f[8 * j + 2 * q + 1] += x.y;
                         }
+                    }
+                }
+                if (args.residual_f != nullptr) {
+                    const float4* rp = reinterpret_cast<const float4*>(args.residual_f + static_cast<size_t>(m) * args.ldr + n0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 r = __ldg(rp + j);
+                        f[4 * j + 0] += r.x;
+                        f[4 * j + 1] += r.y;
+                        f[4 * j + 2] += r.z;
+                        f[4 * j + 3] += r.w;
+                    }
+                }
+                if (args.out_split != nullptr && n0 < args.split_cs) {
+                    __half* base = args.out_split + static_cast<size_t>(m) * (3 * args.split_cs) + n0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 oh, ol;
+                        __half2* hh = reinterpret_cast<__half2*>(&oh);
+                        __half2* hl = reinterpret_cast<__half2*>(&ol);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float a = f[8 * j + 2 * q], b = f[8 * j + 2 * q + 1];
+                            const __half2 hi = __floats2half2_rn(a, b);
+                            const float2 hf = __half22float2(hi);
+                            hh[q] = hi;
+                            hl[q] = __floats2half2_rn(a - hf.x, b - hf.y);
+                        }
+                        reinterpret_cast<uint4*>(base)[j] = oh;
+                        reinterpret_cast<uint4*>(base + args.split_cs)[j] = oh;
+                        reinterpret_cast<uint4*>(base + 2 * args.split_cs)[j] = ol;
                     }
                 }
                 if (args.out_h != nullptr) {

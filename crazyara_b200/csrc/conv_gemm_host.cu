@@ -122,6 +122,13 @@ int conv_layer_init(ConvLayer* L, const __half* act, int boards_cap, int cin, co
     return 0;
 }
 
+void conv_layer_set_precise(ConvLayer* L, const float* residual_f, int ldr, __half* out_split, int split_cs) {
+    L->args.residual_f = residual_f;
+    if (residual_f != nullptr) L->args.ldr = ldr;
+    L->args.out_split = out_split;
+    L->args.split_cs = split_cs;
+}
+
 template <int BN>
 static int launch_bn(const ConvLayer* L, const ConvGemmArgs& a, dim3 grid, cudaStream_t stream) {
     using Cfg = ConvGemmCfg<BN>;

@@ -22,6 +22,10 @@ int conv_layer_init(ConvLayer* L, const __half* act, int boards_cap, int cin, co
                     int ksize, const float* bias, int relu, const __half* residual, int ldr, __half* out_h,
                     float* out_f, int ldo, int bn);
 
+// Precision float32: fp32 residual [M, ldr] instead of the fp16 one, and / or the hi | hi | lo split output
+// [M, 3 * split_cs] (see conv_gemm.cuh); call after conv_layer_init.
+void conv_layer_set_precise(ConvLayer* L, const float* residual_f, int ldr, __half* out_split, int split_cs);
+
 // boards_dev (optional): device-side count of the boards in use, <= boards (see ConvGemmArgs::boards_dev)
 int conv_layer_launch(const ConvLayer* L, int boards, cudaStream_t stream, const int* boards_dev = nullptr);
 

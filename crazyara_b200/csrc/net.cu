@@ -67,6 +67,30 @@ int Net::upload_conv_w(const float* w, int n_out, int cin, int ksize, __half** d
     return 0;
 }
 
+// Precision float32: w [n_out, cin, k, k] fp32 -> fp16 [rows, taps * 3 * cw]; per tap the columns are
+// hi(w) [cw] | lo(w) [cw] | hi(w) [cw], matching activations stored as hi | hi | lo (conv_gemm.cuh).
+int Net::upload_conv_w_split(const float* w, int n_out, int cin, int ksize, __half** dst, int* rows) {
+    const int taps = ksize * ksize;
+    const int cw = round_up(cin, 64);
+    const int r = round_up(n_out, 256);
+    std::vector<__half> h(static_cast<size_t>(r) * taps * 3 * cw, __float2half(0.0f));
+    for (int n = 0; n < n_out; ++n)
+        for (int c = 0; c < cin; ++c)
+            for (int t = 0; t < taps; ++t) {
+                const float v = w[(static_cast<size_t>(n) * cin + c) * taps + t];
+                const __half hi = __float2half_rn(v);
+                const __half lo = __float2half_rn(v - __half2float(hi));
+                __half* col = &h[(static_cast<size_t>(n) * taps + t) * 3 * cw];
+                col[c] = hi;
+                col[cw + c] = lo;
+                col[2 * cw + c] = hi;
+            }
+    if (dalloc(dst, h.size()) != 0) return -1;
+    ARA_CUDA_OK(cudaMemcpy(*dst, h.data(), h.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    *rows = r;
+    return 0;
+}
+
 Net::~Net() {
     cudaSetDevice(device);
     for (int k = 0; k < 3; ++k)
@@ -79,35 +103,7 @@ Net::~Net() {
     if (ev_join) cudaEventDestroy(ev_join);
 }
 
-int Net::init(const char* blob_path, int dev, int batch_size) {
-    device = dev;
-    batch = batch_size;
-    if (batch < 1) return set_error("ara_net_create: batch %d < 1", batch);
-    batch_cap = round_up(batch < 2 ? 2 : batch, 2);
-    ARA_CUDA_OK(cudaSetDevice(device));
-    {
-        cudaDeviceProp prop;
-        ARA_CUDA_OK(cudaGetDeviceProperties(&prop, device));
-        if (prop.major < 10)
-            return set_error("ara_net_create: device %d is sm_%d%d; this library only runs on sm_100a (B200)", device,
-                             prop.major, prop.minor);
-    }
-    ARA_CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    ARA_CUDA_OK(cudaStreamCreateWithFlags(&head_stream, cudaStreamNonBlocking));
-    ARA_CUDA_OK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-    ARA_CUDA_OK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
-    if (const char* e = getenv("ARA_NET_FORK_HEADS")) fork_heads = atoi(e) != 0;
-    {
-        const char* f = getenv("ARA_FUSED_BLOCKS");
-        use_fused = (f != nullptr && f[0] == '1');  // opt-in until it beats the three-kernel path (profiles/README.md)
-    }
-    {
-        const char* f = getenv("ARA_TRUNK");
-        use_trunk = !(f != nullptr && f[0] == '0') && !use_fused;
-    }
-    const char* g = getenv("ARA_NO_GRAPH");
-    use_graph = !(g != nullptr && g[0] == '1');
-
+int Net::read_blob(const char* blob_path, HostWeights* hw) {
     BlobReader rd;
     rd.f = fopen(blob_path, "rb");
     if (!rd.f) return set_error("ara_net_create: cannot open weight blob '%s'", blob_path);
@@ -131,7 +127,7 @@ int Net::init(const char* blob_path, int dev, int batch_size) {
         hdr.policy_channels < 1 || hdr.policy_channels > 256)
         return set_error("ara_net_create: implausible header");
     blocks.resize(hdr.n_blocks);
-    int max_cop = 0;
+    max_cop_ = 0;
     for (auto& b : blocks) {
         int t[3];
         if (!rd.read(t, sizeof(t))) return set_error("ara_net_create: truncated block table");
@@ -140,177 +136,233 @@ int Net::init(const char* blob_path, int dev, int batch_size) {
         b.se_type = t[2];
         if (b.c_op % 32 != 0 || b.c_op < 32 || (b.kernel != 3 && b.kernel != 5) || b.se_type < 0 || b.se_type > 2)
             return set_error("ara_net_create: unsupported block (c_op %d kernel %d se %d)", b.c_op, b.kernel, b.se_type);
-        if (b.c_op > max_cop) max_cop = b.c_op;
+        if (b.c_op > max_cop_) max_cop_ = b.c_op;
     }
-    cin_pad = round_up(hdr.in_channels, 64);
-    ldp = round_up(hdr.policy_channels, 32);
+    const size_t C = hdr.channels;
+    if (!rd.tensor(hw->stem_w, C * hdr.in_channels * 9) || !rd.tensor(hw->stem_b, C)) return -1;
+    hw->blocks.resize(hdr.n_blocks);
+    for (int i = 0; i < hdr.n_blocks; ++i) {
+        const BlockDesc& bd = blocks[i];
+        HostBlock& hb = hw->blocks[i];
+        const size_t cop = bd.c_op, kk = static_cast<size_t>(bd.kernel) * bd.kernel;
+        if (bd.se_type == 1 && (!rd.tensor(hb.se_a, 128 * 256) || !rd.tensor(hb.se_b, 256 * 128))) return -1;
+        if (bd.se_type == 2 && (!rd.tensor(hb.se_a, 256 * 256) || !rd.tensor(hb.se_b, 256))) return -1;
+        if (!rd.tensor(hb.w1, cop * C) || !rd.tensor(hb.b1, cop) || !rd.tensor(hb.wd, cop * kk) || !rd.tensor(hb.bd, cop) ||
+            !rd.tensor(hb.w2, C * cop) || !rd.tensor(hb.b2, C))
+            return -1;
+    }
+    if (!rd.tensor(hw->vh_wv, 8 * 256) || !rd.tensor(hw->vh_bv, 8)) return -1;
+    if (!hdr.wdl_mode) {
+        if (!rd.tensor(hw->vh_a, 256 * 512) || !rd.tensor(hw->vh_ab, 256) || !rd.tensor(hw->vh_b, 256) || !rd.tensor(hw->vh_bb, 1))
+            return -1;
+    } else {
+        if (!rd.tensor(hw->vh_a, 3 * 512) || !rd.tensor(hw->vh_ab, 3) || !rd.tensor(hw->vh_b, 512) || !rd.tensor(hw->vh_bb, 1))
+            return -1;
+    }
+    if (!rd.tensor(hw->pol_w1, C * C * 9) || !rd.tensor(hw->pol_b1, C) ||
+        !rd.tensor(hw->pol_w2, static_cast<size_t>(hdr.policy_channels) * C * 9))
+        return -1;
+    char tail;
+    if (fread(&tail, 1, 1, rd.f) != 0) return set_error("ara_net_create: trailing bytes in weight blob");
+    return 0;
+}
+
+// squeeze-excitation matrices, transposed for coalesced reads: ca_se fc1 [128][256] -> [256][128], fc2 [256][128] ->
+// [128][256]; eca_se centre tap [out][in] -> [in][out] + bias
+static void se_transposed(const BlockDesc& bd, const HostBlock& hb, std::vector<float>* a, std::vector<float>* b) {
+    if (bd.se_type == 1) {
+        a->assign(256 * 128, 0.f);
+        for (int j = 0; j < 128; ++j)
+            for (int k = 0; k < 256; ++k) (*a)[k * 128 + j] = hb.se_a[j * 256 + k];
+        b->assign(128 * 256, 0.f);
+        for (int c = 0; c < 256; ++c)
+            for (int j = 0; j < 128; ++j) (*b)[j * 256 + c] = hb.se_b[c * 128 + j];
+    } else if (bd.se_type == 2) {
+        a->assign(256 * 256, 0.f);
+        for (int c = 0; c < 256; ++c)
+            for (int k = 0; k < 256; ++k) (*a)[k * 256 + c] = hb.se_a[c * 256 + k];
+        *b = hb.se_b;
+    }
+}
+
+int Net::upload_value_head(const HostWeights& hw) {
+    if (upload_f32(hw.vh_wv.data(), hw.vh_wv.size(), hw.vh_wv.size(), &vh_wv)) return -1;
+    if (upload_f32(hw.vh_bv.data(), 8, 8, &vh_bv)) return -1;
+    if (!hdr.wdl_mode) {
+        std::vector<float> t2(512 * 256, 0.f);  // fc1 [256][512] -> [512][256]
+        for (int o = 0; o < 256; ++o)
+            for (int i = 0; i < 512; ++i) t2[i * 256 + o] = hw.vh_a[o * 512 + i];
+        if (upload_f32(t2.data(), t2.size(), t2.size(), &vh_w1t)) return -1;
+        if (upload_f32(hw.vh_ab.data(), 256, 256, &vh_b1)) return -1;
+        if (upload_f32(hw.vh_b.data(), 256, 256, &vh_w2)) return -1;
+        if (upload_f32(hw.vh_bb.data(), 1, 1, &vh_b2)) return -1;
+    } else {
+        if (upload_f32(hw.vh_a.data(), hw.vh_a.size(), hw.vh_a.size(), &vh_wdl_w)) return -1;
+        if (upload_f32(hw.vh_ab.data(), 3, 4, &vh_wdl_b)) return -1;
+        if (upload_f32(hw.vh_b.data(), 512, 512, &vh_plys_w)) return -1;
+        if (upload_f32(hw.vh_bb.data(), 1, 1, &vh_plys_b)) return -1;
+    }
+    return 0;
+}
+
+// Precision float16: stem (tcgen05 implicit GEMM) -> persistent tower kernel -> heads
+int Net::build_half(const HostWeights& hw) {
     const int C = hdr.channels;
     const size_t rows = static_cast<size_t>(batch_cap) * 64;
-
-    // activation buffers
-    if (dalloc(&d_in_f32, static_cast<size_t>(batch) * hdr.in_channels * 64)) return -1;
+    if (hdr.n_blocks > kTrunkMaxBlocks) return set_error("ara_net_create: %d blocks (max %d)", hdr.n_blocks, kTrunkMaxBlocks);
     if (dalloc(&d_in_h, rows * cin_pad)) return -1;
-    if (dalloc(&d_x[0], rows * C)) return -1;
-    if (dalloc(&d_x[1], rows * C)) return -1;
-    if (dalloc(&d_h1, rows * max_cop)) return -1;
-    if (dalloc(&d_h2, rows * max_cop)) return -1;
-    if (dalloc(&d_p1, rows * C)) return -1;
+    if (dalloc(&d_x[0], rows * C) || dalloc(&d_x[1], rows * C) || dalloc(&d_p1, rows * C)) return -1;
+    int wrows = 0;
+    if (upload_conv_w(hw.stem_w.data(), C, hdr.in_channels, 3, &stem_w, &wrows)) return -1;
+    if (upload_f32(hw.stem_b.data(), C, 256, &stem_b)) return -1;
+    if (conv_layer_init(&stem_conv, d_in_h, batch_cap, cin_pad, stem_w, wrows, C, 3, stem_b, 1, nullptr, 0, d_x[0], nullptr, C,
+                        conv_layer_choose_bn(batch, C)))
+        return -1;
+    std::vector<TrunkBlockHost> tb(hdr.n_blocks);
+    std::vector<float> ta, tbv;
+    for (int i = 0; i < hdr.n_blocks; ++i) {
+        const BlockDesc& bd = blocks[i];
+        const HostBlock& hb = hw.blocks[i];
+        tb[i].c_op = bd.c_op;
+        tb[i].ksize = bd.kernel;
+        tb[i].se_type = bd.se_type;
+        tb[i].w1 = hb.w1;
+        tb[i].b1 = hb.b1;
+        tb[i].wd = hb.wd;
+        tb[i].bd = hb.bd;
+        tb[i].w2 = hb.w2;
+        float *b2 = nullptr, *sa = nullptr, *sb = nullptr;
+        if (upload_f32(hb.b2.data(), C, 256, &b2)) return -1;
+        tb[i].b2 = b2;
+        if (bd.se_type != 0) {
+            se_transposed(bd, hb, &ta, &tbv);
+            if (upload_f32(ta.data(), ta.size(), ta.size(), &sa) || upload_f32(tbv.data(), tbv.size(), tbv.size(), &sb)) return -1;
+            tb[i].se_w1t = sa;
+            if (bd.se_type == 1) tb[i].se_w2t = sb;
+            else tb[i].se_b = sb;
+        }
+    }
+    __half* xfinal = d_x[1];
+    if (rise_trunk_init(&trunk_, tb, d_x[0], batch_cap, xfinal)) return -1;
+    if (upload_conv_w(hw.pol_w1.data(), C, C, 3, &pol_w1, &wrows)) return -1;
+    if (upload_f32(hw.pol_b1.data(), C, 256, &pol_b1)) return -1;
+    if (conv_layer_init(&pol_conv1, xfinal, batch_cap, C, pol_w1, wrows, C, 3, pol_b1, 1, nullptr, 0, d_p1, nullptr, C,
+                        conv_layer_choose_bn(batch, C)))
+        return -1;
+    if (upload_conv_w(hw.pol_w2.data(), hdr.policy_channels, C, 3, &pol_w2, &wrows)) return -1;
+    if (conv_layer_init(&pol_conv2, d_p1, batch_cap, C, pol_w2, wrows, hdr.policy_channels, 3, nullptr, 0, nullptr, 0, nullptr,
+                        d_logits, ldp, conv_layer_choose_bn(batch, hdr.policy_channels)))
+        return -1;
+    return 0;
+}
+
+// Precision float32: every layer a launch; GEMMs on tcgen05 with fp16 hi + lo operand splitting (3x the K extent),
+// fp32 activations in HBM between the layers, CUDA-core stages in fp32
+int Net::build_precise(const HostWeights& hw) {
+    const int C = hdr.channels;
+    const size_t rows = static_cast<size_t>(batch_cap) * 64;
+    const int max_cp = round_up(max_cop_, 64);
+    if (dalloc(&d_in_h, rows * 3 * cin_pad)) return -1;
+    for (int k = 0; k < 2; ++k)
+        if (dalloc(&d_xf[k], rows * C) || dalloc(&d_xs[k], rows * 3 * C)) return -1;
+    if (dalloc(&d_h1f, rows * max_cop_) || dalloc(&d_h2s, rows * 3 * max_cp) || dalloc(&d_p1, rows * 3 * C)) return -1;
+    int wrows = 0;
+    if (upload_conv_w_split(hw.stem_w.data(), C, hdr.in_channels, 3, &stem_w, &wrows)) return -1;
+    if (upload_f32(hw.stem_b.data(), C, 256, &stem_b)) return -1;
+    if (conv_layer_init(&stem_conv, d_in_h, batch_cap, 3 * cin_pad, stem_w, wrows, C, 3, stem_b, 1, nullptr, 0, nullptr, d_xf[0], C,
+                        conv_layer_choose_bn(batch, C)))
+        return -1;
+    conv_layer_set_precise(&stem_conv, nullptr, 0, d_xs[0], C);
+    pb_.resize(hdr.n_blocks);
+    std::vector<float> ta, tbv, t2;
+    for (int i = 0; i < hdr.n_blocks; ++i) {
+        const BlockDesc& bd = blocks[i];
+        const HostBlock& hb = hw.blocks[i];
+        PreciseBlock& w = pb_[i];
+        const int cp = round_up(bd.c_op, 64);
+        const int in = i & 1, out = (i + 1) & 1;
+        if (bd.se_type != 0) {
+            se_transposed(bd, hb, &ta, &tbv);
+            if (upload_f32(ta.data(), ta.size(), ta.size(), &w.se_w1t)) return -1;
+            if (upload_f32(tbv.data(), tbv.size(), tbv.size(), bd.se_type == 1 ? &w.se_w2t : &w.se_b)) return -1;
+        }
+        // conv1 1x1 256 -> c_op, ReLU: split X -> fp32 H1
+        if (upload_conv_w_split(hb.w1.data(), bd.c_op, C, 1, &w.w1, &wrows)) return -1;
+        if (upload_f32(hb.b1.data(), bd.c_op, round_up(bd.c_op, 256), &w.b1)) return -1;
+        if (conv_layer_init(&w.conv1, d_xs[in], batch_cap, 3 * C, w.w1, wrows, bd.c_op, 1, w.b1, 1, nullptr, 0, nullptr, d_h1f,
+                            bd.c_op, conv_layer_choose_bn(batch, bd.c_op)))
+            return -1;
+        // depthwise k x k: blob [c_op][k][k] -> device [k*k][c_op]
+        const int kk = bd.kernel * bd.kernel;
+        t2.assign(static_cast<size_t>(kk) * bd.c_op, 0.f);
+        for (int c = 0; c < bd.c_op; ++c)
+            for (int q = 0; q < kk; ++q) t2[static_cast<size_t>(q) * bd.c_op + c] = hb.wd[static_cast<size_t>(c) * kk + q];
+        if (upload_f32(t2.data(), t2.size(), t2.size(), &w.wd)) return -1;
+        if (upload_f32(hb.bd.data(), bd.c_op, cp, &w.bd)) return -1;
+        // conv2 1x1 c_op -> 256 + fp32 residual: split H2 [.., 3*cp] -> fp32 X' and split X'
+        if (upload_conv_w_split(hb.w2.data(), C, bd.c_op, 1, &w.w2, &wrows)) return -1;
+        if (upload_f32(hb.b2.data(), C, 256, &w.b2)) return -1;
+        if (conv_layer_init(&w.conv2, d_h2s, batch_cap, 3 * cp, w.w2, wrows, C, 1, w.b2, 0, nullptr, 0, nullptr, d_xf[out], C,
+                            conv_layer_choose_bn(batch, C)))
+            return -1;
+        conv_layer_set_precise(&w.conv2, d_xf[in], C, d_xs[out], C);
+    }
+    const int fin = hdr.n_blocks & 1;
+    if (upload_conv_w_split(hw.pol_w1.data(), C, C, 3, &pol_w1, &wrows)) return -1;
+    if (upload_f32(hw.pol_b1.data(), C, 256, &pol_b1)) return -1;
+    if (conv_layer_init(&pol_conv1, d_xs[fin], batch_cap, 3 * C, pol_w1, wrows, C, 3, pol_b1, 1, nullptr, 0, nullptr, nullptr, C,
+                        conv_layer_choose_bn(batch, C)))
+        return -1;
+    conv_layer_set_precise(&pol_conv1, nullptr, 0, d_p1, C);
+    if (upload_conv_w_split(hw.pol_w2.data(), hdr.policy_channels, C, 3, &pol_w2, &wrows)) return -1;
+    if (conv_layer_init(&pol_conv2, d_p1, batch_cap, 3 * C, pol_w2, wrows, hdr.policy_channels, 3, nullptr, 0, nullptr, 0, nullptr,
+                        d_logits, ldp, conv_layer_choose_bn(batch, hdr.policy_channels)))
+        return -1;
+    ARA_CUDA_OK(cudaFuncSetAttribute(value_head_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     value_head_smem<float>()));
+    ARA_CUDA_OK(cudaFuncSetAttribute(nchw_f32_to_nhwc_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     hdr.in_channels * 65 * 4));
+    return 0;
+}
+
+int Net::init(const char* blob_path, int dev, int batch_size, int prec) {
+    device = dev;
+    batch = batch_size;
+    precision = prec;
+    if (batch < 1) return set_error("ara_net_create: batch %d < 1", batch);
+    if (precision != 0 && precision != 1)
+        return set_error("ara_net_create: precision %d (0 = float16, 1 = float32)", precision);
+    batch_cap = round_up(batch < 2 ? 2 : batch, 2);
+    ARA_CUDA_OK(cudaSetDevice(device));
+    {
+        cudaDeviceProp prop;
+        ARA_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10)
+            return set_error("ara_net_create: device %d is sm_%d%d; this library only runs on sm_100a (B200)", device,
+                             prop.major, prop.minor);
+    }
+    ARA_CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    ARA_CUDA_OK(cudaStreamCreateWithFlags(&head_stream, cudaStreamNonBlocking));
+    ARA_CUDA_OK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    ARA_CUDA_OK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    if (const char* e = getenv("ARA_NET_FORK_HEADS")) fork_heads = atoi(e) != 0;
+    const char* g = getenv("ARA_NO_GRAPH");
+    use_graph = !(g != nullptr && g[0] == '1');
+
+    HostWeights hw;
+    if (read_blob(blob_path, &hw)) return -1;
+    cin_pad = round_up(hdr.in_channels, 64);
+    ldp = round_up(hdr.policy_channels, 32);
+    const size_t rows = static_cast<size_t>(batch_cap) * 64;
+    if (dalloc(&d_in_f32, static_cast<size_t>(batch) * hdr.in_channels * 64)) return -1;
     if (dalloc(&d_logits, rows * ldp)) return -1;
     if (dalloc(&d_prob, static_cast<size_t>(batch) * n_labels())) return -1;
     if (dalloc(&d_value, batch)) return -1;
     if (dalloc(&d_aux, static_cast<size_t>(batch) * 4)) return -1;
-
-    std::vector<float> t, t2;
-    int wrows = 0;
-    // stem
-    if (!rd.tensor(t, static_cast<size_t>(C) * hdr.in_channels * 9)) return -1;
-    if (upload_conv_w(t.data(), C, hdr.in_channels, 3, &stem_w, &wrows)) return -1;
-    if (!rd.tensor(t, C)) return -1;
-    if (upload_f32(t.data(), C, 256, &stem_b)) return -1;
-    {
-        const int bn = conv_layer_choose_bn(batch, C);
-        if (conv_layer_init(&stem_conv, d_in_h, batch_cap, cin_pad, stem_w, wrows, C, 3, stem_b, 1, nullptr, 0, d_x[0],
-                            nullptr, C, bn))
-            return -1;
-    }
-    bw_.resize(hdr.n_blocks);
-    std::vector<TrunkBlockHost> trunk_blocks(hdr.n_blocks);
-    for (int i = 0; i < hdr.n_blocks; ++i) {
-        const BlockDesc& bd = blocks[i];
-        BlockW& w = bw_[i];
-        TrunkBlockHost& tb = trunk_blocks[i];
-        tb.c_op = bd.c_op;
-        tb.ksize = bd.kernel;
-        tb.se_type = bd.se_type;
-        __half* xin = d_x[i & 1];
-        __half* xout = d_x[(i + 1) & 1];
-        if (bd.se_type == 1) {
-            if (!rd.tensor(t, 128 * 256)) return -1;  // fc1 [128][256]
-            t2.assign(256 * 128, 0.f);
-            for (int j = 0; j < 128; ++j)
-                for (int k = 0; k < 256; ++k) t2[k * 128 + j] = t[j * 256 + k];
-            if (upload_f32(t2.data(), t2.size(), t2.size(), &w.se_w1t)) return -1;
-            if (!rd.tensor(t, 256 * 128)) return -1;  // fc2 [256][128]
-            t2.assign(128 * 256, 0.f);
-            for (int c = 0; c < 256; ++c)
-                for (int j = 0; j < 128; ++j) t2[j * 256 + c] = t[c * 128 + j];
-            if (upload_f32(t2.data(), t2.size(), t2.size(), &w.se_w2t)) return -1;
-        } else if (bd.se_type == 2) {
-            if (!rd.tensor(t, 256 * 256)) return -1;  // centre tap [out][in]
-            t2.assign(256 * 256, 0.f);
-            for (int c = 0; c < 256; ++c)
-                for (int k = 0; k < 256; ++k) t2[k * 256 + c] = t[c * 256 + k];
-            if (upload_f32(t2.data(), t2.size(), t2.size(), &w.se_w1t)) return -1;
-            if (!rd.tensor(t, 256)) return -1;
-            if (upload_f32(t.data(), 256, 256, &w.se_b)) return -1;
-        }
-        // conv1 1x1 256 -> c_op (+ReLU)
-        if (!rd.tensor(t, static_cast<size_t>(bd.c_op) * C)) return -1;
-        tb.w1 = t;
-        if (upload_conv_w(t.data(), bd.c_op, C, 1, &w.w1, &wrows)) return -1;
-        if (!rd.tensor(t, bd.c_op)) return -1;
-        tb.b1 = t;
-        if (upload_f32(t.data(), bd.c_op, round_up(bd.c_op, 256), &w.b1)) return -1;
-        {
-            const int bn = conv_layer_choose_bn(batch, bd.c_op);
-            if (conv_layer_init(&w.conv1, xin, batch_cap, C, w.w1, wrows, bd.c_op, 1, w.b1, 1, nullptr, 0, d_h1, nullptr,
-                                bd.c_op, bn))
-                return -1;
-        }
-        // depthwise k x k: blob [c_op][k][k] -> device [k*k][c_op]
-        const int kk = bd.kernel * bd.kernel;
-        if (!rd.tensor(t, static_cast<size_t>(bd.c_op) * kk)) return -1;
-        tb.wd = t;
-        t2.assign(static_cast<size_t>(kk) * bd.c_op, 0.f);
-        for (int c = 0; c < bd.c_op; ++c)
-            for (int q = 0; q < kk; ++q) t2[static_cast<size_t>(q) * bd.c_op + c] = t[static_cast<size_t>(c) * kk + q];
-        if (upload_f32(t2.data(), t2.size(), t2.size(), &w.wd)) return -1;
-        const int cpad64 = round_up(bd.c_op, 64);
-        {  // padded copy for the fused block kernel: [k*k][cpad64]
-            std::vector<float> t3(static_cast<size_t>(kk) * cpad64, 0.f);
-            for (int c = 0; c < bd.c_op; ++c)
-                for (int q = 0; q < kk; ++q) t3[static_cast<size_t>(q) * cpad64 + c] = t[static_cast<size_t>(c) * kk + q];
-            if (upload_f32(t3.data(), t3.size(), t3.size(), &w.wd_pad)) return -1;
-        }
-        if (!rd.tensor(t, bd.c_op)) return -1;
-        tb.bd = t;
-        if (upload_f32(t.data(), bd.c_op, cpad64, &w.bd)) return -1;
-        // conv2 1x1 c_op -> 256 (+residual)
-        if (!rd.tensor(t, static_cast<size_t>(C) * bd.c_op)) return -1;
-        tb.w2 = t;
-        if (upload_conv_w(t.data(), C, bd.c_op, 1, &w.w2, &wrows)) return -1;
-        if (!rd.tensor(t, C)) return -1;
-        if (upload_f32(t.data(), C, 256, &w.b2)) return -1;
-        tb.b2 = w.b2;
-        tb.se_w1t = w.se_w1t;
-        tb.se_w2t = w.se_w2t;
-        tb.se_b = w.se_b;
-        {
-            const int bn = conv_layer_choose_bn(batch, C);
-            if (conv_layer_init(&w.conv2, d_h2, batch_cap, bd.c_op, w.w2, wrows, C, 1, w.b2, 0, xin, C, xout, nullptr, C,
-                                bn))
-                return -1;
-        }
-        // the same block as ONE fused kernel (rise_block.cuh); w1 rows / b1 are padded to 256, w2 columns to cpad64
-        if (rise_block_init(&w.fused, xin, batch_cap, w.w1, round_up(bd.c_op, 256), w.w2, wrows, cpad64, bd.c_op, bd.kernel, w.b1,
-                            w.wd_pad, w.bd, w.b2, xout))
-            return -1;
-    }
-    __half* xfinal = d_x[hdr.n_blocks & 1];
-    // the whole tower as one persistent kernel: stem output d_x[0] -> xfinal
-    if (hdr.n_blocks > kTrunkMaxBlocks) use_trunk = false;
-    if (use_trunk && rise_trunk_init(&trunk_, trunk_blocks, d_x[0], batch_cap, xfinal)) return -1;
-    trunk_blocks.clear();
-    // value head
-    if (!rd.tensor(t, 8 * 256)) return -1;
-    if (upload_f32(t.data(), t.size(), t.size(), &vh_wv)) return -1;
-    if (!rd.tensor(t, 8)) return -1;
-    if (upload_f32(t.data(), 8, 8, &vh_bv)) return -1;
-    if (!hdr.wdl_mode) {
-        if (!rd.tensor(t, 256 * 512)) return -1;  // fc1 [256][512]
-        t2.assign(512 * 256, 0.f);
-        for (int o = 0; o < 256; ++o)
-            for (int i = 0; i < 512; ++i) t2[i * 256 + o] = t[o * 512 + i];
-        if (upload_f32(t2.data(), t2.size(), t2.size(), &vh_w1t)) return -1;
-        if (!rd.tensor(t, 256)) return -1;
-        if (upload_f32(t.data(), 256, 256, &vh_b1)) return -1;
-        if (!rd.tensor(t, 256)) return -1;
-        if (upload_f32(t.data(), 256, 256, &vh_w2)) return -1;
-        if (!rd.tensor(t, 1)) return -1;
-        if (upload_f32(t.data(), 1, 1, &vh_b2)) return -1;
-    } else {
-        if (!rd.tensor(t, 3 * 512)) return -1;
-        if (upload_f32(t.data(), t.size(), t.size(), &vh_wdl_w)) return -1;
-        if (!rd.tensor(t, 3)) return -1;
-        if (upload_f32(t.data(), 3, 4, &vh_wdl_b)) return -1;
-        if (!rd.tensor(t, 512)) return -1;
-        if (upload_f32(t.data(), 512, 512, &vh_plys_w)) return -1;
-        if (!rd.tensor(t, 1)) return -1;
-        if (upload_f32(t.data(), 1, 1, &vh_plys_b)) return -1;
-    }
-    // policy head
-    if (!rd.tensor(t, static_cast<size_t>(C) * C * 9)) return -1;
-    if (upload_conv_w(t.data(), C, C, 3, &pol_w1, &wrows)) return -1;
-    if (!rd.tensor(t, C)) return -1;
-    if (upload_f32(t.data(), C, 256, &pol_b1)) return -1;
-    {
-        const int bn = conv_layer_choose_bn(batch, C);
-        if (conv_layer_init(&pol_conv1, xfinal, batch_cap, C, pol_w1, wrows, C, 3, pol_b1, 1, nullptr, 0, d_p1, nullptr, C,
-                            bn))
-            return -1;
-    }
-    if (!rd.tensor(t, static_cast<size_t>(hdr.policy_channels) * C * 9)) return -1;
-    if (upload_conv_w(t.data(), hdr.policy_channels, C, 3, &pol_w2, &wrows)) return -1;
-    {
-        const int bn = conv_layer_choose_bn(batch, hdr.policy_channels);
-        if (conv_layer_init(&pol_conv2, d_p1, batch_cap, C, pol_w2, wrows, hdr.policy_channels, 3, nullptr, 0, nullptr, 0,
-                            nullptr, d_logits, ldp, bn))
-            return -1;
-    }
-    {
-        char tail;
-        if (fread(&tail, 1, 1, rd.f) != 0) return set_error("ara_net_create: trailing bytes in weight blob");
-    }
+    if (upload_value_head(hw)) return -1;
+    if (precision == 0 ? build_half(hw) : build_precise(hw)) return -1;
+    ARA_CUDA_OK(cudaFuncSetAttribute(value_head_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     value_head_smem<__half>()));
     ARA_CUDA_OK(cudaFuncSetAttribute(policy_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      n_labels() * 4));
     ARA_CUDA_OK(cudaFuncSetAttribute(nchw_f32_to_nhwc_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -319,49 +371,63 @@ int Net::init(const char* blob_path, int dev, int batch_size) {
     return 0;
 }
 
+int Net::enqueue_precise(int n, cudaStream_t s, bool from_f32, const int* cnt) {
+    const int C = hdr.channels;
+    if (from_f32) {
+        ARA_CUDA_OK(launch_pdl(nchw_f32_to_nhwc_split_kernel, dim3(n), dim3(256), hdr.in_channels * 65 * 4, s, d_in_f32, d_in_h,
+                               hdr.in_channels, cin_pad));
+        ++launches;
+    }
+    if (conv_layer_launch(&stem_conv, n, s, cnt)) return -1;
+    ++launches;
+    for (int i = 0; i < hdr.n_blocks; ++i) {
+        const BlockDesc& bd = blocks[i];
+        PreciseBlock& w = pb_[i];
+        const int in = i & 1;
+        if (bd.se_type != 0) {
+            ARA_CUDA_OK(launch_pdl(se_f32_kernel, dim3(n), dim3(256), 0, s, d_xf[in], d_xs[in], w.se_w1t, w.se_w2t, w.se_b, bd.se_type));
+            ++launches;
+        }
+        if (conv_layer_launch(&w.conv1, n, s)) return -1;
+        const long long total = static_cast<long long>(n) * 64 * bd.c_op;
+        const int grid = static_cast<int>((total + 255) / 256);
+        const int cp = round_up(bd.c_op, 64);
+        if (bd.kernel == 3)
+            ARA_CUDA_OK(launch_pdl(dwconv_f32_kernel<3>, dim3(grid), dim3(256), 0, s, d_h1f, w.wd, w.bd, d_h2s, n, bd.c_op, cp));
+        else
+            ARA_CUDA_OK(launch_pdl(dwconv_f32_kernel<5>, dim3(grid), dim3(256), 0, s, d_h1f, w.wd, w.bd, d_h2s, n, bd.c_op, cp));
+        if (conv_layer_launch(&w.conv2, n, s)) return -1;
+        launches += 3;
+    }
+    const float* xfinal = d_xf[hdr.n_blocks & 1];
+    ValueHeadW vw{vh_wv, vh_bv, vh_w1t, vh_b1, vh_w2, vh_b2, vh_wdl_w, vh_wdl_b, vh_plys_w, vh_plys_b, hdr.wdl_mode};
+    ARA_CUDA_OK(launch_pdl(value_head_kernel<float>, dim3(n), dim3(256), value_head_smem<float>(), s, xfinal, vw, d_value, d_aux, cnt));
+    if (conv_layer_launch(&pol_conv1, n, s, cnt)) return -1;
+    if (conv_layer_launch(&pol_conv2, n, s, cnt)) return -1;
+    ARA_CUDA_OK(launch_pdl(policy_softmax_kernel, dim3(n), dim3(256), n_labels() * 4, s, d_logits, d_prob, hdr.policy_channels, ldp, cnt));
+    launches += 4;
+    ARA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int Net::enqueue(int n, cudaStream_t s, bool from_f32, const int* cnt) {
+    if (precision == 1) return enqueue_precise(n, s, from_f32, cnt);
     if (from_f32) {
         ARA_CUDA_OK(launch_pdl(nchw_f32_to_nhwc_f16_kernel, dim3(n), dim3(256), hdr.in_channels * 65 * 4, s, d_in_f32, d_in_h, hdr.in_channels, cin_pad));
         ++launches;
     }
     if (conv_layer_launch(&stem_conv, n, s, cnt)) return -1;
-    ++launches;
-    if (use_trunk) {
-        if (rise_trunk_launch(&trunk_, n, s, cnt)) return -1;
-        ++launches;
-    }
-    for (int i = 0; i < hdr.n_blocks && !use_trunk; ++i) {
-        const BlockDesc& bd = blocks[i];
-        BlockW& w = bw_[i];
-        __half* xin = d_x[i & 1];
-        if (bd.se_type != 0) {
-            ARA_CUDA_OK(launch_pdl(se_kernel, dim3(n), dim3(256), 0, s, xin, w.se_w1t, w.se_w2t, w.se_b, bd.se_type));
-            ++launches;
-        }
-        if (use_fused) {
-            if (rise_block_launch(&w.fused, n, s)) return -1;
-            ++launches;
-            continue;
-        }
-        if (conv_layer_launch(&w.conv1, n, s)) return -1;
-        const long long total = static_cast<long long>(n) * 64 * (bd.c_op / 8);
-        const int grid = static_cast<int>((total + 255) / 256);
-        if (bd.kernel == 3)
-            ARA_CUDA_OK(launch_pdl(dwconv_kernel<3>, dim3(grid), dim3(256), 0, s, d_h1, w.wd, w.bd, d_h2, n, bd.c_op));
-        else
-            ARA_CUDA_OK(launch_pdl(dwconv_kernel<5>, dim3(grid), dim3(256), 0, s, d_h1, w.wd, w.bd, d_h2, n, bd.c_op));
-        if (conv_layer_launch(&w.conv2, n, s)) return -1;
-        launches += 3;
-    }
-    __half* xfinal = d_x[hdr.n_blocks & 1];
+    if (rise_trunk_launch(&trunk_, n, s, cnt)) return -1;
+    launches += 2;
+    __half* xfinal = d_x[1];
     ValueHeadW vw{vh_wv, vh_bv, vh_w1t, vh_b1, vh_w2, vh_b2, vh_wdl_w, vh_wdl_b, vh_plys_w, vh_plys_b, hdr.wdl_mode};
     if (fork_heads) {  // value head on the side stream (a second branch of the captured graph), policy head on s
         ARA_CUDA_OK(cudaEventRecord(ev_fork, s));
         ARA_CUDA_OK(cudaStreamWaitEvent(head_stream, ev_fork, 0));
-        value_head_kernel<<<dim3(n), dim3(256), 0, head_stream>>>(xfinal, vw, d_value, d_aux, cnt);
+        value_head_kernel<__half><<<dim3(n), dim3(256), value_head_smem<__half>(), head_stream>>>(xfinal, vw, d_value, d_aux, cnt);
         ARA_CUDA_OK(cudaEventRecord(ev_join, head_stream));
     } else {
-        ARA_CUDA_OK(launch_pdl(value_head_kernel, dim3(n), dim3(256), 0, s, xfinal, vw, d_value, d_aux, cnt));
+        ARA_CUDA_OK(launch_pdl(value_head_kernel<__half>, dim3(n), dim3(256), value_head_smem<__half>(), s, xfinal, vw, d_value, d_aux, cnt));
     }
     if (conv_layer_launch(&pol_conv1, n, s, cnt)) return -1;
     if (conv_layer_launch(&pol_conv2, n, s, cnt)) return -1;
@@ -436,7 +502,7 @@ int Net::forward_from_f32_device(int n, cudaStream_t s) {
 }
 
 int Net::trunk_cycles(unsigned long long* out32) {
-    if (!use_trunk || trunk_.d_prof == nullptr) return set_error("trunk kernel not in use");
+    if (precision != 0 || trunk_.d_prof == nullptr) return set_error("trunk kernel not in use");
     ARA_CUDA_OK(cudaSetDevice(device));
     ARA_CUDA_OK(cudaStreamSynchronize(stream));
     ARA_CUDA_OK(cudaMemcpy(out32, trunk_.d_prof, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
@@ -446,10 +512,10 @@ int Net::trunk_cycles(unsigned long long* out32) {
 int Net::kernels_per_forward(bool from_f32) const {
     int k = from_f32 ? 1 : 0;
     k += 1;  // stem
-    if (use_trunk)
-        k += 1;
+    if (precision == 0)
+        k += 1;  // the tower kernel
     else
-        for (const auto& b : blocks) k += (use_fused ? 1 : 3) + (b.se_type != 0 ? 1 : 0);
+        for (const auto& b : blocks) k += 3 + (b.se_type != 0 ? 1 : 0);
     k += 4;  // value head, policy conv x2, softmax
     return k;
 }
@@ -476,9 +542,9 @@ int Net::predict(const float* planes_host, int n, float* value_host, float* prob
 // ------------------------------------------------------------------------------------------- C-ABI
 using ara::Net;
 
-extern "C" ara_net_t ara_net_create(const char* weights_path, int device, int batch_size) {
+extern "C" ara_net_t ara_net_create(const char* weights_path, int device, int batch_size, int precision) {
     std::unique_ptr<Net> net(new Net());
-    if (net->init(weights_path, device, batch_size) != 0) return nullptr;
+    if (net->init(weights_path, device, batch_size, precision) != 0) return nullptr;
     return reinterpret_cast<ara_net_t>(net.release());
 }
 

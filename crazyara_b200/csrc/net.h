@@ -7,7 +7,6 @@
 #include <vector>
 
 #include "conv_gemm_host.h"
-#include "rise_block_host.h"
 #include "rise_trunk_host.h"
 
 namespace ara {
@@ -29,24 +28,33 @@ struct NetHeader {
     int input_version;   // e.g. 10 = v1.0, 30 = v3.0
 };
 
-struct BlockW {
+// Precision float32: one bottleneck block as separate launches on fp32 activations (net.cu, conv_gemm.cuh)
+struct PreciseBlock {
     float *se_w1t = nullptr, *se_w2t = nullptr, *se_b = nullptr;
-    __half* w1 = nullptr;
-    float* b1 = nullptr;
-    float* wd = nullptr;
-    float* bd = nullptr;
-    __half* w2 = nullptr;
-    float* b2 = nullptr;
+    __half *w1 = nullptr, *w2 = nullptr;  // operand-split weights [rows][3 * cw] per tap: hi | lo | hi
+    float *b1 = nullptr, *wd = nullptr, *bd = nullptr, *b2 = nullptr;
     ConvLayer conv1, conv2;
-    float* wd_pad = nullptr;  // [k*k][ceil64(c_op)] for the fused block kernel
-    RiseBlockLayer fused;
+};
+
+// the tensors of a weight blob, host side, in blob order (weights.py)
+struct HostBlock {
+    std::vector<float> se_a, se_b;  // ca_se: fc1 [128][256], fc2 [256][128]; eca_se: centre tap [256][256], bias [256]
+    std::vector<float> w1, b1, wd, bd, w2, b2;
+};
+struct HostWeights {
+    std::vector<float> stem_w, stem_b;
+    std::vector<HostBlock> blocks;
+    std::vector<float> vh_wv, vh_bv, vh_a, vh_ab, vh_b, vh_bb;  // standard: fc1 / b1 / fc2 / b2; WDL: wdl w / b, plys w / b
+    std::vector<float> pol_w1, pol_b1, pol_w2;
 };
 
 class Net {
    public:
     Net() = default;
     ~Net();
-    int init(const char* blob_path, int device, int batch);
+    // precision: 0 = float16 operands / fp32 accumulate (the reference's default `Precision float16`,
+    // uci/optionsuci.cpp:144), 1 = float32 (fp16 hi + lo operand splitting, fp32 activations between the layers)
+    int init(const char* blob_path, int device, int batch, int precision);
     // host-buffer API (reference NeuralNetAPI::predict semantics, synchronous)
     int predict(const float* planes_host, int n, float* value_host, float* prob_host, float* aux_host);
     // device-resident API: input already in in_h (NHWC fp16), outputs stay in d_value / d_prob
@@ -58,6 +66,7 @@ class Net {
     NetHeader hdr{};
     std::vector<BlockDesc> blocks;
     int device = 0;
+    int precision = 0;
     int batch = 0;      // max boards per call
     int batch_cap = 0;  // even, >= 2
     int cin_pad = 0;
@@ -74,27 +83,34 @@ class Net {
 
     // device buffers
     float* d_in_f32 = nullptr;   // [batch, C, 64]
-    __half* d_in_h = nullptr;    // [batch_cap, 64, cin_pad]
-    __half* d_x[2] = {nullptr, nullptr};  // trunk ping-pong [batch_cap*64, 256]
-    __half* d_h1 = nullptr;      // [batch_cap*64, max_cop]
-    __half* d_h2 = nullptr;
-    __half* d_p1 = nullptr;      // [batch_cap*64, 256]
+    __half* d_in_h = nullptr;    // [batch_cap, 64, cin_pad] (float32: [batch_cap, 64, 3 * cin_pad] split)
+    __half* d_x[2] = {nullptr, nullptr};  // float16: stem output / tower output [batch_cap*64, 256]
+    __half* d_p1 = nullptr;      // [batch_cap*64, 256] (float32: [.., 768] split)
     float* d_logits = nullptr;   // [batch_cap*64, ldp]
     float* d_prob = nullptr;     // [batch, L]
     float* d_value = nullptr;    // [batch]
     float* d_aux = nullptr;      // [batch, 4]
+    // float32 only: trunk ping-pong in fp32 + split copies, bottleneck intermediates
+    float* d_xf[2] = {nullptr, nullptr};  // [batch_cap*64, 256]
+    __half* d_xs[2] = {nullptr, nullptr};  // [batch_cap*64, 768]
+    float* d_h1f = nullptr;                // [batch_cap*64, max_cop]
+    __half* d_h2s = nullptr;               // [batch_cap*64, 3 * ceil64(max_cop)]
     long long launches = 0;      // kernels launched so far (bench bookkeeping)
     bool use_graph = true;
-    bool use_fused = false;  // ARA_FUSED_BLOCKS=1: one kernel per bottleneck block (rise_block.cuh)
-    bool use_trunk = true;   // the whole residual tower as one persistent kernel (rise_trunk.cuh); ARA_TRUNK=0 disables
 
    private:
     int enqueue(int n, cudaStream_t s, bool from_f32, const int* boards_dev = nullptr);
+    int read_blob(const char* blob_path, HostWeights* hw);
+    int build_half(const HostWeights& hw);
+    int build_precise(const HostWeights& hw);
+    int upload_value_head(const HostWeights& hw);
+    int enqueue_precise(int n, cudaStream_t s, bool from_f32, const int* boards_dev);
     std::vector<void*> allocs_;
+    int max_cop_ = 0;
     __half* stem_w = nullptr;
     float* stem_b = nullptr;
     ConvLayer stem_conv;
-    std::vector<BlockW> bw_;
+    std::vector<PreciseBlock> pb_;
     RiseTrunk trunk_;
     float *vh_wv = nullptr, *vh_bv = nullptr, *vh_w1t = nullptr, *vh_b1 = nullptr, *vh_w2 = nullptr, *vh_b2 = nullptr;
     float *vh_wdl_w = nullptr, *vh_wdl_b = nullptr, *vh_plys_w = nullptr, *vh_plys_b = nullptr;
@@ -106,6 +122,7 @@ class Net {
     template <typename T>
     int dalloc(T** p, size_t count);
     int upload_conv_w(const float* w, int n_out, int cin, int ksize, __half** dst, int* rows);
+    int upload_conv_w_split(const float* w, int n_out, int cin, int ksize, __half** dst, int* rows);
     int upload_f32(const float* src, size_t count, size_t padded, float** dst);
 };
 

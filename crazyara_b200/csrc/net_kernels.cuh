@@ -1,5 +1,6 @@
-// CUDA-core kernels of the RISE forward pass that surround the tcgen05 GEMMs: layout conversion, depthwise
-// convolution, squeeze-excitation, value head, policy softmax.  All activations are NHWC fp16 ([board*64+sq, C]).
+// CUDA-core kernels of the RISE forward pass that surround the tcgen05 GEMMs: layout conversion, value head, policy
+// softmax; for Precision float32 also depthwise convolution and squeeze-excitation (in Precision float16 those live
+// inside the persistent tower kernel, rise_trunk.cuh).  Activations are NHWC ([board*64+sq, C]).
 // Reference semantics: DeepCrazyhouse/src/domain/neural_net/architectures/pytorch/builder_util.py
 //   _ChannelAttentionModule :83-114, _EfficientChannelAttentionModule :49-80, _ValueHead :246-326,
 //   _BottlekneckResidualBlock :437-475 (depthwise conv + BN + ReLU), softmax appended by the backend
@@ -33,31 +34,53 @@ __global__ void nchw_f32_to_nhwc_f16_kernel(const float* __restrict__ in, __half
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Depthwise KxK convolution (pad K/2) + bias + ReLU.  in/out: [boards*64, C] fp16, w: [K*K][C] fp32 (BN folded),
-// bias: [C] fp32.  One thread = 8 consecutive channels of one square (16-byte vector loads/stores).
-template <int K>
-__global__ void dwconv_kernel(const __half* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
-                              __half* __restrict__ out, int boards, int C) {
+// =============================================================================================
+// Precision float32 (the reference's `Precision float32`): fp32 activations between the layers; every tensor that feeds
+// a tcgen05 GEMM is ALSO stored split as fp16 [hi | hi | lo] with the channel pitch cs (conv_gemm.cuh).  The CUDA-core
+// stages below read / write fp32.
+__device__ __forceinline__ void store_split(__half* row3, int cs, int c, float v) {
+    const __half hi = __float2half_rn(v);
+    row3[c] = hi;
+    row3[cs + c] = hi;
+    row3[2 * cs + c] = __float2half_rn(v - __half2float(hi));
+}
+
+// [n, C, 64] fp32 planes -> [n, 64, 3 * cpad] fp16 split (zero padded channels).  One CTA per board.
+__global__ void nchw_f32_to_nhwc_split_kernel(const float* __restrict__ in, __half* __restrict__ out, int C, int cpad) {
+    extern __shared__ float s_planes[];  // [C][65]
     pdl_wait();
     pdl_launch_dependents();
-    const int vec_per_row = C >> 3;
-    const long long total = static_cast<long long>(boards) * 64 * vec_per_row;
+    const int b = blockIdx.x;
+    const float* src = in + static_cast<size_t>(b) * C * 64;
+    for (int i = threadIdx.x; i < C * 64; i += blockDim.x) {
+        const int c = i >> 6, sq = i & 63;
+        s_planes[c * 65 + sq] = src[i];
+    }
+    __syncthreads();
+    __half* dst = out + static_cast<size_t>(b) * 64 * 3 * cpad;
+    for (int i = threadIdx.x; i < 64 * cpad; i += blockDim.x) {
+        const int sq = i / cpad, c = i - sq * cpad;
+        store_split(dst + static_cast<size_t>(sq) * 3 * cpad, cpad, c, c < C ? s_planes[c * 65 + sq] : 0.0f);
+    }
+}
+
+// Depthwise KxK convolution (pad K/2) + bias + ReLU (builder_util.py:437-475, BN folded).  in: [boards*64, C] fp32,
+// w: [K*K][C] fp32, bias: [C] fp32, out: split [boards*64, 3*cs] (channels C..cs-1 stay zero).  One thread = one
+// channel of one square, channel fastest.
+template <int K>
+__global__ void dwconv_f32_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                                  __half* __restrict__ out, int boards, int C, int cs) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const long long total = static_cast<long long>(boards) * 64 * C;
     const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (idx >= total) return;
-    const int cv = static_cast<int>(idx % vec_per_row);
-    const long long row = idx / vec_per_row;
+    const int c = static_cast<int>(idx % C);
+    const long long row = idx / C;
     const int sq = static_cast<int>(row & 63);
     const long long b = row >> 6;
     const int y = sq >> 3, x = sq & 7;
-    const int c0 = cv << 3;
-    float acc[8];
-    {
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c0));
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4));
-        acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w;
-        acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
-    }
+    float acc = __ldg(bias + c);
     constexpr int R = K / 2;
 #pragma unroll
     for (int dy = -R; dy <= R; ++dy) {
@@ -67,45 +90,32 @@ __global__ void dwconv_kernel(const __half* __restrict__ in, const float* __rest
         for (int dx = -R; dx <= R; ++dx) {
             const int xx = x + dx;
             if (xx < 0 || xx > 7) continue;
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + ((b << 6) + yy * 8 + xx) * C + c0));
-            const float* wp = w + ((dy + R) * K + (dx + R)) * C + c0;
-            const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp));
-            const float4 w1 = __ldg(reinterpret_cast<const float4*>(wp + 4));
-            const __half2* h = reinterpret_cast<const __half2*>(&v);
-            const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]), f2 = __half22float2(h[2]),
-                         f3 = __half22float2(h[3]);
-            acc[0] = fmaf(f0.x, w0.x, acc[0]); acc[1] = fmaf(f0.y, w0.y, acc[1]);
-            acc[2] = fmaf(f1.x, w0.z, acc[2]); acc[3] = fmaf(f1.y, w0.w, acc[3]);
-            acc[4] = fmaf(f2.x, w1.x, acc[4]); acc[5] = fmaf(f2.y, w1.y, acc[5]);
-            acc[6] = fmaf(f3.x, w1.z, acc[6]); acc[7] = fmaf(f3.y, w1.w, acc[7]);
+            acc = fmaf(__ldg(in + ((b << 6) + yy * 8 + xx) * C + c), __ldg(w + ((dy + R) * K + (dx + R)) * C + c), acc);
         }
     }
-    uint4 o;
-    __half2* oh = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) oh[q] = __floats2half2_rn(fmaxf(acc[2 * q], 0.0f), fmaxf(acc[2 * q + 1], 0.0f));
-    *reinterpret_cast<uint4*>(out + row * C + c0) = o;
+    store_split(out + row * 3 * cs, cs, c, fmaxf(acc, 0.0f));
 }
 
-// ---------------------------------------------------------------------------------------------
-// Squeeze-excitation on the 256-channel trunk, in place.  One CTA (256 threads) per board.
+// Squeeze-excitation on the 256-channel trunk (builder_util.py:49-114), fp32 in place + the split copy.  One CTA (256
+// threads) per board.
 //   mode 1 ("ca_se"):  s = hardsigmoid(W2 * relu(W1 * mean))        W1t: [256][128], W2t: [128][256] (transposed)
 //   mode 2 ("eca_se"): s = hardsigmoid(Wc * mean + bc)              W1t: [256][256] centre tap transposed, b: [256]
 __device__ __forceinline__ float hard_sigmoid(float x) { return fminf(fmaxf(x * (1.0f / 6.0f) + 0.5f, 0.0f), 1.0f); }
 
-__global__ void __launch_bounds__(256) se_kernel(__half* __restrict__ x, const float* __restrict__ w1t,
-                                                   const float* __restrict__ w2t, const float* __restrict__ bias,
-                                                   int mode) {
+__global__ void __launch_bounds__(256) se_f32_kernel(float* __restrict__ x, __half* __restrict__ xs,
+                                                       const float* __restrict__ w1t, const float* __restrict__ w2t,
+                                                       const float* __restrict__ bias, int mode) {
     __shared__ float s_pool[256];
     __shared__ float s_hid[128];
     pdl_wait();
     pdl_launch_dependents();
     const int b = blockIdx.x;
     const int c = threadIdx.x;
-    __half* xb = x + static_cast<size_t>(b) * 64 * 256;
+    float* xb = x + static_cast<size_t>(b) * 64 * 256;
+    __half* sb = xs + static_cast<size_t>(b) * 64 * 768;
     float sum = 0.0f;
 #pragma unroll 8
-    for (int sq = 0; sq < 64; ++sq) sum += __half2float(xb[sq * 256 + c]);
+    for (int sq = 0; sq < 64; ++sq) sum += xb[sq * 256 + c];
     s_pool[c] = sum * (1.0f / 64.0f);
     __syncthreads();
     float scale;
@@ -126,8 +136,9 @@ __global__ void __launch_bounds__(256) se_kernel(__half* __restrict__ x, const f
     }
 #pragma unroll 8
     for (int sq = 0; sq < 64; ++sq) {
-        const float v = __half2float(xb[sq * 256 + c]) * scale;
-        xb[sq * 256 + c] = __float2half_rn(v);
+        const float v = xb[sq * 256 + c] * scale;
+        xb[sq * 256 + c] = v;
+        store_split(sb + sq * 768, 256, c, v);
     }
 }
 
@@ -151,11 +162,17 @@ struct ValueHeadW {
     int wdl_mode;
 };
 
-__global__ void __launch_bounds__(256) value_head_kernel(const __half* __restrict__ x, ValueHeadW w,
+__device__ __forceinline__ float act_to_float(__half v) { return __half2float(v); }
+__device__ __forceinline__ float act_to_float(float v) { return v; }
+
+template <typename T>  // T = __half (Precision float16) or float (Precision float32)
+__global__ void __launch_bounds__(256) value_head_kernel(const T* __restrict__ x, ValueHeadW w,
                                                            float* __restrict__ value, float* __restrict__ aux,
                                                            const int* __restrict__ boards_dev) {
     if (boards_dev != nullptr && static_cast<int>(blockIdx.x) >= *boards_dev) return;  // row without input
-    __shared__ __half s_x[64 * 264];  // padded rows
+    constexpr int kPitch = 256 + 16 / static_cast<int>(sizeof(T));  // padded rows
+    extern __shared__ __align__(16) uint8_t s_x_raw[];
+    T* s_x = reinterpret_cast<T*>(s_x_raw);
     __shared__ float s_wv[8 * 256];
     __shared__ float s_f[512];
     __shared__ float s_red[8];
@@ -163,20 +180,22 @@ __global__ void __launch_bounds__(256) value_head_kernel(const __half* __restric
     pdl_launch_dependents();
     const int b = blockIdx.x;
     const int t = threadIdx.x;
-    const __half* xb = x + static_cast<size_t>(b) * 64 * 256;
-    for (int i = t; i < 64 * 32; i += 256) {  // 32 x uint4 per row
-        const int sq = i >> 5, v = i & 31;
-        *reinterpret_cast<uint4*>(&s_x[sq * 264 + v * 8]) = __ldg(reinterpret_cast<const uint4*>(xb + sq * 256 + v * 8));
+    const T* xb = x + static_cast<size_t>(b) * 64 * 256;
+    constexpr int kVec = 16 / static_cast<int>(sizeof(T));  // elements per 16-byte vector
+    constexpr int kVecRow = 256 / kVec;
+    for (int i = t; i < 64 * kVecRow; i += 256) {
+        const int sq = i / kVecRow, v = i - sq * kVecRow;
+        *reinterpret_cast<uint4*>(&s_x[sq * kPitch + v * kVec]) = __ldg(reinterpret_cast<const uint4*>(xb + sq * 256 + v * kVec));
     }
     for (int i = t; i < 8 * 256; i += 256) s_wv[i] = __ldg(w.wv + i);
     __syncthreads();
     for (int o = t; o < 512; o += 256) {
         const int j = o >> 6, sq = o & 63;
         float acc = __ldg(w.bv + j);
-        const __half* xr = &s_x[sq * 264];
+        const T* xr = &s_x[sq * kPitch];
         const float* wr = &s_wv[j * 256];
 #pragma unroll 8
-        for (int c = 0; c < 256; ++c) acc = fmaf(__half2float(xr[c]), wr[c], acc);
+        for (int c = 0; c < 256; ++c) acc = fmaf(act_to_float(xr[c]), wr[c], acc);
         s_f[o] = fmaxf(acc, 0.0f);
     }
     __syncthreads();
@@ -229,6 +248,9 @@ __global__ void __launch_bounds__(256) value_head_kernel(const __half* __restric
         }
     }
 }
+
+template <typename T>
+constexpr int value_head_smem() { return 64 * (256 + 16 / static_cast<int>(sizeof(T))) * static_cast<int>(sizeof(T)); }
 
 // ---------------------------------------------------------------------------------------------
 // Policy softmax over all P*64 logits of a board (illegal moves included, as the reference backend does).

@@ -234,6 +234,32 @@ __device__ __forceinline__ void encode_planes_nhwc_f16(const Board& b, int mode,
         }
     }
 }
+// Precision float32: the same rows with every channel as the fp16 pair hi | hi | lo (conv_gemm.cuh), [64, 3 * cpad]
+__device__ __forceinline__ void encode_planes_nhwc_split(const Board& b, int mode, int version, __half* out, int cpad) {
+    const PlaneCtx p = make_plane_ctx(b, mode, true);
+    LaneCaptureSink sink;
+    sink.lane = threadIdx.x & 31;
+    for_each_plane(p, version, sink);
+    const int lane = sink.lane;
+    const __half z = __float2half_rn(0.0f);
+    const __half h0 = __float2half_rn(sink.v0), h1 = __float2half_rn(sink.v1), h2 = __float2half_rn(sink.v2);
+    const __half l0 = __float2half_rn(sink.v0 - __half2float(h0)), l1 = __float2half_rn(sink.v1 - __half2float(h1)),
+                 l2 = __float2half_rn(sink.v2 - __half2float(h2));
+#pragma unroll 2
+    for (int sq = 0; sq < 64; ++sq) {
+        __half* row = out + sq * 3 * cpad;
+        const bool b0 = (sink.m0 >> sq) & 1, b1 = (sink.m1 >> sq) & 1, b2 = (sink.m2 >> sq) & 1;
+        row[lane] = row[cpad + lane] = b0 ? h0 : z;
+        row[2 * cpad + lane] = b0 ? l0 : z;
+        row[lane + 32] = row[cpad + lane + 32] = b1 ? h1 : z;
+        row[2 * cpad + lane + 32] = b1 ? l1 : z;
+        if (cpad > 64) {
+            row[lane + 64] = row[cpad + lane + 64] = b2 ? h2 : z;
+            row[2 * cpad + lane + 64] = b2 ? l2 : z;
+            row[lane + 96] = row[cpad + lane + 96] = row[2 * cpad + lane + 96] = z;
+        }
+    }
+}
 #endif
 
 }  // namespace ara

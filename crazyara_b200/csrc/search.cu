@@ -26,16 +26,23 @@ namespace ara {
 struct DevWriterFactory {
     __half* base;
     int cpad;
+    int split;  // Precision float32: rows of 3 * cpad halves, every channel as hi | hi | lo (conv_gemm.cuh)
     struct Target {
         __half* out;
         int cpad;
+        int split;
         ARA_HD void encode(const Board& b, int mode, int version) const {
 #if defined(__CUDA_ARCH__)
-            encode_planes_nhwc_f16(b, mode, version, out, cpad);
+            if (split)
+                encode_planes_nhwc_split(b, mode, version, out, cpad);
+            else
+                encode_planes_nhwc_f16(b, mode, version, out, cpad);
 #endif
         }
     };
-    ARA_HD Target make(int slot) const { return Target{base + static_cast<size_t>(slot) * 64 * cpad, cpad}; }
+    ARA_HD Target make(int slot) const {
+        return Target{base + static_cast<size_t>(slot) * 64 * cpad * (split ? 3 : 1), cpad, split};
+    }
 };
 struct NullWriterFactory {  // fake backend: no planes needed
     struct Target {
@@ -86,14 +93,15 @@ __global__ void __launch_bounds__(32) pack_kernel(TreeDev* trees, int n_trees, i
 }
 
 // one warp per (tree, new leaf): move lists, edges, policy indices, input planes of all new leaves in parallel
-__global__ void __launch_bounds__(32) expand_kernel(const TreeDev* trees, SearchParams sp, int batch, __half* in_h, int cpad) {
+__global__ void __launch_bounds__(32) expand_kernel(const TreeDev* trees, SearchParams sp, int batch, __half* in_h, int cpad,
+                                                    int split) {
     __shared__ WarpScratch ws;
     const int tree = blockIdx.x / batch, b = blockIdx.x - tree * batch;
     const TreeDev t = trees[tree];
     if (b >= t.st->n_new || t.st->error) return;
     const int nid = t.new_node[b];
     if (in_h != nullptr) {
-        const DevWriterFactory wf{in_h, cpad};
+        const DevWriterFactory wf{in_h, cpad, split};
         const auto target = wf.make(t.slot_base + b);
         expand_pending(t, sp, ws, nid, &target);
     } else {
@@ -418,7 +426,7 @@ int Search::enqueue_iteration(bool with_events) {
     if (with_events) prof_event();
     select_kernel<<<n_trees, 32, 0, stream_>>>(d_trees_, sp);
     if (n_trees > 1) pack_kernel<<<1, 32, 0, stream_>>>(d_trees_, n_trees, d_count_);
-    expand_kernel<<<n_trees * B, 32, 0, stream_>>>(d_trees_, sp, B, in_h, cpad);
+    expand_kernel<<<n_trees * B, 32, 0, stream_>>>(d_trees_, sp, B, in_h, cpad, net_ ? net_->precision : 0);
     if (with_events) prof_event();
     if (net_) {
         if (net_->forward_device(n_trees * B, stream_, n_trees > 1 ? d_count_ : nullptr)) return -1;
@@ -491,7 +499,7 @@ int Search::go() {
         pack_kernel<<<1, 32, 0, stream_>>>(d_trees_, n_trees, d_count_);
         ++launches;
     }
-    expand_kernel<<<n_trees * B, 32, 0, stream_>>>(d_trees_, sp, B, in_h, cpad);
+    expand_kernel<<<n_trees * B, 32, 0, stream_>>>(d_trees_, sp, B, in_h, cpad, net_ ? net_->precision : 0);
     if (net_) {
         // a single-tree search only needs row 0; the new roots of a multi-tree search are packed into the first rows
         if (net_->forward_device(n_trees == 1 ? 1 : n_trees * B, stream_, n_trees > 1 ? d_count_ : nullptr)) return -1;

@@ -21,10 +21,14 @@ using Action = unsigned short;
 
 class NeuralNetAPI {
    public:
-    NeuralNetAPI(const std::string& ctx, int deviceID, unsigned int batchSize, const std::string& modelFile)
+    // precision: the UCI option `Precision` (uci/optionsuci.cpp:144): "float16" (default) or "float32"
+    NeuralNetAPI(const std::string& ctx, int deviceID, unsigned int batchSize, const std::string& modelFile,
+                 const std::string& precision = "float16")
         : deviceID_(deviceID), batchSize_(batchSize) {
         if (ctx != "gpu") throw std::invalid_argument("crazyara_b200 has no CPU context");
-        net_ = ara_net_create(modelFile.c_str(), deviceID, static_cast<int>(batchSize));
+        if (precision != "float16" && precision != "float32") throw std::invalid_argument("Precision must be float16 or float32");
+        net_ = ara_net_create(modelFile.c_str(), deviceID, static_cast<int>(batchSize),
+                              precision == "float32" ? ARA_PRECISION_FLOAT32 : ARA_PRECISION_FLOAT16);
         if (net_ == nullptr) throw std::invalid_argument(ara_last_error());
         int b = 0;
         ara_net_shape(net_, &nbInputChannels_, &nbPolicyValues_, &nbAux_, &isPolicyMap_, &version_, &b);

@@ -32,7 +32,8 @@ struct Options {
                                              {"Virtual_Mix_Threshold", "1000"}, {"First_Device_ID", "0"},
                                              {"UCI_Chess960", "false"},     {"Input_Version", "0"},    {"Dirichlet_Seed", "42"},
                                              {"Move_Overhead", "20"},       {"Timed_Search_Nodes", "1000000"},
-                                             {"Reuse_Tree", "true"},           {"Use_NPS_Time_Manager", "true"}};
+                                             {"Reuse_Tree", "true"},           {"Use_NPS_Time_Manager", "true"},
+                                             {"Precision", "float16"}};
     int i(const std::string& k) const { return std::stoi(kv.at(k)); }
     bool b(const std::string& k) const { return kv.at(k) == "true"; }
 };
@@ -96,7 +97,8 @@ int main() {
         agent.reset();
         net.reset();
         if (!opt.kv["Model_Path"].empty())
-            net.reset(new NeuralNetAPI("gpu", opt.i("First_Device_ID"), static_cast<unsigned>(s.batch_size), opt.kv["Model_Path"]));
+            net.reset(new NeuralNetAPI("gpu", opt.i("First_Device_ID"), static_cast<unsigned>(s.batch_size), opt.kv["Model_Path"],
+                                       opt.kv["Precision"]));
         // a time-limited search has no visit budget to size the node pool from
         // a kept subtree lives in the same pools as the next search: room for a few searches before a fresh tree
         const long budget = s.simulations ? s.simulations : s.nodes;

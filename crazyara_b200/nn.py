@@ -16,12 +16,13 @@ def _fptr(a):
 
 
 class NeuralNetAPI:
-    def __init__(self, ctx="gpu", deviceID=0, batchSize=8, modelDirectory="", enableTensorrt=True):
+    def __init__(self, ctx="gpu", deviceID=0, batchSize=8, modelDirectory="", enableTensorrt=True, precision="float16"):
+        """precision: the reference's UCI option `Precision` (uci/optionsuci.cpp:144): "float16" (default) or "float32"."""
         if ctx != "gpu":
             raise AraError("crazyara_b200 has no CPU context (ctx must be 'gpu')")
         L = lib()
         L.ara_net_create.restype = ctypes.c_void_p
-        L.ara_net_create.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int]
+        L.ara_net_create.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
         L.ara_net_destroy.argtypes = [ctypes.c_void_p]
         L.ara_net_shape.argtypes = [ctypes.c_void_p] + [ctypes.POINTER(ctypes.c_int)] * 6
         L.ara_net_predict.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.c_int,
@@ -31,7 +32,10 @@ class NeuralNetAPI:
                                              ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p)]
         L.ara_net_launch_count.restype = ctypes.c_longlong
         L.ara_net_launch_count.argtypes = [ctypes.c_void_p]
-        self._h = L.ara_net_create(modelDirectory.encode(), deviceID, batchSize)
+        if precision not in ("float16", "float32"):
+            raise AraError(f"Precision must be float16 or float32, not {precision!r}")
+        self.precision = precision
+        self._h = L.ara_net_create(modelDirectory.encode(), deviceID, batchSize, 1 if precision == "float32" else 0)
         if not self._h:
             raise AraError(L.ara_last_error().decode())
         v = [ctypes.c_int() for _ in range(6)]

@@ -21,7 +21,12 @@ const char* ara_last_error(void);
  *
  * ara_net_create  <-> TensorrtAPI::TensorrtAPI + NeuralNetAPI::initialize (nn/tensorrtapi.cpp:43-63,
  *                     nn/neuralnetapi.cpp:93-99): loads an ARAB2001 weight blob (crazyara_b200/weights.py), binds
- *                     device buffers and one CUDA stream on `device`, fixed maximum batch size.
+ *                     device buffers and one CUDA stream on `device`, fixed maximum batch size.  `precision` is the
+ *                     reference's UCI option `Precision` (uci/optionsuci.cpp:144, nn/tensorrtapi.cpp:334-360):
+ *                     ARA_PRECISION_FLOAT16 (its default) = fp16 tensor-core operands, fp32 accumulation, fp16
+ *                     activations; ARA_PRECISION_FLOAT32 = fp32-accurate: the same tcgen05 GEMMs with every operand
+ *                     carried as an fp16 hi + lo pair (3x the K extent), fp32 activations between the layers --
+ *                     value / probabilities within 1e-4 of an fp32 evaluation (tests/test_net_gpu.py).
  * ara_net_shape   <-> get_nb_input_values_total / get_nb_policy_values / get_nb_auxiliary_outputs /
  *                     is_policy_map / get_version / get_batch_size (nn/neuralnetapi.h:116-293).
  * ara_net_predict <-> NeuralNetAPI::predict(float* inputPlanes, float* valueOutput, float* probOutputs,
@@ -30,7 +35,9 @@ const char* ara_last_error(void);
  *                     order channel*64+square), aux [n, A].  Synchronous.  n <= batch_size rows are evaluated
  *                     (the reference always runs the full batch; n < B just skips the unused rows).
  */
-ara_net_t ara_net_create(const char* weights_path, int device, int batch_size);
+#define ARA_PRECISION_FLOAT16 0
+#define ARA_PRECISION_FLOAT32 1
+ara_net_t ara_net_create(const char* weights_path, int device, int batch_size, int precision);
 void ara_net_destroy(ara_net_t net);
 int ara_net_shape(ara_net_t net, int* in_channels, int* n_labels, int* n_aux, int* is_policy_map, int* input_version,
                   int* batch_size);

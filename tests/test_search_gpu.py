@@ -64,13 +64,13 @@ def test_gpu_multi_tree_search_matches_single_tree():
         assert_same_search(ro, r)
 
 
-def _make_net(tmp_path, arch, batch, version):
+def _make_net(tmp_path, arch, batch, version, precision="float16"):
     from crazyara_b200.nn import NeuralNetAPI
     from crazyara_b200.weights import export_blob
     from oracle import net as onet
     sd = onet.make_state_dict(arch, 0)
     blob = export_blob(sd, arch, str(tmp_path / f"{arch['name']}.arab"), input_version=version)
-    return NeuralNetAPI("gpu", 0, batch, blob)
+    return NeuralNetAPI("gpu", 0, batch, blob, precision=precision)
 
 
 def _net_fn(net):
@@ -115,6 +115,44 @@ def test_gpu_search_real_net_equals_oracle_driven_by_same_net(tmp_path, variant,
     rg2 = _gpu_search(vid, None, False, premoves, st2, net=net)[0]
     assert_same_search(ro2, rg2)
     net.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant,vid,mode,arch_name,cin,pch,version,batch,sims",
+                         [("crazyhouse", 1, "crazyhouse", "risev2", 34, 81, 1, 8, 400),
+                          ("chess", 0, "chess", "risev33", 52, 76, 3, 16, 600)])
+def test_gpu_search_float32_net_against_oracle_search_with_the_fp32_oracle_network(tmp_path, variant, vid, mode, arch_name,
+                                                                                    cin, pch, version, batch, sims):
+    """End to end against the reference chain: the ORACLE search driven by the ORACLE's fp32 torch network (oracle/net.py,
+    pinned to the reference's module) vs the GPU search with the Precision float32 GPU network.  Network outputs agree
+    to ~1e-6, not to the bit, so a visit can land on a neighbouring move where two PUCT scores are that close; the
+    contract is north_star's: root value, root priors, Q and the posterior within 1e-4, the same best move, and visit
+    counts that differ by a handful at most."""
+    from oracle import net as onet
+    arch = onet.arch_risev2(cin, pch) if arch_name == "risev2" else onet.arch_risev33(cin, pch, True)
+    sd = onet.make_state_dict(arch, 0)
+    net = _make_net(tmp_path, arch, batch, version * 10, precision="float32")
+    st = osr.default_settings(mode, batch_size=batch, simulations=sims, input_version=version)
+
+    def oracle_net(planes):
+        r = onet.forward(sd, arch, planes)
+        return r["value"], r["prob"]
+    pos = Position(variant=variant)
+    ro = osr.Search(st).run(pos, oracle_net)
+    rg = _gpu_search(vid, None, False, [], st, net=net)[0]
+    net.close()
+    assert rg["error"] == 0 and ro["moves"][ro["best_idx"]] == rg["moves"][rg["best_idx"]]
+    og = {m: i for i, m in enumerate(rg["moves"])}
+    perm = [og[m] for m in ro["moves"]]     # near-equal priors may swap two neighbours in the sorted order
+    np.testing.assert_allclose(rg["prior"][perm], ro["prior"], atol=1e-4, rtol=0)
+    assert abs(ro["root_value"] - rg["root_value"]) < 1e-4
+    assert ro["visit_sum"] == rg["visit_sum"]
+    dv = np.abs(ro["visits"].astype(np.int64) - rg["visits"][perm].astype(np.int64))
+    assert dv.sum() <= max(4, ro["visit_sum"] // 100), dv
+    same = dv == 0                          # Q / posterior of the moves whose visit counts agree
+    np.testing.assert_allclose(rg["q"][perm][same], ro["q"][same], atol=1e-4, rtol=0)
+    if dv.sum() == 0:
+        np.testing.assert_allclose(rg["policy"][perm], ro["policy"], atol=1e-4, rtol=0)
 
 
 @pytest.mark.gpu

@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(32) pack_kernel(TreeDev* trees, int n_trees, i
     int base = 0;
     for (int i0 = 0; i0 < n_trees; i0 += 32) {
         const int i = i0 + static_cast<int>(threadIdx.x);
-        const int n = i < n_trees ? (trees[i].st->error ? 0 : trees[i].st->n_new) : 0;
+        const int n = i < n_trees ? (trees[i].st->error ? 0 : trees[i].bs->n_new) : 0;
         int incl = n;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(32) expand_kernel(const TreeDev* trees, Search
     __shared__ WarpScratch ws;
     const int tree = blockIdx.x / batch, b = blockIdx.x - tree * batch;
     const TreeDev t = trees[tree];
-    if (b >= t.st->n_new || t.st->error) return;
+    if (b >= t.bs->n_new || t.st->error) return;
     const int nid = t.new_node[b];
     if (in_h != nullptr) {
         const DevWriterFactory wf{in_h, cpad, split};
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(32) scatter_kernel(const TreeDev* trees, Searc
     __shared__ WarpScratch ws;
     const int tree = blockIdx.x / batch, b = blockIdx.x - tree * batch;
     const TreeDev t = trees[tree];
-    if (b >= t.st->n_new || t.st->error) return;
+    if (b >= t.bs->n_new || t.st->error) return;
     scatter_pending(t, sp, ws, b, values, probs, n_labels);
 }
 
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(32) scatter_prepare_kernel(const TreeDev* tree
     const TreeDev t = trees[tree];
     if (t.st->error) return;
     if (item < batch) {
-        if (item >= t.st->n_new) return;
+        if (item >= t.bs->n_new) return;
         scatter_pending(t, sp, ws, item, values, probs, n_labels);
         __syncwarp();
     }
@@ -167,7 +167,7 @@ __global__ void fake_eval_kernel(const TreeDev* trees, int n_trees, int batch, f
     const int tree = blockIdx.x / batch, b = blockIdx.x - tree * batch;
     if (tree >= n_trees) return;
     const TreeDev t = trees[tree];
-    if (b >= t.st->n_new) return;
+    if (b >= t.bs->n_new) return;
     const int slot = t.slot_base + b;  // row of this leaf in the (possibly packed) batch
     const uint64_t key = t.hdr[t.new_node[b]].key;
     if (threadIdx.x == 0) values[slot] = fake_value(key);
@@ -363,7 +363,7 @@ int Search::init(Net* net, const SearchParams& params, int device, int trees, in
             dalloc(&t.cbase, max_edges_) ||
             dalloc(&t.move, max_edges_) || dalloc(&t.vl, max_edges_) || dalloc(&t.etype, max_edges_))
             return -1;
-        if (dalloc(&t.st, 1)) return -1;
+        if (dalloc(&t.st, 1) || dalloc(&t.bs, 1)) return -1;
         if (dalloc(&t.new_node, B) || dalloc(&t.traj_node, static_cast<size_t>(2) * B * kMaxDepth) ||
             dalloc(&t.traj_ci, static_cast<size_t>(2) * B * kMaxDepth) || dalloc(&t.traj_len, 2 * B) ||
             dalloc(&t.traj_edge, static_cast<size_t>(2) * B * kMaxDepth))
@@ -658,6 +658,7 @@ extern "C" void ara_search_default_settings(ara_search_settings_t* s, int mode) 
     s->virtual_style = ara::VS_VIRTUAL_MIX;
     s->virtual_mix_threshold = 1000;
     s->seed = 42;
+    s->threads = 1;  // the deterministic parity setting; the reference's UCI default is 2 (uci/optionsuci.cpp:182)
     s->mode = mode;
     s->input_version = mode == ara::MODE_CHESS ? 3 : 1;
 }

@@ -51,6 +51,10 @@ struct SearchParams {
     unsigned long long seed;
     int mode;
     int input_version;
+    int threads;                 // 1 or 2 logical search threads per tree (search.cu)
+    int epsilon_greedy_counter;  // 0 = off
+    int epsilon_checks_counter;  // 0 = off
+    int reserved;
 };
 
 struct alignas(16) NodeHdr {  // 64 B: one line per visited node on the select path
@@ -76,16 +80,26 @@ struct alignas(16) NodeHdr {  // 64 B: one line per visited node on the select p
 static_assert(sizeof(NodeHdr) == 64, "NodeHdr must be 64 bytes");
 static_assert(kMaxDepth * sizeof(uint64_t) >= kMaxMoves * sizeof(float), "fill_nn_results borrows path_key as float[kMaxMoves]");
 
+// One mini-batch in flight (the members of a SearchThread of the reference that describe its current batch).  A search
+// with Threads = 2 has two per tree: two logical search threads take turns on the tree (search.cu), each with its own
+// new leaves, trajectories and rows of the network batch.
+struct BatchState {
+    int n_new;   // new leaves waiting for network results (newNodes)
+    int n_coll;  // collision trajectories to revert (collisionTrajectories)
+    int n_exp;   // expansions of the mini-batch (entries of exp_parent)
+    int done;    // this thread's run_search_thread loop has ended (searchthread.cpp:418-426); it never starts again
+};
+
 struct TreeState {
     int n_nodes;
     int n_edges;
-    int n_new;
-    int n_coll;
+    int pad0_;
+    int pad1_;
     int root;        // node id of the current root (0 for a new tree, the re-rooted child when the tree is reused)
     int next_root;   // candidate root after ara_search_apply_move (MCTSAgent::ownNextRoot / opponentsNextRoot), -1 none
     int next_valid;  // apply_move has been called since the last search: only next_root may be reused
-    int n_exp;     // expansions of the last mini-batch (entries of exp_parent)
-    int done;      // search loop condition failed (limits reached / root solved)
+    int live_threads;  // logical search threads whose loop has not ended yet
+    int done;      // nothing (more) to search: terminal root, or every thread's loop condition has failed
     int error;     // 1 node pool, 2 edge pool, 3 depth overflow
     unsigned iterations;
     unsigned evals;
@@ -138,6 +152,8 @@ struct TreeDev {
     uint8_t* vl;
     uint8_t* etype;
     TreeState* st;
+    BatchState* bs;  // the mini-batch this view of the tree works on (everything from exp_parent to traj_len and slot_base
+                     // below belongs to it; the pools above are the tree's)
     // "prepared child": at every node exactly one child can be expanded next (index no_visit_idx-1, opened in prior
     // order); its position, repetition state and terminal verdict depend on the node alone (the tree has no
     // transpositions), so they are computed ahead of time by parallel warps (prepare_child) and the sequential
@@ -734,11 +750,12 @@ ARA_HD void prepare_child(const TreeDev& t, WarpScratch& ws, int X) {
 // item < B: the new leaves of the last mini-batch (their first child); item >= B: the nodes expanded in it
 ARA_HD void prepare_item(const TreeDev& t, const SearchParams& sp, WarpScratch& ws, int item) {
     const TreeState& st = *t.st;
+    const BatchState& bs = *t.bs;
     if (st.error) return;
     const int B = sp.batch_size;
     if (item < B) {
-        if (item < st.n_new) prepare_child(t, ws, t.new_node[item]);
-    } else if (item - B < st.n_exp) {
+        if (item < bs.n_new) prepare_child(t, ws, t.new_node[item]);
+    } else if (item - B < bs.n_exp) {
         prepare_child(t, ws, t.exp_parent[item - B]);
     }
 }
@@ -937,10 +954,10 @@ ARA_HD void apply_dirichlet_to_root(const TreeDev& t, const SearchParams& sp, Wa
 // input planes are produced afterwards by expand_pending, one warp per leaf.
 ARA_HD void create_mini_batch_impl(const TreeDev& t, const SearchParams& sp, WarpScratch& ws) {
     TreeState& st = *t.st;
-    if (ARA_LANE == 0) st.n_exp = 0;
-    ARA_WARP_SYNC();
-    if (st.done || st.error) {
-        if (ARA_LANE == 0) st.n_new = 0, st.n_coll = 0;
+    BatchState& bs = *t.bs;  // (global memory: touched at the start and the end only)
+    int n_exp = 0;           // lane 0's count of exp_parent entries
+    if (st.done || st.error || bs.done) {
+        if (ARA_LANE == 0) bs.n_new = 0, bs.n_coll = 0, bs.n_exp = 0;
         return;
     }
     // run_search_thread loop condition (searchthread.cpp:326-340, :418-426), checked before every iteration
@@ -952,7 +969,12 @@ ARA_HD void create_mini_batch_impl(const TreeDev& t, const SearchParams& sp, War
         // time-limited searches whose pool is exhausted before their time)
         const bool pool_ok = st.n_nodes + 3 * sp.batch_size + 8 <= t.max_nodes;
         if (!(limits_ok && r.node_type == NT_UNSOLVED) || r.n_moves <= 1 || !pool_ok) {
-            if (ARA_LANE == 0) st.done = 1, st.n_new = 0, st.n_coll = 0;
+            // this thread leaves its loop (for good, like a returning run_search_thread); the search is over when the
+            // last thread has left
+            if (ARA_LANE == 0) {
+                bs.done = 1, bs.n_new = 0, bs.n_coll = 0, bs.n_exp = 0;
+                if (--st.live_threads <= 0) st.done = 1;
+            }
             return;
         }
     }
@@ -1013,7 +1035,7 @@ ARA_HD void create_mini_batch_impl(const TreeDev& t, const SearchParams& sp, War
                     // increment_no_visit_idx: open the next-best sibling (its edge slots are pre-initialised)
                     if (h.no_visit_idx < h.n_moves) t.hdr[cur].no_visit_idx = static_cast<uint16_t>(h.no_visit_idx + 1);
                     if (prepared) t.prep_ci[slot] = -1;
-                    if (st.n_exp < 3 * B) t.exp_parent[st.n_exp++] = cur;
+                    if (n_exp < 3 * B) t.exp_parent[n_exp++] = cur;
                 }
                 ARA_WARP_SYNC();
                 ARA_PROF(st, 1, tq);
@@ -1069,8 +1091,9 @@ ARA_HD void create_mini_batch_impl(const TreeDev& t, const SearchParams& sp, War
         else ++n_new;
     }
     if (ARA_LANE == 0) {
-        st.n_new = n_new;
-        st.n_coll = n_coll;
+        bs.n_new = n_new;
+        bs.n_coll = n_coll;
+        bs.n_exp = n_exp;
         st.iterations++;
         st.evals += static_cast<unsigned>(n_new);
     }
@@ -1101,9 +1124,8 @@ ARA_HD void scatter_pending(const TreeDev& t, const SearchParams& sp, WarpScratc
 // real_visits 1 and value_sum double(v), so its node value is the network value itself).  Reads nothing the scatter
 // step writes and writes nothing the scatter / prepare steps read, so it may run beside them.
 ARA_HD void backup_results(const TreeDev& t, const SearchParams& sp, const float* values) {
-    const TreeState& st = *t.st;
     const int B = sp.batch_size;
-    const int n_new = st.n_new, n_coll = st.n_coll;
+    const int n_new = t.bs->n_new, n_coll = t.bs->n_coll;
     // backup_value (node.h:819-843) without solver: the levels of one trajectory are distinct nodes/edges, so lane d
     // updates depth d of every trajectory, in trajectory order (value sign alternates with the distance to the leaf).
     // Backups that share a node or an edge share its depth and therefore its lane, which preserves the reference's
@@ -1220,9 +1242,11 @@ ARA_HD void create_root(const TreeDev& t, const SearchParams& sp, WarpScratch& w
         st.next_valid = 0;
         st.n_nodes = 0;
         st.n_edges = 0;
-        st.n_new = 0;
-        st.n_coll = 0;
-        st.n_exp = 0;
+        t.bs->n_new = 0;
+        t.bs->n_coll = 0;
+        t.bs->n_exp = 0;
+        t.bs->done = 0;
+        st.live_threads = sp.threads == 2 ? 2 : 1;
         st.done = 0;
         st.error = 0;
         st.iterations = 0;
@@ -1241,7 +1265,7 @@ ARA_HD void create_root(const TreeDev& t, const SearchParams& sp, WarpScratch& w
         if (is_term) {
             st.done = 1;
         } else {
-            st.n_new = 1;  // the root is the single "new node" of the first network call
+            t.bs->n_new = 1;  // the root is the single "new node" of the first network call
             t.new_node[0] = 0;
             t.traj_len[0] = 0;
             st.evals = 1;
@@ -1290,7 +1314,8 @@ ARA_HD int reuse_root(const TreeDev& t, const SearchParams& sp, const Board* roo
             NodeHdr& h = t.hdr[cand];
             st.root = cand;
             h.parent = -1;  // make_to_root: the path walks of prepare_child stop here
-            st.n_new = st.n_coll = st.n_exp = 0;
+            t.bs->n_new = t.bs->n_coll = t.bs->n_exp = t.bs->done = 0;
+            st.live_threads = sp.threads == 2 ? 2 : 1;
             st.done = ((h.flags & NF_TERMINAL) || h.n_moves == 0) ? 1 : 0;
             st.iterations = 0;
             st.evals = 0;

@@ -29,7 +29,8 @@ class SearchSettings(ctypes.Structure):
                 ("q_veto_delta", ctypes.c_float), ("cpuct_init", ctypes.c_float), ("cpuct_base", ctypes.c_float),
                 ("mcts_solver", ctypes.c_int), ("virtual_style", ctypes.c_int), ("virtual_mix_threshold", ctypes.c_uint),
                 ("simulations", ctypes.c_uint), ("nodes", ctypes.c_uint), ("seed", ctypes.c_ulonglong),
-                ("mode", ctypes.c_int), ("input_version", ctypes.c_int)]
+                ("mode", ctypes.c_int), ("input_version", ctypes.c_int), ("threads", ctypes.c_int),
+                ("epsilon_greedy_counter", ctypes.c_int), ("epsilon_checks_counter", ctypes.c_int), ("reserved", ctypes.c_int)]
 
 
 class TimeControl(ctypes.Structure):

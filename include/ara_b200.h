@@ -127,6 +127,13 @@ typedef struct ara_search_settings_s {
     unsigned long long seed;        /* explicit seed of the Dirichlet generator (the reference has none) */
     int mode;                       /* 0 MODE_CRAZYHOUSE, 1 MODE_CHESS, 2 MODE_LICHESS */
     int input_version;              /* input representation version 1, 2, 3 */
+    int threads;                    /* Threads: 1 (deterministic parity mode) or 2 (the reference's default,
+                                       uci/optionsuci.cpp:182): two logical search threads take turns on the tree in a
+                                       fixed schedule, so that one thread's network batch is evaluated while the other
+                                       thread selects its next one */
+    int epsilon_greedy_counter;     /* round(100 / Centi_Epsilon_Greedy), 0 = off (uci/crazyara.cpp:748-749) */
+    int epsilon_checks_counter;     /* round(100 / Centi_Epsilon_Checks), 0 = off */
+    int reserved;
 } ara_search_settings_t;
 
 /* What update_eval_info (evalinfo.cpp:195-249) exposes: per root move visits / Q / prior / MCTS posterior, best

@@ -80,6 +80,21 @@ struct OSearch {
     uint32_t* actions_buf;
     int n_actions_buf, actions_cap;
     float* planes;
+    /* Threads = 2: the batch state above belongs to the logical search thread `active`; the other thread's is parked
+       here and swapped in by use_thread (every SearchThread of the reference owns these members, searchthread.h:48-75) */
+    struct OParked {
+        ONode** new_nodes;
+        int* new_stm;
+        int n_new;
+        Traj* new_traj;
+        Traj* coll_traj;
+        int n_coll;
+        Traj cur;
+        uint32_t* actions_buf;
+        int n_actions_buf, actions_cap;
+        float* planes;
+    } parked;
+    int active;
     unsigned long long num_nodes, sum_select_k, sum_depth;
     ONode** all_nodes;
     size_t n_all, cap_all;
@@ -102,6 +117,7 @@ void osettings_default(OSettings* s, int mode) { /* uci/optionsuci.cpp:66-220 (n
     s->simulations = 0;
     s->nodes = 0;
     s->seed = 42;
+    s->threads = 1; /* the deterministic parity setting; the reference's UCI default is 2 (optionsuci.cpp:182) */
     s->mode = mode;
     s->input_version = mode == OMODE_CHESS ? 3 : 1;
 }
@@ -496,7 +512,34 @@ OSearch* osearch_new(const OSettings* st) {
     s->planes = (float*)calloc((size_t)B * (size_t)s->channels * 64, sizeof(float));
     s->actions_cap = 256;
     s->actions_buf = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)s->actions_cap);
+    s->parked.new_nodes = (ONode**)calloc((size_t)B, sizeof(ONode*));
+    s->parked.new_stm = (int*)calloc((size_t)B, sizeof(int));
+    s->parked.new_traj = (Traj*)calloc((size_t)B, sizeof(Traj));
+    s->parked.coll_traj = (Traj*)calloc((size_t)B, sizeof(Traj));
+    s->parked.planes = (float*)calloc((size_t)B * (size_t)s->channels * 64, sizeof(float));
+    s->parked.actions_cap = 256;
+    s->parked.actions_buf = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)s->parked.actions_cap);
+    s->active = 0;
     return s;
+}
+/* makes logical search thread t (0 or 1) the owner of the batch members */
+static void use_thread(OSearch* s, int t) {
+    if (s->active == t) return;
+    struct OParked tmp = s->parked;
+#define SWAPF(f) s->parked.f = s->f, s->f = tmp.f
+    SWAPF(new_nodes);
+    SWAPF(new_stm);
+    SWAPF(n_new);
+    SWAPF(new_traj);
+    SWAPF(coll_traj);
+    SWAPF(n_coll);
+    SWAPF(cur);
+    SWAPF(actions_buf);
+    SWAPF(n_actions_buf);
+    SWAPF(actions_cap);
+    SWAPF(planes);
+#undef SWAPF
+    s->active = t;
 }
 static void free_tree(OSearch* s) {
     for (size_t i = 0; i < s->n_all; ++i) node_free(s->all_nodes[i]);
@@ -506,6 +549,18 @@ static void free_tree(OSearch* s) {
     s->next_root_valid = 0;
 }
 void osearch_free(OSearch* s) {
+    use_thread(s, 0);
+    for (int i = 0; i < s->st.batch_size; ++i) {
+        free(s->parked.new_traj[i].steps);
+        free(s->parked.coll_traj[i].steps);
+    }
+    free(s->parked.cur.steps);
+    free(s->parked.new_nodes);
+    free(s->parked.new_stm);
+    free(s->parked.new_traj);
+    free(s->parked.coll_traj);
+    free(s->parked.planes);
+    free(s->parked.actions_buf);
     free_tree(s);
     free(s->all_nodes);
     for (int i = 0; i < s->st.batch_size; ++i) {
@@ -524,6 +579,23 @@ void osearch_free(OSearch* s) {
 int osearch_channels(const OSearch* s) { return s->channels; }
 int osearch_nb_labels(const OSearch* s) { return s->n_labels; }
 const float* osearch_planes(const OSearch* s) { return s->planes; }
+/* Threads = 2: the same entry points for logical search thread t */
+int osearch_create_mini_batch_t(OSearch* s, int t) {
+    use_thread(s, t);
+    return osearch_create_mini_batch(s);
+}
+void osearch_apply_results_t(OSearch* s, int t, const float* values, const float* probs) {
+    use_thread(s, t);
+    osearch_apply_results(s, values, probs);
+}
+const float* osearch_planes_t(OSearch* s, int t) {
+    use_thread(s, t);
+    return s->planes;
+}
+void osearch_batch_keys_t(OSearch* s, int t, unsigned long long* out) {
+    use_thread(s, t);
+    osearch_batch_keys(s, out);
+}
 void osearch_batch_keys(const OSearch* s, unsigned long long* out) {
     if (s->n_new == 0) {
         out[0] = s->root->key;
@@ -555,7 +627,9 @@ int osearch_set_root(OSearch* s, const OPos* pos) {
     s->next_root = NULL;
     s->next_root_valid = 0;
     s->sum_select_k = s->sum_depth = 0;
+    use_thread(s, 0);
     s->n_new = s->n_coll = 0;
+    s->parked.n_new = s->parked.n_coll = 0;
     if (cand != NULL && cand->key == pos->key && cand->has_d && cand->visit_sum - cand->free_visits > 0) {
         /* the rest of the old tree is only garbage-collected by the reference; here it stays allocated */
         s->root = cand;

@@ -30,6 +30,10 @@ typedef struct OSettings {
     unsigned long long seed; /* explicit seed for the Dirichlet noise generator */
     int mode;             /* OMODE_* build mode: decides plane layout and label set */
     int input_version;    /* 1, 2, 3 */
+    int threads;                /* SearchSettings::threads: 1, or 2 in the fixed schedule described below */
+    int epsilon_greedy_counter; /* SearchSettings::epsilonGreedyCounter, 0 = off */
+    int epsilon_checks_counter; /* SearchSettings::epsilonChecksCounter, 0 = off */
+    int reserved;
 } OSettings;
 
 typedef struct OSearch OSearch;
@@ -49,6 +53,14 @@ void osearch_root_results(OSearch* s, const float* value, const float* prob);
 int osearch_create_mini_batch(OSearch* s);
 /* set_nn_results_to_child_nodes + backup_value_outputs + backup_collisions */
 void osearch_apply_results(OSearch* s, const float* values, const float* probs);
+/* Threads = 2 (the reference's default, uci/optionsuci.cpp:182): the same three entry points for logical search thread
+ * t in {0, 1}.  The two threads take turns on the tree in a fixed schedule (oracle/search.py, Search.run(threads=2)):
+ *   sel(0) sel(1) | bk(0) sel(0) bk(1) sel(1) | bk(0) sel(0) ...   with every thread testing the loop condition before
+ * its own sel -- one of the interleavings two real threads of the reference can produce (each phase atomic). */
+int osearch_create_mini_batch_t(OSearch* s, int t);
+void osearch_apply_results_t(OSearch* s, int t, const float* values, const float* probs);
+const float* osearch_planes_t(OSearch* s, int t);
+void osearch_batch_keys_t(OSearch* s, int t, unsigned long long* out);
 /* run_search_thread loop condition: is_running && nodes_limits_ok && is_root_node_unsolved */
 int osearch_continue(const OSearch* s);
 const float* osearch_planes(const OSearch* s);

@@ -4,12 +4,22 @@
 // (agents/mctsagent.cpp:292-337) with Threads = 1, over the State shim (pommermanstate.h), the blaze stand-in
 // (blaze/Math.h) and the network stand-in below.  oracle/mcts.c, the restatement every device test is compared with, is
 // itself compared with THIS in tests/test_ref_mcts.py: that is what pins the search oracle to the reference's code.
+#include <chrono>
+#include <condition_variable>
 #include <cstring>
 #include <iostream>
 #include <memory>
 #include <sstream>
 
+#include <blaze/Math.h>  // (the stand-in: pulls the standard headers in before the access hack below)
+// Threads = 2 is driven in a FIXED schedule (ref_mcts_run below), which needs the two halves of
+// SearchThread::thread_iteration (searchthread.cpp:403-416) separately; they are private members.  Access specifiers
+// do not change the classes' layout, so the reference's own translation units (compiled unchanged) link as they are.
+#define private public
+#define protected public
 #include "agents/mctsagent.h"
+#undef private
+#undef protected
 #include "evalinfo.h"
 #include "nn/neuralnetapi.h"
 #include "stateobj.h"
@@ -143,8 +153,9 @@ int ref_mcts_run(const char* fen, int variant, int is960, const char* const* uci
     {
         std::vector<std::unique_ptr<NeuralNetAPI>> single;
         single.emplace_back(new ShimNet(1, fn, ctx));
-        std::vector<std::vector<std::unique_ptr<NeuralNetAPI>>> batches(1);
-        batches[0].emplace_back(new ShimNet(st->batch_size, fn, ctx));
+        ss.threads = st->threads == 2 ? 2 : 1;
+        std::vector<std::vector<std::unique_ptr<NeuralNetAPI>>> batches(ss.threads);
+        for (auto& b : batches) b.emplace_back(new ShimNet(st->batch_size, fn, ctx));  // one net per thread (mctsagent.cpp:54-56)
         MCTSAgent agent(single, batches, &ss, &ps);
         StateObj state;
         state.set(fen != nullptr && fen[0] ? fen : StateConstants::start_fen(variant), is960 != 0, variant);
@@ -156,7 +167,78 @@ int ref_mcts_run(const char* fen, int variant, int is960, const char* const* uci
         agent.set_search_settings(&state, &limits, &eval);
         ref_seed_node_generator(st->seed);
         eval.start = chrono::steady_clock::now();
-        agent.evaluate_board_state();
+        if (st->threads != 2) {
+            agent.evaluate_board_state();
+        } else {
+            // MCTSAgent::evaluate_board_state (agents/mctsagent.cpp:292-337) with run_mcts_search's two OS threads
+            // replaced by one of the interleavings they can produce: the fixed schedule of oracle/mcts.h
+            //     sel(0) sel(1) | bk(0) sel(0) bk(1) sel(1) | ...
+            // sel = the loop test of run_search_thread (searchthread.cpp:418-426) + create_mini_batch,
+            // bk  = the rest of thread_iteration (:403-416): predict, set_nn_results_to_child_nodes, the backups.
+            ss.threads = 2;
+            agent.rootState = unique_ptr<StateObj>(state.clone());
+            eval.nodesPreSearch = agent.init_root_node(&state);
+            eval.isChess960 = state.is_chess960();
+            Node* root = agent.rootNode.get();
+            if (root->get_number_child_nodes() == 1) {
+                agent.handle_single_move();
+            } else if (root->get_number_child_nodes() > 1) {
+                if (ss.dirichletEpsilon > 0.009f) {
+                    root->apply_dirichlet_noise_to_prior_policy(&ss);
+                    root->fully_expand_node();
+                }
+                if (!root->is_root_node()) root->make_to_root();
+                SearchThread* th[2] = {agent.searchThreads[0], agent.searchThreads[1]};
+                bool alive[2] = {true, true}, pending[2] = {false, false};
+                for (SearchThread* t : th) {
+                    t->set_root_node(root);
+                    t->set_root_state(agent.rootState.get());
+                    t->set_search_limits(&limits);
+                    t->set_reached_tablebases(false);
+                    t->set_is_running(true);
+                    t->reset_stats();
+                }
+                // the loop test of run_search_thread; nodes_limits_ok / is_root_node_unsolved (searchthread.cpp:326-340) are
+                // declared inline but defined in the .cpp, so they cannot be called from here: their two expressions
+                auto loop_ok = [&](SearchThread* t) {
+                    const Node* r = t->rootNode;
+                    const SearchLimits* l = t->searchLimits;
+                    const bool limits = (l->nodes == 0 || r->get_node_count() < l->nodes) &&
+                                        (l->simulations == 0 || r->get_visits() < l->simulations) &&
+                                        (l->nodesLimit == 0 || r->get_node_count() < l->nodesLimit);
+                    return t->is_running() && limits && r->get_node_type() == UNSOLVED;
+                };
+                auto sel = [&](int i) {
+                    SearchThread* t = th[i];
+                    if (!(alive[i] && loop_ok(t))) {
+                        alive[i] = false;
+                        return;
+                    }
+                    t->create_mini_batch();
+                    pending[i] = true;
+                };
+                auto bk = [&](int i) {
+                    SearchThread* t = th[i];
+                    if (!pending[i]) return;
+                    if (t->newNodes->size() != 0) {
+                        t->nets[t->select_nn_index()]->predict(t->inputPlanes, t->valueOutputs, t->probOutputs, t->auxiliaryOutputs);
+                        t->set_nn_results_to_child_nodes();
+                    }
+                    t->backup_value_outputs();
+                    t->backup_collisions();
+                    pending[i] = false;
+                };
+                sel(0);
+                sel(1);
+                while (pending[0] || pending[1])
+                    for (int i = 0; i < 2; ++i) {
+                        bk(i);
+                        sel(i);
+                    }
+                agent.update_stats();
+            }
+            update_eval_info(eval, root, agent.tbHits, agent.maxDepth, &ss);
+        }
 
         const Node* root = agent.get_root_node();
         memset(out, 0, sizeof(*out));

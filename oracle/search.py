@@ -18,7 +18,8 @@ class OSettings(ctypes.Structure):
                 ("q_veto_delta", ctypes.c_float), ("cpuct_init", ctypes.c_float), ("cpuct_base", ctypes.c_float),
                 ("mcts_solver", ctypes.c_int), ("virtual_style", ctypes.c_int), ("virtual_mix_threshold", ctypes.c_uint),
                 ("simulations", ctypes.c_uint), ("nodes", ctypes.c_uint), ("seed", ctypes.c_ulonglong),
-                ("mode", ctypes.c_int), ("input_version", ctypes.c_int)]
+                ("mode", ctypes.c_int), ("input_version", ctypes.c_int), ("threads", ctypes.c_int),
+                ("epsilon_greedy_counter", ctypes.c_int), ("epsilon_checks_counter", ctypes.c_int), ("reserved", ctypes.c_int)]
 
 
 def default_settings(mode, **kw):
@@ -62,6 +63,11 @@ def _lib():
         for name in ("osearch_num_nodes", "osearch_sum_select_k", "osearch_sum_depth"):
             getattr(L, name).restype = ctypes.c_ulonglong
             getattr(L, name).argtypes = [ctypes.c_void_p]
+        L.osearch_create_mini_batch_t.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.osearch_apply_results_t.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        L.osearch_planes_t.restype = ctypes.c_void_p
+        L.osearch_planes_t.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.osearch_batch_keys_t.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
         L.odirichlet_noise.argtypes = [ctypes.c_ulonglong, ctypes.c_int, ctypes.c_float, ctypes.c_void_p]
         L.osearch_batch_keys.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.ofake_eval.argtypes = [ctypes.c_ulonglong, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
@@ -96,7 +102,56 @@ class Search:
         self.L.osearch_batch_keys(self.h, k.ctypes.data)
         return k[:n]
 
-    def run(self, pos, net_fn, max_iterations=1 << 30, with_keys=False):
+    def _eval_thread(self, t, n, net_fn, with_keys):
+        """network call for the batch of logical search thread t: planes (and keys) of its n new leaves"""
+        ptr = self.L.osearch_planes_t(self.h, t)
+        planes = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_float)),
+                                       shape=(self.batch, self.channels, 8, 8))[:n].copy()
+        if not with_keys:
+            v, p = net_fn(planes)
+        else:
+            k = np.zeros(max(n, 1), np.uint64)
+            self.L.osearch_batch_keys_t(self.h, t, k.ctypes.data)
+            v, p = net_fn(planes, k[:n])
+        return np.ascontiguousarray(v, np.float32), np.ascontiguousarray(p, np.float32)
+
+    def _run_two_threads(self, net_fn, max_iterations, with_keys):
+        """Threads = 2 in the fixed schedule of oracle/mcts.h: each logical thread is run_search_thread
+        (searchthread.cpp:418-426) -- while the loop condition holds: create_mini_batch, predict, back up -- and the two
+        alternate phase by phase, thread 1 half an iteration behind thread 0."""
+        L, h = self.L, self.h
+        pending = [None, None]   # per thread: number of new leaves of the batch waiting for its backup, None = no batch
+        alive = [True, True]
+        iters = evals = 0
+
+        def sel(t):
+            nonlocal iters, evals
+            if not (alive[t] and L.osearch_continue(h) and iters < max_iterations):
+                alive[t] = False
+                return
+            pending[t] = L.osearch_create_mini_batch_t(h, t)
+            iters += 1
+            evals += pending[t]
+
+        def bk(t):
+            if pending[t] is None:
+                return
+            n = pending[t]
+            if n > 0:
+                v, p = self._eval_thread(t, n, net_fn, with_keys)
+            else:
+                v, p = np.zeros(1, np.float32), np.zeros(1, np.float32)
+            L.osearch_apply_results_t(h, t, v.ctypes.data, p.ctypes.data)
+            pending[t] = None
+        sel(0)
+        sel(1)
+        while pending[0] is not None or pending[1] is not None:
+            for t in (0, 1):
+                bk(t)
+                sel(t)
+        return iters, evals
+
+    def run(self, pos, net_fn, max_iterations=1 << 30, with_keys=False, threads=1):
         """Returns the result dict of update_eval_info (evalinfo.cpp:195-249) plus counters."""
         L, h = self.L, self.h
         self.pos = pos
@@ -115,7 +170,11 @@ class Search:
             else:
                 self.nodes_pre_search = L.osearch_root_visits(h) - L.osearch_root_free_visits(h)
                 L.osearch_root_reused(h)
-            if L.osearch_root_num_children(h) > 1:
+            if L.osearch_root_num_children(h) > 1 and threads == 2:
+                it2, ev2 = self._run_two_threads(net_fn, max_iterations, with_keys)
+                iters += it2
+                evals += ev2
+            elif L.osearch_root_num_children(h) > 1:
                 while L.osearch_continue(h) and iters < max_iterations:
                     n = L.osearch_create_mini_batch(h)
                     if n > 0:

@@ -150,6 +150,12 @@ class HeSearch:
         L.he_search_root_results.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.he_search_apply_results.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.he_search_batch_keys.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.he_search_create_mini_batch_t.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.he_search_thread_done.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.he_search_apply_results_t.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        L.he_search_planes_t.restype = ctypes.c_void_p
+        L.he_search_planes_t.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.he_search_batch_keys_t.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
         L.he_search_result.restype = ctypes.POINTER(SearchResult)
         L.he_search_result.argtypes = [ctypes.c_void_p]
         L.he_fake_eval.argtypes = [ctypes.c_ulonglong, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
@@ -189,7 +195,45 @@ class HeSearch:
         return dict(node_count=i[0], first_visits=i[1], second_visits=i[2], max_q_is_max_visits=int(i[3]), valid=int(i[4]),
                     q_first=f[0], q_second=f[1], value_eval=f[2])
 
-    def run(self, he_state, net_fn, with_keys=False):
+    def _eval_thread(self, t, n, net_fn, with_keys):
+        np = self.np
+        ptr = self.L.he_search_planes_t(self.h, t)
+        planes = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_float)),
+                                       shape=(self.batch, self.channels, 8, 8))[:n].copy()
+        if not with_keys:
+            v, p = net_fn(planes)
+        else:
+            k = np.zeros(max(n, 1), np.uint64)
+            self.L.he_search_batch_keys_t(self.h, t, k.ctypes.data)
+            v, p = net_fn(planes, k[:n])
+        return np.ascontiguousarray(v, np.float32), np.ascontiguousarray(p, np.float32)
+
+    def _run_two_threads(self, net_fn, with_keys):
+        """Threads = 2: the schedule of oracle/mcts.h as the device runs it -- the loop condition lives inside
+        create_mini_batch (`done`), a thread whose select finds it set produces an empty batch; one more turn of both
+        threads drains the batch still in flight."""
+        L, h, np = self.L, self.h, self.np
+        pending = [None, None]
+
+        def sel(t):
+            n = L.he_search_create_mini_batch_t(h, t)
+            pending[t] = None if L.he_search_thread_done(h, t) else n
+
+        def bk(t):
+            if pending[t] is None:
+                return
+            n = pending[t]
+            v, p = self._eval_thread(t, n, net_fn, with_keys) if n > 0 else (np.zeros(1, np.float32), np.zeros(1, np.float32))
+            L.he_search_apply_results_t(h, t, v.ctypes.data, p.ctypes.data)
+            pending[t] = None
+        sel(0)
+        sel(1)
+        while pending[0] is not None or pending[1] is not None:
+            for t in (0, 1):
+                bk(t)
+                sel(t)
+
+    def run(self, he_state, net_fn, with_keys=False, threads=1):
         L, h, np = self.L, self.h, self.np
         n = L.he_search_set_root(h, he_state.h)
         self.reused = n == 2
@@ -200,7 +244,9 @@ class HeSearch:
                 v, p = net_fn(self._planes(1), self._keys(1)) if with_keys else net_fn(self._planes(1))
                 v, p = np.ascontiguousarray(v, np.float32), np.ascontiguousarray(p, np.float32)
             L.he_search_root_results(h, v.ctypes.data, p.ctypes.data)
-            while True:
+            if threads == 2:
+                self._run_two_threads(net_fn, with_keys)
+            while threads != 2:
                 n = L.he_search_create_mini_batch(h)
                 if L.he_search_done(h):
                     break

@@ -79,9 +79,19 @@ struct HostWriterFactory {
     Target make(int slot) const { return Target{base + static_cast<size_t>(slot) * channels * 64}; }
 };
 
+// one mini-batch in flight (a logical search thread): its arrays, its view of the tree, its planes
+struct HeBatch {
+    BatchState bs;
+    TreeDev t;
+    std::vector<int32_t> new_node, traj_node, traj_len, exp_parent;
+    std::vector<uint16_t> traj_ci;
+    std::vector<uint32_t> traj_edge;
+    std::vector<float> planes;
+};
+
 struct HeSearch {
     SearchParams sp;
-    TreeDev t;
+    TreeDev& t = batch[0].t;  // root creation, results, tree reuse go through the first view
     TreeState st;
     std::vector<NodeHdr> hdr;
     std::vector<Board> board;
@@ -90,18 +100,15 @@ struct HeSearch {
     std::vector<int32_t> child;
     std::vector<Move> move;
     std::vector<uint8_t> vl, etype;
-    std::vector<int32_t> new_node, traj_node, traj_len;
-    std::vector<uint16_t> traj_ci;
-    std::vector<uint32_t> traj_edge, cbase;
+    std::vector<uint32_t> cbase;
     std::vector<Board> prep_board;
     std::vector<int16_t> prep_ci;
     std::vector<uint8_t> prep_term;
-    std::vector<int32_t> exp_parent;
     std::vector<uint64_t> hist_keys;
     std::vector<int16_t> hist_reps;
     std::vector<float> lut;
     std::vector<double> sqrt_lut;
-    std::vector<float> planes;
+    HeBatch batch[2];
     WarpScratch ws;
     int channels, n_labels;
     Board root;
@@ -124,103 +131,119 @@ HeSearch* he_search_new(const SearchParams* sp, int max_nodes, int max_edges) {
     s->move.resize(max_edges);
     s->vl.resize(max_edges);
     s->etype.resize(max_edges);
-    s->new_node.resize(B);
-    s->traj_node.resize(2 * B * kMaxDepth);
-    s->traj_ci.resize(2 * B * kMaxDepth);
-    s->traj_len.resize(2 * B);
-    s->traj_edge.resize(2 * B * kMaxDepth);
     s->channels = planes_channels(sp->mode, sp->input_version);
     s->n_labels = (sp->mode == MODE_CRAZYHOUSE ? 81 : (sp->mode == MODE_CHESS ? 76 : 84)) * 64;
-    s->planes.assign(static_cast<size_t>(B) * s->channels * 64, 0.0f);
     const int lut_len = 1 << 16;
     s->lut.resize(lut_len);
     for (int i = 0; i < lut_len; ++i) s->lut[i] = logf((static_cast<float>(i) + sp->cpuct_base + 1) / sp->cpuct_base) + sp->cpuct_init;
+    s->sqrt_lut.resize(lut_len);
+    for (int i = 0; i < lut_len; ++i) s->sqrt_lut[i] = sqrt(static_cast<double>(i));
     memset(&s->st, 0, sizeof(s->st));
-    TreeDev& t = s->t;
-    t.hdr = s->hdr.data();
-    t.board = s->board.data();
-    t.P = s->P.data();
-    t.Q = s->Q.data();
-    t.N = s->N.data();
-    t.child = s->child.data();
-    t.cbase = s->cbase.data();
-    t.move = s->move.data();
-    t.vl = s->vl.data();
-    t.etype = s->etype.data();
-    t.st = &s->st;
-    t.new_node = s->new_node.data();
-    t.traj_node = s->traj_node.data();
-    t.traj_ci = s->traj_ci.data();
-    t.traj_len = s->traj_len.data();
-    t.traj_edge = s->traj_edge.data();
     s->prep_board.resize(static_cast<size_t>(max_nodes) * kPrepSlots);
     s->prep_ci.assign(static_cast<size_t>(max_nodes) * kPrepSlots, -1);
     s->prep_term.resize(static_cast<size_t>(max_nodes) * kPrepSlots);
-    s->exp_parent.resize(3 * B);
-    t.prep_board = s->prep_board.data();
-    t.prep_ci = s->prep_ci.data();
-    t.prep_term = s->prep_term.data();
-    t.exp_parent = s->exp_parent.data();
-    t.hist_keys = nullptr;
-    t.hist_reps = nullptr;
-    t.hist_len = 0;
-    t.cput_lut = s->lut.data();
-    s->sqrt_lut.resize(lut_len);
-    for (int i = 0; i < lut_len; ++i) s->sqrt_lut[i] = sqrt(static_cast<double>(i));
-    t.sqrt_lut = s->sqrt_lut.data();
-    t.cput_lut_len = lut_len;
-    t.max_nodes = max_nodes;
-    t.max_edges = max_edges;
-    t.slot_base = 0;
+    for (HeBatch& bt : s->batch) {
+        memset(&bt.bs, 0, sizeof(bt.bs));
+        bt.new_node.resize(B);
+        bt.traj_node.resize(2 * B * kMaxDepth);
+        bt.traj_ci.resize(2 * B * kMaxDepth);
+        bt.traj_len.resize(2 * B);
+        bt.traj_edge.resize(2 * B * kMaxDepth);
+        bt.exp_parent.resize(3 * B);
+        bt.planes.assign(static_cast<size_t>(B) * s->channels * 64, 0.0f);
+        TreeDev& t = bt.t;
+        t.hdr = s->hdr.data();
+        t.board = s->board.data();
+        t.P = s->P.data();
+        t.Q = s->Q.data();
+        t.N = s->N.data();
+        t.child = s->child.data();
+        t.cbase = s->cbase.data();
+        t.move = s->move.data();
+        t.vl = s->vl.data();
+        t.etype = s->etype.data();
+        t.st = &s->st;
+        t.bs = &bt.bs;
+        t.new_node = bt.new_node.data();
+        t.traj_node = bt.traj_node.data();
+        t.traj_ci = bt.traj_ci.data();
+        t.traj_len = bt.traj_len.data();
+        t.traj_edge = bt.traj_edge.data();
+        t.exp_parent = bt.exp_parent.data();
+        t.prep_board = s->prep_board.data();
+        t.prep_ci = s->prep_ci.data();
+        t.prep_term = s->prep_term.data();
+        t.hist_keys = nullptr;
+        t.hist_reps = nullptr;
+        t.hist_len = 0;
+        t.cput_lut = s->lut.data();
+        t.sqrt_lut = s->sqrt_lut.data();
+        t.cput_lut_len = lut_len;
+        t.max_nodes = max_nodes;
+        t.max_edges = max_edges;
+        t.slot_base = 0;
+    }
     return s;
 }
 void he_search_free(HeSearch* s) { delete s; }
 int he_search_channels(const HeSearch* s) { return s->channels; }
 int he_search_n_labels(const HeSearch* s) { return s->n_labels; }
-const float* he_search_planes(const HeSearch* s) { return s->planes.data(); }
+const float* he_search_planes_t(const HeSearch* s, int th) { return s->batch[th].planes.data(); }
+const float* he_search_planes(const HeSearch* s) { return he_search_planes_t(s, 0); }
 
 int he_search_set_root(HeSearch* s, const HeState* root) {
     s->root = root->b;
     s->hist_keys = root->keys;
     s->hist_reps = root->reps;
-    s->t.hist_keys = s->hist_keys.data();
-    s->t.hist_reps = s->hist_reps.data();
-    s->t.hist_len = static_cast<int>(s->hist_keys.size());
+    for (HeBatch& bt : s->batch) {
+        bt.t.hist_keys = s->hist_keys.data();
+        bt.t.hist_reps = s->hist_reps.data();
+        bt.t.hist_len = static_cast<int>(s->hist_keys.size());
+        memset(&bt.bs, 0, sizeof(bt.bs));
+    }
+    HeBatch& b0 = s->batch[0];
     if (reuse_root(s->t, s->sp, &s->root)) return s->st.done ? 0 : 2;  // 2: the kept subtree is searched on
     create_root(s->t, s->sp, s->ws, &s->root);
-    HostWriterFactory wf{s->planes.data(), s->channels};
-    for (int b = 0; b < s->st.n_new; ++b) {
+    HostWriterFactory wf{b0.planes.data(), s->channels};
+    for (int b = 0; b < b0.bs.n_new; ++b) {
         const auto target = wf.make(b);
-        expand_pending(s->t, s->sp, s->ws, s->new_node[b], &target);
+        expand_pending(s->t, s->sp, s->ws, b0.new_node[b], &target);
     }
-    return s->st.n_new;
+    return b0.bs.n_new;
 }
 void he_search_apply_move(HeSearch* s, unsigned short move) { advance_root(s->t, move); }
 void he_search_root_results(HeSearch* s, const float* values, const float* probs) {
     backup_results(s->t, s->sp, values);  // (independent of the scatter step: the device runs them side by side)
-    for (int b = 0; b < s->st.n_new; ++b) scatter_pending(s->t, s->sp, s->ws, b, values, probs, s->n_labels);
+    for (int b = 0; b < s->batch[0].bs.n_new; ++b) scatter_pending(s->t, s->sp, s->ws, b, values, probs, s->n_labels);
     finalize_root(s->t, s->sp, s->ws);
     for (int item = 0; item < 4 * s->sp.batch_size; ++item) prepare_item(s->t, s->sp, s->ws, item);
 }
-int he_search_create_mini_batch(HeSearch* s) {
-    create_mini_batch(s->t, s->sp, s->ws);
-    HostWriterFactory wf{s->planes.data(), s->channels};
-    for (int b = 0; b < s->st.n_new; ++b) {
+// logical search thread `th` (0 or 1): SearchThread::create_mini_batch / the rest of thread_iteration
+int he_search_create_mini_batch_t(HeSearch* s, int th) {
+    HeBatch& bt = s->batch[th];
+    create_mini_batch(bt.t, s->sp, s->ws);
+    HostWriterFactory wf{bt.planes.data(), s->channels};
+    for (int b = 0; b < bt.bs.n_new; ++b) {
         const auto target = wf.make(b);
-        expand_pending(s->t, s->sp, s->ws, s->new_node[b], &target);
+        expand_pending(bt.t, s->sp, s->ws, bt.new_node[b], &target);
     }
-    return s->st.n_new;
+    return bt.bs.n_new;
 }
-void he_search_apply_results(HeSearch* s, const float* values, const float* probs) {
-    backup_results(s->t, s->sp, values);
-    for (int b = 0; b < s->st.n_new; ++b) scatter_pending(s->t, s->sp, s->ws, b, values, probs, s->n_labels);
-    for (int item = 0; item < 4 * s->sp.batch_size; ++item) prepare_item(s->t, s->sp, s->ws, item);
+void he_search_apply_results_t(HeSearch* s, int th, const float* values, const float* probs) {
+    HeBatch& bt = s->batch[th];
+    backup_results(bt.t, s->sp, values);
+    for (int b = 0; b < bt.bs.n_new; ++b) scatter_pending(bt.t, s->sp, s->ws, b, values, probs, s->n_labels);
+    for (int item = 0; item < 4 * s->sp.batch_size; ++item) prepare_item(bt.t, s->sp, s->ws, item);
 }
+int he_search_create_mini_batch(HeSearch* s) { return he_search_create_mini_batch_t(s, 0); }
+void he_search_apply_results(HeSearch* s, const float* values, const float* probs) { he_search_apply_results_t(s, 0, values, probs); }
+void he_search_batch_keys_t(const HeSearch* s, int th, unsigned long long* out) {
+    for (int i = 0; i < s->batch[th].bs.n_new; ++i) out[i] = s->hdr[s->batch[th].new_node[i]].key;
+}
+void he_search_batch_keys(const HeSearch* s, unsigned long long* out) { he_search_batch_keys_t(s, 0, out); }
 int he_search_done(const HeSearch* s) { return s->st.done || s->st.error; }
+int he_search_thread_done(const HeSearch* s, int th) { return s->st.done || s->st.error || s->batch[th].bs.done; }
 int he_search_error(const HeSearch* s) { return s->st.error; }
-void he_search_batch_keys(const HeSearch* s, unsigned long long* out) {
-    for (int i = 0; i < s->st.n_new; ++i) out[i] = s->hdr[s->new_node[i]].key;
-}
 const SearchResult* he_search_result(HeSearch* s) {
     collect_result(s->t, s->sp, &s->result);
     return &s->result;

@@ -31,10 +31,10 @@ def _bits(a):
     return np.asarray(a, np.float32).view(np.uint32)
 
 
-def assert_oracle_equals_reference(pos, fen, vid, is960, premoves, st):
+def assert_oracle_equals_reference(pos, fen, vid, is960, premoves, st, threads=1):
     S = osr.Search(st)
     net = osr.hash_net(S.n_labels)
-    ro = S.run(pos, net, with_keys=True)
+    ro = S.run(pos, net, with_keys=True, threads=threads)
     rr = refmcts.run(pos, fen, vid, is960, premoves, st, net_fn=net, channels=S.channels, n_labels=S.n_labels)
     assert ro["visit_sum"] > 0
     assert ro["moves"] == rr["moves"]                      # same prior order (no ties with this network)
@@ -68,3 +68,20 @@ def test_oracle_search_equals_the_compiled_reference_search_on_random_cases(seed
     root.push_uci(*played)
     assert root.fen() == pos.fen()
     assert_oracle_equals_reference(pos, None, vid, False, played, st)
+
+
+# Threads = 2: the reference counts the virtual visits in flight on an edge in a uint8 (nodedata.h:93, asserted in
+# node.h:506), so Batch_Size x Threads must stay below 256 -- the B = 128 cases cannot run with two threads there
+CASES_2T = [c for c in CASES if 2 * c[6] < 256]
+
+
+@pytest.mark.parametrize("case", CASES_2T, ids=[f"{c[0]}-b{c[6]}-s{c[7]}-{i}" for i, c in enumerate(CASES_2T)])
+def test_oracle_two_thread_schedule_equals_the_compiled_reference_search(case):
+    """Threads = 2 (the reference's default): two SearchThread objects of the compiled reference driven in the fixed
+    schedule of oracle/mcts.h -- sel(0) sel(1) | bk(0) sel(0) bk(1) sel(1) | ... , one of the interleavings its two OS
+    threads can produce -- against the oracle's two logical threads in the same schedule: identical bits."""
+    variant, vid, mode, fen, is960, premoves, batch, sims, extra = case
+    st = case_settings(mode, batch, sims, dict(extra, threads=2))
+    pos = Position(fen, variant, is960)
+    pos.push_uci(*premoves)
+    assert_oracle_equals_reference(pos, fen, vid, is960, premoves, st, threads=2)

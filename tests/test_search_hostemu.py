@@ -81,6 +81,24 @@ def test_hostemu_search_equals_oracle(case):
     assert_same_search(ro, rh)
 
 
+@pytest.mark.parametrize("case", CASES, ids=[f"{c[0]}-b{c[6]}-s{c[7]}-{i}" for i, c in enumerate(CASES)])
+def test_hostemu_two_thread_search_equals_oracle(case):
+    """Threads = 2: two logical search threads per tree in the fixed schedule of oracle/mcts.h (one thread's batch is at
+    the network while the other selects); the device code with two batch slots against the oracle's two threads."""
+    variant, vid, mode, fen, is960, premoves, batch, sims, extra = case
+    st = case_settings(mode, batch, sims, dict(extra, threads=2))
+    pos = Position(fen, variant, is960)
+    he = HeState(pos.fen(), vid, is960)
+    for u in premoves:
+        pos.push_uci(u)
+        he.do_move(he.move_from_uci(u))
+    S = osr.Search(st)
+    ro = S.run(pos, osr.fake_net(S.n_labels), with_keys=True, threads=2)
+    rh = HeSearch(st).run(he, osr.fake_net(S.n_labels), with_keys=True, threads=2)
+    assert ro["visit_sum"] > 0
+    assert_same_search(ro, rh)
+
+
 def test_fake_backends_identical():
     import ctypes
     from oracle.search import _lib

@@ -213,6 +213,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--sims", type=int, default=3200)
     ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--threads", type=int, default=1, choices=[1, 2], help="Threads: 1 = deterministic parity mode, 2 = the "
+                    "reference's default (two logical search threads: one selects while the other's batch is evaluated)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU arm (profiling runs)")
     ap.add_argument("--cpu-sims", type=int, default=1280, help="bounded CPU sample: simulations per CPU search")
     ap.add_argument("--trees", type=int, default=32, help="extra leg: concurrent searches per GPU (0 = skip)")
@@ -268,7 +270,7 @@ def main():
     tmp = tempfile.mkdtemp(prefix="ara_bench_")
     blob = export_blob(synthetic.random_state_dict(arch, 0), arch, os.path.join(tmp, f"risev2_{rank}.arab"), input_version=10)
     net = NeuralNetAPI("gpu", local_rank, args.batch, blob)
-    settings = default_settings("crazyhouse", batch_size=args.batch, simulations=args.sims)
+    settings = default_settings("crazyhouse", batch_size=args.batch, simulations=args.sims, threads=args.threads)
     agent = MCTSAgent(net, settings, local_rank, 1)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 

@@ -22,6 +22,10 @@ int conv_layer_init(ConvLayer* L, const __half* act, int boards_cap, int cin, co
                     int ksize, const float* bias, int relu, const __half* residual, int ldr, __half* out_h,
                     float* out_f, int ldo, int bn);
 
+// activations [boards_cap, 8, 8, cin] fp16 as the 4-D map the A operand is fetched through (conv_layer_init builds the
+// same one): lets a layer be re-pointed at another input buffer
+int make_act_tensor_map(CUtensorMap* m, const __half* act, int boards_cap, int cin);
+
 // Precision float32: fp32 residual [M, ldr] instead of the fp16 one, and / or the hi | hi | lo split output
 // [M, 3 * split_cs] (see conv_gemm.cuh); call after conv_layer_init.
 void conv_layer_set_precise(ConvLayer* L, const float* residual_f, int ldr, __half* out_split, int split_cs);

@@ -93,7 +93,7 @@ int Net::upload_conv_w_split(const float* w, int n_out, int cin, int ksize, __ha
 
 Net::~Net() {
     cudaSetDevice(device);
-    for (int k = 0; k < 3; ++k)
+    for (int k = 0; k < 4; ++k)
         for (auto& g : graphs_[k]) cudaGraphExecDestroy(g.second);
     for (void* p : allocs_) cudaFree(p);
     rise_trunk_destroy(&trunk_);
@@ -361,6 +361,7 @@ int Net::init(const char* blob_path, int dev, int batch_size, int prec) {
     if (dalloc(&d_aux, static_cast<size_t>(batch) * 4)) return -1;
     if (upload_value_head(hw)) return -1;
     if (precision == 0 ? build_half(hw) : build_precise(hw)) return -1;
+    io_in_h[0] = d_in_h, io_prob[0] = d_prob, io_value[0] = d_value, io_aux[0] = d_aux;
     ARA_CUDA_OK(cudaFuncSetAttribute(value_head_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      value_head_smem<__half>()));
     ARA_CUDA_OK(cudaFuncSetAttribute(policy_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -371,14 +372,26 @@ int Net::init(const char* blob_path, int dev, int batch_size, int prec) {
     return 0;
 }
 
-int Net::enqueue_precise(int n, cudaStream_t s, bool from_f32, const int* cnt) {
-    const int C = hdr.channels;
+int Net::enable_second_io() {
+    if (io_in_h[1] != nullptr) return 0;
+    ARA_CUDA_OK(cudaSetDevice(device));
+    const size_t rows = static_cast<size_t>(batch_cap) * 64;
+    const int cin = precision == 0 ? cin_pad : 3 * cin_pad;
+    if (dalloc(&io_in_h[1], rows * cin)) return -1;
+    if (dalloc(&io_prob[1], static_cast<size_t>(batch) * n_labels())) return -1;
+    if (dalloc(&io_value[1], batch) || dalloc(&io_aux[1], static_cast<size_t>(batch) * 4)) return -1;
+    stem_conv2 = stem_conv;  // same weights, epilogue and outputs; only the activation map differs
+    if (make_act_tensor_map(&stem_conv2.tm_a, io_in_h[1], batch_cap, cin)) return -1;
+    return 0;
+}
+
+int Net::enqueue_precise(int n, cudaStream_t s, bool from_f32, const int* cnt, int io) {
     if (from_f32) {
-        ARA_CUDA_OK(launch_pdl(nchw_f32_to_nhwc_split_kernel, dim3(n), dim3(256), hdr.in_channels * 65 * 4, s, d_in_f32, d_in_h,
+        ARA_CUDA_OK(launch_pdl(nchw_f32_to_nhwc_split_kernel, dim3(n), dim3(256), hdr.in_channels * 65 * 4, s, d_in_f32, io_in_h[io],
                                hdr.in_channels, cin_pad));
         ++launches;
     }
-    if (conv_layer_launch(&stem_conv, n, s, cnt)) return -1;
+    if (conv_layer_launch(io ? &stem_conv2 : &stem_conv, n, s, cnt)) return -1;
     ++launches;
     for (int i = 0; i < hdr.n_blocks; ++i) {
         const BlockDesc& bd = blocks[i];
@@ -401,22 +414,22 @@ int Net::enqueue_precise(int n, cudaStream_t s, bool from_f32, const int* cnt) {
     }
     const float* xfinal = d_xf[hdr.n_blocks & 1];
     ValueHeadW vw{vh_wv, vh_bv, vh_w1t, vh_b1, vh_w2, vh_b2, vh_wdl_w, vh_wdl_b, vh_plys_w, vh_plys_b, hdr.wdl_mode};
-    ARA_CUDA_OK(launch_pdl(value_head_kernel<float>, dim3(n), dim3(256), value_head_smem<float>(), s, xfinal, vw, d_value, d_aux, cnt));
+    ARA_CUDA_OK(launch_pdl(value_head_kernel<float>, dim3(n), dim3(256), value_head_smem<float>(), s, xfinal, vw, io_value[io], io_aux[io], cnt));
     if (conv_layer_launch(&pol_conv1, n, s, cnt)) return -1;
     if (conv_layer_launch(&pol_conv2, n, s, cnt)) return -1;
-    ARA_CUDA_OK(launch_pdl(policy_softmax_kernel, dim3(n), dim3(256), n_labels() * 4, s, d_logits, d_prob, hdr.policy_channels, ldp, cnt));
+    ARA_CUDA_OK(launch_pdl(policy_softmax_kernel, dim3(n), dim3(256), n_labels() * 4, s, d_logits, io_prob[io], hdr.policy_channels, ldp, cnt));
     launches += 4;
     ARA_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-int Net::enqueue(int n, cudaStream_t s, bool from_f32, const int* cnt) {
-    if (precision == 1) return enqueue_precise(n, s, from_f32, cnt);
+int Net::enqueue(int n, cudaStream_t s, bool from_f32, const int* cnt, int io) {
+    if (precision == 1) return enqueue_precise(n, s, from_f32, cnt, io);
     if (from_f32) {
-        ARA_CUDA_OK(launch_pdl(nchw_f32_to_nhwc_f16_kernel, dim3(n), dim3(256), hdr.in_channels * 65 * 4, s, d_in_f32, d_in_h, hdr.in_channels, cin_pad));
+        ARA_CUDA_OK(launch_pdl(nchw_f32_to_nhwc_f16_kernel, dim3(n), dim3(256), hdr.in_channels * 65 * 4, s, d_in_f32, io_in_h[io], hdr.in_channels, cin_pad));
         ++launches;
     }
-    if (conv_layer_launch(&stem_conv, n, s, cnt)) return -1;
+    if (conv_layer_launch(io ? &stem_conv2 : &stem_conv, n, s, cnt)) return -1;
     if (rise_trunk_launch(&trunk_, n, s, cnt)) return -1;
     launches += 2;
     __half* xfinal = d_x[1];
@@ -424,44 +437,46 @@ int Net::enqueue(int n, cudaStream_t s, bool from_f32, const int* cnt) {
     if (fork_heads) {  // value head on the side stream (a second branch of the captured graph), policy head on s
         ARA_CUDA_OK(cudaEventRecord(ev_fork, s));
         ARA_CUDA_OK(cudaStreamWaitEvent(head_stream, ev_fork, 0));
-        value_head_kernel<__half><<<dim3(n), dim3(256), value_head_smem<__half>(), head_stream>>>(xfinal, vw, d_value, d_aux, cnt);
+        value_head_kernel<__half><<<dim3(n), dim3(256), value_head_smem<__half>(), head_stream>>>(xfinal, vw, io_value[io], io_aux[io], cnt);
         ARA_CUDA_OK(cudaEventRecord(ev_join, head_stream));
     } else {
-        ARA_CUDA_OK(launch_pdl(value_head_kernel<__half>, dim3(n), dim3(256), value_head_smem<__half>(), s, xfinal, vw, d_value, d_aux, cnt));
+        ARA_CUDA_OK(launch_pdl(value_head_kernel<__half>, dim3(n), dim3(256), value_head_smem<__half>(), s, xfinal, vw, io_value[io], io_aux[io], cnt));
     }
     if (conv_layer_launch(&pol_conv1, n, s, cnt)) return -1;
     if (conv_layer_launch(&pol_conv2, n, s, cnt)) return -1;
-    ARA_CUDA_OK(launch_pdl(policy_softmax_kernel, dim3(n), dim3(256), n_labels() * 4, s, d_logits, d_prob, hdr.policy_channels, ldp, cnt));
+    ARA_CUDA_OK(launch_pdl(policy_softmax_kernel, dim3(n), dim3(256), n_labels() * 4, s, d_logits, io_prob[io], hdr.policy_channels, ldp, cnt));
     if (fork_heads) ARA_CUDA_OK(cudaStreamWaitEvent(s, ev_join, 0));
     launches += 4;
     ARA_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-int Net::forward_device(int n, cudaStream_t s, const int* cnt) {
+int Net::forward_device(int n, cudaStream_t s, const int* cnt, int io) {
     if (n < 1 || n > batch) return set_error("forward: n=%d outside [1,%d]", n, batch);
-    if (!use_graph) return enqueue(n, s, false, cnt);
+    if (io != 0 && (io != 1 || io_in_h[1] == nullptr)) return set_error("forward: input/output set %d not enabled", io);
+    if (!use_graph) return enqueue(n, s, false, cnt, io);
     {   // inside somebody else's capture (the search's iteration graph) the kernels go in directly
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
         ARA_CUDA_OK(cudaStreamIsCapturing(s, &cs));
-        if (cs == cudaStreamCaptureStatusActive) return enqueue(n, s, false, cnt);
+        if (cs == cudaStreamCaptureStatusActive) return enqueue(n, s, false, cnt, io);
     }
-    const int gk = cnt != nullptr ? 2 : 0;
-    if (cnt != nullptr && cnt != count_ptr_) {  // graphs captured with another counter are of no use
-        for (auto& g : graphs_[2]) cudaGraphExecDestroy(g.second);
-        graphs_[2].clear();
-        count_ptr_ = cnt;
+    const int gk = io == 1 ? 3 : (cnt != nullptr ? 2 : 0);
+    const int*& baked = io == 1 ? count_ptr2_ : count_ptr_;
+    if ((gk == 3 || cnt != nullptr) && cnt != baked) {  // graphs captured with another counter are of no use
+        for (auto& g : graphs_[gk]) cudaGraphExecDestroy(g.second);
+        graphs_[gk].clear();
+        baked = cnt;
     }
     auto& graphs = graphs_[gk];
     auto it = graphs.find(n);
     if (it == graphs.end()) {
         // warm-up launch outside capture (sets function attributes), then capture
-        if (enqueue(n, s, false, cnt)) return -1;
+        if (enqueue(n, s, false, cnt, io)) return -1;
         ARA_CUDA_OK(cudaStreamSynchronize(s));
         const long long before = launches;
         cudaGraph_t g;
         ARA_CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-        int rc = enqueue(n, s, false, cnt);
+        int rc = enqueue(n, s, false, cnt, io);
         cudaError_t e = cudaStreamEndCapture(s, &g);
         launches = before;
         if (rc) return -1;

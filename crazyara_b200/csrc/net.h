@@ -60,7 +60,10 @@ class Net {
     // device-resident API: input already in in_h (NHWC fp16), outputs stay in d_value / d_prob
     // boards_dev (optional): device-side count (<= n) of the input rows that really hold positions -- the launch is
     // sized for n, thread blocks of the rows beyond the count leave at once; the pointer is baked into the CUDA graph
-    int forward_device(int n, cudaStream_t stream, const int* boards_dev = nullptr);
+    // io: which input / output buffer set (0, or 1 after enable_second_io()): a search with Threads = 2 keeps two
+    // batches in flight -- one set is being written / read by the tree kernels while the other is at the network
+    int forward_device(int n, cudaStream_t stream, const int* boards_dev = nullptr, int io = 0);
+    int enable_second_io();
     int forward_from_f32_device(int n, cudaStream_t stream);  // converts d_in_f32 -> in_h first
 
     NetHeader hdr{};
@@ -90,6 +93,11 @@ class Net {
     float* d_prob = nullptr;     // [batch, L]
     float* d_value = nullptr;    // [batch]
     float* d_aux = nullptr;      // [batch, 4]
+    // second input / output set (enable_second_io): [1] of each pair, [0] aliases the members above
+    __half* io_in_h[2] = {nullptr, nullptr};
+    float* io_prob[2] = {nullptr, nullptr};
+    float* io_value[2] = {nullptr, nullptr};
+    float* io_aux[2] = {nullptr, nullptr};
     // float32 only: trunk ping-pong in fp32 + split copies, bottleneck intermediates
     float* d_xf[2] = {nullptr, nullptr};  // [batch_cap*64, 256]
     __half* d_xs[2] = {nullptr, nullptr};  // [batch_cap*64, 768]
@@ -99,17 +107,18 @@ class Net {
     bool use_graph = true;
 
    private:
-    int enqueue(int n, cudaStream_t s, bool from_f32, const int* boards_dev = nullptr);
+    int enqueue(int n, cudaStream_t s, bool from_f32, const int* boards_dev = nullptr, int io = 0);
     int read_blob(const char* blob_path, HostWeights* hw);
     int build_half(const HostWeights& hw);
     int build_precise(const HostWeights& hw);
     int upload_value_head(const HostWeights& hw);
-    int enqueue_precise(int n, cudaStream_t s, bool from_f32, const int* boards_dev);
+    int enqueue_precise(int n, cudaStream_t s, bool from_f32, const int* boards_dev, int io);
     std::vector<void*> allocs_;
     int max_cop_ = 0;
     __half* stem_w = nullptr;
     float* stem_b = nullptr;
     ConvLayer stem_conv;
+    ConvLayer stem_conv2;  // the stem reading the second input set
     std::vector<PreciseBlock> pb_;
     RiseTrunk trunk_;
     float *vh_wv = nullptr, *vh_bv = nullptr, *vh_w1t = nullptr, *vh_b1 = nullptr, *vh_w2 = nullptr, *vh_b2 = nullptr;
@@ -117,7 +126,8 @@ class Net {
     __half *pol_w1 = nullptr, *pol_w2 = nullptr;
     float* pol_b1 = nullptr;
     ConvLayer pol_conv1, pol_conv2;
-    std::map<int, cudaGraphExec_t> graphs_[3];  // plain, from fp32 input, with a device-side count
+    std::map<int, cudaGraphExec_t> graphs_[4];  // plain, from fp32 input, with a device-side count (io 0), the same for io 1
+    const int* count_ptr2_ = nullptr;
     const int* count_ptr_ = nullptr;            // the pointer the graphs_[2] entries were captured with
     template <typename T>
     int dalloc(T** p, size_t count);

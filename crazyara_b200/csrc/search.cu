@@ -206,6 +206,32 @@ class Search {
     cudaStream_t side_stream_ = nullptr;  // second branch of an iteration (value backups)
     cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr;
     int enqueue_iteration(bool with_events);
+    // ---- Threads = 2 (sp.threads): two logical search threads per tree, each with its own batch state ("slot": views
+    // of the trees with their own new-leaf / trajectory arrays, their own rows of the network's second input / output
+    // set).  The tree kernels of both threads run on stream_ in the fixed order
+    //     S0 S1 | U0 S0 U1 S1 | U0 S0 ...     (S = select + pack + expand, U = scatter + prepare || backup)
+    // and each thread's network forward on net_stream_, between its S and its next U: while one thread's batch is at
+    // the network the other thread selects.  (oracle/mcts.h describes the schedule; tests compare all three.)
+    int threads_ = 1;
+    bool primed_ = false;                  // S0 S1 of the current go have been enqueued
+    TreeDev* d_trees_slot_[2] = {nullptr, nullptr};
+    std::vector<TreeDev> h_trees1_;        // slot 1 views (h_trees_ = slot 0)
+    struct SlotArrays {                    // per tree: the batch arrays of slot 1
+        int32_t *exp_parent, *new_node, *traj_node, *traj_len;
+        uint16_t* traj_ci;
+        uint32_t* traj_edge;
+        BatchState* bs;
+    };
+    std::vector<SlotArrays> slot1_;
+    int* d_count_slot_[2] = {nullptr, nullptr};
+    float *d_values_slot_[2] = {nullptr, nullptr}, *d_probs_slot_[2] = {nullptr, nullptr};  // fake backend, per slot
+    cudaStream_t net_stream_ = nullptr;
+    cudaEvent_t ev_sel_[2] = {nullptr, nullptr}, ev_net_[2] = {nullptr, nullptr};
+    cudaGraphExec_t slot_graph_[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [slot][with update]
+    bool slot_warm_ = false;
+    int enqueue_slot(int slot, bool with_update);
+    int enqueue_slot_tree_ops(int slot, bool with_update);
+    int iterate2(int cycles);
     int* d_count_ = nullptr;  // multi-tree searches: rows of the network batch in use (written by pack_kernel)
     RootTimeStats* d_tstats_ = nullptr;
     RootTimeStats* h_tstats_ = nullptr;  // pinned
@@ -259,6 +285,17 @@ cudaEvent_t Search::prof_event() {
 }
 int Search::prof_collect() {  // events come in groups of four: before select, before net, after net, after apply
     select_ms = net_ms = apply_ms = 0.0;
+    if (threads_ == 2) {  // groups of four per turn: tree ops begin / end on stream_, forward begin / end on net_stream_;
+                          // select_ms = the tree stream's time (backups + scatter + select + expand), apply_ms stays 0
+        for (size_t i = 0; i + 3 < prof_used_; i += 4) {
+            float a = 0, b = 0;
+            ARA_CUDA_OK(cudaEventElapsedTime(&a, prof_events_[i], prof_events_[i + 1]));
+            ARA_CUDA_OK(cudaEventElapsedTime(&b, prof_events_[i + 2], prof_events_[i + 3]));
+            select_ms += a;
+            net_ms += b;
+        }
+        return 0;
+    }
     for (size_t i = 0; i + 3 < prof_used_; i += 4) {
         float a = 0, b = 0, c = 0;
         ARA_CUDA_OK(cudaEventElapsedTime(&a, prof_events_[i], prof_events_[i + 1]));
@@ -290,6 +327,15 @@ Search::~Search() {
     if (d_tstats_) cudaFree(d_tstats_);
     if (d_count_) cudaFree(d_count_);
     if (iter_graph_) cudaGraphExecDestroy(iter_graph_);
+    for (auto& a : slot_graph_)
+        for (auto g : a)
+            if (g) cudaGraphExecDestroy(g);
+    if (net_stream_) cudaStreamDestroy(net_stream_);
+    for (cudaEvent_t e : ev_sel_)
+        if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : ev_net_)
+        if (e) cudaEventDestroy(e);
+    if (d_count_slot_[1]) cudaFree(d_count_slot_[1]);
     if (side_stream_) cudaStreamDestroy(side_stream_);
     if (ev_fork_) cudaEventDestroy(ev_fork_);
     if (ev_join_) cudaEventDestroy(ev_join_);
@@ -308,6 +354,12 @@ int Search::init(Net* net, const SearchParams& params, int device, int trees, in
     if (n_trees < 1) return set_error("ara_search_create: n_trees %d < 1", n_trees);
     if (planes_channels(sp.mode, sp.input_version) < 0)
         return set_error("ara_search_create: unsupported mode %d / input version %d", sp.mode, sp.input_version);
+    if (sp.threads == 0) sp.threads = 1;
+    if (sp.threads != 1 && sp.threads != 2) return set_error("ara_search_create: Threads %d (1 or 2)", sp.threads);
+    // the virtual visits in flight on an edge are counted in a uint8 like the reference's (nodedata.h:93)
+    if (sp.threads * sp.batch_size > 255 && sp.threads > 1)
+        return set_error("ara_search_create: Threads %d x Batch_Size %d exceeds the 255 virtual visits an edge can carry", sp.threads, sp.batch_size);
+    threads_ = sp.threads;
     ARA_CUDA_OK(cudaSetDevice(device_));
     {
         cudaDeviceProp prop;
@@ -331,7 +383,7 @@ int Search::init(Net* net, const SearchParams& params, int device, int trees, in
     if (max_nodes <= 0) {
         const unsigned budget = sp.simulations ? sp.simulations : (sp.nodes ? sp.nodes * 2 : 0);
         if (budget == 0) return set_error("ara_search_create: max_nodes must be given when neither Simulations nor Nodes is set");
-        max_nodes = static_cast<int>(budget) + 4 * sp.batch_size + 64;
+        max_nodes = static_cast<int>(budget) + 4 * sp.batch_size * sp.threads + 64;
     }
     max_nodes_ = max_nodes;
     // edge pool: average legal moves per node is ~35 (chess) but drop-heavy crazyhouse positions reach 200-300
@@ -384,12 +436,38 @@ int Search::init(Net* net, const SearchParams& params, int device, int trees, in
         d_states_[i] = t.st;
     }
     if (dalloc(&d_trees_, n_trees) || dalloc(&d_roots_, n_trees) || dalloc(&d_results_, n_trees)) return -1;
+    d_trees_slot_[0] = d_trees_;
+    if (threads_ == 2) {
+        slot1_.resize(n_trees);
+        for (int i = 0; i < n_trees; ++i) {
+            SlotArrays& a = slot1_[i];
+            if (dalloc(&a.new_node, B) || dalloc(&a.traj_node, static_cast<size_t>(2) * B * kMaxDepth) ||
+                dalloc(&a.traj_ci, static_cast<size_t>(2) * B * kMaxDepth) || dalloc(&a.traj_len, 2 * B) ||
+                dalloc(&a.traj_edge, static_cast<size_t>(2) * B * kMaxDepth) || dalloc(&a.exp_parent, 3 * B) || dalloc(&a.bs, 1))
+                return -1;
+        }
+        if (dalloc(&d_trees_slot_[1], n_trees)) return -1;
+        if (net_ != nullptr) {
+            if (net_->enable_second_io()) return -1;
+        } else {
+            d_values_slot_[0] = d_values_, d_probs_slot_[0] = d_probs_;
+            if (dalloc(&d_values_slot_[1], static_cast<size_t>(n_trees) * sp.batch_size)) return -1;
+            if (dalloc(&d_probs_slot_[1], static_cast<size_t>(n_trees) * sp.batch_size * n_labels_)) return -1;
+        }
+        ARA_CUDA_OK(cudaStreamCreateWithFlags(&net_stream_, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            ARA_CUDA_OK(cudaEventCreateWithFlags(&ev_sel_[k], cudaEventDisableTiming));
+            ARA_CUDA_OK(cudaEventCreateWithFlags(&ev_net_[k], cudaEventDisableTiming));
+        }
+        ARA_CUDA_OK(cudaMalloc(&d_count_slot_[1], sizeof(int)));
+    }
     h_roots_.resize(n_trees);
     results.resize(n_trees);
     ARA_CUDA_OK(cudaMallocHost(&h_done_, sizeof(int) * n_trees));
     ARA_CUDA_OK(cudaMallocHost(&h_tstats_, sizeof(RootTimeStats)));
     ARA_CUDA_OK(cudaMalloc(&d_tstats_, sizeof(RootTimeStats)));
     ARA_CUDA_OK(cudaMalloc(&d_count_, sizeof(int)));
+    d_count_slot_[0] = d_count_;
     if (const char* e = getenv("ARA_ITER_GRAPH")) use_iter_graph_ = atoi(e) != 0;
     ARA_CUDA_OK(cudaStreamCreateWithFlags(&side_stream_, cudaStreamNonBlocking));
     ARA_CUDA_OK(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
@@ -449,7 +527,91 @@ int Search::enqueue_iteration(bool with_events) {
 // `count` iterations.  Outside profiling runs an iteration is ONE graph launch: the kernels of an iteration never
 // change (same pointers, same grids), so the sequence is captured once per handle -- the network's own graph becomes a
 // child node -- and the dependent-launch gaps between the seven search kernels shrink to graph-edge latency.
+// Threads = 2: the tree kernels of one turn of logical thread `slot` -- U (the backups and the scatter / prepare step of
+// its previous batch) then S (its next select, pack, expand) -- on stream_.
+int Search::enqueue_slot_tree_ops(int slot, bool with_update) {
+    const int B = sp.batch_size;
+    TreeDev* trees = d_trees_slot_[slot];
+    const float* values = net_ ? net_->io_value[slot] : d_values_slot_[slot];
+    const float* probs = net_ ? net_->io_prob[slot] : d_probs_slot_[slot];
+    if (with_update) {
+        ARA_CUDA_OK(cudaEventRecord(ev_fork_, stream_));
+        ARA_CUDA_OK(cudaStreamWaitEvent(side_stream_, ev_fork_, 0));
+        backup_kernel<<<n_trees, 32, 0, side_stream_>>>(trees, sp, 0, values);
+        ARA_CUDA_OK(cudaEventRecord(ev_join_, side_stream_));
+        scatter_prepare_kernel<<<n_trees * 4 * B, 32, 0, stream_>>>(trees, sp, B, 4 * B, values, probs, n_labels_);
+        ARA_CUDA_OK(cudaStreamWaitEvent(stream_, ev_join_, 0));
+    }
+    select_kernel<<<n_trees, 32, 0, stream_>>>(trees, sp);
+    pack_kernel<<<1, 32, 0, stream_>>>(trees, n_trees, d_count_slot_[slot]);
+    expand_kernel<<<n_trees * B, 32, 0, stream_>>>(trees, sp, B, net_ ? net_->io_in_h[slot] : nullptr, net_ ? net_->cin_pad : 0,
+                                                    net_ ? net_->precision : 0);
+    return 0;
+}
+
+// one turn of logical thread `slot`: wait for its batch at the network, U + S on the tree stream, then hand the new batch
+// to the network stream
+int Search::enqueue_slot(int slot, bool with_update) {
+    const int B = sp.batch_size;
+    if (with_update) ARA_CUDA_OK(cudaStreamWaitEvent(stream_, ev_net_[slot], 0));
+    const bool graphed = use_iter_graph_ && !profile;
+    cudaGraphExec_t& ge = slot_graph_[slot][with_update ? 1 : 0];
+    if (profile) prof_event();
+    if (graphed && ge != nullptr) {
+        ARA_CUDA_OK(cudaGraphLaunch(ge, stream_));
+    } else if (graphed && slot_warm_) {
+        cudaGraph_t g;
+        ARA_CUDA_OK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+        const int rc = enqueue_slot_tree_ops(slot, with_update);
+        const cudaError_t e = cudaStreamEndCapture(stream_, &g);
+        if (rc) return -1;
+        ARA_CUDA_OK(e);
+        ARA_CUDA_OK(cudaGraphInstantiate(&ge, g, 0));
+        cudaGraphDestroy(g);
+        ARA_CUDA_OK(cudaGraphLaunch(ge, stream_));
+    } else {
+        if (enqueue_slot_tree_ops(slot, with_update)) return -1;
+    }
+    if (profile) prof_event();
+    launches += 3 + (with_update ? 2 : 0);
+    ARA_CUDA_OK(cudaEventRecord(ev_sel_[slot], stream_));
+    ARA_CUDA_OK(cudaStreamWaitEvent(net_stream_, ev_sel_[slot], 0));
+    if (profile) {
+        cudaEvent_t e = prof_event();  // (recorded on stream_; re-record it on the network stream)
+        ARA_CUDA_OK(cudaEventRecord(e, net_stream_));
+    }
+    if (net_) {
+        if (net_->forward_device(n_trees * B, net_stream_, d_count_slot_[slot], slot)) return -1;
+    } else {
+        fake_eval_kernel<<<n_trees * B, 128, 0, net_stream_>>>(d_trees_slot_[slot], n_trees, B, d_values_slot_[slot],
+                                                               d_probs_slot_[slot], n_labels_);
+        ++launches;
+    }
+    if (profile) {
+        cudaEvent_t e = prof_event();
+        ARA_CUDA_OK(cudaEventRecord(e, net_stream_));
+    }
+    ARA_CUDA_OK(cudaEventRecord(ev_net_[slot], net_stream_));
+    ++net_forwards;
+    return 0;
+}
+
+// `cycles` turns of both logical threads (two mini-batches each cycle)
+int Search::iterate2(int cycles) {
+    if (!primed_) {  // S0 S1: nothing to back up yet (the root's batch was applied by the root phase)
+        if (enqueue_slot(0, false) || enqueue_slot(1, false)) return -1;
+        primed_ = true;
+        slot_warm_ = true;
+        --cycles;
+    }
+    for (int c = 0; c < cycles; ++c)
+        if (enqueue_slot(0, true) || enqueue_slot(1, true)) return -1;
+    ARA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int Search::iterate(int count) {
+    if (threads_ == 2) return iterate2((count + 1) / 2);
     const int search_kernels = 4 + (n_trees > 1 ? 1 : 0) + (net_ ? 0 : 1);
     const bool graphed = use_iter_graph_ && !profile;
     for (int it = 0; it < count; ++it) {
@@ -490,6 +652,18 @@ int Search::go() {
     ARA_CUDA_OK(cudaEventRecord(ev0_, stream_));
     ARA_CUDA_OK(cudaMemcpyAsync(d_trees_, h_trees_.data(), sizeof(TreeDev) * n_trees, cudaMemcpyHostToDevice, stream_));
     ARA_CUDA_OK(cudaMemcpyAsync(d_roots_, h_roots_.data(), sizeof(Board) * n_trees, cudaMemcpyHostToDevice, stream_));
+    if (threads_ == 2) {  // the second thread's views of the trees: same pools, its own batch arrays
+        h_trees1_ = h_trees_;
+        for (int i = 0; i < n_trees; ++i) {
+            TreeDev& t = h_trees1_[i];
+            const SlotArrays& a = slot1_[i];
+            t.exp_parent = a.exp_parent, t.new_node = a.new_node, t.traj_node = a.traj_node, t.traj_len = a.traj_len;
+            t.traj_ci = a.traj_ci, t.traj_edge = a.traj_edge, t.bs = a.bs;
+            ARA_CUDA_OK(cudaMemsetAsync(a.bs, 0, sizeof(BatchState), stream_));
+        }
+        ARA_CUDA_OK(cudaMemcpyAsync(d_trees_slot_[1], h_trees1_.data(), sizeof(TreeDev) * n_trees, cudaMemcpyHostToDevice, stream_));
+        primed_ = false;
+    }
     __half* in_h = net_ ? net_->d_in_h : nullptr;
     const int cpad = net_ ? net_->cin_pad : 0;
     const int B = sp.batch_size;

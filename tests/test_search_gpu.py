@@ -42,6 +42,35 @@ def test_gpu_search_equals_oracle_fake_backend(case):
     assert_same_search(ro, rg)
 
 
+CASES_2T = [c for c in CASES if 2 * c[6] < 256]  # Threads x Batch_Size < 256 (uint8 virtual-visit counter, as in the reference)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES_2T, ids=[f"{c[0]}-b{c[6]}-s{c[7]}-{i}" for i, c in enumerate(CASES_2T)])
+def test_gpu_two_thread_search_equals_oracle_fake_backend(case):
+    """Threads = 2 on the device: two logical search threads per tree, their tree kernels on one stream in the fixed
+    schedule of oracle/mcts.h, their network batches on a second stream (one thread selects while the other's batch is
+    evaluated).  Deterministic, so visit counts / Q / priors / posterior are the oracle's bits in this mode too."""
+    variant, vid, mode, fen, is960, premoves, batch, sims, extra = case
+    st = case_settings(mode, batch, sims, dict(extra, threads=2))
+    pos = Position(fen, variant, is960)
+    pos.push_uci(*premoves)
+    S = osr.Search(st)
+    ro = S.run(pos, osr.fake_net(S.n_labels), with_keys=True, threads=2)
+    rg = _gpu_search(vid, fen, is960, premoves, st)[0]
+    assert_same_search(ro, rg)
+
+
+@pytest.mark.gpu
+def test_gpu_two_thread_multi_tree_search_matches_single_tree():
+    st = osr.default_settings("crazyhouse", batch_size=8, simulations=300, node_policy_temperature=1.7, threads=2)
+    pos = Position(variant="crazyhouse")
+    S = osr.Search(st)
+    ro = S.run(pos, osr.fake_net(S.n_labels), with_keys=True, threads=2)
+    for r in _gpu_search(1, None, False, [], st, n_trees=5):
+        assert_same_search(ro, r)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("seed", range(32))
 def test_gpu_search_equals_oracle_random_cases(seed):
@@ -114,6 +143,13 @@ def test_gpu_search_real_net_equals_oracle_driven_by_same_net(tmp_path, variant,
     ro2 = osr.Search(st2).run(pos, _net_fn(net))
     rg2 = _gpu_search(vid, None, False, premoves, st2, net=net)[0]
     assert_same_search(ro2, rg2)
+    # Threads = 2 with the real network (second input / output set of the net, forwards on the network stream)
+    if 2 * batch < 256:
+        st3 = osr.default_settings(mode, batch_size=batch, simulations=sims, input_version=version, threads=2)
+        st3.node_policy_temperature = 1.7
+        ro3 = osr.Search(st3).run(pos, _net_fn(net), threads=2)
+        rg3 = _gpu_search(vid, None, False, premoves, st3, net=net)[0]
+        assert_same_search(ro3, rg3)
     net.close()
 
 

@@ -19,7 +19,16 @@ int set_error(const char* fmt, ...) {
     return -1;
 }
 
+static thread_local int g_pdl_suspended = 0;
+PdlSuspend::PdlSuspend(bool on) : on_(on) {
+    if (on_) ++g_pdl_suspended;
+}
+PdlSuspend::~PdlSuspend() {
+    if (on_) --g_pdl_suspended;
+}
+
 bool pdl_enabled() {
+    if (g_pdl_suspended > 0) return false;
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("ARA_NO_PDL");

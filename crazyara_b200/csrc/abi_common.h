@@ -20,6 +20,19 @@ int set_error(const char* fmt, ...);
 // Launch with programmatic stream serialization (PDL): the kernel may start while its predecessor in the stream is
 // still draining; kernels call pdl_wait() before touching the predecessor's outputs.  ARA_NO_PDL=1 disables it.
 bool pdl_enabled();
+// While one lives on the calling thread, launch_pdl launches (and captures) plain kernels.  A search with Threads = 2 runs
+// the network on a second stream beside the tree kernels; thread blocks of early-launched network kernels parked at
+// their griddepcontrol.wait then delay the tree stream's launches (measured: 29.8 ms per headline search with the
+// attribute, 21.4 ms without), so that mode captures the network without it.
+struct PdlSuspend {
+    explicit PdlSuspend(bool on);
+    ~PdlSuspend();
+    PdlSuspend(const PdlSuspend&) = delete;
+    PdlSuspend& operator=(const PdlSuspend&) = delete;
+
+   private:
+    bool on_;
+};
 template <typename... KArgs, typename... Args>
 cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
     cudaLaunchConfig_t cfg = {};

@@ -454,6 +454,9 @@ int Net::enqueue(int n, cudaStream_t s, bool from_f32, const int* cnt, int io) {
 int Net::forward_device(int n, cudaStream_t s, const int* cnt, int io) {
     if (n < 1 || n > batch) return set_error("forward: n=%d outside [1,%d]", n, batch);
     if (io != 0 && (io != 1 || io_in_h[1] == nullptr)) return set_error("forward: input/output set %d not enabled", io);
+    // two input / output sets = a search with Threads = 2: this forward runs on the network stream beside the other
+    // thread's tree kernels (see PdlSuspend)
+    PdlSuspend no_pdl(io_in_h[1] != nullptr);
     if (!use_graph) return enqueue(n, s, false, cnt, io);
     {   // inside somebody else's capture (the search's iteration graph) the kernels go in directly
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;

@@ -51,11 +51,17 @@ struct NullWriterFactory {  // fake backend: no planes needed
     ARA_HD Target make(int) const { return Target{}; }
 };
 
-__global__ void __launch_bounds__(32) root_kernel(const TreeDev* trees, SearchParams sp, const Board* roots) {
+// limits: per tree {simulations, nodes} of this go (ara_search_set_limits), or the settings' for every tree
+__global__ void __launch_bounds__(32) root_kernel(const TreeDev* trees, SearchParams sp, const Board* roots, const uint2* limits) {
     __shared__ WarpScratch ws;
     const TreeDev t = trees[blockIdx.x];
     // the subtree kept by ara_search_apply_move is searched on if it is this position, else a new tree starts
     if (!reuse_root(t, sp, &roots[blockIdx.x])) create_root(t, sp, ws, &roots[blockIdx.x]);
+    __syncwarp();
+    if (threadIdx.x == 0) {
+        t.st->limit_simulations = limits[blockIdx.x].x;
+        t.st->limit_nodes = limits[blockIdx.x].y;
+    }
 }
 
 // MCTSAgent::apply_move_to_tree for one tree
@@ -232,6 +238,9 @@ class Search {
     int enqueue_slot(int slot, bool with_update);
     int enqueue_slot_tree_ops(int slot, bool with_update);
     int iterate2(int cycles);
+    std::vector<uint2> h_limits_;  // per tree {simulations, nodes} of the next go
+    uint2* d_limits_ = nullptr;
+    int set_limits(int tree, unsigned simulations, unsigned nodes);
     int* d_count_ = nullptr;  // multi-tree searches: rows of the network batch in use (written by pack_kernel)
     RootTimeStats* d_tstats_ = nullptr;
     RootTimeStats* h_tstats_ = nullptr;  // pinned
@@ -435,7 +444,12 @@ int Search::init(Net* net, const SearchParams& params, int device, int trees, in
         t.slot_base = i * B;
         d_states_[i] = t.st;
     }
-    if (dalloc(&d_trees_, n_trees) || dalloc(&d_roots_, n_trees) || dalloc(&d_results_, n_trees)) return -1;
+    if (dalloc(&d_trees_, n_trees) || dalloc(&d_roots_, n_trees) || dalloc(&d_results_, n_trees) || dalloc(&d_limits_, n_trees)) return -1;
+    h_limits_.assign(n_trees, make_uint2(sp.simulations, sp.nodes));
+    for (int i = 0; i < n_trees; ++i) {  // the trees' Dirichlet generators (TreeState::rng)
+        const uint32_t x = minstd_seed(sp.seed, i);
+        ARA_CUDA_OK(cudaMemcpy(&d_states_[i]->rng, &x, sizeof(x), cudaMemcpyHostToDevice));
+    }
     d_trees_slot_[0] = d_trees_;
     if (threads_ == 2) {
         slot1_.resize(n_trees);
@@ -454,7 +468,13 @@ int Search::init(Net* net, const SearchParams& params, int device, int trees, in
             if (dalloc(&d_values_slot_[1], static_cast<size_t>(n_trees) * sp.batch_size)) return -1;
             if (dalloc(&d_probs_slot_[1], static_cast<size_t>(n_trees) * sp.batch_size * n_labels_)) return -1;
         }
-        ARA_CUDA_OK(cudaStreamCreateWithFlags(&net_stream_, cudaStreamNonBlocking));
+        {   // the network stream yields to the tree stream: a pending select / expand launch is never queued behind the
+            // thread blocks of a convolution grid
+            int lo = 0, hi = 0;
+            ARA_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            const char* e = getenv("ARA_NET_STREAM_PRIO");
+            ARA_CUDA_OK(cudaStreamCreateWithPriority(&net_stream_, cudaStreamNonBlocking, (e && atoi(e) == 0) ? hi : lo));
+        }
         for (int k = 0; k < 2; ++k) {
             ARA_CUDA_OK(cudaEventCreateWithFlags(&ev_sel_[k], cudaEventDisableTiming));
             ARA_CUDA_OK(cudaEventCreateWithFlags(&ev_net_[k], cudaEventDisableTiming));
@@ -668,7 +688,8 @@ int Search::go() {
     const int cpad = net_ ? net_->cin_pad : 0;
     const int B = sp.batch_size;
     // root: create, expand, evaluate (set_root_node_predictions), scatter, prepare_node_for_visits (+ Dirichlet)
-    root_kernel<<<n_trees, 32, 0, stream_>>>(d_trees_, sp, d_roots_);
+    ARA_CUDA_OK(cudaMemcpyAsync(d_limits_, h_limits_.data(), sizeof(uint2) * n_trees, cudaMemcpyHostToDevice, stream_));
+    root_kernel<<<n_trees, 32, 0, stream_>>>(d_trees_, sp, d_roots_, d_limits_);
     if (n_trees > 1) {
         pack_kernel<<<1, 32, 0, stream_>>>(d_trees_, n_trees, d_count_);
         ++launches;
@@ -777,6 +798,14 @@ int Search::go() {
     return 0;
 }
 
+int Search::set_limits(int tree, unsigned simulations, unsigned nodes) {
+    if (tree < -1 || tree >= n_trees) return set_error("ara_search_set_limits: tree %d out of range", tree);
+    if (simulations == 0 && nodes == 0) return set_error("ara_search_set_limits: neither Simulations nor Nodes given");
+    for (int i = 0; i < n_trees; ++i)
+        if (tree < 0 || tree == i) h_limits_[i] = make_uint2(simulations, nodes);
+    return 0;
+}
+
 int Search::read_time_stats(RootStatsHost* out) {
     time_stats_kernel<<<1, 32, 0, stream_>>>(d_trees_, d_tstats_);
     ++launches;
@@ -875,6 +904,11 @@ extern "C" int ara_search_apply_move(ara_search_t h, int tree, unsigned short mo
     if (h == nullptr) return ara::set_error("ara_search_apply_move: null handle");
     return reinterpret_cast<Search*>(h)->apply_move(tree, move);
 }
+extern "C" int ara_search_set_limits(ara_search_t h, int tree, unsigned simulations, unsigned nodes) {
+    if (h == nullptr) return ara::set_error("ara_search_set_limits: null handle");
+    return reinterpret_cast<Search*>(h)->set_limits(tree, simulations, nodes);
+}
+
 extern "C" int ara_search_stop(ara_search_t h) {
     if (h == nullptr) return ara::set_error("ara_search_stop: null handle");
     reinterpret_cast<Search*>(h)->request_stop();

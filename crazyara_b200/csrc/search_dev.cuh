@@ -93,7 +93,14 @@ struct BatchState {
 struct TreeState {
     int n_nodes;
     int n_edges;
-    int pad0_;
+    // Dirichlet generator (minstd_rand0 state): seeded once when the search handle is created -- from the settings' seed
+    // and the tree's index -- and ADVANCED by every root noise draw, like the reference's one process-wide
+    // std::default_random_engine (util/randomgen.h:35): successive searches, and different trees, see different noise
+    uint32_t rng;
+    // SearchLimits of the current go (searchlimits.h): by default the settings' values; ara_search_set_limits overrides
+    // them per tree (self-play jitters the node budget of every search, rl/selfplay.cpp:146-152)
+    uint32_t limit_simulations;
+    uint32_t limit_nodes;
     int pad1_;
     int root;        // node id of the current root (0 for a new tree, the re-rooted child when the tree is reused)
     int next_root;   // candidate root after ara_search_apply_move (MCTSAgent::ownNextRoot / opponentsNextRoot), -1 none
@@ -896,6 +903,13 @@ ARA_HD float canonical_f(MinStd& g) {
     if (r >= 1.0f) r = 0.99999994f;  // nextafterf(1, 0)
     return r;
 }
+// std::default_random_engine(seed): minstd_rand0 state = seed mod (2^31 - 1), 0 -> 1; tree `index` of a handle is seeded
+// with seed ^ index * golden ratio, so that tree 0 uses the settings' seed itself
+ARA_HD uint32_t minstd_seed(unsigned long long seed, int index) {
+    const unsigned long long s = seed ^ (static_cast<unsigned long long>(index) * 0x9E3779B97F4A7C15ULL);
+    const uint32_t x = static_cast<uint32_t>(s % 2147483647ULL);
+    return x == 0 ? 1u : x;
+}
 ARA_HD float gamma_f(MinStd& g, float alpha) {
     const float malpha = alpha < 1.0f ? alpha + 1.0f : alpha;
     const float a1 = malpha - 1.0f / 3.0f;
@@ -934,8 +948,7 @@ ARA_HD void apply_dirichlet_to_root(const TreeDev& t, const SearchParams& sp, Wa
     NodeHdr& h = t.hdr[t.st->root];
     const int n = h.n_moves;
     MinStd g;
-    g.x = static_cast<uint32_t>(sp.seed % 2147483647ULL);
-    if (g.x == 0) g.x = 1;
+    g.x = t.st->rng;  // (never 0: minstd_seed)
     float sum = 0.0f;
     for (int i = 0; i < n; ++i) {
         ws.sort_p[i] = gamma_f(g, sp.dirichlet_alpha);
@@ -945,6 +958,7 @@ ARA_HD void apply_dirichlet_to_root(const TreeDev& t, const SearchParams& sp, Wa
         const float noise = ws.sort_p[i] / sum;
         t.P[h.edge_base + i] = (1 - sp.dirichlet_epsilon) * t.P[h.edge_base + i] + sp.dirichlet_epsilon * noise;
     }
+    t.st->rng = g.x;
     h.no_visit_idx = static_cast<uint16_t>(n);  // fully_expand_node (edges are pre-initialised)
     h.flags |= NF_SORTED | NF_HAS_D;
 }
@@ -964,7 +978,8 @@ ARA_HD void create_mini_batch_impl(const TreeDev& t, const SearchParams& sp, War
     {
         const NodeHdr& r = t.hdr[st.root];
         const uint32_t node_count = r.visit_sum - r.free_visits;
-        const bool limits_ok = (sp.nodes == 0 || node_count < sp.nodes) && (sp.simulations == 0 || r.visit_sum < sp.simulations);
+        const bool limits_ok = (st.limit_nodes == 0 || node_count < st.limit_nodes) &&
+                               (st.limit_simulations == 0 || r.visit_sum < st.limit_simulations);
         // (a pool sized for a visit budget can never trip the last test before the budget does; it only ends
         // time-limited searches whose pool is exhausted before their time)
         const bool pool_ok = st.n_nodes + 3 * sp.batch_size + 8 <= t.max_nodes;
@@ -1247,6 +1262,8 @@ ARA_HD void create_root(const TreeDev& t, const SearchParams& sp, WarpScratch& w
         t.bs->n_exp = 0;
         t.bs->done = 0;
         st.live_threads = sp.threads == 2 ? 2 : 1;
+        st.limit_simulations = sp.simulations;
+        st.limit_nodes = sp.nodes;
         st.done = 0;
         st.error = 0;
         st.iterations = 0;
@@ -1316,6 +1333,8 @@ ARA_HD int reuse_root(const TreeDev& t, const SearchParams& sp, const Board* roo
             h.parent = -1;  // make_to_root: the path walks of prepare_child stop here
             t.bs->n_new = t.bs->n_coll = t.bs->n_exp = t.bs->done = 0;
             st.live_threads = sp.threads == 2 ? 2 : 1;
+            st.limit_simulations = sp.simulations;
+            st.limit_nodes = sp.nodes;
             st.done = ((h.flags & NF_TERMINAL) || h.n_moves == 0) ? 1 : 0;
             st.iterations = 0;
             st.evals = 0;

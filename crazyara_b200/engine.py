@@ -111,6 +111,7 @@ def _L():
                                               ctypes.c_float, ctypes.c_float]
         L.ara_time_continue_search.argtypes = [vp, ctypes.c_double, ctypes.c_float, vp, vp]
         L.ara_search_set_movetime.argtypes = [vp, ctypes.c_double]
+        L.ara_search_set_limits.argtypes = [vp, ci, ctypes.c_uint, ctypes.c_uint]
         L.ara_search_profile.argtypes = [vp] + [vp] * 4
         L.ara_search_last_go_ms.restype = ctypes.c_double
         L.ara_search_last_go_ms.argtypes = [vp]
@@ -336,6 +337,10 @@ class MCTSAgent:
     def set_movetime(self, ms):
         """SearchLimits::movetime: following searches also stop after `ms` of wall time (0 = off)."""
         check(_L().ara_search_set_movetime(self._h, float(ms)))
+
+    def set_search_limits(self, simulations, nodes, tree=-1):
+        """SearchLimits::simulations / nodes of the following searches of `tree` (-1 = all trees) instead of the settings'."""
+        check(_L().ara_search_set_limits(self._h, int(tree), int(simulations), int(nodes)))
 
     def set_profile(self, on=True):
         check(_L().ara_search_set_profile(self._h, int(on)))

@@ -124,7 +124,9 @@ typedef struct ara_search_settings_s {
     unsigned virtual_mix_threshold; /* Virtual_Mix_Threshold */
     unsigned simulations;           /* SearchLimits::simulations (0 = no limit) */
     unsigned nodes;                 /* SearchLimits::nodes (0 = no limit) */
-    unsigned long long seed;        /* explicit seed of the Dirichlet generator (the reference has none) */
+    unsigned long long seed;        /* seed of the Dirichlet generators: tree i of a handle starts from seed ^ i * 0x9E37..., and
+                                       every root noise draw advances it (the reference seeds one process-wide
+                                       std::default_random_engine from std::random_device, util/randomgen.h:35) */
     int mode;                       /* 0 MODE_CRAZYHOUSE, 1 MODE_CHESS, 2 MODE_LICHESS */
     int input_version;              /* input representation version 1, 2, 3 */
     int threads;                    /* Threads: 1 (deterministic parity mode) or 2 (the reference's default,
@@ -172,6 +174,11 @@ void ara_search_destroy(ara_search_t s);
 /* root position of tree `tree` plus the (key, repetition) history of the game before it, oldest first */
 int ara_search_set_position(ara_search_t s, int tree, const ara_board_t* root, const unsigned long long* hist_keys,
                             const short* hist_reps, int hist_len);
+/* SearchLimits of the following go calls (searchlimits.h:37-61): simulations / nodes of tree `tree` (-1 = every tree)
+ * instead of the settings' values.  The node pool is sized at creation, so the limits must stay within the budget the
+ * handle was created for (ara_search_create max_nodes).  Self-play jitters the node budget of every search
+ * (SelfPlay::adjust_node_count, rl/selfplay.cpp:146-152). */
+int ara_search_set_limits(ara_search_t s, int tree, unsigned simulations, unsigned nodes);
 /* runs all trees to their limits (synchronous) and fetches the results */
 int ara_search_go(ara_search_t s);
 int ara_search_result(ara_search_t s, int tree, ara_search_result_t* out);

@@ -62,6 +62,10 @@ typedef struct {
 
 enum { NB_NEW = 0, NB_COLLISION, NB_TERMINAL, NB_TRANSPOSITION };
 
+typedef struct {
+    uint32_t x; /* minstd_rand0 state = std::default_random_engine */
+} MinStd;
+
 struct OSearch {
     OSettings st;
     int channels, n_labels;
@@ -95,6 +99,7 @@ struct OSearch {
         float* planes;
     } parked;
     int active;
+    MinStd rng; /* the Dirichlet generator */
     unsigned long long num_nodes, sum_select_k, sum_depth;
     ONode** all_nodes;
     size_t n_all, cap_all;
@@ -123,9 +128,6 @@ void osettings_default(OSettings* s, int mode) { /* uci/optionsuci.cpp:66-220 (n
 }
 
 /* ------------------------------------------------------------------ Dirichlet noise: libstdc++ restatement */
-typedef struct {
-    uint32_t x;
-} MinStd;
 static uint32_t minstd_next(MinStd* g) {
     g->x = (uint32_t)(((uint64_t)g->x * 16807ULL) % 2147483647ULL);
     return g->x;
@@ -169,16 +171,22 @@ static float gamma_f(MinStd* g, float alpha) { /* std::gamma_distribution<float>
     while (u == 0.0);
     return powf(u, 1.0f / alpha) * a1 * v * 1.0f;
 }
-void odirichlet_noise(unsigned long long seed, int n, float alpha, float* out) {
-    MinStd g;
-    g.x = (uint32_t)(seed % 2147483647ULL);
-    if (g.x == 0) g.x = 1;
+static void dirichlet_noise_g(MinStd* g, int n, float alpha, float* out) { /* get_dirichlet_noise blazeutil.h:113-124 */
     float sum = 0.0f;
     for (int i = 0; i < n; ++i) {
-        out[i] = gamma_f(&g, alpha);
+        out[i] = gamma_f(g, alpha);
         sum += out[i];
     }
     for (int i = 0; i < n; ++i) out[i] /= sum;
+}
+static uint32_t minstd_seed(unsigned long long seed) { /* std::default_random_engine(seed) */
+    const uint32_t x = (uint32_t)(seed % 2147483647ULL);
+    return x == 0 ? 1u : x;
+}
+void odirichlet_noise(unsigned long long seed, int n, float alpha, float* out) { /* a fresh generator */
+    MinStd g;
+    g.x = minstd_seed(seed);
+    dirichlet_noise_g(&g, n, alpha, out);
 }
 
 /* ------------------------------------------------------------------ helpers */
@@ -520,6 +528,7 @@ OSearch* osearch_new(const OSettings* st) {
     s->parked.actions_cap = 256;
     s->parked.actions_buf = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)s->parked.actions_cap);
     s->active = 0;
+    s->rng.x = minstd_seed(st->seed);
     return s;
 }
 /* makes logical search thread t (0 or 1) the owner of the batch members */
@@ -651,7 +660,9 @@ int osearch_set_root(OSearch* s, const OPos* pos) {
 static void root_noise_and_open(OSearch* s) {
     if (s->st.dirichlet_epsilon > 0.009f) { /* mctsagent.cpp:311-316 */
         float* noise = (float*)malloc(sizeof(float) * (size_t)s->root->n_actions);
-        odirichlet_noise(s->st.seed, s->root->n_actions, s->st.dirichlet_alpha, noise);
+        /* the reference's generator is process-wide (util/randomgen.h:35) and advances from search to search; here it
+           belongs to the OSearch, seeded once from the settings */
+        dirichlet_noise_g(&s->rng, s->root->n_actions, s->st.dirichlet_alpha, noise);
         for (int i = 0; i < s->root->n_actions; ++i)
             s->root->policy[i] = (1 - s->st.dirichlet_epsilon) * s->root->policy[i] + s->st.dirichlet_epsilon * noise[i];
         free(noise);

@@ -61,11 +61,14 @@ class ShimNet : public NeuralNetAPI {
     void predict(float* planes, float* value, float* prob, float*) override {
         std::vector<unsigned long long> keys(batchSize, 0);
         int n = 0;  // slots that have been written at least once (the reference evaluates stale slots too and ignores them)
-        for (unsigned i = 0; i < batchSize; ++i) {
-            auto it = refshim::plane_keys().find(planes + static_cast<size_t>(i) * nbNNInputValues);
-            if (it == refshim::plane_keys().end()) break;
-            keys[i] = it->second;
-            n = static_cast<int>(i) + 1;
+        {
+            std::lock_guard<std::mutex> lock(refshim::maps_mutex());
+            for (unsigned i = 0; i < batchSize; ++i) {
+                auto it = refshim::plane_keys().find(planes + static_cast<size_t>(i) * nbNNInputValues);
+                if (it == refshim::plane_keys().end()) break;
+                keys[i] = it->second;
+                n = static_cast<int>(i) + 1;
+            }
         }
         if (fn_ != nullptr) {
             fn_(ctx_, planes, keys.data(), n, value, prob);
@@ -167,7 +170,8 @@ int ref_mcts_run(const char* fen, int variant, int is960, const char* const* uci
         agent.set_search_settings(&state, &limits, &eval);
         ref_seed_node_generator(st->seed);
         eval.start = chrono::steady_clock::now();
-        if (st->threads != 2) {
+        if (st->threads != 2 || st->reserved == 1) {
+            // Threads 1, or (reserved == 1: bench.py's CPU arm) the reference's own OS threads, unscheduled
             agent.evaluate_board_state();
         } else {
             // MCTSAgent::evaluate_board_state (agents/mctsagent.cpp:292-337) with run_mcts_search's two OS threads

@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cstring>
 #include <iostream>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -45,6 +46,11 @@ inline std::unordered_map<const float*, unsigned long long>& plane_keys() {
     static std::unordered_map<const float*, unsigned long long> m;
     return m;
 }
+// the two maps are shared by the search threads when the reference runs its own OS threads (bench.py's CPU arm)
+inline std::mutex& maps_mutex() {
+    static std::mutex m;
+    return m;
+}
 }  // namespace refshim
 
 class StateConstantsPommerman : public StateConstantsInterface<StateConstantsPommerman> {
@@ -66,6 +72,7 @@ class StateConstantsPommerman : public StateConstantsInterface<StateConstantsPom
     }
     template <PolicyType p, MirrorType m>
     static MoveIdx action_to_index(Action action) {
+        std::lock_guard<std::mutex> lock(refshim::maps_mutex());
         auto& c = refshim::index_cache();
         const uint32_t base = static_cast<uint32_t>(action) | (m == mirrored ? 1u << 20 : 0u);
         auto it = c.find(base);
@@ -92,6 +99,7 @@ class PommermanState : public State {
         uint32_t mv[OPOS_MAX_MOVES];
         const int n = opos_legal_moves(&pos, mv);
         std::vector<std::pair<int, uint32_t>> keyed(n);
+        std::lock_guard<std::mutex> lock(refshim::maps_mutex());
         auto& c = refshim::index_cache();
         for (int i = 0; i < n; ++i) {
             const int idx = opolicy_move_index(&pos, mv[i], refshim::config().mode, 1);
@@ -108,6 +116,7 @@ class PommermanState : public State {
         int v = version::get_major(version);
         if (v == 0) v = 1;
         oplanes_encode(&pos, refshim::config().mode, v, normalize, planes);
+        std::lock_guard<std::mutex> lock(refshim::maps_mutex());
         refshim::plane_keys()[planes] = pos.key;
     }
     unsigned int steps_from_null() const override { return pos.game_ply; }

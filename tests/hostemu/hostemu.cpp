@@ -139,6 +139,7 @@ HeSearch* he_search_new(const SearchParams* sp, int max_nodes, int max_edges) {
     s->sqrt_lut.resize(lut_len);
     for (int i = 0; i < lut_len; ++i) s->sqrt_lut[i] = sqrt(static_cast<double>(i));
     memset(&s->st, 0, sizeof(s->st));
+    s->st.rng = minstd_seed(sp->seed, 0);
     s->prep_board.resize(static_cast<size_t>(max_nodes) * kPrepSlots);
     s->prep_ci.assign(static_cast<size_t>(max_nodes) * kPrepSlots, -1);
     s->prep_term.resize(static_cast<size_t>(max_nodes) * kPrepSlots);

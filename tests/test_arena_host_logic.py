@@ -11,10 +11,16 @@ class FakeAgent:
     """MCTSAgent's surface as the arena uses it; 'search' = uniform policy over the legal moves, seeded best move."""
     created = []
 
+    best_move_q = 0.25  # EvalInfo::bestMoveQ[0] of every stand-in search
+
     def __init__(self, net, settings, device=0, n_trees=1, max_nodes=0):
         self.n_trees, self.states, self.applied = n_trees, [None] * n_trees, []
         self.rng = np.random.default_rng(len(FakeAgent.created))
+        self.seed, self.limits = int(settings.seed), []
         FakeAgent.created.append(self)
+
+    def set_search_limits(self, simulations, nodes, tree=-1):
+        self.limits.append((tree, simulations, nodes))
 
     def set_position(self, state, tree=0):
         self.states[tree] = state
@@ -25,8 +31,8 @@ class FakeAgent:
             moves = [st.action_to_uci(a) for a in st.legal_actions()]
             k = len(moves)
             pol = np.full(k, 1.0 / k) if k else np.zeros(0)
-            self.res.append(dict(moves=moves, policy=pol, q=np.zeros(k, np.float32), best_idx=int(self.rng.integers(k)) if k else -1,
-                                 nodes=10, nodes_pre_search=0))
+            self.res.append(dict(moves=moves, policy=pol, q=np.full(k, -0.5, np.float32), best_idx=int(self.rng.integers(k)) if k else -1,
+                                 nodes=10, nodes_pre_search=0, best_move_q=FakeAgent.best_move_q))
 
     def result(self, tree=0):
         return self.res[tree]
@@ -89,6 +95,57 @@ def test_games_results_pgn_and_samples(monkeypatch, tmp_path):
     assert np.allclose(pol.sum(axis=1), 1.0, atol=1e-5)
 
 
+def test_reference_self_play_details(monkeypatch, tmp_path):
+    """What SelfPlay::generate_game does around the search (rl/selfplay.cpp:192-261): the exported q is bestMoveQ[0] (not
+    the sampled move's edge Q), the node budget is jittered per search, every game group draws its own Dirichlet seed,
+    the temperature decays with the ply, low policy entries are clipped before export, games can be resigned."""
+    from crazyara_b200.export import TrainDataExporter
+    ex = TrainDataExporter(str(tmp_path / "d.zarr"), "crazyhouse", channels=34, number_chunks=40, chunk_size=16)
+    arena = _arena(monkeypatch, tmp_path, exporter=ex, net=[None, None], n_games=4, max_plies=20)
+    res = arena.run(min_games=4, max_steps=200)
+    n = read_dataset(str(tmp_path / "d.zarr"), "start_indices")[ex.game_idx]
+    q = read_dataset(str(tmp_path / "d.zarr"), "y_best_move_q")[:n]
+    assert n > 0 and np.allclose(q, FakeAgent.best_move_q)            # not the -0.5 of the per-move Q vector
+    assert FakeAgent.created[0].seed != FakeAgent.created[1].seed     # groups (and processes, via `seed`) differ
+    lim = [nodes for a in FakeAgent.created for (_, _, nodes) in a.limits]
+    assert len(lim) >= res["moves"] and min(lim) >= 760 and max(lim) <= 840 and len(set(lim)) > 3   # 800 +- 5 %
+    # temperature decay (get_current_temperature): ply 0 flattens with T = 0.8, ply 10 sharpens with T = 0.8 * 0.92^10
+    arena.temperature_moves, arena.temperature = 15, 0.8
+    pol = np.array([0.7, 0.2, 0.1])
+    picks0 = [arena._pick(dict(policy=pol, best_idx=0), 0) for _ in range(4000)]
+    picks10 = [arena._pick(dict(policy=pol, best_idx=0), 10) for _ in range(4000)]
+    p0 = pol ** (1 / 0.8) / (pol ** (1 / 0.8)).sum()
+    t10 = 0.8 * 0.92 ** 10
+    p10 = pol ** (1 / t10) / (pol ** (1 / t10)).sum()
+    assert abs(np.mean(np.array(picks0) == 0) - p0[0]) < 0.03 and abs(np.mean(np.array(picks10) == 0) - p10[0]) < 0.03
+    assert arena._pick(dict(policy=pol, best_idx=2), 15) == 2         # after Temperature_Moves: the best move
+    # sharpen_distribution (blazeutil.h:94-105) and apply_quantile_clipping (agent.cpp:118-127)
+    assert np.allclose(sp.sharpen_distribution(np.array([0.5, 0.495, 0.005]), 0.01), [0.5 / 0.995, 0.495 / 0.995, 0.0])
+    assert np.allclose(sp.sharpen_distribution(np.array([0.004, 0.003]), 0.01), [0.004, 0.003])   # max below thresh: untouched
+    assert np.allclose(sp.quantile_clip(np.array([0.6, 0.3, 0.06, 0.04]), 0.25), [0.6 / 0.9, 0.3 / 0.9, 0, 0])
+    # resignation: the mover's bestMoveQ below the threshold ends the game in favour of the side then to move
+    FakeAgent.best_move_q = -0.95
+    try:
+        arena2 = _arena(monkeypatch, tmp_path, n_games=2, max_plies=50, resign_probability=1.0)
+        arena2.run(max_steps=1)
+        assert arena2.resigned == 2 and [f[:2] for f in arena2.finished] == [(1, sp.TERMINAL_WIN)] * 2
+        assert all(f[2] == 1 for f in arena2.finished)                # black to move after white's first move: black wins
+    finally:
+        FakeAgent.best_move_q = 0.25
+
+
+def test_mixed_variant_games(monkeypatch, tmp_path):
+    """BASELINE cfg 5: King of the Hill and Three-check side by side (one variant per game, cycled); a finished game is
+    replaced by a new game of the same variant."""
+    FakeAgent.created = []
+    monkeypatch.setattr(sp, "MCTSAgent", FakeAgent)
+    st = sp.rl_settings("lichess")
+    arena = sp.Arena(None, st, variant=[2, 3], n_games=4, temperature_moves=0, max_plies=6, seed=1, resign_probability=0.0)
+    assert [s.variant for s in arena.states] == [2, 3, 2, 3]
+    arena.run(max_steps=7)   # every game is adjudicated at 6 plies and restarted
+    assert len(arena.finished) >= 4 and [s.variant for s in arena.states] == [2, 3, 2, 3]
+
+
 def test_game_groups_split_the_games(monkeypatch, tmp_path):
     arena = _arena(monkeypatch, tmp_path, net=[None, None], n_games=4, max_plies=12)
     assert [a.n_trees for a in FakeAgent.created] == [2, 2]
@@ -118,7 +175,7 @@ def test_launcher_worker_end_to_end(monkeypatch, tmp_path, capsys):
     monkeypatch.setattr(sp, "encode_planes", lambda boards, mode, version, normalize=False: np.ones((len(boards), 34, 8, 8), np.float32))
     monkeypatch.setattr(nn_mod, "NeuralNetAPI", FakeNet)
     plan = sp.plan_workers(8, [0, 1], str(tmp_path))
-    args = argparse.Namespace(model="m.arab", mode="crazyhouse", variant=1, chess960=False, input_version=1, batch_size=8,
+    args = argparse.Namespace(model="m.arab", mode="crazyhouse", variant="1", chess960=False, input_version=1, batch_size=8,
                               nodes=800, max_plies=16, chunks=4, seed=1, export=True, pgn=True, games_per_worker=4, seconds=30.0)
     sp._worker(plan[1], args)
     out = capsys.readouterr().out

@@ -293,9 +293,12 @@ def test_gpu_packed_multi_tree_batches_equal_single_tree_searches(tmp_path):
     together = multi.results()
     multi.close()
     for t, moves in enumerate(lines):
+        # tree t of a handle seeds its Dirichlet generator with seed ^ t * golden ratio (TreeState::rng): searched
+        # alone, the position gets that seed as tree 0 of its own handle
+        s.seed = (st.seed ^ (t * 0x9E3779B97F4A7C15)) & 0xFFFFFFFFFFFFFFFF
         alone = MCTSAgent(net, s, 0, 1)
         r = alone.evaluate_board_state(BoardState().set("", False, 1).do_uci(*moves))
         alone.close()
-        assert_same_search(r, together[t])   # (every tree draws its Dirichlet noise from the same seed)
+        assert_same_search(r, together[t])
         assert together[t]["evals"] > 0
     net.close()

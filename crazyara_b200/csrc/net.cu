@@ -555,6 +555,31 @@ int Net::predict(const float* planes_host, int n, float* value_host, float* prob
     return 0;
 }
 
+int Net::predict_priors(const float* planes_host, int n, const int* policy_idx, const int* counts, int stride, float* value_host,
+                        float* priors_host, float* aux_host) {
+    ARA_CUDA_OK(cudaSetDevice(device));
+    if (n < 1 || n > batch) return set_error("ara_net_predict_priors: n=%d outside [1,%d]", n, batch);
+    if (!planes_host || !value_host || !policy_idx || !counts || !priors_host || stride < 1 || stride > 512)
+        return set_error("ara_net_predict_priors: bad arguments");
+    if (stride > gather_stride) {
+        if (dalloc(&d_gather_idx, static_cast<size_t>(batch) * stride) || dalloc(&d_gather_out, static_cast<size_t>(batch) * stride)) return -1;
+        if (d_gather_cnt == nullptr && dalloc(&d_gather_cnt, batch)) return -1;
+        gather_stride = stride;
+    }
+    ARA_CUDA_OK(cudaMemcpyAsync(d_in_f32, planes_host, static_cast<size_t>(n) * hdr.in_channels * 64 * 4, cudaMemcpyHostToDevice, stream));
+    ARA_CUDA_OK(cudaMemcpyAsync(d_gather_idx, policy_idx, static_cast<size_t>(n) * stride * 4, cudaMemcpyHostToDevice, stream));
+    ARA_CUDA_OK(cudaMemcpyAsync(d_gather_cnt, counts, static_cast<size_t>(n) * 4, cudaMemcpyHostToDevice, stream));
+    if (forward_from_f32_device(n, stream)) return -1;
+    gather_priors_kernel<<<n, 128, 0, stream>>>(d_prob, n_labels(), d_gather_idx, d_gather_cnt, stride, d_gather_out);
+    ++launches;
+    ARA_CUDA_OK(cudaMemcpyAsync(value_host, d_value, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, stream));
+    ARA_CUDA_OK(cudaMemcpyAsync(priors_host, d_gather_out, static_cast<size_t>(n) * stride * 4, cudaMemcpyDeviceToHost, stream));
+    if (aux_host != nullptr && hdr.wdl_mode)
+        ARA_CUDA_OK(cudaMemcpyAsync(aux_host, d_aux, static_cast<size_t>(n) * 4 * 4, cudaMemcpyDeviceToHost, stream));
+    ARA_CUDA_OK(cudaStreamSynchronize(stream));
+    return 0;
+}
+
 }  // namespace ara
 
 // ------------------------------------------------------------------------------------------- C-ABI
@@ -575,7 +600,8 @@ extern "C" int ara_net_shape(ara_net_t h, int* in_channels, int* n_labels, int* 
     if (in_channels) *in_channels = net->hdr.in_channels;
     if (n_labels) *n_labels = net->n_labels();
     if (n_aux) *n_aux = net->n_aux();
-    if (is_policy_map) *is_policy_map = 1;
+    if (is_policy_map) *is_policy_map = 1;  // the policy head is a convolution onto P x 8 x 8 planes (builder_util.py:206-243,
+                                            // select_policy_from_plane): every blob this loader accepts is a policy map
     if (input_version) *input_version = net->hdr.input_version;
     if (batch_size) *batch_size = net->batch;
     return 0;
@@ -584,6 +610,24 @@ extern "C" int ara_net_shape(ara_net_t h, int* in_channels, int* n_labels, int* 
 extern "C" int ara_net_predict(ara_net_t h, const float* planes, int n, float* value, float* prob, float* aux) {
     if (h == nullptr) return ara::set_error("ara_net_predict: null handle");
     return reinterpret_cast<Net*>(h)->predict(planes, n, value, prob, aux);
+}
+
+extern "C" int ara_net_predict_priors(ara_net_t h, const float* planes, int n, const int* policy_idx, const int* counts, int stride,
+                                      float* value, float* priors_out, float* aux) {
+    if (h == nullptr) return ara::set_error("ara_net_predict_priors: null handle");
+    return reinterpret_cast<Net*>(h)->predict_priors(planes, n, policy_idx, counts, stride, value, priors_out, aux);
+}
+
+extern "C" void* ara_host_alloc(unsigned long long bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+        ara::set_error("ara_host_alloc: cudaMallocHost(%llu) failed", bytes);
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void ara_host_free(void* p) {
+    if (p != nullptr) cudaFreeHost(p);
 }
 
 extern "C" int ara_net_forward_device(ara_net_t h, const float* planes_dev, int n, float** value_dev, float** prob_dev) {

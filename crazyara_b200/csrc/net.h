@@ -57,6 +57,9 @@ class Net {
     int init(const char* blob_path, int device, int batch, int precision);
     // host-buffer API (reference NeuralNetAPI::predict semantics, synchronous)
     int predict(const float* planes_host, int n, float* value_host, float* prob_host, float* aux_host);
+    // the same forward, but only the policy entries named by policy_idx come back (ara_net_predict_priors)
+    int predict_priors(const float* planes_host, int n, const int* policy_idx, const int* counts, int stride, float* value_host,
+                       float* priors_host, float* aux_host);
     // device-resident API: input already in in_h (NHWC fp16), outputs stay in d_value / d_prob
     // boards_dev (optional): device-side count (<= n) of the input rows that really hold positions -- the launch is
     // sized for n, thread blocks of the rows beyond the count leave at once; the pointer is baked into the CUDA graph
@@ -103,6 +106,10 @@ class Net {
     __half* d_xs[2] = {nullptr, nullptr};  // [batch_cap*64, 768]
     float* d_h1f = nullptr;                // [batch_cap*64, max_cop]
     __half* d_h2s = nullptr;               // [batch_cap*64, 3 * ceil64(max_cop)]
+    int* d_gather_idx = nullptr;   // predict_priors: [batch, gather_stride] policy indices, [batch] counts, [batch, stride] priors
+    int* d_gather_cnt = nullptr;
+    float* d_gather_out = nullptr;
+    int gather_stride = 0;
     long long launches = 0;      // kernels launched so far (bench bookkeeping)
     bool use_graph = true;
 

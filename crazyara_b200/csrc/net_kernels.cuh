@@ -309,4 +309,16 @@ __global__ void __launch_bounds__(256) policy_softmax_kernel(const float* __rest
     for (int i = t; i < L; i += 256) pb[i] = s_l[i] * inv;
 }
 
+// Node::set_probabilities_for_moves (node.cpp:961-979) for a whole batch: out[b][i] = prob[b][idx[b][i]], i < counts[b].
+// One CTA per position.
+__global__ void gather_priors_kernel(const float* __restrict__ prob, int n_labels, const int* __restrict__ idx,
+                                     const int* __restrict__ counts, int stride, float* __restrict__ out) {
+    const int b = blockIdx.x;
+    const int k = min(counts[b], stride);
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        const int j = idx[static_cast<size_t>(b) * stride + i];
+        out[static_cast<size_t>(b) * stride + i] = (j >= 0 && j < n_labels) ? __ldg(prob + static_cast<size_t>(b) * n_labels + j) : 0.0f;
+    }
+}
+
 }  // namespace ara

@@ -163,6 +163,10 @@ __global__ void __launch_bounds__(32) result_kernel(const TreeDev* trees, Search
     if (threadIdx.x == 0) collect_result(t, sp, &out[blockIdx.x]);
 }
 
+__global__ void __launch_bounds__(32) node_view_kernel(const TreeDev* trees, int tree, int node_id, NodeView* out) {
+    collect_node_view(trees[tree], node_id, out);
+}
+
 __global__ void __launch_bounds__(32) time_stats_kernel(const TreeDev* trees, RootTimeStats* out) {
     const TreeDev t = trees[blockIdx.x];
     if (threadIdx.x == 0) collect_time_stats(t, &out[blockIdx.x]);
@@ -190,6 +194,11 @@ class Search {
     int apply_move(int tree, unsigned short move);
     void request_stop() { stop_requested_.store(true, std::memory_order_relaxed); }
     int fetch_results();
+    int begin();
+    int step(int n_batches);
+    int poll_running();
+    int node_view(int tree, int node_id, NodeView* out);
+    NodeView* d_node_view_ = nullptr;
     int debug_cycles(int tree, unsigned long long* out8) {
         TreeState st;
         ARA_CUDA_OK(cudaMemcpy(&st, d_states_[tree], sizeof(st), cudaMemcpyDeviceToHost));
@@ -345,6 +354,7 @@ Search::~Search() {
     for (cudaEvent_t e : ev_net_)
         if (e) cudaEventDestroy(e);
     if (d_count_slot_[1]) cudaFree(d_count_slot_[1]);
+    if (d_node_view_) cudaFree(d_node_view_);
     if (side_stream_) cudaStreamDestroy(side_stream_);
     if (ev_fork_) cudaEventDestroy(ev_fork_);
     if (ev_join_) cudaEventDestroy(ev_join_);
@@ -663,7 +673,8 @@ int Search::iterate(int count) {
     return 0;
 }
 
-int Search::go() {
+// MCTSAgent::evaluate_board_state up to the first mini-batch: roots created (or taken over), evaluated, noised
+int Search::begin() {
     ARA_CUDA_OK(cudaSetDevice(device_));
     prof_used_ = 0;
     net_forwards = 0;
@@ -708,6 +719,54 @@ int Search::go() {
     prepare_kernel<<<n_trees * 4 * B, 32, 0, stream_>>>(d_trees_, sp, 4 * B);
     launches += 5;
     ARA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// how many trees are still searching (reads the `done` flags; synchronises the search stream)
+int Search::poll_running() {
+    for (int i = 0; i < n_trees; ++i)
+        ARA_CUDA_OK(cudaMemcpyAsync(&h_done_[i], &d_states_[i]->done, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    ARA_CUDA_OK(cudaStreamSynchronize(stream_));
+    int running = 0;
+    for (int i = 0; i < n_trees; ++i) running += h_done_[i] == 0;
+    if (running) {
+        for (int i = 0; i < n_trees; ++i) {
+            TreeState st;
+            ARA_CUDA_OK(cudaMemcpy(&st, d_states_[i], sizeof(st), cudaMemcpyDeviceToHost));
+            if (st.error)
+                return set_error("ara_search: device search error %d (1 node pool, 2 edge pool, 3 depth > %d)", st.error, kMaxDepth);
+        }
+    }
+    return running;
+}
+
+// SearchThread::thread_iteration n times (Threads = 2: n turns of each thread); returns the trees still running
+int Search::step(int n_batches) {
+    ARA_CUDA_OK(cudaSetDevice(device_));
+    if (!searched_) return set_error("ara_search_step: ara_search_begin has not been called");
+    if (n_batches < 1) return set_error("ara_search_step: n_batches %d < 1", n_batches);
+    if (iterate(threads_ == 2 ? 2 * n_batches : n_batches)) return -1;
+    const int running = poll_running();
+    if (running < 0 || fetch_results()) return -1;  // ara_search_result between steps shows the tree as it is now
+    return running;
+}
+
+int Search::node_view(int tree, int node_id, NodeView* out) {
+    if (tree < 0 || tree >= n_trees) return set_error("ara_search_node: tree %d out of range", tree);
+    if (!searched_) return set_error("ara_search_node: no search has been started on this handle");
+    ARA_CUDA_OK(cudaSetDevice(device_));
+    if (d_node_view_ == nullptr) ARA_CUDA_OK(cudaMalloc(&d_node_view_, sizeof(NodeView)));
+    node_view_kernel<<<1, 32, 0, stream_>>>(d_trees_, tree, node_id, d_node_view_);
+    ++launches;
+    ARA_CUDA_OK(cudaMemcpyAsync(out, d_node_view_, sizeof(NodeView), cudaMemcpyDeviceToHost, stream_));
+    ARA_CUDA_OK(cudaStreamSynchronize(stream_));
+    if (out->node_id < 0) return set_error("ara_search_node: tree %d has no node %d", tree, node_id);
+    return 0;
+}
+
+int Search::go() {
+    if (begin()) return -1;
+    const int B = sp.batch_size;
     // main loop: enqueue the iterations the visit budget certainly needs, then poll `done` in small chunks
     unsigned budget = sp.simulations ? sp.simulations : sp.nodes;
     int first = budget ? static_cast<int>(budget / (static_cast<unsigned>(B) * 1u)) : 8;
@@ -893,6 +952,20 @@ extern "C" int ara_search_go(ara_search_t h) {
     if (s->go()) return -1;
     return s->fetch_results();
 }
+static_assert(sizeof(ara_node_view_t) == sizeof(ara::NodeView), "node view layout");
+extern "C" int ara_search_begin(ara_search_t h) {
+    if (h == nullptr) return ara::set_error("ara_search_begin: null handle");
+    return reinterpret_cast<Search*>(h)->begin();
+}
+extern "C" int ara_search_step(ara_search_t h, int n_batches) {
+    if (h == nullptr) return ara::set_error("ara_search_step: null handle");
+    return reinterpret_cast<Search*>(h)->step(n_batches);
+}
+extern "C" int ara_search_node(ara_search_t h, int tree, int node_id, ara_node_view_t* out) {
+    if (h == nullptr || out == nullptr) return ara::set_error("ara_search_node: null argument");
+    return reinterpret_cast<Search*>(h)->node_view(tree, node_id, reinterpret_cast<ara::NodeView*>(out));
+}
+
 extern "C" int ara_search_result(ara_search_t h, int tree, ara_search_result_t* out) {
     if (h == nullptr || out == nullptr) return ara::set_error("ara_search_result: null argument");
     Search* s = reinterpret_cast<Search*>(h);

@@ -1438,6 +1438,78 @@ struct SearchResult {
     Move pv[kMaxDepth];
 };
 
+// What Node's getters expose (node.h:97-124, :345-460) and Node::print_node_statistics prints (node.cpp:1248-1301) for
+// one node of the device-resident tree.  Same layout as ara_node_view_t (include/ara_b200.h).
+struct NodeView {
+    int node_id;
+    int parent;         // -1 for the root of the tree
+    int parent_child_idx;
+    int n_moves;        // Node::get_number_child_nodes
+    int no_visit_idx;   // children opened so far (Node::get_no_visit_idx); 0 until the node is a playout node
+    int node_type;      // 0 win, 1 draw, 2 loss, 3 unsolved
+    int flags;          // 1 terminal, 2 has network results, 4 playout node (NodeData exists), 8 sorted
+    int checkmate_idx;  // 65535 none
+    int end_in_ply;
+    int n_unsolved;
+    int repetition;
+    int pad_;
+    unsigned visit_sum;    // Node::get_visits
+    unsigned real_visits;  // Node::get_real_visits
+    unsigned free_visits;
+    float value;           // Node::get_value = valueSum / realVisits
+    double value_sum;
+    unsigned long long key;  // Node::hash_key
+    Move moves[kMaxMoves];       // Node::get_action(i)
+    int32_t child[kMaxMoves];    // node id of child i, -1 = not expanded (Node::get_child_node)
+    uint32_t visits[kMaxMoves];  // childNumberVisits
+    float q[kMaxMoves];          // qValues
+    float prior[kMaxMoves];      // policyProbSmall
+    uint8_t vl[kMaxMoves];       // virtualLossCounter
+    uint8_t child_type[kMaxMoves];
+};
+ARA_HD void collect_node_view(const TreeDev& t, int nid, NodeView* v) {  // lane-strided; nid < 0 = the current root
+    const TreeState& st = *t.st;
+    const int id = nid < 0 ? st.root : nid;
+    const bool ok = id >= 0 && id < st.n_nodes;
+    if (ARA_LANE == 0) {
+        v->node_id = ok ? id : -1;
+        v->n_moves = 0;
+    }
+    ARA_WARP_SYNC();
+    if (!ok) return;
+    const NodeHdr& h = t.hdr[id];
+    if (ARA_LANE == 0) {
+        v->parent = h.parent;
+        v->parent_child_idx = h.parent_ci;
+        v->n_moves = h.n_moves;
+        v->no_visit_idx = (h.flags & NF_HAS_D) ? h.no_visit_idx : 0;
+        v->node_type = h.node_type;
+        v->flags = h.flags;
+        v->checkmate_idx = h.checkmate_idx;
+        v->end_in_ply = h.end_in_ply;
+        v->n_unsolved = h.n_unsolved;
+        v->repetition = h.repetition;
+        v->pad_ = 0;
+        v->visit_sum = h.visit_sum;
+        v->real_visits = h.real_visits;
+        v->free_visits = h.free_visits;
+        v->value = h.real_visits ? node_value(h) : 0.0f;
+        v->value_sum = h.value_sum;
+        v->key = h.key;
+    }
+    const bool has_edges = (h.flags & NF_HAS_NN) != 0;  // edges exist once the node has been expanded and evaluated
+    for (int i = ARA_LANE; i < h.n_moves; i += ARA_WARP_N) {
+        const uint32_t e = h.edge_base + static_cast<uint32_t>(i);
+        v->moves[i] = t.move[e];
+        v->child[i] = has_edges ? t.child[e] : -1;
+        v->visits[i] = has_edges ? t.N[e] : 0;
+        v->q[i] = has_edges ? t.Q[e] : kQInit;
+        v->prior[i] = has_edges ? t.P[e] : 0.0f;
+        v->vl[i] = has_edges ? t.vl[e] : 0;
+        v->child_type[i] = has_edges ? t.etype[e] : NT_UNSOLVED;
+    }
+}
+
 ARA_HD int mcts_policy(const TreeDev& t, const SearchParams& sp, const NodeHdr& h, double* out) {  // node.cpp:1070-1109
     const int k = h.no_visit_idx;
     const uint32_t e = h.edge_base;

@@ -68,6 +68,17 @@ class SearchResult(ctypes.Structure):
                 ("prior", ctypes.c_float * 512), ("policy", ctypes.c_double * 512), ("pv", ctypes.c_uint16 * 256)]
 
 
+class NodeView(ctypes.Structure):
+    """ara_node_view_t: one node of the device-resident tree (Node's getters, node.h:345-460)."""
+    _fields_ = [("node_id", ctypes.c_int), ("parent", ctypes.c_int), ("parent_child_idx", ctypes.c_int), ("n_moves", ctypes.c_int),
+                ("no_visit_idx", ctypes.c_int), ("node_type", ctypes.c_int), ("flags", ctypes.c_int), ("checkmate_idx", ctypes.c_int),
+                ("end_in_ply", ctypes.c_int), ("n_unsolved", ctypes.c_int), ("repetition", ctypes.c_int), ("pad_", ctypes.c_int),
+                ("visit_sum", ctypes.c_uint), ("real_visits", ctypes.c_uint), ("free_visits", ctypes.c_uint), ("value", ctypes.c_float),
+                ("value_sum", ctypes.c_double), ("key", ctypes.c_ulonglong), ("moves", ctypes.c_uint16 * 512),
+                ("child", ctypes.c_int32 * 512), ("visits", ctypes.c_uint32 * 512), ("q", ctypes.c_float * 512),
+                ("prior", ctypes.c_float * 512), ("vl", ctypes.c_uint8 * 512), ("child_type", ctypes.c_uint8 * 512)]
+
+
 _SIGS = False
 
 
@@ -101,6 +112,9 @@ def _L():
         L.ara_search_destroy.argtypes = [vp]
         L.ara_search_set_position.argtypes = [vp, ci, vp, vp, vp, ci]
         L.ara_search_go.argtypes = [vp]
+        L.ara_search_begin.argtypes = [vp]
+        L.ara_search_step.argtypes = [vp, ci]
+        L.ara_search_node.argtypes = [vp, ci, ci, vp]
         L.ara_search_result.argtypes = [vp, ci, vp]
         L.ara_search_set_profile.argtypes = [vp, ci]
         L.ara_search_apply_move.argtypes = [vp, ci, ctypes.c_ushort]
@@ -298,6 +312,33 @@ class MCTSAgent:
             self.set_position(state, 0)
         check(_L().ara_search_go(self._h))
         return self.result(0)
+
+    # ---- SearchThread / Node surface (searchthread.h, node.h): drive the search one mini-batch at a time, read the tree
+    def begin(self, state=None):
+        """MCTSAgent::evaluate_board_state up to the first mini-batch (roots created or taken over, evaluated, noised)."""
+        if state is not None:
+            self.set_position(state, 0)
+        check(_L().ara_search_begin(self._h))
+
+    def thread_iteration(self, n_batches=1):
+        """SearchThread::thread_iteration n times; returns the number of trees whose search loop has not ended."""
+        rc = _L().ara_search_step(self._h, int(n_batches))
+        if rc < 0:
+            raise AraError(lib().ara_last_error().decode())
+        return rc
+
+    def node(self, node_id=-1, tree=0):
+        """Read-only view of one node (Node's getters): dict with the children's moves / visits / Q / priors / node ids."""
+        v = NodeView()
+        check(_L().ara_search_node(self._h, tree, int(node_id), ctypes.byref(v)))
+        st = self._states[tree]
+        k = v.n_moves
+        return dict(node_id=v.node_id, parent=v.parent, n_moves=k, no_visit_idx=v.no_visit_idx, node_type=v.node_type,
+                    is_terminal=bool(v.flags & 1), has_nn_results=bool(v.flags & 2), is_playout_node=bool(v.flags & 4),
+                    visits=v.visit_sum, real_visits=v.real_visits, free_visits=v.free_visits, value=v.value, key=v.key,
+                    moves=[move_to_uci(m, st.is960 if st is not None else False) for m in v.moves[:k]],
+                    child=list(v.child[:k]), child_visits=np.array(v.visits[:k], np.uint32), q=np.array(v.q[:k], np.float32),
+                    prior=np.array(v.prior[:k], np.float32), virtual_loss=np.array(v.vl[:k], np.uint8))
 
     def result(self, tree=0):
         r = SearchResult()

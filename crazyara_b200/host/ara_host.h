@@ -4,6 +4,8 @@
 //   SearchSettings / SearchLimits   engine/src/agents/config/searchsettings.h, searchlimits.h
 //   EvalInfo       engine/src/evalinfo.h
 //   MCTSAgent      engine/src/agents/mctsagent.h: evaluate_board_state() -> device-resident search
+//   SearchThread   engine/src/searchthread.h: thread_iteration() = one mini-batch of the device search (ara_search_step)
+//   Node           engine/src/node.h: read-only view of a node of the device-resident tree (ara_search_node)
 // Errors are rethrown as std::runtime_error / std::invalid_argument like the reference's backends do.
 #pragma once
 #include <cmath>
@@ -156,6 +158,90 @@ inline int value_to_centipawn(float value, float param) {  // evalinfo.cpp:102-1
     return static_cast<int>(-(sgn * std::log(1.0f - std::fabs(value)) / std::log(param)) * 100.0f);
 }
 
+// Node (engine/src/node.h:97-124): the getters the reference's UCI / agent code reads (node.h:345-460), over one
+// ara_search_node snapshot.  Read-only: the tree lives on the device and is changed by the search kernels only.
+class Node {
+   public:
+    Node(ara_search_t search, int tree, int nodeId) : search_(search), tree_(tree), view_(new ara_node_view_t) {
+        if (ara_search_node(search, tree, nodeId, view_.get()) != 0) throw std::runtime_error(ara_last_error());
+    }
+    size_t get_number_child_nodes() const { return static_cast<size_t>(view_->n_moves); }
+    unsigned get_no_visit_idx() const { return static_cast<unsigned>(view_->no_visit_idx); }
+    unsigned get_visits() const { return view_->visit_sum; }
+    unsigned get_real_visits() const { return view_->real_visits; }
+    unsigned get_free_visits() const { return view_->free_visits; }
+    unsigned get_node_count() const { return view_->visit_sum - view_->free_visits; }  // node.cpp:1303-1306
+    float get_value() const { return view_->value; }
+    double get_value_sum() const { return view_->value_sum; }
+    unsigned long long hash_key() const { return view_->key; }
+    int get_node_type() const { return view_->node_type; }  // 0 win, 1 draw, 2 loss, 3 unsolved
+    bool is_terminal() const { return (view_->flags & 1) != 0; }
+    bool has_nn_results() const { return (view_->flags & 2) != 0; }
+    bool is_playout_node() const { return (view_->flags & 4) != 0; }
+    bool is_root_node() const { return view_->parent < 0; }
+    int get_checkmate_idx() const { return view_->checkmate_idx; }
+    int get_end_in_ply() const { return view_->end_in_ply; }
+    Action get_action(size_t childIdx) const { return view_->moves[childIdx]; }
+    std::vector<Action> get_legal_actions() const { return std::vector<Action>(view_->moves, view_->moves + view_->n_moves); }
+    std::vector<unsigned> get_child_number_visits() const { return std::vector<unsigned>(view_->visits, view_->visits + view_->no_visit_idx); }
+    std::vector<float> get_q_values() const { return std::vector<float>(view_->q, view_->q + view_->no_visit_idx); }
+    std::vector<float> get_policy_prob_small() const { return std::vector<float>(view_->prior, view_->prior + view_->n_moves); }
+    float get_q_value(size_t childIdx) const { return view_->q[childIdx]; }
+    unsigned get_virtual_loss_counter(size_t childIdx) const { return view_->vl[childIdx]; }
+    // Node::get_child_node: a fresh view of the child, or nullptr while it has not been expanded
+    std::unique_ptr<Node> get_child_node(size_t childIdx) const {
+        if (childIdx >= get_number_child_nodes() || view_->child[childIdx] < 0) return nullptr;
+        return std::unique_ptr<Node>(new Node(search_, tree_, view_->child[childIdx]));
+    }
+    int id() const { return view_->node_id; }
+    const ara_node_view_t& view() const { return *view_; }
+
+   private:
+    ara_search_t search_;
+    int tree_;
+    std::unique_ptr<ara_node_view_t> view_;
+};
+
+// SearchThread (engine/src/searchthread.h): set_root_state + thread_iteration() drive the device search one mini-batch
+// at a time (searchthread.cpp:403-416: create_mini_batch, predict, set_nn_results_to_child_nodes, the backups -- all on
+// the device), get_root_node() reads the tree.  One tree per SearchThread.
+class SearchThread {
+   public:
+    SearchThread(NeuralNetAPI* net, const ara_search_settings_t& settings, int deviceID = 0, int maxNodes = 0) : settings_(settings) {
+        search_ = ara_search_create(net ? net->handle() : nullptr, &settings_, deviceID, 1, maxNodes);
+        if (search_ == nullptr) throw std::invalid_argument(ara_last_error());
+    }
+    ~SearchThread() { ara_search_destroy(search_); }
+    SearchThread(const SearchThread&) = delete;
+    // set_root_state + set_root_node + the root's evaluation (MCTSAgent::evaluate_board_state up to the first iteration)
+    void set_root_state(const BoardState& state) {
+        ara_board_t root;
+        const unsigned long long* keys = nullptr;
+        const short* reps = nullptr;
+        int n = 0;
+        ara_state_board(state.handle(), &root);
+        ara_state_history(state.handle(), &keys, &reps, &n);
+        if (ara_search_set_position(search_, 0, &root, keys, reps, n) != 0 || ara_search_begin(search_) != 0)
+            throw std::runtime_error(ara_last_error());
+        running_ = true;
+    }
+    // one mini-batch; false once the loop condition of run_search_thread (searchthread.cpp:418-426) has failed
+    bool thread_iteration() {
+        const int rc = ara_search_step(search_, 1);
+        if (rc < 0) throw std::runtime_error(ara_last_error());
+        running_ = rc > 0;
+        return running_;
+    }
+    bool is_running() const { return running_; }
+    Node get_root_node() const { return Node(search_, 0, -1); }
+    ara_search_t handle() const { return search_; }
+
+   private:
+    ara_search_settings_t settings_;
+    ara_search_t search_ = nullptr;
+    bool running_ = false;
+};
+
 class MCTSAgent {
    public:
     MCTSAgent(NeuralNetAPI* net, const SearchSettings& settings, int deviceID = 0, int maxNodes = 0) : settings_(settings) {
@@ -223,6 +309,8 @@ class MCTSAgent {
     }
     bool useNPSTimemanager = true;  // UCI option Use_NPS_Time_Manager
     const ara_search_result_t& last_result() const { return result_; }
+    // MCTSAgent::get_root_node: read-only view of the root of the last search
+    Node get_root_node() const { return Node(search_, 0, -1); }
     // MCTSAgent::apply_move_to_tree: the subtree behind `move` is kept for the next search
     void apply_move_to_tree(Action move) {
         if (ara_search_apply_move(search_, 0, move) != 0) throw std::runtime_error(ara_last_error());

@@ -110,10 +110,13 @@ int main() {
         ready = true;
     };
     new_game();
-    // `go infinite` runs on a worker thread so that `stop` can be read meanwhile (the reference's search threads +
-    // CrazyAra::stop_search, crazyara.cpp); every other search is synchronous as before
+    // every `go` runs on a worker thread so that `stop` / `isready` are read while it searches (the reference's search
+    // threads + CrazyAra::stop_search, crazyara.cpp).  `stop` and `quit` end the running search; any other command first
+    // waits for a limited search (nodes / time) to finish by itself -- scripted sessions keep their results -- and ends
+    // an infinite one.
     std::thread worker;
     std::atomic<bool> searching{false};
+    bool infiniteSearch = false;
     auto print_result = [&]() {
         if (info.nodesPreSearch) std::cout << "info string reused " << info.nodesPreSearch << " nodes" << std::endl;
         std::cout << "info depth " << info.depth << " nodes " << info.nodes << " nps " << info.calculate_nps() << " score cp "
@@ -121,9 +124,9 @@ int main() {
         for (Action a : info.pv) std::cout << " " << state.action_to_uci(a);
         std::cout << "\nbestmove " << (info.bestMove ? state.action_to_uci(info.bestMove) : std::string("(none)")) << std::endl;
     };
-    auto stop_and_join = [&]() {
+    auto stop_and_join = [&](bool stop) {
         if (!worker.joinable()) return;
-        while (searching.load()) {  // a stop that arrives before the search loop has started would be reset by it
+        while (stop && searching.load()) {  // a stop that arrives before the search loop has started would be reset by it
             agent->stop();
             std::this_thread::sleep_for(std::chrono::milliseconds(2));
         }
@@ -134,12 +137,12 @@ int main() {
         std::istringstream ss(line);
         std::string cmd;
         ss >> cmd;
-        if (worker.joinable()) {  // an infinite search is (or was) running
+        if (worker.joinable()) {  // a search is (or was) running
             if (cmd == "isready" && searching.load()) {
                 std::cout << "readyok" << std::endl;
                 continue;
             }
-            stop_and_join();  // `stop`, or any command that needs the engine: end the search first
+            stop_and_join(cmd == "stop" || cmd == "quit" || infiniteSearch);
             if (cmd == "stop") continue;
         } else if (cmd == "stop") {
             continue;
@@ -225,24 +228,10 @@ int main() {
                 if (!ready) prepare();
                 const bool inGame = lim.time[0] != 0 || lim.time[1] != 0 || lim.movestogo != 0;  // is_game_sceneario
                 agent->clear_time_control();
+                const bool report = timed && inGame && !lim.infinite;
                 if (lim.infinite) {
                     agent->set_movetime(0.0);
-                    searched = true;
-                    searchedBase = gameBase;
-                    searchedMoves = gameMoves;
-                    searching.store(true);
-                    worker = std::thread([&]() {
-                        try {
-                            agent->evaluate_board_state(state, info);
-                            print_result();
-                        } catch (const std::exception& e) {
-                            std::cout << "info string error: " << e.what() << std::endl;
-                        }
-                        searching.store(false);
-                    });
-                    continue;
-                }
-                if (timed) {
+                } else if (timed) {
                     const int me = state.side_to_move();
                     const long overhead = opt.i("Move_Overhead");
                     const long ms = time_for_move(lim, me, state.move_number(), overhead);
@@ -257,18 +246,27 @@ int main() {
                     agent->set_movetime(0.0);
                 }
                 agent->useNPSTimemanager = opt.b("Use_NPS_Time_Manager");
-                agent->evaluate_board_state(state, info);
-                if (timed && inGame) {
-                    const ara_time_report_t tr = agent->time_report();
-                    if (tr.early_stopped)
-                        std::cout << "info string Early stopping" << (tr.early_stopped == 1 ? " (max nodes)" : "")
-                                  << ", saved time: " << static_cast<long>(tr.saved_ms) << std::endl;
-                    if (tr.prolonged) std::cout << "info string Increase search time" << std::endl;
-                }
                 searched = true;
                 searchedBase = gameBase;
                 searchedMoves = gameMoves;
-                print_result();
+                infiniteSearch = lim.infinite;
+                searching.store(true);
+                worker = std::thread([&, report]() {
+                    try {
+                        agent->evaluate_board_state(state, info);
+                        if (report) {
+                            const ara_time_report_t tr = agent->time_report();
+                            if (tr.early_stopped)
+                                std::cout << "info string Early stopping" << (tr.early_stopped == 1 ? " (max nodes)" : "")
+                                          << ", saved time: " << static_cast<long>(tr.saved_ms) << std::endl;
+                            if (tr.prolonged) std::cout << "info string Increase search time" << std::endl;
+                        }
+                        print_result();
+                    } catch (const std::exception& e) {
+                        std::cout << "info string error: " << e.what() << std::endl;
+                    }
+                    searching.store(false);
+                });
             } else if (cmd == "benchmark") {  // CrazyAra::benchmark (crazyara.cpp:287-330): `benchmark <movetime ms>`
                 long moveTime = 3000;
                 ss >> moveTime;
@@ -351,6 +349,6 @@ int main() {
             std::cout << "info string error: " << e.what() << std::endl;
         }
     }
-    stop_and_join();
+    stop_and_join(true);
     return 0;
 }

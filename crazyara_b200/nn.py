@@ -11,6 +11,9 @@ import numpy as np
 from ._lib import AraError, check, lib
 
 
+_PINNED = {}  # pinned_array: address -> owner whose finaliser frees the block
+
+
 def _fptr(a):
     return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
 
@@ -30,6 +33,12 @@ class NeuralNetAPI:
                                       ctypes.POINTER(ctypes.c_float)]
         L.ara_net_forward_device.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                              ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p)]
+        L.ara_net_predict_priors.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.c_int, ctypes.c_void_p,
+                                             ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_float),
+                                             ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]
+        L.ara_host_alloc.restype = ctypes.c_void_p
+        L.ara_host_alloc.argtypes = [ctypes.c_ulonglong]
+        L.ara_host_free.argtypes = [ctypes.c_void_p]
         L.ara_net_launch_count.restype = ctypes.c_longlong
         L.ara_net_launch_count.argtypes = [ctypes.c_void_p]
         if precision not in ("float16", "float32"):
@@ -71,6 +80,38 @@ class NeuralNetAPI:
                 raise AraError("predict buffers must be C-contiguous float32")
         aux = _fptr(auxiliaryOutputs) if auxiliaryOutputs is not None else None
         check(lib().ara_net_predict(self._h, _fptr(inputPlanes), n, _fptr(valueOutput), _fptr(probOutputs), aux))
+
+    def predict_priors(self, inputPlanes, policyIdx, counts, valueOutput, priorsOutput, auxiliaryOutputs=None, n=None):
+        """fill_nn_results for a host-side tree (searchthread.cpp:290-299, node.cpp:961-979): like predict, but only the
+        policy entries policyIdx[b][:counts[b]] of every position come back (priorsOutput [n, stride] float32)."""
+        n = self.batchSize if n is None else n
+        for a in (inputPlanes, valueOutput, priorsOutput):
+            if a.dtype != np.float32 or not a.flags["C_CONTIGUOUS"]:
+                raise AraError("predict buffers must be C-contiguous float32")
+        idx = np.ascontiguousarray(policyIdx, np.int32)
+        cnt = np.ascontiguousarray(counts, np.int32)
+        if idx.shape != priorsOutput.shape:
+            raise AraError("policyIdx and priorsOutput must have the same [n, stride] shape")
+        aux = _fptr(auxiliaryOutputs) if auxiliaryOutputs is not None else None
+        check(lib().ara_net_predict_priors(self._h, _fptr(inputPlanes), n, idx.ctypes.data, cnt.ctypes.data, idx.shape[1],
+                                           _fptr(valueOutput), _fptr(priorsOutput), aux))
+
+    @staticmethod
+    def pinned_array(shape, dtype=np.float32):
+        """A numpy array over pinned host memory (ara_host_alloc = cudaMallocHost, as neuralnetapiuser.cpp:52-59 allocates
+        the predict buffers); freed when the array is garbage-collected."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = lib().ara_host_alloc(n)
+        if not p:
+            raise AraError(lib().ara_last_error().decode())
+        buf = (ctypes.c_char * n).from_address(p)
+        arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+        class _Owner:
+            def __del__(self, p=p):
+                lib().ara_host_free(p)
+        _PINNED[arr.ctypes.data] = _Owner()
+        return arr
 
     def forward_device(self, planes_dev_ptr, n):
         """planes already in HBM ([n, C, 8, 8] fp32 device pointer, or 0 to use the encoded NHWC input buffer).

@@ -47,6 +47,17 @@ int ara_net_predict(ara_net_t net, const float* planes, int n, float* value, flo
  * pointer, or NULL to evaluate the net's own NHWC fp16 input buffer filled by ara_encode_planes_device. */
 int ara_net_forward_device(ara_net_t net, const float* planes_dev, int n, float** value_dev, float** prob_dev);
 
+/* fill_nn_results for a host that keeps its own tree (searchthread.cpp:290-299 -> Node::set_probabilities_for_moves,
+ * node.cpp:961-979): like ara_net_predict, but instead of the whole soft-maxed policy (L floats per position: 1.3 MB
+ * at 64 x 5184) only the entries of each position's legal moves come back.  policy_idx [n][stride]: index into the
+ * policy vector per legal move (ara_legal_moves gives them), counts [n] how many; priors_out [n][stride]. */
+int ara_net_predict_priors(ara_net_t net, const float* planes, int n, const int* policy_idx, const int* counts, int stride,
+                           float* value, float* priors_out, float* aux);
+/* Pinned host memory for the caller-owned predict buffers, as NeuralNetAPIUser allocates them under TensorRT
+ * (cudaMallocHost, nn/neuralnetapiuser.cpp:52-59): copies from / to it overlap and run at full PCIe / C2C speed. */
+void* ara_host_alloc(unsigned long long bytes);
+void ara_host_free(void* p);
+
 /* Number of CUDA kernels this net has launched so far (bench bookkeeping). */
 long long ara_net_launch_count(ara_net_t net);
 /* profiling builds (-DARA_TRUNK_PROF) only: SM-clock cycles of CTA 0 of the last trunk-kernel launch, [0..15] MMA
@@ -182,6 +193,46 @@ int ara_search_set_limits(ara_search_t s, int tree, unsigned simulations, unsign
 /* runs all trees to their limits (synchronous) and fetches the results */
 int ara_search_go(ara_search_t s);
 int ara_search_result(ara_search_t s, int tree, ara_search_result_t* out);
+/* ---- stepping and inspection: SearchThread::thread_iteration (searchthread.cpp:403-416) and the Node getters
+ * (node.h:97-124, :345-460; Node::print_node_statistics node.cpp:1248-1301) for a host that drives the search itself.
+ *   ara_search_begin: MCTSAgent::evaluate_board_state up to the first mini-batch (agents/mctsagent.cpp:292-322): roots
+ *                     created or taken over from the kept subtrees, evaluated, Dirichlet noise applied.
+ *   ara_search_step:  n_batches more mini-batches per tree (thread_iteration n times; with Threads = 2, n_batches turns
+ *                     of each thread); synchronous; returns the number of trees whose search loop has NOT ended yet
+ *                     (0 = every tree is done; further calls are no-ops), or -1 on error.
+ *   ara_search_go == ara_search_begin + ara_search_step until 0 (+ the time management).  ara_search_result may be
+ *   called between steps.
+ *   ara_search_node:  a read-only view of one node (node_id from ara_node_view_t.child[]; -1 = the current root). */
+typedef struct ara_node_view_s {
+    int node_id;          /* -1: no such node */
+    int parent;           /* node id of the parent, -1 for the root of the tree */
+    int parent_child_idx;
+    int n_moves;          /* Node::get_number_child_nodes */
+    int no_visit_idx;     /* Node::get_no_visit_idx: children opened so far */
+    int node_type;        /* 0 win, 1 draw, 2 loss, 3 unsolved (nodedata.h NodeType) */
+    int flags;            /* 1 terminal, 2 has NN results, 4 playout node, 8 sorted */
+    int checkmate_idx;    /* 65535 = none */
+    int end_in_ply;
+    int n_unsolved;
+    int repetition;
+    int pad_;
+    unsigned visit_sum;   /* Node::get_visits */
+    unsigned real_visits; /* Node::get_real_visits */
+    unsigned free_visits;
+    float value;          /* Node::get_value */
+    double value_sum;
+    unsigned long long key;      /* Node::hash_key */
+    unsigned short moves[512];   /* Node::get_action(i), 16-bit move codes, sorted by prior once the node is visited */
+    int child[512];              /* node id of child i or -1 (Node::get_child_node) */
+    unsigned visits[512];        /* childNumberVisits */
+    float q[512];                /* qValues */
+    float prior[512];            /* policyProbSmall */
+    unsigned char vl[512];       /* virtualLossCounter */
+    unsigned char child_type[512];
+} ara_node_view_t;
+int ara_search_begin(ara_search_t s);
+int ara_search_step(ara_search_t s, int n_batches);
+int ara_search_node(ara_search_t s, int tree, int node_id, ara_node_view_t* out);
 /* per-phase device times of the last go (CUDA events on the search stream); enable before ara_search_go */
 /* MCTSAgent::apply_move_to_tree (agents/mctsagent.cpp:230-247): tells the tree which move was played.  The next go
  * on the position after that move (after both moves, when called twice) continues on the subtree behind it

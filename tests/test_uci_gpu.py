@@ -108,3 +108,44 @@ def test_uci_benchmark_and_inference_commands(tmp_path):
     assert "info string batch-size: 16" in out
     rate = [float(l.split()[-2]) for l in out.splitlines() if l.startswith("info string Evaluations per second:")]
     assert len(rate) == 1 and rate[0] > 100.0
+
+
+@pytest.mark.gpu
+def test_uci_go_infinite_and_stop_on_the_device():
+    """`go infinite` on the real device search: `isready` is answered while it runs, `stop` ends it (ara_search_stop inside
+    the go loop) and the best move of the tree searched so far comes back; a `stop` during a timed `go` ends that too."""
+    import time
+    from tests.test_uci_host_logic import Engine
+    exe = os.path.join(ROOT, "crazyara_b200", "ara_uci")
+    e = Engine(dict(os.environ))
+    e.send("uci")
+    e.read_until("uciok", timeout=60)
+    e.send("setoption name UCI_Variant value crazyhouse")
+    e.send("setoption name Batch_Size value 16")
+    e.send("position startpos moves e2e4")
+    e.send("go infinite")
+    time.sleep(0.5)
+    e.send("isready")
+    assert e.read_until("readyok", timeout=60) and not any(l.startswith("bestmove") for l in e.lines)
+    t0 = time.time()
+    e.send("stop")
+    best = e.read_until("bestmove", timeout=30)
+    assert time.time() - t0 < 2.0 and len(best.split()[1]) >= 4
+    info = [l for l in e.lines if l.startswith("info depth")][-1]
+    nodes = int(info.split(" nodes ")[1].split()[0])
+    assert nodes > 1000                                   # half a second of searching on the fake backend
+    # a timed search is stoppable too (every go runs on the worker thread)
+    e.send("go movetime 5000")
+    time.sleep(0.3)
+    t0 = time.time()
+    e.send("stop")
+    e.read_until("bestmove", timeout=30)
+    assert time.time() - t0 < 2.0
+    # and a limited search that is not stopped runs to its limit while the next command waits for it
+    e.send("setoption name Simulations value 400")
+    e.send("go nodes 400")
+    e.send("isready")
+    e.read_until("bestmove", timeout=60)
+    e.send("quit")
+    e.close()
+    assert e.p.returncode == 0 and os.path.exists(exe)

@@ -49,6 +49,7 @@ typedef struct ONode {
     uint32_t free_visits, visit_sum;
     int checkmate_idx, end_in_ply, no_visit_idx, n_unsolved;
     int node_type;
+    int inspected; /* NodeData::inspected: select_enhanced_move has looked at this node's unopened checks */
 } ONode;
 
 typedef struct {
@@ -65,6 +66,45 @@ enum { NB_NEW = 0, NB_COLLISION, NB_TERMINAL, NB_TRANSPOSITION };
 typedef struct {
     uint32_t x; /* minstd_rand0 state = std::default_random_engine */
 } MinStd;
+
+/* glibc's rand() (stdlib/random_r.c, TYPE_3: x^31 + x^3 + 1 additive feedback over 31 words, seeded by the 16807
+ * Lehmer generator, first 310 outputs discarded) -- what the reference's epsilon-greedy exploration draws from
+ * (`rand() % counter`, searchthread.cpp:171-185, :124-162, :497-501).  Pinned to the live libc by tests. */
+typedef struct {
+    int32_t r[34];
+    int f, b; /* front / rear index */
+} GlibcRand;
+static void glibc_srand(GlibcRand* g, unsigned seed) {
+    if (seed == 0) seed = 1;
+    g->r[0] = (int32_t)seed;
+    int32_t word = (int32_t)seed;
+    for (int i = 1; i < 31; ++i) {
+        const long hi = word / 127773, lo = word % 127773;
+        long w = 16807 * lo - 2836 * hi;
+        if (w < 0) w += 2147483647;
+        word = (int32_t)w;
+        g->r[i] = word;
+    }
+    g->f = 3;
+    g->b = 0;
+    for (int i = 0; i < 310; ++i) {
+        g->r[g->f] = (int32_t)((uint32_t)g->r[g->f] + (uint32_t)g->r[g->b]);
+        g->f = (g->f + 1) % 31;
+        g->b = (g->b + 1) % 31;
+    }
+}
+static int glibc_rand(GlibcRand* g) {
+    const uint32_t v = (uint32_t)g->r[g->f] + (uint32_t)g->r[g->b];
+    g->r[g->f] = (int32_t)v;
+    g->f = (g->f + 1) % 31;
+    g->b = (g->b + 1) % 31;
+    return (int)(v >> 1);
+}
+void oglibc_rand_sequence(unsigned seed, int n, int* out) { /* test hook */
+    GlibcRand g;
+    glibc_srand(&g, seed);
+    for (int i = 0; i < n; ++i) out[i] = glibc_rand(&g);
+}
 
 struct OSearch {
     OSettings st;
@@ -100,6 +140,7 @@ struct OSearch {
     } parked;
     int active;
     MinStd rng; /* the Dirichlet generator */
+    GlibcRand crand; /* rand() of the epsilon-greedy exploration: seeded once (srand(seed)), advances across searches */
     unsigned long long num_nodes, sum_select_k, sum_depth;
     ONode** all_nodes;
     size_t n_all, cap_all;
@@ -529,6 +570,7 @@ OSearch* osearch_new(const OSettings* st) {
     s->parked.actions_buf = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)s->parked.actions_cap);
     s->active = 0;
     s->rng.x = minstd_seed(st->seed);
+    glibc_srand(&s->crand, (unsigned)st->seed);
     return s;
 }
 /* makes logical search thread t (0 or 1) the owner of the batch members */
@@ -677,11 +719,83 @@ void osearch_root_results(OSearch* s, const float* value, const float* prob) {
 /* reused root: it already has its network results and NodeData; the noise is applied to it like to a new root */
 void osearch_root_reused(OSearch* s) { root_noise_and_open(s); }
 
-static ONode* get_new_child_to_evaluate(OSearch* s, int* type) { /* searchthread.cpp:164-271 (eps features off) */
+static int get_best_action_index(const ONode* n, const OSettings* st, int fast);
+
+/* ---- epsilon-greedy / epsilon-check exploration (searchthread.cpp:124-185, :451-473, :497-501) */
+static int get_random_depth(OSearch* s) { /* :497-501: ceil(-log2(1 - r/100) - 1), r = rand() % 100 + 1 */
+    const int r = glibc_rand(&s->crand) % 100 + 1;
+    const double d = ceil(-log2(1 - r / 100.0) - 1);
+    /* r = 100: size_t(+inf) -- formally undefined; GCC on x86-64 converts through cvttsd2si(x - 2^63) ^ 2^63 = 0
+       (checked against the compiled reference, tests/test_ref_mcts.py): depth 0 */
+    return d > 1e18 ? 0 : (int)d;
+}
+static void push_action(OSearch* s, uint32_t a) {
+    if (s->n_actions_buf == s->actions_cap) {
+        s->actions_cap *= 2;
+        s->actions_buf = (uint32_t*)realloc(s->actions_buf, sizeof(uint32_t) * (size_t)s->actions_cap);
+    }
+    s->actions_buf[s->n_actions_buf++] = a;
+}
+/* :144-162: walks down the most visited line for a random number of plies; the trajectory starts at the node reached */
+static ONode* get_starting_node(OSearch* s, ONode* cur, int* depth, int* ci) {
+    const int d = get_random_depth(s);
+    for (int k = 0; k < d; ++k) {
+        *ci = get_best_action_index(cur, &s->st, 1);
+        ONode* next = cur->child[*ci];
+        if (next == NULL || !next->has_d || next->visit_sum < (uint32_t)s->st.epsilon_greedy_counter || next->node_type != ONT_UNSOLVED) break;
+        push_action(s, cur->actions[*ci]);
+        cur = next;
+        ++*depth;
+    }
+    return cur;
+}
+static void random_playout(OSearch* s, ONode* cur, int* ci) { /* :124-142 */
+    if (cur->n_actions == cur->no_visit_idx) { /* is_fully_expanded */
+        const int idx = (int)((size_t)glibc_rand(&s->crand) % (size_t)cur->n_actions);
+        ONode* c = cur->child[idx];
+        if (c == NULL || !c->has_d || c->node_type == ONT_UNSOLVED) {
+            *ci = idx;
+            return;
+        }
+        *ci = -1;
+    } else {
+        *ci = cur->no_visit_idx < cur->n_actions - 1 ? cur->no_visit_idx : cur->n_actions - 1;
+        increment_no_visit_idx(cur);
+    }
+}
+static int select_enhanced_move(OSearch* s, ONode* cur) { /* :451-473: an unopened move that gives check */
+    if (cur->has_d && !cur->inspected && !cur->is_terminal) {
+        OPos* pos = (OPos*)malloc(sizeof(OPos));
+        opos_copy(pos, &s->root_state);
+        for (int i = 0; i < s->n_actions_buf; ++i) opos_do_move(pos, s->actions_buf[i]);
+        for (int c = cur->no_visit_idx; c < cur->n_actions; ++c)
+            if (opos_gives_check(pos, cur->actions[c])) {
+                for (int i = cur->no_visit_idx; i < c + 1; ++i) increment_no_visit_idx(cur);
+                free(pos);
+                return c;
+            }
+        free(pos);
+        cur->inspected = 1;
+    }
+    return -1;
+}
+
+static ONode* get_new_child_to_evaluate(OSearch* s, int* type) { /* searchthread.cpp:164-271 */
     ONode* cur = s->root;
     int depth = 0;
+    int forced = -1; /* childIdx chosen by the exploration branches, (uint16_t)-1 in the reference */
+    const int egc = s->st.epsilon_greedy_counter, ecc = s->st.epsilon_checks_counter;
+    if (egc && s->root->has_d && glibc_rand(&s->crand) % egc == 0) {
+        cur = get_starting_node(s, cur, &depth, &forced);
+        random_playout(s, cur, &forced);
+    } else if (ecc && s->root->has_d && glibc_rand(&s->crand) % ecc == 0) {
+        cur = get_starting_node(s, cur, &depth, &forced);
+        forced = select_enhanced_move(s, cur);
+        if (forced == -1) random_playout(s, cur, &forced);
+    }
     for (;;) {
-        const int ci = select_child_node(s, cur);
+        const int ci = forced != -1 ? forced : select_child_node(s, cur);
+        forced = -1;
         apply_virtual_loss_to_child(cur, ci, &s->st);
         traj_push(&s->cur, cur, ci);
         ONode* next = cur->child[ci];
@@ -717,11 +831,7 @@ static ONode* get_new_child_to_evaluate(OSearch* s, int* type) { /* searchthread
             s->sum_depth += (unsigned long long)depth;
             return next;
         }
-        if (s->n_actions_buf == s->actions_cap) {
-            s->actions_cap *= 2;
-            s->actions_buf = (uint32_t*)realloc(s->actions_buf, sizeof(uint32_t) * (size_t)s->actions_cap);
-        }
-        s->actions_buf[s->n_actions_buf++] = cur->actions[ci];
+        push_action(s, cur->actions[ci]);
         cur = next;
     }
 }

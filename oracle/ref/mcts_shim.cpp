@@ -128,8 +128,8 @@ int ref_mcts_run(const char* fen, int variant, int is960, const char* const* uci
     ss.qValueWeight = st->q_value_weight;
     ss.qVetoDelta = st->q_veto_delta;
     ss.verbose = false;
-    ss.epsilonChecksCounter = 0;  // Centi_Epsilon_Checks 0 (crazyara.cpp:748: round(100/0) -> 0 on x86-64)
-    ss.epsilonGreedyCounter = 0;
+    ss.epsilonChecksCounter = static_cast<uint_fast8_t>(st->epsilon_checks_counter);  // round(100 / Centi_Epsilon_Checks), 0 = off
+    ss.epsilonGreedyCounter = static_cast<uint_fast8_t>(st->epsilon_greedy_counter);  // (crazyara.cpp:748-749)
     ss.useMCGS = false;
     ss.cpuctInit = st->cpuct_init;
     ss.cpuctBase = st->cpuct_base;
@@ -169,6 +169,7 @@ int ref_mcts_run(const char* fen, int variant, int is960, const char* const* uci
         EvalInfo eval;
         agent.set_search_settings(&state, &limits, &eval);
         ref_seed_node_generator(st->seed);
+        srand(static_cast<unsigned>(st->seed));  // the exploration branches draw from the C library's rand()
         eval.start = chrono::steady_clock::now();
         if (st->threads != 2 || st->reserved == 1) {
             // Threads 1, or (reserved == 1: bench.py's CPU arm) the reference's own OS threads, unscheduled

@@ -68,6 +68,7 @@ def _lib():
         L.osearch_planes_t.restype = ctypes.c_void_p
         L.osearch_planes_t.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.osearch_batch_keys_t.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        L.oglibc_rand_sequence.argtypes = [ctypes.c_uint, ctypes.c_int, ctypes.c_void_p]
         L.odirichlet_noise.argtypes = [ctypes.c_ulonglong, ctypes.c_int, ctypes.c_float, ctypes.c_void_p]
         L.osearch_batch_keys.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.ofake_eval.argtypes = [ctypes.c_ulonglong, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]

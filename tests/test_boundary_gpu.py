@@ -37,7 +37,9 @@ def test_stepping_equals_go_and_the_oracle(threads):
         if not running:
             break
     stepped = agent.result(0)
-    assert steps >= 400 // (8 * threads) and seen == sorted(seen) and seen[0] < seen[-1]
+    assert steps >= 400 // (8 * threads) and seen[0] < seen[-1]
+    if threads == 1:   # (with two threads a step can end with fewer visits: the other thread's collisions were reverted)
+        assert seen == sorted(seen)
     assert agent.thread_iteration(3) == 0 and agent.result(0)["visit_sum"] == stepped["visit_sum"]   # further steps: no-ops
     assert_same_search(whole, stepped)
     ost = osr.default_settings("crazyhouse", batch_size=8, simulations=400, threads=threads)

@@ -85,3 +85,32 @@ def test_oracle_two_thread_schedule_equals_the_compiled_reference_search(case):
     pos = Position(fen, variant, is960)
     pos.push_uci(*premoves)
     assert_oracle_equals_reference(pos, fen, vid, is960, premoves, st, threads=2)
+
+
+def test_glibc_rand_restatement_equals_libc():
+    """oracle/mcts.c restates glibc's rand() (the exploration branches draw `rand() % counter`); the device code restates it
+    again (search_dev.cuh): both pinned to the live libc here / in tests/test_glibc_flt32.py."""
+    import ctypes
+    L = osr._lib()
+    libc = ctypes.CDLL("libc.so.6")
+    for seed in (1, 42, 0, 123456789, 2**32 - 1):
+        out = np.zeros(2000, np.int32)
+        L.oglibc_rand_sequence(seed, len(out), out.ctypes.data)
+        libc.srand(seed)
+        assert [libc.rand() for _ in range(len(out))] == out.tolist()
+
+
+EPS = dict(epsilon_greedy_counter=20, epsilon_checks_counter=100)  # the UCI defaults Centi_Epsilon_Greedy 5, _Checks 1
+
+
+@pytest.mark.parametrize("threads", [1, 2])
+@pytest.mark.parametrize("case", CASES_2T, ids=[f"{c[0]}-b{c[6]}-s{c[7]}-{i}" for i, c in enumerate(CASES_2T)])
+def test_epsilon_exploration_equals_the_compiled_reference_search(case, threads):
+    """Centi_Epsilon_Greedy 5 / Centi_Epsilon_Checks 1 (the reference's UCI defaults, optionsuci.cpp:89-90): random
+    playouts and unexplored checks below a randomly deep node of the main line (searchthread.cpp:124-185, :451-473),
+    driven by the C library's rand() seeded with the settings' seed."""
+    variant, vid, mode, fen, is960, premoves, batch, sims, extra = case
+    st = case_settings(mode, batch, sims, dict(extra, threads=threads, **EPS))
+    pos = Position(fen, variant, is960)
+    pos.push_uci(*premoves)
+    assert_oracle_equals_reference(pos, fen, vid, is960, premoves, st, threads=threads)

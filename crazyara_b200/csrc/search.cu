@@ -71,10 +71,12 @@ __global__ void __launch_bounds__(32) advance_kernel(const TreeDev* trees, int t
 }
 
 // one warp per tree: the sequential part of SearchThread::create_mini_batch
+// EPS: with the epsilon-greedy / epsilon-check exploration (its own kernel: the ordinary select stays as lean as it is)
+template <bool EPS>
 __global__ void __launch_bounds__(32) select_kernel(const TreeDev* trees, SearchParams sp) {
     __shared__ WarpScratch ws;
     const TreeDev t = trees[blockIdx.x];
-    create_mini_batch(t, sp, ws);
+    create_mini_batch<EPS>(t, sp, ws);
 }
 
 // Multi-tree searches: the new leaves of all trees are packed into consecutive rows of the network batch (tree i gets
@@ -228,6 +230,7 @@ class Search {
     // and each thread's network forward on net_stream_, between its S and its next U: while one thread's batch is at
     // the network the other thread selects.  (oracle/mcts.h describes the schedule; tests compare all three.)
     int threads_ = 1;
+    bool eps_ = false;  // epsilon-greedy / epsilon-check exploration on: the select_kernel<true> instantiation
     bool primed_ = false;                  // S0 S1 of the current go have been enqueued
     TreeDev* d_trees_slot_[2] = {nullptr, nullptr};
     std::vector<TreeDev> h_trees1_;        // slot 1 views (h_trees_ = slot 0)
@@ -379,6 +382,9 @@ int Search::init(Net* net, const SearchParams& params, int device, int trees, in
     if (sp.threads * sp.batch_size > 255 && sp.threads > 1)
         return set_error("ara_search_create: Threads %d x Batch_Size %d exceeds the 255 virtual visits an edge can carry", sp.threads, sp.batch_size);
     threads_ = sp.threads;
+    if (sp.epsilon_greedy_counter < 0 || sp.epsilon_greedy_counter > 255 || sp.epsilon_checks_counter < 0 || sp.epsilon_checks_counter > 255)
+        return set_error("ara_search_create: epsilon counters must be in [0, 255] (round(100 / Centi_Epsilon_*), uint8 in the reference)");
+    eps_ = sp.epsilon_greedy_counter != 0 || sp.epsilon_checks_counter != 0;
     ARA_CUDA_OK(cudaSetDevice(device_));
     {
         cudaDeviceProp prop;
@@ -459,6 +465,10 @@ int Search::init(Net* net, const SearchParams& params, int device, int trees, in
     for (int i = 0; i < n_trees; ++i) {  // the trees' Dirichlet generators (TreeState::rng)
         const uint32_t x = minstd_seed(sp.seed, i);
         ARA_CUDA_OK(cudaMemcpy(&d_states_[i]->rng, &x, sizeof(x), cudaMemcpyHostToDevice));
+        TreeState tmp;  // rand() of the exploration branches: srand(seed ^ tree index * golden ratio)
+        crand_seed(tmp.crand_r, &tmp.crand_f, static_cast<unsigned>(sp.seed ^ (static_cast<unsigned long long>(i) * 0x9E3779B97F4A7C15ULL)));
+        ARA_CUDA_OK(cudaMemcpy(d_states_[i]->crand_r, tmp.crand_r, sizeof(tmp.crand_r), cudaMemcpyHostToDevice));
+        ARA_CUDA_OK(cudaMemcpy(&d_states_[i]->crand_f, &tmp.crand_f, sizeof(tmp.crand_f), cudaMemcpyHostToDevice));
     }
     d_trees_slot_[0] = d_trees_;
     if (threads_ == 2) {
@@ -532,7 +542,8 @@ int Search::enqueue_iteration(bool with_events) {
     const float* values = net_ ? net_->d_value : d_values_;
     const float* probs = net_ ? net_->d_prob : d_probs_;
     if (with_events) prof_event();
-    select_kernel<<<n_trees, 32, 0, stream_>>>(d_trees_, sp);
+    if (eps_) select_kernel<true><<<n_trees, 32, 0, stream_>>>(d_trees_, sp);
+    else select_kernel<false><<<n_trees, 32, 0, stream_>>>(d_trees_, sp);
     if (n_trees > 1) pack_kernel<<<1, 32, 0, stream_>>>(d_trees_, n_trees, d_count_);
     expand_kernel<<<n_trees * B, 32, 0, stream_>>>(d_trees_, sp, B, in_h, cpad, net_ ? net_->precision : 0);
     if (with_events) prof_event();
@@ -572,7 +583,8 @@ int Search::enqueue_slot_tree_ops(int slot, bool with_update) {
         scatter_prepare_kernel<<<n_trees * 4 * B, 32, 0, stream_>>>(trees, sp, B, 4 * B, values, probs, n_labels_);
         ARA_CUDA_OK(cudaStreamWaitEvent(stream_, ev_join_, 0));
     }
-    select_kernel<<<n_trees, 32, 0, stream_>>>(trees, sp);
+    if (eps_) select_kernel<true><<<n_trees, 32, 0, stream_>>>(trees, sp);
+    else select_kernel<false><<<n_trees, 32, 0, stream_>>>(trees, sp);
     pack_kernel<<<1, 32, 0, stream_>>>(trees, n_trees, d_count_slot_[slot]);
     expand_kernel<<<n_trees * B, 32, 0, stream_>>>(trees, sp, B, net_ ? net_->io_in_h[slot] : nullptr, net_ ? net_->cin_pad : 0,
                                                     net_ ? net_->precision : 0);

@@ -31,7 +31,7 @@ constexpr int kNoCheckmate = 65535;
 constexpr float kQInit = -1.0f;
 enum : int { VS_VIRTUAL_LOSS = 0, VS_VIRTUAL_VISIT = 1, VS_VIRTUAL_OFFSET = 2, VS_VIRTUAL_MIX = 3 };
 enum : int { NT_WIN = 0, NT_DRAW = 1, NT_LOSS = 2, NT_UNSOLVED = 3 };
-enum : int { NF_TERMINAL = 1, NF_HAS_NN = 2, NF_HAS_D = 4, NF_SORTED = 8 };
+enum : int { NF_TERMINAL = 1, NF_HAS_NN = 2, NF_HAS_D = 4, NF_SORTED = 8, NF_INSPECTED = 16 };
 
 // Same layout as OSettings (oracle/mcts.h) and ara_search_settings_t (include/ara_b200.h).
 struct SearchParams {
@@ -117,6 +117,10 @@ struct TreeState {
     // SM-clock cycles spent per phase of create_mini_batch (lane 0): 0 descent, 1 board copy + do_move, 2 repetition +
     // move generation, 3 node/edge allocation + init, 4 plane encoding, 5 terminal backups, 6 trajectory bookkeeping
     unsigned long long prof[8];
+    // rand() of the epsilon-greedy / epsilon-check exploration: glibc's TYPE_3 generator (crand_next), seeded when the
+    // handle is created (srand(seed ^ tree index)) and advanced across searches like the C library's process-wide state
+    int32_t crand_r[31];
+    int32_t crand_f;  // front index; the rear index is (front + 28) % 31
 };
 
 #if defined(__CUDA_ARCH__)
@@ -386,12 +390,13 @@ ARA_HD SelectPick pick_fast(const TreeDev& t, const NodeHdr& h, const EdgeRegs& 
     return r;
 }
 
+// forced >= 0: the child index was chosen by the exploration prologue (eps_prologue) -- no selection, the visit only
 ARA_HD SelectStep select_and_visit(const TreeDev& t, const SearchParams& sp, int nid, const NodeHdr& h,
-                                   const EdgeRegs& pre) {
+                                   const EdgeRegs& pre, int forced = -1) {
     NodeHdr* hp = &t.hdr[nid];
     const int k = h.no_visit_idx;
     const uint32_t e = h.edge_base;
-    const bool single = k == 1 || h.checkmate_idx != kNoCheckmate;
+    const bool single = forced >= 0 || k == 1 || h.checkmate_idx != kNoCheckmate;
     ARA_FINE_T0(tf);
     // (prefetching every open child's header and edge lines here was measured: 2 % slower, the issue slots cost more
     // than the earlier start of the round trip saves)
@@ -402,7 +407,7 @@ ARA_HD SelectStep select_and_visit(const TreeDev& t, const SearchParams& sp, int
     ARA_FINE(t.st, 4, tf, pre.c ^ static_cast<int>(pre.n) ^ __double2hiint(sqrt_new));
     SelectPick pk;
     if (single) {  // only one open child, or a forced win
-        pk.ci = k == 1 ? 0 : h.checkmate_idx;
+        pk.ci = forced >= 0 ? forced : (k == 1 ? 0 : h.checkmate_idx);
         pk.owner = ARA_LANE == (pk.ci & (ARA_WARP_N - 1));
         pk.x = pre;
         if (pk.owner && pk.ci != ARA_LANE) pk.x = load_edge(t, e + pk.ci);
@@ -434,6 +439,7 @@ ARA_HD SelectStep select_and_visit(const TreeDev& t, const SearchParams& sp, int
         t.vl[ee] = static_cast<uint8_t>(pk.x.vl + 1);
     }
     if (ARA_LANE == 0) {
+        // (sum_select_k counts what select_child_node reads: nothing for a forced child, nor for its two shortcuts)
         if (!single) t.st->sum_select_k += static_cast<unsigned long long>(k);
         hp->visit_sum = vs_new;
         hp->cput = cput_new;
@@ -963,9 +969,136 @@ ARA_HD void apply_dirichlet_to_root(const TreeDev& t, const SearchParams& sp, Wa
     h.flags |= NF_SORTED | NF_HAS_D;
 }
 
+// ------------------------------------------------------------------ epsilon-greedy / epsilon-check exploration
+// (searchthread.cpp:124-185, :451-473, :497-501; Centi_Epsilon_Greedy 5 and Centi_Epsilon_Checks 1 in the reference's
+// default UCI option set, optionsuci.cpp:89-90).  Lane 0 only, global memory: 6 % of the playouts take this path.
+// glibc rand(): r[f] += r[f - 3 mod 31]; output >> 1 (stdlib/random_r.c, TYPE_3); seeding: crand_seed.
+ARA_HD void crand_seed(int32_t* r, int32_t* f, unsigned seed) {
+    if (seed == 0) seed = 1;
+    r[0] = static_cast<int32_t>(seed);
+    int32_t word = static_cast<int32_t>(seed);
+    for (int i = 1; i < 31; ++i) {
+        const long long hi = word / 127773, lo = word % 127773;
+        long long w = 16807 * lo - 2836 * hi;
+        if (w < 0) w += 2147483647;
+        word = static_cast<int32_t>(w);
+        r[i] = word;
+    }
+    int fi = 3, bi = 0;
+    for (int i = 0; i < 310; ++i) {
+        r[fi] = static_cast<int32_t>(static_cast<uint32_t>(r[fi]) + static_cast<uint32_t>(r[bi]));
+        fi = (fi + 1) % 31;
+        bi = (bi + 1) % 31;
+    }
+    *f = fi;
+}
+ARA_HD int crand_next(TreeState& st) {
+    const int fi = st.crand_f, bi = (fi + 28) % 31;
+    const uint32_t v = static_cast<uint32_t>(st.crand_r[fi]) + static_cast<uint32_t>(st.crand_r[bi]);
+    st.crand_r[fi] = static_cast<int32_t>(v);
+    st.crand_f = (fi + 1) % 31;
+    return static_cast<int>(v >> 1);
+}
+// get_random_depth (searchthread.cpp:497-501): ceil(-log2(1 - r / 100.0) - 1) for r = rand() % 100 + 1, tabulated with
+// the host libm; r = 100 gives size_t(+inf), which GCC on x86-64 turns into 0 (checked against the compiled reference)
+ARA_HD int eps_random_depth(int r) {
+    return r <= 50 ? 0 : r <= 75 ? 1 : r <= 87 ? 2 : r <= 93 ? 3 : r <= 96 ? 4 : r <= 98 ? 5 : r == 99 ? 6 : 0;
+}
+// get_best_action_index(node, fast = true) (node.cpp:1123-1143)
+ARA_HD int eps_best_action_fast(const TreeDev& t, const NodeHdr& h) {
+    if (h.checkmate_idx != kNoCheckmate) return h.checkmate_idx;
+    if (h.node_type == NT_LOSS) {
+        int longest = 0, idx = 0;
+        for (int i = 0; i < h.n_moves; ++i) {
+            const int c = t.child[h.edge_base + i];
+            const int e = c >= 0 ? t.hdr[c].end_in_ply : 0;
+            if (e > longest) longest = e, idx = i;
+        }
+        return idx;
+    }
+    int b = 0;
+    for (int i = 1; i < h.no_visit_idx; ++i)
+        if (t.N[h.edge_base + i] > t.N[h.edge_base + b]) b = i;
+    return b;
+}
+ARA_HD void eps_increment_no_visit_idx(NodeHdr& h) {  // Node::increment_no_visit_idx (node.cpp:571-580)
+    if (h.no_visit_idx < h.n_moves) ++h.no_visit_idx;
+}
+// random_playout (searchthread.cpp:124-142): the forced child index, or -1 for the ordinary selection
+ARA_HD int eps_random_playout(const TreeDev& t, TreeState& st, int cur) {
+    NodeHdr& h = t.hdr[cur];
+    if (h.n_moves == h.no_visit_idx) {  // is_fully_expanded
+        const int idx = static_cast<int>(static_cast<unsigned long long>(crand_next(st)) % static_cast<unsigned long long>(h.n_moves));
+        const int c = t.child[h.edge_base + idx];
+        if (c < 0 || !(t.hdr[c].flags & NF_HAS_D) || t.hdr[c].node_type == NT_UNSOLVED) return idx;
+        return -1;
+    }
+    const int idx = h.no_visit_idx < h.n_moves - 1 ? h.no_visit_idx : h.n_moves - 1;
+    eps_increment_no_visit_idx(h);
+    return idx;
+}
+// select_enhanced_move (searchthread.cpp:451-473): the first unopened move that gives check, opened with everything
+// before it; a node is inspected once.  `scratch`: a board to play the moves on.
+ARA_HD int eps_select_enhanced_move(const TreeDev& t, int cur, Board& scratch) {
+    NodeHdr& h = t.hdr[cur];
+    if (!(h.flags & NF_HAS_D) || (h.flags & NF_INSPECTED) || (h.flags & NF_TERMINAL)) return -1;
+    for (int c = h.no_visit_idx; c < h.n_moves; ++c) {
+        scratch = t.board[cur];
+        do_move(scratch, t.move[h.edge_base + c]);
+        if (in_check(scratch)) {  // State::gives_check
+            for (int i = h.no_visit_idx; i < c + 1; ++i) eps_increment_no_visit_idx(h);
+            return c;
+        }
+    }
+    h.flags |= NF_INSPECTED;
+    return -1;
+}
+// The exploration prologue of get_new_child_to_evaluate (searchthread.cpp:171-185): may move the start of the playout
+// down the most visited line (get_starting_node, :144-162: the trajectory -- and therefore the backup -- begins THERE)
+// and force its first child.  Lane 0 computes, all lanes get (cur, depth, forced); the keys of the skipped levels go to
+// ws.path_key / path_rep like the descent's.
+ARA_HD void eps_prologue(const TreeDev& t, const SearchParams& sp, WarpScratch& ws, int* cur_io, int* depth_io, int* forced_io) {
+    int cur = *cur_io, depth = 0, forced = -1;
+    if (ARA_LANE == 0) {
+        TreeState& st = *t.st;
+        const int egc = sp.epsilon_greedy_counter, ecc = sp.epsilon_checks_counter;
+        const bool playout_root = (t.hdr[st.root].flags & NF_HAS_D) != 0;
+        int branch = 0;  // 1 random playout, 2 enhanced move
+        if (egc && playout_root && crand_next(st) % egc == 0) branch = 1;
+        else if (ecc && playout_root && crand_next(st) % ecc == 0) branch = 2;
+        if (branch) {
+            const int d = eps_random_depth(crand_next(st) % 100 + 1);  // get_starting_node
+            for (int k = 0; k < d && depth < kMaxDepth - 1; ++k) {
+                const NodeHdr& h = t.hdr[cur];
+                const int ci = eps_best_action_fast(t, h);
+                const int next = t.child[h.edge_base + ci];
+                if (next < 0) break;
+                const NodeHdr& nh = t.hdr[next];
+                if (!(nh.flags & NF_HAS_D) || nh.visit_sum < static_cast<uint32_t>(egc) || nh.node_type != NT_UNSOLVED) break;
+                ws.path_key[depth] = h.key;
+                ws.path_rep[depth] = h.repetition;
+                cur = next;
+                ++depth;
+            }
+            if (branch == 2) forced = eps_select_enhanced_move(t, cur, ws.child);
+            if (forced < 0) forced = eps_random_playout(t, st, cur);
+        }
+        ws.bcast[0] = cur, ws.bcast[1] = depth, ws.bcast[2] = forced;
+    }
+    ARA_WARP_SYNC();
+    *cur_io = ws.bcast[0];
+    *depth_io = ws.bcast[1];
+    *forced_io = ws.bcast[2];
+    ARA_WARP_SYNC();
+}
+
 // ------------------------------------------------------------------ one mini-batch: SearchThread::create_mini_batch
 // Sequential per tree (one warp).  New leaves are only created here (expand_node_seq); their move lists, edges and
 // input planes are produced afterwards by expand_pending, one warp per leaf.
+// EPS: epsilon-greedy / epsilon-check exploration compiled in (its own instantiation: the ordinary descent stays as lean
+// as it is).  With it a playout may start below the root: `depth` counts plies below the root (path keys, repetition),
+// `tlen` the trajectory entries (what is stored and backed up).
+template <bool EPS>
 ARA_HD void create_mini_batch_impl(const TreeDev& t, const SearchParams& sp, WarpScratch& ws) {
     TreeState& st = *t.st;
     BatchState& bs = *t.bs;  // (global memory: touched at the start and the end only)
@@ -997,7 +1130,12 @@ ARA_HD void create_mini_batch_impl(const TreeDev& t, const SearchParams& sp, War
     int n_new = 0, n_coll = 0, n_term = 0;
     while (n_new < B && n_coll != B && n_term < 2 * B) {
         int cur = st.root, depth = 0, type = -1, leaf = -1;  // type: 0 new, 1 collision, 2 terminal
+        int forced = -1, skipped = 0;  // EPS: first child forced by the prologue; plies skipped above the trajectory
         long long tq = ARA_CLOCK();
+        if (EPS) {
+            eps_prologue(t, sp, ws, &cur, &depth, &forced);
+            skipped = depth;
+        }
         NodeHdr h;
         load_hdr(&h, &t.hdr[cur]);
         EdgeRegs pre = load_edge(t, h.edge_base + ARA_LANE);
@@ -1007,13 +1145,15 @@ ARA_HD void create_mini_batch_impl(const TreeDev& t, const SearchParams& sp, War
                 type = -2;
                 break;
             }
-            const SelectStep step = select_and_visit(t, sp, cur, h, pre);
+            const SelectStep step = EPS ? select_and_visit(t, sp, cur, h, pre, forced) : select_and_visit(t, sp, cur, h, pre);
+            forced = -1;
             const int ci = step.ci;
             const int next = step.child;
             if (ARA_LANE == 0) {
-                ws.traj_node[depth] = cur;
-                ws.traj_ci[depth] = static_cast<uint16_t>(ci);
-                ws.traj_edge[depth] = h.edge_base + static_cast<uint32_t>(ci);
+                const int ti = depth - skipped;
+                ws.traj_node[ti] = cur;
+                ws.traj_ci[ti] = static_cast<uint16_t>(ci);
+                ws.traj_edge[ti] = h.edge_base + static_cast<uint32_t>(ci);
                 ws.path_key[depth] = h.key;
                 ws.path_rep[depth] = h.repetition;
             }
@@ -1084,18 +1224,18 @@ ARA_HD void create_mini_batch_impl(const TreeDev& t, const SearchParams& sp, War
             if (ARA_LANE == 0) {
                 st.sum_depth += static_cast<unsigned long long>(depth);
                 // terminal: free backup, sequential leaf -> root because the MCTS solver propagates bottom-up
-                backup_value(t, sp, node_value(t.hdr[leaf]), ws.traj_node, ws.traj_ci, depth, true, sp.mcts_solver != 0);
+                backup_value(t, sp, node_value(t.hdr[leaf]), ws.traj_node, ws.traj_ci, depth - skipped, true, sp.mcts_solver != 0);
             }
         } else {
             const int row = type == 1 ? B + n_coll : n_new;
-            for (int i = ARA_LANE; i < depth; i += ARA_WARP_N) {
+            for (int i = ARA_LANE; i < depth - skipped; i += ARA_WARP_N) {
                 t.traj_node[row * kMaxDepth + i] = ws.traj_node[i];
                 t.traj_ci[row * kMaxDepth + i] = ws.traj_ci[i];
                 t.traj_edge[row * kMaxDepth + i] = ws.traj_edge[i];
             }
             if (ARA_LANE == 0) {
                 st.sum_depth += static_cast<unsigned long long>(depth);
-                t.traj_len[row] = depth;
+                t.traj_len[row] = depth - skipped;
                 if (type == 0) t.new_node[n_new] = leaf;
             }
         }
@@ -1115,13 +1255,14 @@ ARA_HD void create_mini_batch_impl(const TreeDev& t, const SearchParams& sp, War
     ARA_WARP_SYNC();
 }
 
+template <bool EPS>
 ARA_HD void create_mini_batch(const TreeDev& t_in, const SearchParams& sp, WarpScratch& ws) {
     // every `st.x += ...` of the sequential loop would otherwise be a global-memory round trip on the critical path
     TreeDev t = t_in;
     if (ARA_LANE == 0) ws.st_local = *t_in.st;
     ARA_WARP_SYNC();
     t.st = &ws.st_local;
-    create_mini_batch_impl(t, sp, ws);
+    create_mini_batch_impl<EPS>(t, sp, ws);
     ARA_WARP_SYNC();
     if (ARA_LANE == 0) *t_in.st = ws.st_local;
     ARA_WARP_SYNC();

@@ -6,6 +6,7 @@
 // the ThreadManager's early stopping / prolongation rules run on top (ara_search_set_time_control).
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <chrono>
 #include <thread>
 #include <iomanip>
@@ -33,7 +34,11 @@ struct Options {
                                              {"UCI_Chess960", "false"},     {"Input_Version", "0"},    {"Dirichlet_Seed", "42"},
                                              {"Move_Overhead", "20"},       {"Timed_Search_Nodes", "1000000"},
                                              {"Reuse_Tree", "true"},           {"Use_NPS_Time_Manager", "true"},
-                                             {"Precision", "float16"}};
+                                             {"Precision", "float16"},
+                                             // the reference's defaults (optionsuci.cpp:89-90, :182); Threads 1 and both epsilons 0
+                                             // give the deterministic single-threaded search
+                                             {"Threads", "2"},              {"Centi_Epsilon_Greedy", "5"},
+                                             {"Centi_Epsilon_Checks", "1"}};
     int i(const std::string& k) const { return std::stoi(kv.at(k)); }
     bool b(const std::string& k) const { return kv.at(k) == "true"; }
 };
@@ -93,6 +98,10 @@ int main() {
         s.virtual_style = vs == "virtual_loss" ? 0 : (vs == "virtual_visit" ? 1 : 3);
         s.virtual_mix_threshold = static_cast<unsigned>(opt.i("Virtual_Mix_Threshold"));
         s.seed = static_cast<unsigned long long>(opt.i("Dirichlet_Seed"));
+        s.threads = opt.i("Threads") >= 2 && 2 * s.batch_size <= 255 ? 2 : 1;  // (two logical threads at most; see ara_b200.h)
+        // round(100 / centi), 0 = off (uci/crazyara.cpp:748-749)
+        s.epsilon_greedy_counter = opt.i("Centi_Epsilon_Greedy") > 0 ? static_cast<int>(std::lround(100.0 / opt.i("Centi_Epsilon_Greedy"))) : 0;
+        s.epsilon_checks_counter = opt.i("Centi_Epsilon_Checks") > 0 ? static_cast<int>(std::lround(100.0 / opt.i("Centi_Epsilon_Checks"))) : 0;
         if (opt.i("Input_Version") > 0) s.input_version = opt.i("Input_Version");
         agent.reset();
         net.reset();

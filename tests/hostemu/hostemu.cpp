@@ -140,6 +140,7 @@ HeSearch* he_search_new(const SearchParams* sp, int max_nodes, int max_edges) {
     for (int i = 0; i < lut_len; ++i) s->sqrt_lut[i] = sqrt(static_cast<double>(i));
     memset(&s->st, 0, sizeof(s->st));
     s->st.rng = minstd_seed(sp->seed, 0);
+    crand_seed(s->st.crand_r, &s->st.crand_f, static_cast<unsigned>(sp->seed));
     s->prep_board.resize(static_cast<size_t>(max_nodes) * kPrepSlots);
     s->prep_ci.assign(static_cast<size_t>(max_nodes) * kPrepSlots, -1);
     s->prep_term.resize(static_cast<size_t>(max_nodes) * kPrepSlots);
@@ -222,7 +223,10 @@ void he_search_root_results(HeSearch* s, const float* values, const float* probs
 // logical search thread `th` (0 or 1): SearchThread::create_mini_batch / the rest of thread_iteration
 int he_search_create_mini_batch_t(HeSearch* s, int th) {
     HeBatch& bt = s->batch[th];
-    create_mini_batch(bt.t, s->sp, s->ws);
+    if (s->sp.epsilon_greedy_counter != 0 || s->sp.epsilon_checks_counter != 0)
+        create_mini_batch<true>(bt.t, s->sp, s->ws);
+    else
+        create_mini_batch<false>(bt.t, s->sp, s->ws);
     HostWriterFactory wf{bt.planes.data(), s->channels};
     for (int b = 0; b < bt.bs.n_new; ++b) {
         const auto target = wf.make(b);

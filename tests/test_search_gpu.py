@@ -62,6 +62,22 @@ def test_gpu_two_thread_search_equals_oracle_fake_backend(case):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("threads", [1, 2])
+@pytest.mark.parametrize("case", CASES_2T[::2], ids=[f"{c[0]}-b{c[6]}-s{c[7]}-{i}" for i, c in enumerate(CASES_2T[::2])])
+def test_gpu_epsilon_exploration_equals_oracle(case, threads):
+    """Centi_Epsilon_Greedy 5 / Centi_Epsilon_Checks 1 (the reference's UCI defaults) on the device: select_kernel<true>
+    with glibc's rand() restated; the oracle it is compared with equals the compiled reference (tests/test_ref_mcts.py)."""
+    variant, vid, mode, fen, is960, premoves, batch, sims, extra = case
+    st = case_settings(mode, batch, sims, dict(extra, threads=threads, epsilon_greedy_counter=20, epsilon_checks_counter=100))
+    pos = Position(fen, variant, is960)
+    pos.push_uci(*premoves)
+    S = osr.Search(st)
+    ro = S.run(pos, osr.fake_net(S.n_labels), with_keys=True, threads=threads)
+    rg = _gpu_search(vid, fen, is960, premoves, st)[0]
+    assert_same_search(ro, rg)
+
+
+@pytest.mark.gpu
 def test_gpu_two_thread_multi_tree_search_matches_single_tree():
     st = osr.default_settings("crazyhouse", batch_size=8, simulations=300, node_policy_temperature=1.7, threads=2)
     pos = Position(variant="crazyhouse")

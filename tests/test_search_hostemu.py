@@ -99,6 +99,29 @@ def test_hostemu_two_thread_search_equals_oracle(case):
     assert_same_search(ro, rh)
 
 
+EPS = dict(epsilon_greedy_counter=20, epsilon_checks_counter=100)  # UCI defaults Centi_Epsilon_Greedy 5, Centi_Epsilon_Checks 1
+
+
+@pytest.mark.parametrize("threads", [1, 2])
+@pytest.mark.parametrize("case", CASES, ids=[f"{c[0]}-b{c[6]}-s{c[7]}-{i}" for i, c in enumerate(CASES)])
+def test_hostemu_epsilon_exploration_equals_oracle(case, threads):
+    """The reference's default exploration (searchthread.cpp:124-185, :451-473): random playouts / unexplored checks below
+    a randomly deep node of the main line, drawn from glibc's rand() -- restated in the device code (select_kernel<true>)
+    and in the oracle, which tests/test_ref_mcts.py pins to the compiled reference."""
+    variant, vid, mode, fen, is960, premoves, batch, sims, extra = case
+    st = case_settings(mode, batch, sims, dict(extra, threads=threads, **EPS))
+    pos = Position(fen, variant, is960)
+    he = HeState(pos.fen(), vid, is960)
+    for u in premoves:
+        pos.push_uci(u)
+        he.do_move(he.move_from_uci(u))
+    S = osr.Search(st)
+    ro = S.run(pos, osr.fake_net(S.n_labels), with_keys=True, threads=threads)
+    rh = HeSearch(st).run(he, osr.fake_net(S.n_labels), with_keys=True, threads=threads)
+    assert ro["visit_sum"] > 0
+    assert_same_search(ro, rh)
+
+
 def test_fake_backends_identical():
     import ctypes
     from oracle.search import _lib

@@ -5,6 +5,9 @@ import subprocess
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# the UCI defaults are the reference's (Threads 2, epsilon-greedy 5 %, epsilon-checks 1 %); comparisons with a Python agent
+# built from default_settings() (the deterministic single-threaded set) switch them off
+PARITY = ["setoption name Threads value 1", "setoption name Centi_Epsilon_Greedy value 0", "setoption name Centi_Epsilon_Checks value 0"]
 
 
 @pytest.mark.gpu
@@ -12,7 +15,7 @@ def test_uci_binary_matches_python_agent():
     exe = os.path.join(ROOT, "crazyara_b200", "ara_uci")
     if not os.path.exists(exe):
         subprocess.run(["make", "-C", ROOT, "crazyara_b200/ara_uci"], check=True)
-    script = "\n".join(["uci", "setoption name UCI_Variant value crazyhouse", "setoption name Batch_Size value 8",
+    script = "\n".join(["uci", "setoption name UCI_Variant value crazyhouse", "setoption name Batch_Size value 8", *PARITY,
                         "setoption name Simulations value 200", "setoption name Centi_Node_Temperature value 100",
                         "isready", "position startpos moves e2e4 e7e5", "go", "root", "quit"]) + "\n"
     out = subprocess.run([exe], input=script, capture_output=True, text=True, timeout=120).stdout
@@ -68,7 +71,7 @@ def test_uci_position_extension_reuses_the_tree():
     r1 = agent.evaluate_board_state(st)
     assert r1["nodes_pre_search"] > 0
     exe = os.path.join(ROOT, "crazyara_b200", "ara_uci")
-    head = ["uci", "setoption name UCI_Variant value crazyhouse", "setoption name Batch_Size value 8",
+    head = ["uci", "setoption name UCI_Variant value crazyhouse", "setoption name Batch_Size value 8", *PARITY,
             "setoption name Simulations value 300", "setoption name Centi_Node_Temperature value 100", "isready"]
     game = ["position startpos", "go", f"position startpos moves {best} {reply}", "go", "quit"]
     out = subprocess.run([exe], input="\n".join(head + game) + "\n", capture_output=True, text=True, timeout=120).stdout

@@ -235,7 +235,7 @@ class Search {
     TreeDev* d_trees_slot_[2] = {nullptr, nullptr};
     std::vector<TreeDev> h_trees1_;        // slot 1 views (h_trees_ = slot 0)
     struct SlotArrays {                    // per tree: the batch arrays of slot 1
-        int32_t *exp_parent, *new_node, *traj_node, *traj_len;
+        int32_t *exp_parent, *new_node, *traj_node, *traj_len, *traj_start;
         uint16_t* traj_ci;
         uint32_t* traj_edge;
         BatchState* bs;
@@ -442,7 +442,7 @@ int Search::init(Net* net, const SearchParams& params, int device, int trees, in
             return -1;
         if (dalloc(&t.st, 1) || dalloc(&t.bs, 1)) return -1;
         if (dalloc(&t.new_node, B) || dalloc(&t.traj_node, static_cast<size_t>(2) * B * kMaxDepth) ||
-            dalloc(&t.traj_ci, static_cast<size_t>(2) * B * kMaxDepth) || dalloc(&t.traj_len, 2 * B) ||
+            dalloc(&t.traj_ci, static_cast<size_t>(2) * B * kMaxDepth) || dalloc(&t.traj_len, 2 * B) || dalloc(&t.traj_start, 2 * B) ||
             dalloc(&t.traj_edge, static_cast<size_t>(2) * B * kMaxDepth))
             return -1;
         const size_t slots = static_cast<size_t>(max_nodes_) * kPrepSlots;
@@ -476,7 +476,7 @@ int Search::init(Net* net, const SearchParams& params, int device, int trees, in
         for (int i = 0; i < n_trees; ++i) {
             SlotArrays& a = slot1_[i];
             if (dalloc(&a.new_node, B) || dalloc(&a.traj_node, static_cast<size_t>(2) * B * kMaxDepth) ||
-                dalloc(&a.traj_ci, static_cast<size_t>(2) * B * kMaxDepth) || dalloc(&a.traj_len, 2 * B) ||
+                dalloc(&a.traj_ci, static_cast<size_t>(2) * B * kMaxDepth) || dalloc(&a.traj_len, 2 * B) || dalloc(&a.traj_start, 2 * B) ||
                 dalloc(&a.traj_edge, static_cast<size_t>(2) * B * kMaxDepth) || dalloc(&a.exp_parent, 3 * B) || dalloc(&a.bs, 1))
                 return -1;
         }
@@ -701,7 +701,7 @@ int Search::begin() {
             TreeDev& t = h_trees1_[i];
             const SlotArrays& a = slot1_[i];
             t.exp_parent = a.exp_parent, t.new_node = a.new_node, t.traj_node = a.traj_node, t.traj_len = a.traj_len;
-            t.traj_ci = a.traj_ci, t.traj_edge = a.traj_edge, t.bs = a.bs;
+            t.traj_ci = a.traj_ci, t.traj_edge = a.traj_edge, t.bs = a.bs, t.traj_start = a.traj_start;
             ARA_CUDA_OK(cudaMemsetAsync(a.bs, 0, sizeof(BatchState), stream_));
         }
         ARA_CUDA_OK(cudaMemcpyAsync(d_trees_slot_[1], h_trees1_.data(), sizeof(TreeDev) * n_trees, cudaMemcpyHostToDevice, stream_));

@@ -177,7 +177,8 @@ struct TreeDev {
     int32_t* traj_node;     // [2B][kMaxDepth]   rows 0..B-1 new leaves, B..2B-1 collisions
     uint16_t* traj_ci;      // [2B][kMaxDepth]
     uint32_t* traj_edge;    // [2B][kMaxDepth]   absolute edge index (edge_base + ci) of every step
-    int32_t* traj_len;      // [2B]
+    int32_t* traj_len;      // [2B]   plies below the root of the trajectory's leaf
+    int32_t* traj_start;    // [2B]   first ply that belongs to the trajectory (0 unless the exploration started it deeper)
     const uint64_t* hist_keys;  // positions before the root, oldest first
     const int16_t* hist_reps;
     int hist_len;
@@ -1150,10 +1151,11 @@ ARA_HD void create_mini_batch_impl(const TreeDev& t, const SearchParams& sp, War
             const int ci = step.ci;
             const int next = step.child;
             if (ARA_LANE == 0) {
-                const int ti = depth - skipped;
-                ws.traj_node[ti] = cur;
-                ws.traj_ci[ti] = static_cast<uint16_t>(ci);
-                ws.traj_edge[ti] = h.edge_base + static_cast<uint32_t>(ci);
+                // (indexed by the ply below the root even when the trajectory starts deeper -- EPS --: the backup kernel
+                // gives every ply its own lane, which is what keeps two trajectories' updates of one node in order)
+                ws.traj_node[depth] = cur;
+                ws.traj_ci[depth] = static_cast<uint16_t>(ci);
+                ws.traj_edge[depth] = h.edge_base + static_cast<uint32_t>(ci);
                 ws.path_key[depth] = h.key;
                 ws.path_rep[depth] = h.repetition;
             }
@@ -1224,18 +1226,20 @@ ARA_HD void create_mini_batch_impl(const TreeDev& t, const SearchParams& sp, War
             if (ARA_LANE == 0) {
                 st.sum_depth += static_cast<unsigned long long>(depth);
                 // terminal: free backup, sequential leaf -> root because the MCTS solver propagates bottom-up
-                backup_value(t, sp, node_value(t.hdr[leaf]), ws.traj_node, ws.traj_ci, depth - skipped, true, sp.mcts_solver != 0);
+                backup_value(t, sp, node_value(t.hdr[leaf]), ws.traj_node + skipped, ws.traj_ci + skipped, depth - skipped, true,
+                             sp.mcts_solver != 0);
             }
         } else {
             const int row = type == 1 ? B + n_coll : n_new;
-            for (int i = ARA_LANE; i < depth - skipped; i += ARA_WARP_N) {
+            for (int i = skipped + ARA_LANE; i < depth; i += ARA_WARP_N) {
                 t.traj_node[row * kMaxDepth + i] = ws.traj_node[i];
                 t.traj_ci[row * kMaxDepth + i] = ws.traj_ci[i];
                 t.traj_edge[row * kMaxDepth + i] = ws.traj_edge[i];
             }
             if (ARA_LANE == 0) {
                 st.sum_depth += static_cast<unsigned long long>(depth);
-                t.traj_len[row] = depth - skipped;
+                t.traj_len[row] = depth;
+                if (EPS) t.traj_start[row] = skipped;  // (stays 0 without the exploration)
                 if (type == 0) t.new_node[n_new] = leaf;
             }
         }
@@ -1309,6 +1313,7 @@ ARA_HD void backup_results(const TreeDev& t, const SearchParams& sp, const float
         const int dd = d < kMaxDepth ? d : kMaxDepth - 1;
         const float* leaf_values = values + t.slot_base;
         int len_n = n_new > 0 ? t.traj_len[0] : 0, len_nn = n_new > 1 ? t.traj_len[1] : 0;
+        int start_n = n_new > 0 ? t.traj_start[0] : 0, start_nn = n_new > 1 ? t.traj_start[1] : 0;
         float leaf_n = n_new > 0 ? leaf_values[0] : 0.0f, leaf_nn = n_new > 1 ? leaf_values[1] : 0.0f;
         int nid_n = n_new > 0 ? t.traj_node[dd] : -1, nid_nn = n_new > 1 ? t.traj_node[kMaxDepth + dd] : -1;
         uint32_t e_n = n_new > 0 ? t.traj_edge[dd] : 0, e_nn = n_new > 1 ? t.traj_edge[kMaxDepth + dd] : 0;
@@ -1316,26 +1321,27 @@ ARA_HD void backup_results(const TreeDev& t, const SearchParams& sp, const float
         uint32_t p_rv = 0, p_n = 0;
         float p_q = 0.0f;
         uint8_t p_vl = 0;
-        if (n_new > 0 && d < len_n) {  // pre-load of trajectory 0
+        if (n_new > 0 && d < len_n && d >= start_n) {  // pre-load of trajectory 0
             p_vsum = t.hdr[nid_n].value_sum, p_rv = t.hdr[nid_n].real_visits;
             p_q = t.Q[e_n], p_n = t.N[e_n], p_vl = t.vl[e_n];
         }
         for (int b = 0; b < n_new; ++b) {
-            const int len = len_n, nid = nid_n;
+            const int len = len_n, start = start_n, nid = nid_n;
             const uint32_t e = e_n;
             const float leaf_v = leaf_n;
             const double l_vsum = p_vsum;
             const uint32_t l_rv = p_rv, l_n = p_n;
             const float l_q = p_q;
             const uint8_t l_vl = p_vl;
-            len_n = len_nn, leaf_n = leaf_nn, nid_n = nid_nn, e_n = e_nn;
+            len_n = len_nn, start_n = start_nn, leaf_n = leaf_nn, nid_n = nid_nn, e_n = e_nn;
             if (b + 2 < n_new) {
                 len_nn = t.traj_len[b + 2];
+                start_nn = t.traj_start[b + 2];
                 leaf_nn = leaf_values[b + 2];
                 nid_nn = t.traj_node[(b + 2) * kMaxDepth + dd];
                 e_nn = t.traj_edge[(b + 2) * kMaxDepth + dd];
             }
-            const bool active = d < len;
+            const bool active = d < len && d >= start;
             if (active) {  // move the register copies on to this trajectory's node / edge (stores first)
                 if (nid != c_nid) {
                     if (c_nid >= 0) t.hdr[c_nid].value_sum = c_vsum, t.hdr[c_nid].real_visits = c_rv;
@@ -1351,7 +1357,7 @@ ARA_HD void backup_results(const TreeDev& t, const SearchParams& sp, const float
                     c_vl = l_vl;
                 }
             }
-            if (b + 1 < n_new && d < len_n) {  // pre-load of trajectory b+1, in flight during the arithmetic below
+            if (b + 1 < n_new && d < len_n && d >= start_n) {  // pre-load of trajectory b+1, in flight during the arithmetic below
                 p_vsum = t.hdr[nid_n].value_sum, p_rv = t.hdr[nid_n].real_visits;
                 p_q = t.Q[e_n], p_n = t.N[e_n], p_vl = t.vl[e_n];
             }
@@ -1380,7 +1386,7 @@ ARA_HD void backup_results(const TreeDev& t, const SearchParams& sp, const float
     for (int c = 0; c < n_coll; ++c) {
         const int row = B + c;
         const int len = t.traj_len[row];
-        for (int i = ARA_LANE; i < len; i += ARA_WARP_N)
+        for (int i = t.traj_start[row] + ARA_LANE; i < len; i += ARA_WARP_N)
             revert_virtual_loss(t, sp, t.traj_node[row * kMaxDepth + i], t.traj_ci[row * kMaxDepth + i]);
     }
     ARA_WARP_SYNC();

@@ -83,7 +83,7 @@ struct HostWriterFactory {
 struct HeBatch {
     BatchState bs;
     TreeDev t;
-    std::vector<int32_t> new_node, traj_node, traj_len, exp_parent;
+    std::vector<int32_t> new_node, traj_node, traj_len, traj_start, exp_parent;
     std::vector<uint16_t> traj_ci;
     std::vector<uint32_t> traj_edge;
     std::vector<float> planes;
@@ -150,6 +150,7 @@ HeSearch* he_search_new(const SearchParams* sp, int max_nodes, int max_edges) {
         bt.traj_node.resize(2 * B * kMaxDepth);
         bt.traj_ci.resize(2 * B * kMaxDepth);
         bt.traj_len.resize(2 * B);
+        bt.traj_start.assign(2 * B, 0);
         bt.traj_edge.resize(2 * B * kMaxDepth);
         bt.exp_parent.resize(3 * B);
         bt.planes.assign(static_cast<size_t>(B) * s->channels * 64, 0.0f);
@@ -170,6 +171,7 @@ HeSearch* he_search_new(const SearchParams* sp, int max_nodes, int max_edges) {
         t.traj_node = bt.traj_node.data();
         t.traj_ci = bt.traj_ci.data();
         t.traj_len = bt.traj_len.data();
+        t.traj_start = bt.traj_start.data();
         t.traj_edge = bt.traj_edge.data();
         t.exp_parent = bt.exp_parent.data();
         t.prep_board = s->prep_board.data();

@@ -66,16 +66,25 @@ def test_arena_writes_pgn(tmp_path):
 
 @pytest.mark.gpu
 def test_arena_game_groups_on_separate_threads():
-    """Two groups of games with an agent each, searched concurrently from two host threads: the games are the ones a
-    single-group arena with the same seed plays (trees never interact; every tree draws the same Dirichlet seed)."""
+    """Two groups of games with an agent each, searched concurrently from two host threads.  Trees never interact, so the
+    games are reproducible whatever the interleaving of the two host threads: two such arenas with the same seed play the
+    same games.  (Every tree and every group draws its own Dirichlet noise -- seeds derived from the arena's -- so a
+    one-group arena plays different games.)"""
     from crazyara_b200.selfplay import Arena, rl_settings
     st = rl_settings("crazyhouse", batch_size=8, nodes=60, simulations=240)
-    a1 = Arena(None, st, variant=1, n_games=4, temperature_moves=0, max_plies=20, seed=2)
-    a2 = Arena([None, None], st, variant=1, n_games=4, temperature_moves=0, max_plies=20, seed=2)
+    kw = dict(variant=1, n_games=4, temperature_moves=0, max_plies=20, seed=2, node_random_factor=0.0)
+    a2 = Arena([None, None], st, **kw)
+    a3 = Arena([None, None], st, **kw)
+    a1 = Arena(None, st, **kw)
+    differs = False
     for _ in range(6):
         a1.step()
         a2.step()
-        assert [s.fen() for s in a1.states] == [s.fen() for s in a2.states]
-    assert a2.nodes == a1.nodes > 0
-    a1.close()
-    a2.close()
+        a3.step()
+        assert [s.fen() for s in a2.states] == [s.fen() for s in a3.states]
+        differs = differs or [s.fen() for s in a1.states] != [s.fen() for s in a2.states]
+    assert a2.nodes == a3.nodes > 0 and differs
+    # within an arena the games differ from each other too (per-tree generators): not four copies of one game
+    assert len({s.fen() for s in a2.states}) > 1
+    for a in (a1, a2, a3):
+        a.close()

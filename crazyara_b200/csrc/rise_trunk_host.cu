@@ -90,7 +90,6 @@ int rise_trunk_init(RiseTrunk* T, const std::vector<TrunkBlockHost>& blocks, con
     T->args.prof = static_cast<unsigned long long*>(T->d_prof);
     ARA_CUDA_OK(cudaFuncSetAttribute(rise_trunk_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRtSmemBytes));
     ARA_CUDA_OK(cudaFuncSetAttribute(rise_trunk_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRtSmemBytes));
-    ARA_CUDA_OK(cudaFuncSetAttribute(rise_trunk_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRtSmemBytes));
     {
         int dev = 0;
         cudaDeviceProp prop;
@@ -108,28 +107,7 @@ int rise_trunk_launch(const RiseTrunk* T, int boards, cudaStream_t stream, const
     // one board per CTA while that still fits the GPU in one wave (twice the SMs on a small batch), else two
     const char* force = getenv("ARA_TRUNK_ROWS");
     const bool one_board = force ? atoi(force) == 64 : boards <= T->sm_count;
-    // ARA_TRUNK_SPLIT=2: a pair of CTAs per board (alternate chunks, partial sums exchanged through distributed shared
-    // memory), so that 64 boards occupy 128 SMs.  Correct, but measured SLOWER (330 vs 272 us per forward at 64
-    // boards): the two cross-CTA hand-overs per block cost more than halving the chunk work saves.  Opt-in only.
-    const char* split = getenv("ARA_TRUNK_SPLIT");
-    const bool pair = one_board && !force && split && atoi(split) == 2 && 2 * boards <= T->sm_count;
-    if (pair) {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(2 * boards);
-        cfg.blockDim = dim3(kRtThreads);
-        cfg.dynamicSmemBytes = kRtSmemBytes;
-        cfg.stream = stream;
-        cudaLaunchAttribute attr[2];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[1].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = pdl_enabled() ? 2 : 1;
-        ARA_CUDA_OK(cudaLaunchKernelEx(&cfg, rise_trunk_kernel<64, 2>, a));
-    } else if (one_board)
+    if (one_board)
         ARA_CUDA_OK(launch_pdl(rise_trunk_kernel<64>, dim3(boards), dim3(kRtThreads), kRtSmemBytes, stream, a));
     else
         ARA_CUDA_OK(launch_pdl(rise_trunk_kernel<128>, dim3((boards + 1) / 2), dim3(kRtThreads), kRtSmemBytes, stream, a));

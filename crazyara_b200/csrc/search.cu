@@ -412,7 +412,13 @@ int Search::init(Net* net, const SearchParams& params, int device, int trees, in
     }
     max_nodes_ = max_nodes;
     // edge pool: average legal moves per node is ~35 (chess) but drop-heavy crazyhouse positions reach 200-300
-    max_edges_ = max_nodes * (sp.mode == MODE_CHESS ? 128 : 320) + 1024;
+    {
+        // sized for the worst case per node; computed in 64 bits: 2^24 nodes x 320 edges does not fit an int
+        const long long want = static_cast<long long>(max_nodes) * (sp.mode == MODE_CHESS ? 128 : 320) + 1024;
+        if (want > 2147483647LL)
+            return set_error("ara_search_create: a pool of %d nodes needs %lld edge slots (more than 2^31 - 1); lower max_nodes", max_nodes, want);
+        max_edges_ = static_cast<int>(want);
+    }
     const int B = sp.batch_size;
     // cput look-up table with the HOST libm: bit-identical to the reference's scalar code (node.cpp:1243-1246)
     {

@@ -19,6 +19,7 @@
 #include "ara_b200.h"
 #include "net.h"
 #include "search_dev.cuh"
+#include "search_wave.cuh"
 #include "time_manager.h"
 
 namespace ara {
@@ -77,6 +78,16 @@ __global__ void __launch_bounds__(32) select_kernel(const TreeDev* trees, Search
     __shared__ WarpScratch ws;
     const TreeDev t = trees[blockIdx.x];
     create_mini_batch<EPS>(t, sp, ws);
+}
+
+// The same mini-batch by kWaveWarps warps per tree (search_wave.cuh): consecutive playouts of one tree overlap, the result
+// is the sequential one.  Used when there are too few trees to fill the SMs with one warp each.
+__global__ void __launch_bounds__(32 * kWaveWarps) select_wave_kernel(const TreeDev* trees, SearchParams sp) {
+    extern __shared__ __align__(16) unsigned char wave_smem[];
+    WaveShared& S = *reinterpret_cast<WaveShared*>(wave_smem);
+    WaveWarp& W = reinterpret_cast<WaveWarp*>(wave_smem + kWaveSharedBytes)[threadIdx.x >> 5];
+    const TreeDev t = trees[blockIdx.x];
+    wave_mini_batch(t, sp, S, W);
 }
 
 // Multi-tree searches: the new leaves of all trees are packed into consecutive rows of the network batch (tree i gets
@@ -231,6 +242,12 @@ class Search {
     // the network the other thread selects.  (oracle/mcts.h describes the schedule; tests compare all three.)
     int threads_ = 1;
     bool eps_ = false;  // epsilon-greedy / epsilon-check exploration on: the select_kernel<true> instantiation
+    bool wave_ = false;  // few trees: select_wave_kernel (several warps per tree) instead of one warp per tree
+    void launch_select(const TreeDev* trees) {
+        if (eps_) select_kernel<true><<<n_trees, 32, 0, stream_>>>(trees, sp);
+        else if (wave_) select_wave_kernel<<<n_trees, 32 * kWaveWarps, kWaveSmemBytes, stream_>>>(trees, sp);
+        else select_kernel<false><<<n_trees, 32, 0, stream_>>>(trees, sp);
+    }
     bool primed_ = false;                  // S0 S1 of the current go have been enqueued
     TreeDev* d_trees_slot_[2] = {nullptr, nullptr};
     std::vector<TreeDev> h_trees1_;        // slot 1 views (h_trees_ = slot 0)
@@ -391,6 +408,11 @@ int Search::init(Net* net, const SearchParams& params, int device, int trees, in
         ARA_CUDA_OK(cudaGetDeviceProperties(&prop, device_));
         if (prop.major < 10) return set_error("ara_search_create: device %d is not sm_100 (B200)", device_);
     }
+    // few trees cannot fill 148 SMs with one warp each: their playouts overlap inside a CTA instead (search_wave.cuh)
+    wave_ = !eps_ && n_trees <= 32 && sp.batch_size >= 8;
+    if (const char* e = getenv("ARA_WAVE")) wave_ = !eps_ && atoi(e) != 0;
+    if (wave_)
+        ARA_CUDA_OK(cudaFuncSetAttribute(select_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kWaveSmemBytes)));
     n_labels_ = (sp.mode == MODE_CRAZYHOUSE ? 81 : (sp.mode == MODE_CHESS ? 76 : 84)) * 64;
     if (net_ != nullptr) {
         if (net_->batch < n_trees * sp.batch_size)
@@ -548,8 +570,7 @@ int Search::enqueue_iteration(bool with_events) {
     const float* values = net_ ? net_->d_value : d_values_;
     const float* probs = net_ ? net_->d_prob : d_probs_;
     if (with_events) prof_event();
-    if (eps_) select_kernel<true><<<n_trees, 32, 0, stream_>>>(d_trees_, sp);
-    else select_kernel<false><<<n_trees, 32, 0, stream_>>>(d_trees_, sp);
+    launch_select(d_trees_);
     if (n_trees > 1) pack_kernel<<<1, 32, 0, stream_>>>(d_trees_, n_trees, d_count_);
     expand_kernel<<<n_trees * B, 32, 0, stream_>>>(d_trees_, sp, B, in_h, cpad, net_ ? net_->precision : 0);
     if (with_events) prof_event();
@@ -589,8 +610,7 @@ int Search::enqueue_slot_tree_ops(int slot, bool with_update) {
         scatter_prepare_kernel<<<n_trees * 4 * B, 32, 0, stream_>>>(trees, sp, B, 4 * B, values, probs, n_labels_);
         ARA_CUDA_OK(cudaStreamWaitEvent(stream_, ev_join_, 0));
     }
-    if (eps_) select_kernel<true><<<n_trees, 32, 0, stream_>>>(trees, sp);
-    else select_kernel<false><<<n_trees, 32, 0, stream_>>>(trees, sp);
+    launch_select(trees);
     pack_kernel<<<1, 32, 0, stream_>>>(trees, n_trees, d_count_slot_[slot]);
     expand_kernel<<<n_trees * B, 32, 0, stream_>>>(trees, sp, B, net_ ? net_->io_in_h[slot] : nullptr, net_ ? net_->cin_pad : 0,
                                                     net_ ? net_->precision : 0);

@@ -660,12 +660,10 @@ ARA_HD int leaf_verdict(const TreeDev& t, WarpScratch& ws, int depth) {
 }
 
 // tt_known >= 0: ws.child comes from the node's prepared-child slot (repetition already set, verdict known).
-ARA_HD int expand_node_seq(const TreeDev& t, const SearchParams& sp, WarpScratch& ws, int parent, int ci, int depth,
-                           int* is_terminal, int tt_known = -1, uint32_t parent_edge_base = 0) {
+// The ordered half of expand_node_seq: node id, header, child link, board (verdict `tt` already known).
+ARA_HD int expand_node_alloc(const TreeDev& t, const SearchParams& sp, WarpScratch& ws, int parent, int ci, int tt,
+                             uint32_t parent_edge_base) {
     Board& b = ws.child;
-    long long tp = ARA_CLOCK();
-    const int tt = tt_known >= 0 ? tt_known : leaf_verdict(t, ws, depth);
-    ARA_PROF(*t.st, 2, tp);
     int nid = -1;
     if (ARA_LANE == 0) {
         TreeState& st = *t.st;
@@ -712,9 +710,17 @@ ARA_HD int expand_node_seq(const TreeDev& t, const SearchParams& sp, WarpScratch
         }
     }
     nid = bcast0(nid);
-    *is_terminal = tt != TERM_NONE;
     if (nid < 0) return -1;
     copy_board(&t.board[nid], &b);
+    return nid;
+}
+ARA_HD int expand_node_seq(const TreeDev& t, const SearchParams& sp, WarpScratch& ws, int parent, int ci, int depth,
+                           int* is_terminal, int tt_known = -1, uint32_t parent_edge_base = 0) {
+    long long tp = ARA_CLOCK();
+    const int tt = tt_known >= 0 ? tt_known : leaf_verdict(t, ws, depth);
+    ARA_PROF(*t.st, 2, tp);
+    *is_terminal = tt != TERM_NONE;
+    const int nid = expand_node_alloc(t, sp, ws, parent, ci, tt, parent_edge_base);
     ARA_PROF(*t.st, 3, tp);
     return nid;
 }

@@ -15,8 +15,17 @@ constexpr int kTrunkAuxBytes = 3712;   // 64 f32 + 64 f32 + 25 * 64 f16
 constexpr int kTrunkW1Image = 36864;   // tile + aux, padded to 1 KB
 constexpr int kTrunkW2Image = 32768;
 
+// rise_trunk_t.cuh (one board per CTA, channels in M) streams the same weights as PAIRS of chunks, four 32 KB units per
+// pair: W1 rows (the pair's 128 operating channels) x K panels {0,1} | {2,3}, then W2 output-channel halves {0..127} |
+// {128..255} x the pair's 128 K.  Every unit is two 128-row K-major panels of 16 KB.  Per pair also a vector record:
+//   b1[128] f32 | bd[128] f32 | wd[k*k][128] f16
+constexpr int kTrunkTUnit = 32768;
+constexpr int kTrunkTAux = 7680;  // 512 + 512 + 25 * 256, padded to 256 B
+constexpr int kTrunkTLag = 3;     // MMA2 of a pair is issued this many pairs behind its MMA1 (the stream follows that order)
+
 struct TrunkBlock {
     int n_chunks;     // ceil(Cop / 64)
+    int pair0;        // index of the block's first chunk pair (rise_trunk_t.cuh)
     int ksize;        // depthwise kernel: 3 or 5
     int se_type;      // 0 none, 1 ca_se, 2 eca_se (applied to the block input, in place)
     int chunk0;       // index of the block's first chunk in the image arrays
@@ -34,6 +43,10 @@ struct TrunkArgs {
     const __half* x_in;     // [M, 256] stem output
     __half* out;            // [M, 256]
     const int* boards_dev;     // device-side count of the boards in use (or nullptr): CTAs beyond it leave at once
+    const uint8_t* t_img;      // rise_trunk_t.cuh: [pairs][4][kTrunkTUnit]
+    const uint8_t* t_aux;      // [pairs][kTrunkTAux]
+    const int* t_seq;          // unit index (into t_img) of every unit of the stream, in consumption order
+    int t_units;
     unsigned long long* prof;  // profiling builds (-DARA_TRUNK_PROF): [2][16] cycle counters of CTA 0, else unused
     TrunkBlock blk[kTrunkMaxBlocks];
 };

@@ -4,6 +4,7 @@
 #include <cstring>
 
 #include "rise_trunk.cuh"
+#include "rise_trunk_t.cuh"
 
 namespace ara {
 
@@ -85,6 +86,66 @@ int rise_trunk_init(RiseTrunk* T, const std::vector<TrunkBlockHost>& blocks, con
     ARA_CUDA_OK(cudaMemcpy(T->d_w2, w2.data(), w2.size(), cudaMemcpyHostToDevice));
     T->args.w1_img = static_cast<const uint8_t*>(T->d_w1);
     T->args.w2_img = static_cast<const uint8_t*>(T->d_w2);
+    // the same weights for rise_trunk_t.cuh: chunk PAIRS (channels in M), four 32 KB units per pair, and the unit order
+    // of the stream (MMA2 of a pair follows kTrunkTLag pairs behind its MMA1; mirrored by the kernel's MMA issuer)
+    {
+        int pairs = 0;
+        for (int i = 0; i < nb; ++i) {
+            T->args.blk[i].pair0 = pairs;
+            pairs += (T->args.blk[i].n_chunks + 1) / 2;
+        }
+        std::vector<uint8_t> img(static_cast<size_t>(pairs) * 4 * kTrunkTUnit, 0);
+        std::vector<uint8_t> aux(static_cast<size_t>(pairs) * kTrunkTAux, 0);
+        std::vector<int> seq;
+        for (int i = 0; i < nb; ++i) {
+            const TrunkBlockHost& h = blocks[i];
+            const TrunkBlock& B = T->args.blk[i];
+            const int kk = h.ksize * h.ksize, P = (B.n_chunks + 1) / 2;
+            for (int p = 0; p < P; ++p) {
+                uint8_t* unit = img.data() + static_cast<size_t>(B.pair0 + p) * 4 * kTrunkTUnit;
+                uint8_t* ax = aux.data() + static_cast<size_t>(B.pair0 + p) * kTrunkTAux;
+                float* ax_b1 = reinterpret_cast<float*>(ax);
+                float* ax_bd = reinterpret_cast<float*>(ax + 512);
+                __half* ax_wd = reinterpret_cast<__half*>(ax + 1024);
+                for (int r = 0; r < 128; ++r) {
+                    const int c = p * 128 + r;  // operating channel
+                    if (c >= h.c_op) break;
+                    // W1: row = operating channel of the pair, K = the 256 trunk channels in 4 panels (2 per unit)
+                    for (int k = 0; k < 256; ++k)
+                        *reinterpret_cast<__half*>(unit + (k >> 7) * kTrunkTUnit + ((k >> 6) & 1) * 16384 + sw128_offset(r, k & 63)) =
+                            __float2half_rn(h.w1[static_cast<size_t>(c) * 256 + k]);
+                    // W2: row = trunk channel (two halves of 128 = two units), K = the pair's operating channels in 2 panels
+                    for (int n = 0; n < 256; ++n)
+                        *reinterpret_cast<__half*>(unit + (2 + (n >> 7)) * kTrunkTUnit + (r >> 6) * 16384 + sw128_offset(n & 127, r & 63)) =
+                            __float2half_rn(h.w2[static_cast<size_t>(n) * h.c_op + c]);
+                    ax_b1[r] = h.b1[c];
+                    ax_bd[r] = h.bd[c];
+                    for (int q = 0; q < kk; ++q) ax_wd[q * 128 + r] = __float2half_rn(h.wd[static_cast<size_t>(c) * kk + q]);
+                }
+            }
+            auto w2_units = [&](int p) {
+                seq.push_back((B.pair0 + p) * 4 + 2);
+                seq.push_back((B.pair0 + p) * 4 + 3);
+            };
+            for (int p = 0; p < P; ++p) {
+                seq.push_back((B.pair0 + p) * 4 + 0);
+                seq.push_back((B.pair0 + p) * 4 + 1);
+                if (p >= kTrunkTLag) w2_units(p - kTrunkTLag);
+            }
+            for (int p = P > kTrunkTLag ? P - kTrunkTLag : 0; p < P; ++p) w2_units(p);
+        }
+        ARA_CUDA_OK(cudaMalloc(&T->d_timg, img.size()));
+        ARA_CUDA_OK(cudaMalloc(&T->d_taux, aux.size()));
+        ARA_CUDA_OK(cudaMalloc(&T->d_tseq, seq.size() * sizeof(int)));
+        ARA_CUDA_OK(cudaMemcpy(T->d_timg, img.data(), img.size(), cudaMemcpyHostToDevice));
+        ARA_CUDA_OK(cudaMemcpy(T->d_taux, aux.data(), aux.size(), cudaMemcpyHostToDevice));
+        ARA_CUDA_OK(cudaMemcpy(T->d_tseq, seq.data(), seq.size() * sizeof(int), cudaMemcpyHostToDevice));
+        T->args.t_img = static_cast<const uint8_t*>(T->d_timg);
+        T->args.t_aux = static_cast<const uint8_t*>(T->d_taux);
+        T->args.t_seq = static_cast<const int*>(T->d_tseq);
+        T->args.t_units = static_cast<int>(seq.size());
+        ARA_CUDA_OK(cudaFuncSetAttribute(rise_trunk_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRttSmemBytes));
+    }
     ARA_CUDA_OK(cudaMalloc(&T->d_prof, 32 * sizeof(unsigned long long)));
     ARA_CUDA_OK(cudaMemset(T->d_prof, 0, 32 * sizeof(unsigned long long)));
     T->args.prof = static_cast<unsigned long long*>(T->d_prof);
@@ -107,7 +168,15 @@ int rise_trunk_launch(const RiseTrunk* T, int boards, cudaStream_t stream, const
     // one board per CTA while that still fits the GPU in one wave (twice the SMs on a small batch), else two
     const char* force = getenv("ARA_TRUNK_ROWS");
     const bool one_board = force ? atoi(force) == 64 : boards <= T->sm_count;
-    if (one_board)
+    // small batches: channels in the tensor core's M dimension (rise_trunk_t.cuh; ARA_TRUNK_T=0: the M = 64 variant of
+    // rise_trunk.cuh instead -- same bits, slower)
+    static const bool transposed = [] {
+        const char* e = getenv("ARA_TRUNK_T");
+        return e == nullptr || atoi(e) != 0;
+    }();
+    if (one_board && transposed)
+        ARA_CUDA_OK(launch_pdl(rise_trunk_t_kernel, dim3(boards), dim3(kRttThreads), kRttSmemBytes, stream, a));
+    else if (one_board)
         ARA_CUDA_OK(launch_pdl(rise_trunk_kernel<64>, dim3(boards), dim3(kRtThreads), kRtSmemBytes, stream, a));
     else
         ARA_CUDA_OK(launch_pdl(rise_trunk_kernel<128>, dim3((boards + 1) / 2), dim3(kRtThreads), kRtSmemBytes, stream, a));
@@ -118,6 +187,10 @@ void rise_trunk_destroy(RiseTrunk* T) {
     if (T->d_w1) cudaFree(T->d_w1);
     if (T->d_w2) cudaFree(T->d_w2);
     if (T->d_prof) cudaFree(T->d_prof);
+    if (T->d_timg) cudaFree(T->d_timg);
+    if (T->d_taux) cudaFree(T->d_taux);
+    if (T->d_tseq) cudaFree(T->d_tseq);
+    T->d_timg = T->d_taux = T->d_tseq = nullptr;
     for (void* p : T->d_se) cudaFree(p);
     T->d_se.clear();
     T->d_w1 = T->d_w2 = T->d_prof = nullptr;

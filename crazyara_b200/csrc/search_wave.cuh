@@ -24,7 +24,10 @@
 #if defined(__CUDACC__)
 namespace ara {
 
-constexpr int kWaveWarps = 6;
+#if !defined(ARA_WAVE_WARPS)
+#define ARA_WAVE_WARPS 6
+#endif
+constexpr int kWaveWarps = ARA_WAVE_WARPS;
 constexpr int kWaveNone = 0x7fffffff;
 constexpr int kWaveLevelBits = 10;
 constexpr int kWaveLevelOver = (1 << kWaveLevelBits) - 1;  // the playout's descent is over: it passes every deeper ply
@@ -53,6 +56,22 @@ struct alignas(16) WaveWarp {
 };
 constexpr size_t kWaveSharedBytes = (sizeof(WaveShared) + 15) / 16 * 16;
 constexpr size_t kWaveSmemBytes = kWaveSharedBytes + kWaveWarps * sizeof(WaveWarp);
+
+// -DARA_PROF_FINE: warp-cycles per phase, summed over the warps into TreeState::prof (tools/prof_select.py):
+// 0 start gate, 1 ply hand-off waits, 2 steps (loads, argmax, stores), 3 leaf preparation, 4 commit wait, 5 commit,
+// 6 answering a terminal's abort, 7 number of playouts taken back
+#if defined(ARA_PROF_FINE)
+#define WAVE_PROF(S, idx, t0)                                                                          \
+    do {                                                                                               \
+        const long long now_ = clock64();                                                              \
+        if (ARA_LANE == 0) atomicAdd(&(S).st.prof[idx], static_cast<unsigned long long>(now_ - (t0))); \
+        (t0) = now_;                                                                                   \
+    } while (0)
+#define WAVE_COUNT(S, idx) do { if (ARA_LANE == 0) atomicAdd(&(S).st.prof[idx], 1ull); } while (0)
+#else
+#define WAVE_PROF(S, idx, t0) do { } while (0)
+#define WAVE_COUNT(S, idx) do { } while (0)
+#endif
 
 __device__ __forceinline__ void wave_fail(WaveShared& S, int code) {
     if (ARA_LANE == 0) {
@@ -237,11 +256,15 @@ __device__ void wave_mini_batch(const TreeDev& t_in, const SearchParams& sp, Wav
 
     for (int k = w; !__any_sync(0xffffffffu, S.over != 0); k += kWaveWarps) {
     restart:
+        long long tw = clock64();
+        (void)tw;
         // ---------------------------------------------------------------- start gate
         for (int spin = 0;; ++spin) {
             if (__any_sync(0xffffffffu, S.over != 0)) goto out;
             if (__any_sync(0xffffffffu, S.abort_at != kWaveNone)) {
+                WAVE_PROF(S, 0, tw);
                 wave_answer_abort(S, t, sp, W, w, -1, 0);
+                WAVE_PROF(S, 6, tw);
                 continue;
             }
             bool go = false;
@@ -266,6 +289,7 @@ __device__ void wave_mini_batch(const TreeDev& t_in, const SearchParams& sp, Wav
             S.started = k;
         }
         __syncwarp();
+        WAVE_PROF(S, 0, tw);
         {
             // ------------------------------------------------------------ descent
             int cur = root, depth = 0, type = -1, leaf = -1, ci = 0;
@@ -273,6 +297,7 @@ __device__ void wave_mini_batch(const TreeDev& t_in, const SearchParams& sp, Wav
             NodeHdr h;
             EdgeRegs pre;
             int rc = wave_acquire(S, w, k, 0, cur);
+            WAVE_PROF(S, 1, tw);
             if (rc == 0) {
                 load_hdr(&h, &t.hdr[cur]);
                 pre = load_edge(t, h.edge_base + ARA_LANE);
@@ -320,7 +345,9 @@ __device__ void wave_mini_batch(const TreeDev& t_in, const SearchParams& sp, Wav
                     break;
                 }
                 if (!fresh) {
+                    WAVE_PROF(S, 2, tw);
                     rc = wave_acquire(S, w, k, depth, next);
+                    WAVE_PROF(S, 1, tw);
                     if (rc) break;
                     load_hdr(&ch, &t.hdr[next]);
                     cpre = load_edge(t, step.cb + ARA_LANE);
@@ -331,6 +358,7 @@ __device__ void wave_mini_batch(const TreeDev& t_in, const SearchParams& sp, Wav
             }
             int tt = TERM_NONE, slot = 0;
             bool prepared = false;
+            WAVE_PROF(S, 2, tw);
             if (rc == 0) {
                 __syncwarp();
                 if (ARA_LANE == 0) S.state[w] = (k << kWaveLevelBits) | kWaveLevelOver;
@@ -354,6 +382,7 @@ __device__ void wave_mini_batch(const TreeDev& t_in, const SearchParams& sp, Wav
                         tt = leaf_verdict(t, ws, depth);
                     }
                 }
+                WAVE_PROF(S, 3, tw);
                 // ---------------------------------------------------------- wait for the commit turn
                 for (int spin = 0;; ++spin) {
                     const int ab = S.abort_at, ov = S.over, c = S.committed;
@@ -374,9 +403,12 @@ __device__ void wave_mini_batch(const TreeDev& t_in, const SearchParams& sp, Wav
                     wave_backoff();
                 }
             }
+            WAVE_PROF(S, 4, tw);
             if (rc == 2) goto out;
             if (rc == 1) {
                 wave_answer_abort(S, t, sp, W, w, k, depth);
+                WAVE_PROF(S, 6, tw);
+                WAVE_COUNT(S, 7);
                 goto restart;
             }
             __threadfence_block();
@@ -447,6 +479,7 @@ __device__ void wave_mini_batch(const TreeDev& t_in, const SearchParams& sp, Wav
                 if (type == 2) S.abort_at = kWaveNone;
             }
             __syncwarp();
+            WAVE_PROF(S, 5, tw);
         }
     }
 out:

@@ -22,6 +22,9 @@ names = ["descent", "copy+do_move", "rep+movegen", "node init", "planes", "termi
 fine = "fine" in os.environ.get("ARA_B200_LIB", "")
 if fine:  # -DARA_PROF_FINE build: slots 4/7/5 are sub-intervals of the descent
     names[4], names[7], names[5] = "  descent: edge wait", "  descent: puct+argmax", "  descent: child hdr wait (+term. backup)"
+if os.environ.get("ARA_WAVE", "1") != "0":  # the wavefront kernel's own slots (search_wave.cuh), warp-cycles over all its warps
+    fine = False
+    names = ["start gate", "ply hand-off wait", "steps", "leaf preparation", "commit wait", "commit", "abort answered", "(playouts taken back)"]
 tot = sum(out) - (out[4] + out[7] + out[5] if fine else 0)
 print("profile", agent.profile(), "go ms", agent.last_go_ms(), "avg depth", r["sum_depth"] / max(1, r["visit_sum"]),
       "sum_k/visit", r["sum_select_k"] / max(1, r["visit_sum"]), "tree nodes", r["tree_nodes"])

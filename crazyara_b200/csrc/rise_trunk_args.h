@@ -19,13 +19,16 @@ constexpr int kTrunkW2Image = 32768;
 // pair: W1 rows (the pair's 128 operating channels) x K panels {0,1} | {2,3}, then W2 output-channel halves {0..127} |
 // {128..255} x the pair's 128 K.  Every unit is two 128-row K-major panels of 16 KB.  Per pair also a vector record:
 //   b1[128] f32 | bd[128] f32 | wd[k*k][128] f16
+// The fp16 squeeze-excitation matrices of a block travel in the same stream, as four units ahead of the block's pairs
+// (ca_se: [256][128] then [128][256]; eca_se: [256][256]), so that no load competes with the copy engine for the SM's port.
 constexpr int kTrunkTUnit = 32768;
 constexpr int kTrunkTAux = 7680;  // 512 + 512 + 25 * 256, padded to 256 B
-constexpr int kTrunkTLag = 3;     // MMA2 of a pair is issued this many pairs behind its MMA1 (the stream follows that order)
+constexpr int kTrunkTLag = 2;     // MMA2 of a pair is issued this many pairs behind its MMA1 (the stream follows that order)
 
 struct TrunkBlock {
     int n_chunks;     // ceil(Cop / 64)
     int pair0;        // index of the block's first chunk pair (rise_trunk_t.cuh)
+    int se_seq0;      // rise_trunk_t.cuh: position in the unit stream of the block's four squeeze-excitation units
     int ksize;        // depthwise kernel: 3 or 5
     int se_type;      // 0 none, 1 ca_se, 2 eca_se (applied to the block input, in place)
     int chunk0;       // index of the block's first chunk in the image arrays

@@ -94,7 +94,10 @@ int rise_trunk_init(RiseTrunk* T, const std::vector<TrunkBlockHost>& blocks, con
             T->args.blk[i].pair0 = pairs;
             pairs += (T->args.blk[i].n_chunks + 1) / 2;
         }
-        std::vector<uint8_t> img(static_cast<size_t>(pairs) * 4 * kTrunkTUnit, 0);
+        int n_se = 0;
+        for (int i = 0; i < nb; ++i) n_se += blocks[i].se_type != 0 ? 1 : 0;
+        std::vector<uint8_t> img(static_cast<size_t>(pairs + n_se) * 4 * kTrunkTUnit, 0);
+        int se_idx = 0;
         std::vector<uint8_t> aux(static_cast<size_t>(pairs) * kTrunkTAux, 0);
         std::vector<int> seq;
         for (int i = 0; i < nb; ++i) {
@@ -122,6 +125,17 @@ int rise_trunk_init(RiseTrunk* T, const std::vector<TrunkBlockHost>& blocks, con
                     ax_bd[r] = h.bd[c];
                     for (int q = 0; q < kk; ++q) ax_wd[q * 128 + r] = __float2half_rn(h.wd[static_cast<size_t>(c) * kk + q]);
                 }
+            }
+            if (h.se_type != 0) {  // the block's squeeze-excitation matrices (fp16, as the kernel's FC loops index them): 128 KB
+                const size_t n1 = h.se_type == 1 ? 256 * 128 : 256 * 256, n2 = h.se_type == 1 ? 128 * 256 : 0;
+                std::vector<float> f(n1 + n2);
+                ARA_CUDA_OK(cudaMemcpy(f.data(), h.se_w1t, n1 * 4, cudaMemcpyDeviceToHost));
+                if (n2) ARA_CUDA_OK(cudaMemcpy(f.data() + n1, h.se_w2t, n2 * 4, cudaMemcpyDeviceToHost));
+                __half* dst = reinterpret_cast<__half*>(img.data() + static_cast<size_t>(pairs + se_idx) * 4 * kTrunkTUnit);
+                for (size_t k = 0; k < n1 + n2; ++k) dst[k] = __float2half_rn(f[k]);
+                T->args.blk[i].se_seq0 = static_cast<int>(seq.size());
+                for (int u = 0; u < 4; ++u) seq.push_back((pairs + se_idx) * 4 + u);
+                ++se_idx;
             }
             auto w2_units = [&](int p) {
                 seq.push_back((B.pair0 + p) * 4 + 2);

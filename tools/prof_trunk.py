@@ -32,7 +32,11 @@ if L.ara_net_debug_trunk_cycles(net._h, out) != 0:
 mma = ["issue + misc", "wait H2 (compute warps)", "wait W2 ring", "wait X tile (block boundary)", "wait D1 buffer",
        "wait W1 ring"]
 cmp_ = ["X load", "SE + tile hand-over", "wait D1 (tensor core)", "TMEM read-out", "wait chunk vectors", "barrier 1",
-        "H1 write", "barrier 2", "depthwise", "wait H2 buffer", "H2 write", "wait D2", "block epilogue"]
+        "H1 write", "barrier 2", "depthwise", "wait H2 buffer", "H2 write", "wait D2", "block epilogue (D2 + b2 + X)", "SE of the next block (rest)", "tile store + hand-over", "  SE: pooling", "  SE: fc1", "  SE: hidden", "  SE: fc2"]
+if os.environ.get("ARA_TRUNK_T", "1") != "0" and B <= 148:  # rise_trunk_t.cuh's slots
+    mma = ["issue + misc", "wait X tile (block boundary)", "wait H2 (compute warps)", "wait weight stream", "wait D1 buffer"]
+    cmp_ = ["X load", "SE + tile hand-over", "wait D1 (tensor core)", "TMEM read-out + relu", "wait H2 buffer", "depthwise + H2 write",
+            "wait D2", "block epilogue (D2 + b2 + X)", "SE of the next block (rest)", "tile store + hand-over", "  SE: pooling", "  SE: fc1", "  SE: hidden", "  SE: fc2"]
 for title, names, base in (("MMA issuer warp", mma, 0), ("compute warp 2", cmp_, 16)):
     vals = [out[base + i] for i in range(len(names))]
     tot = sum(vals)

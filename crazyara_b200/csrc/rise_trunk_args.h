@@ -29,6 +29,7 @@ struct TrunkBlock {
     int n_chunks;     // ceil(Cop / 64)
     int pair0;        // index of the block's first chunk pair (rise_trunk_t.cuh)
     int se_seq0;      // rise_trunk_t.cuh: position in the unit stream of the block's four squeeze-excitation units
+    int se_seq0c[2];  // rise_trunk_c.cuh: the same in the stream of cluster rank 0 / 1
     int ksize;        // depthwise kernel: 3 or 5
     int se_type;      // 0 none, 1 ca_se, 2 eca_se (applied to the block input, in place)
     int chunk0;       // index of the block's first chunk in the image arrays
@@ -50,6 +51,8 @@ struct TrunkArgs {
     const uint8_t* t_aux;      // [pairs][kTrunkTAux]
     const int* t_seq;          // unit index (into t_img) of every unit of the stream, in consumption order
     int t_units;
+    const int* c_seq[2];       // rise_trunk_c.cuh: the unit streams of cluster rank 0 / 1 (half the weights each)
+    int c_units[2];
     unsigned long long* prof;  // profiling builds (-DARA_TRUNK_PROF): [2][16] cycle counters of CTA 0, else unused
     TrunkBlock blk[kTrunkMaxBlocks];
 };

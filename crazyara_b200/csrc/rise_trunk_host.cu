@@ -5,6 +5,7 @@
 
 #include "rise_trunk.cuh"
 #include "rise_trunk_t.cuh"
+#include "rise_trunk_c.cuh"
 
 namespace ara {
 
@@ -100,6 +101,7 @@ int rise_trunk_init(RiseTrunk* T, const std::vector<TrunkBlockHost>& blocks, con
         int se_idx = 0;
         std::vector<uint8_t> aux(static_cast<size_t>(pairs) * kTrunkTAux, 0);
         std::vector<int> seq;
+        std::vector<int> cseq[2];  // rise_trunk_c.cuh: rank r streams W1 of its own pairs and its half of every W2
         for (int i = 0; i < nb; ++i) {
             const TrunkBlockHost& h = blocks[i];
             const TrunkBlock& B = T->args.blk[i];
@@ -135,6 +137,10 @@ int rise_trunk_init(RiseTrunk* T, const std::vector<TrunkBlockHost>& blocks, con
                 for (size_t k = 0; k < n1 + n2; ++k) dst[k] = __float2half_rn(f[k]);
                 T->args.blk[i].se_seq0 = static_cast<int>(seq.size());
                 for (int u = 0; u < 4; ++u) seq.push_back((pairs + se_idx) * 4 + u);
+                for (int r = 0; r < 2; ++r) {
+                    T->args.blk[i].se_seq0c[r] = static_cast<int>(cseq[r].size());
+                    for (int u = 0; u < 4; ++u) cseq[r].push_back((pairs + se_idx) * 4 + u);
+                }
                 ++se_idx;
             }
             auto w2_units = [&](int p) {
@@ -147,6 +153,16 @@ int rise_trunk_init(RiseTrunk* T, const std::vector<TrunkBlockHost>& blocks, con
                 if (p >= kTrunkTLag) w2_units(p - kTrunkTLag);
             }
             for (int p = P > kTrunkTLag ? P - kTrunkTLag : 0; p < P; ++p) w2_units(p);
+            for (int r = 0; r < 2; ++r) {
+                for (int p = 0; p < P; ++p) {
+                    if (((B.pair0 + p) & 1) == r) {
+                        cseq[r].push_back((B.pair0 + p) * 4 + 0);
+                        cseq[r].push_back((B.pair0 + p) * 4 + 1);
+                    }
+                    if (p >= kTrunkTLag) cseq[r].push_back((B.pair0 + p - kTrunkTLag) * 4 + 2 + r);
+                }
+                for (int p = P > kTrunkTLag ? P - kTrunkTLag : 0; p < P; ++p) cseq[r].push_back((B.pair0 + p) * 4 + 2 + r);
+            }
         }
         ARA_CUDA_OK(cudaMalloc(&T->d_timg, img.size()));
         ARA_CUDA_OK(cudaMalloc(&T->d_taux, aux.size()));
@@ -159,6 +175,14 @@ int rise_trunk_init(RiseTrunk* T, const std::vector<TrunkBlockHost>& blocks, con
         T->args.t_seq = static_cast<const int*>(T->d_tseq);
         T->args.t_units = static_cast<int>(seq.size());
         ARA_CUDA_OK(cudaFuncSetAttribute(rise_trunk_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRttSmemBytes));
+        ARA_CUDA_OK(cudaMalloc(&T->d_cseq, (cseq[0].size() + cseq[1].size()) * sizeof(int)));
+        ARA_CUDA_OK(cudaMemcpy(T->d_cseq, cseq[0].data(), cseq[0].size() * sizeof(int), cudaMemcpyHostToDevice));
+        ARA_CUDA_OK(cudaMemcpy(static_cast<int*>(T->d_cseq) + cseq[0].size(), cseq[1].data(), cseq[1].size() * sizeof(int), cudaMemcpyHostToDevice));
+        T->args.c_seq[0] = static_cast<const int*>(T->d_cseq);
+        T->args.c_seq[1] = static_cast<const int*>(T->d_cseq) + cseq[0].size();
+        T->args.c_units[0] = static_cast<int>(cseq[0].size());
+        T->args.c_units[1] = static_cast<int>(cseq[1].size());
+        ARA_CUDA_OK(cudaFuncSetAttribute(rise_trunk_c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRtcSmemBytes));
     }
     ARA_CUDA_OK(cudaMalloc(&T->d_prof, 32 * sizeof(unsigned long long)));
     ARA_CUDA_OK(cudaMemset(T->d_prof, 0, 32 * sizeof(unsigned long long)));
@@ -188,7 +212,28 @@ int rise_trunk_launch(const RiseTrunk* T, int boards, cudaStream_t stream, const
         const char* e = getenv("ARA_TRUNK_T");
         return e == nullptr || atoi(e) != 0;
     }();
-    if (one_board && transposed)
+    // ... on CTA pairs while two CTAs per board still fit one wave (rise_trunk_c.cuh; ARA_TRUNK_PAIR=0: one CTA per board)
+    static const bool paired = [] {
+        const char* e = getenv("ARA_TRUNK_PAIR");
+        return e == nullptr || atoi(e) != 0;
+    }();
+    if (one_board && transposed && paired && 2 * boards <= T->sm_count) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * boards);
+        cfg.blockDim = dim3(kRtcThreads);
+        cfg.dynamicSmemBytes = kRtcSmemBytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = pdl_enabled() ? 2 : 1;
+        ARA_CUDA_OK(cudaLaunchKernelEx(&cfg, rise_trunk_c_kernel, a));
+    } else if (one_board && transposed)
         ARA_CUDA_OK(launch_pdl(rise_trunk_t_kernel, dim3(boards), dim3(kRttThreads), kRttSmemBytes, stream, a));
     else if (one_board)
         ARA_CUDA_OK(launch_pdl(rise_trunk_kernel<64>, dim3(boards), dim3(kRtThreads), kRtSmemBytes, stream, a));
@@ -204,6 +249,8 @@ void rise_trunk_destroy(RiseTrunk* T) {
     if (T->d_timg) cudaFree(T->d_timg);
     if (T->d_taux) cudaFree(T->d_taux);
     if (T->d_tseq) cudaFree(T->d_tseq);
+    if (T->d_cseq) cudaFree(T->d_cseq);
+    T->d_cseq = nullptr;
     T->d_timg = T->d_taux = T->d_tseq = nullptr;
     for (void* p : T->d_se) cudaFree(p);
     T->d_se.clear();

@@ -30,6 +30,7 @@ struct RiseTrunk {
     void* d_timg = nullptr;  // rise_trunk_t.cuh: pair images, vector records, unit order
     void* d_taux = nullptr;
     void* d_tseq = nullptr;
+    void* d_cseq = nullptr;  // rise_trunk_c.cuh: unit order of the two cluster ranks
     int sm_count = 148;
     void* d_prof = nullptr;  // [2][16] cycle counters, written only by -DARA_TRUNK_PROF builds
     std::vector<void*> d_se;  // fp16 copies of the squeeze-excitation matrices

@@ -31,7 +31,7 @@ else:
     d = tempfile.mkdtemp()
     for mode in ("0", "1"):
         env = dict(os.environ, ARA_TRUNK_T=mode)
-        r = subprocess.run([sys.executable, __file__, mode, d], env=env, capture_output=True, text=True, timeout=300)
+        r = subprocess.run([sys.executable, __file__, mode, d], env=env, capture_output=True, text=True, timeout=100)
         print(r.stdout[-2000:], r.stderr[-2000:])
     for name in ("risev2", "risev33"):
         for B in (64, 5, 1):

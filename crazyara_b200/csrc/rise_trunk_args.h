@@ -24,6 +24,10 @@ constexpr int kTrunkW2Image = 32768;
 constexpr int kTrunkTUnit = 32768;
 constexpr int kTrunkTAux = 7680;  // 512 + 512 + 25 * 256, padded to 256 B
 constexpr int kTrunkTLag = 2;     // MMA2 of a pair is issued this many pairs behind its MMA1 (the stream follows that order)
+#if !defined(ARA_TRUNK_CLAG)
+#define ARA_TRUNK_CLAG 3
+#endif
+constexpr int kTrunkCLag = ARA_TRUNK_CLAG;  // the same for rise_trunk_c.cuh (an H2 buffer crosses the cluster first)
 
 struct TrunkBlock {
     int n_chunks;     // ceil(Cop / 64)

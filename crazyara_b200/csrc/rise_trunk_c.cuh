@@ -238,9 +238,9 @@ __global__ void __launch_bounds__(kRtcThreads, 1) rise_trunk_c_kernel(const __gr
                     __syncwarp();
                     ++n_own;
                 }
-                if (i >= kTrunkTLag) mma2(i - kTrunkTLag);
+                if (i >= kTrunkCLag) mma2(i - kTrunkCLag);
             }
-            for (int i = P > kTrunkTLag ? P - kTrunkTLag : 0; i < P; ++i) mma2(i);
+            for (int i = P > kTrunkCLag ? P - kTrunkCLag : 0; i < P; ++i) mma2(i);
             if (lane == 0) umma_commit_mc(blk_done, 3);
             __syncwarp();
         }

@@ -159,9 +159,9 @@ int rise_trunk_init(RiseTrunk* T, const std::vector<TrunkBlockHost>& blocks, con
                         cseq[r].push_back((B.pair0 + p) * 4 + 0);
                         cseq[r].push_back((B.pair0 + p) * 4 + 1);
                     }
-                    if (p >= kTrunkTLag) cseq[r].push_back((B.pair0 + p - kTrunkTLag) * 4 + 2 + r);
+                    if (p >= kTrunkCLag) cseq[r].push_back((B.pair0 + p - kTrunkCLag) * 4 + 2 + r);
                 }
-                for (int p = P > kTrunkTLag ? P - kTrunkTLag : 0; p < P; ++p) cseq[r].push_back((B.pair0 + p) * 4 + 2 + r);
+                for (int p = P > kTrunkCLag ? P - kTrunkCLag : 0; p < P; ++p) cseq[r].push_back((B.pair0 + p) * 4 + 2 + r);
             }
         }
         ARA_CUDA_OK(cudaMalloc(&T->d_timg, img.size()));

@@ -208,15 +208,11 @@ int rise_trunk_launch(const RiseTrunk* T, int boards, cudaStream_t stream, const
     const bool one_board = force ? atoi(force) == 64 : boards <= T->sm_count;
     // small batches: channels in the tensor core's M dimension (rise_trunk_t.cuh; ARA_TRUNK_T=0: the M = 64 variant of
     // rise_trunk.cuh instead -- same bits, slower)
-    static const bool transposed = [] {
-        const char* e = getenv("ARA_TRUNK_T");
-        return e == nullptr || atoi(e) != 0;
-    }();
+    const char* et = getenv("ARA_TRUNK_T");
+    const bool transposed = et == nullptr || atoi(et) != 0;
     // ... on CTA pairs while two CTAs per board still fit one wave (rise_trunk_c.cuh; ARA_TRUNK_PAIR=0: one CTA per board)
-    static const bool paired = [] {
-        const char* e = getenv("ARA_TRUNK_PAIR");
-        return e == nullptr || atoi(e) != 0;
-    }();
+    const char* ep = getenv("ARA_TRUNK_PAIR");
+    const bool paired = ep == nullptr || atoi(ep) != 0;
     if (one_board && transposed && paired && 2 * boards <= T->sm_count) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(2 * boards);

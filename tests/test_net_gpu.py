@@ -151,16 +151,25 @@ def test_float16_and_float32_networks_agree(tmp_path, monkeypatch, name, cin, pc
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,cin,pch", [("risev2", 34, 81), ("risev33", 52, 76)])
 def test_tower_variants_are_bit_identical(tmp_path, monkeypatch, name, cin, pch):
-    """One board per CTA (small batches) and two boards per CTA (large batches) must give the same bits: a search with
-    many trees evaluates the same positions in bigger batches than a single-tree search."""
+    """The four tower kernels must give the same bits: a search with many trees evaluates the same positions in bigger
+    batches than a single-tree search.  Two boards per CTA (large batches); one board per CTA with the squares in the
+    tensor core's M (the old small-batch kernel); one board per CTA with the channels in M (rise_trunk_t.cuh); one board per
+    CTA pair, each CTA streaming half of the weights (rise_trunk_c.cuh, the default up to 74 boards)."""
     arch = onet.arch_risev2(cin, pch) if name == "risev2" else onet.arch_risev33(cin, pch, True)
-    x = golden_input(arch, n=5, seed=11)
-    outs = []
-    for rows in ("64", "128"):  # (forcing the row count also switches the CTA-pair chunk split off)
-        monkeypatch.setenv("ARA_TRUNK_ROWS", rows)
-        net, _ = _make_net(tmp_path, arch, 5, 10 if name == "risev2" else 30)
-        v, p = np.zeros(5, np.float32), np.zeros((5, pch * 64), np.float32)
-        net.predict(x, v, p, None, n=5)
-        net.close()
-        outs.append((v, p))
-    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    variants = [{"ARA_TRUNK_ROWS": "128"}, {"ARA_TRUNK_ROWS": "64", "ARA_TRUNK_T": "0"}, {"ARA_TRUNK_PAIR": "0"}, {}]
+    for n in (5, 64):  # (64: every SM of the wave busy, the hand-offs see real contention)
+        x = golden_input(arch, n=n, seed=11)
+        outs = []
+        for env in variants:
+            for k in ("ARA_TRUNK_ROWS", "ARA_TRUNK_T", "ARA_TRUNK_PAIR"):
+                monkeypatch.delenv(k, raising=False)
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            net, _ = _make_net(tmp_path, arch, n, 10 if name == "risev2" else 30)
+            v, p = np.zeros(n, np.float32), np.zeros((n, pch * 64), np.float32)
+            for _ in range(3):  # (repeated: a race between the hand-offs would not show every time)
+                net.predict(x, v, p, None, n=n)
+                outs.append((v.copy(), p.copy()))
+            net.close()
+        for v, p in outs[1:]:
+            assert np.array_equal(v, outs[0][0]) and np.array_equal(p, outs[0][1])

@@ -25,7 +25,7 @@
 namespace ara {
 
 #if !defined(ARA_WAVE_WARPS)
-#define ARA_WAVE_WARPS 6
+#define ARA_WAVE_WARPS 12
 #endif
 constexpr int kWaveWarps = ARA_WAVE_WARPS;
 constexpr int kWaveNone = 0x7fffffff;

@@ -318,3 +318,35 @@ def test_gpu_packed_multi_tree_batches_equal_single_tree_searches(tmp_path):
         assert_same_search(r, together[t])
         assert together[t]["evals"] > 0
     net.close()
+
+
+# Positions in which many playouts of a mini-batch end in terminal nodes: in the wavefront select kernel
+# (search_wave.cuh) every terminal commit makes the younger playouts in flight take their virtual visits back and
+# start again -- wide mini-batches, so that many playouts are in flight when that happens.
+TERMINAL_HEAVY = [
+    ("chess", 0, "chess", "6k1/5ppp/8/8/8/8/8/R3K2R w KQ - 0 1", 32, 1200, dict(mcts_solver=0)),
+    ("chess", 0, "chess", "6k1/5ppp/8/8/8/8/8/R3K2R w KQ - 0 1", 64, 1600, dict()),
+    ("chess", 0, "chess", "7k/5Q2/6K1/8/8/8/8/8 w - - 0 1", 64, 2000, dict(mcts_solver=0)),
+    ("chess", 0, "chess", "7k/5Q2/6K1/8/8/8/8/8 w - - 0 1", 16, 600, dict(mcts_solver=0, virtual_style=0)),
+    ("crazyhouse", 1, "crazyhouse", "4R2b/1N3rkb/1p2P1pp/p2P4/2P1P3/8/PP4Q1/3R3K[QRBBNNNPPPPpp] w - - 2 53", 32, 1500,
+     dict(mcts_solver=0)),
+    ("crazyhouse", 1, "crazyhouse", "4R2b/1N3rkb/1p2P1pp/p2P4/2P1P3/8/PP4Q1/3R3K[QRBBNNNPPPPpp] w - - 2 53", 64, 1500,
+     dict(node_policy_temperature=1.7, virtual_mix_threshold=50)),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("threads", [1, 2])
+@pytest.mark.parametrize("case", TERMINAL_HEAVY, ids=[f"{c[0]}-b{c[4]}-s{c[5]}-{i}" for i, c in enumerate(TERMINAL_HEAVY)])
+def test_gpu_wavefront_select_with_many_terminal_playouts(case, threads, monkeypatch):
+    variant, vid, mode, fen, batch, sims, extra = case
+    st = case_settings(mode, batch, sims, dict(extra, threads=threads))
+    pos = Position(fen, variant, False)
+    S = osr.Search(st)
+    ro = S.run(pos, osr.fake_net(S.n_labels), with_keys=True, threads=threads)
+    monkeypatch.delenv("ARA_WAVE", raising=False)
+    rg = _gpu_search(vid, fen, False, [], st)[0]          # the wavefront kernel (one tree, Batch_Size >= 8)
+    assert_same_search(ro, rg)
+    monkeypatch.setenv("ARA_WAVE", "0")
+    rs = _gpu_search(vid, fen, False, [], st)[0]          # one warp per tree
+    assert_same_search(ro, rs)

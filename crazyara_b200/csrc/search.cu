@@ -71,6 +71,106 @@ __global__ void __launch_bounds__(32) advance_kernel(const TreeDev* trees, int t
     if (threadIdx.x == 0) advance_root(t, move);
 }
 
+// ------------------------------------------------------------------ node-pool compaction (tree reuse over long games)
+// A kept subtree lives wherever its nodes were allocated: after a few searches the pools are full of the dead siblings
+// of the moves that were played, and reuse_root would have to start a new tree.  Instead the subtree behind the new
+// root is copied to the front of a second set of pools (node ids and edge ranges keep their relative order, so the new
+// root becomes node 0), the pool pointers are swapped and the search goes on with every statistic it had.
+struct CompactInfo {
+    int need;    // the kept subtree is the searched position but the pools have no room left for another search
+    int cand;    // its root
+    int n_nodes, n_edges;
+};
+__global__ void __launch_bounds__(32) compact_decide_kernel(const TreeDev* trees, SearchParams sp, const Board* roots, CompactInfo* info) {
+    if (threadIdx.x != 0) return;
+    const TreeDev t = trees[blockIdx.x];
+    const int cand = kept_subtree_root(t, &roots[blockIdx.x]);
+    CompactInfo c;
+    c.cand = cand;
+    c.n_nodes = t.st->n_nodes;
+    c.n_edges = t.st->n_edges;
+    c.need = cand >= 0 && !pools_have_room(sp, t.max_nodes, t.max_edges, c.n_nodes, c.n_edges);
+    info[blockIdx.x] = c;
+}
+// keep_n[i] = 1 if node i lies in the subtree of `cand`, keep_e[i] = its number of edges then
+__global__ void compact_mark_kernel(TreeDev t, int cand, int n_nodes, int* keep_n, int* keep_e) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    int j = i;
+    while (j > cand) j = t.hdr[j].parent;  // (a child is always allocated after its parent)
+    const bool keep = j == cand;
+    keep_n[i] = keep ? 1 : 0;
+    keep_e[i] = keep ? t.hdr[i].n_moves : 0;
+}
+// exclusive prefix sum of a[0..n) in place, one thread block; total[0] = the sum
+__global__ void __launch_bounds__(1024) compact_scan_kernel(int* a, int n, int* total) {
+    __shared__ int part[1024];
+    const int per = (n + 1023) / 1024;
+    const int lo = threadIdx.x * per, hi = min(n, lo + per);
+    int s = 0;
+    for (int i = lo; i < hi; ++i) s += a[i];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        const int v = threadIdx.x >= off ? part[threadIdx.x - off] : 0;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int run = part[threadIdx.x] - s;
+    for (int i = lo; i < hi; ++i) {
+        const int v = a[i];
+        a[i] = run;
+        run += v;
+    }
+    if (threadIdx.x == 1023) *total = part[1023];
+}
+// one warp per node of the old pools: a kept node and its edges go to their new places in `d`
+__global__ void compact_gather_kernel(TreeDev s, TreeDev d, int cand, int n_nodes, const int* new_id, const int* new_eb) {
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= n_nodes) return;
+    {   // (the marks were overwritten by their prefix sums: walk up again)
+        int a = i;
+        while (a > cand) a = s.hdr[a].parent;
+        if (a != cand) return;
+    }
+    const int j = new_id[i];
+    const NodeHdr h = s.hdr[i];
+    if (lane < 4) reinterpret_cast<uint4*>(&d.hdr[j])[lane] = reinterpret_cast<const uint4*>(&s.hdr[i])[lane];
+    else if (lane < 12) reinterpret_cast<uint4*>(&d.board[j])[lane - 4] = reinterpret_cast<const uint4*>(&s.board[i])[lane - 4];
+    else if (lane < 12 + 8 * kPrepSlots && lane < 32) {
+        const int q = lane - 12;
+        reinterpret_cast<uint4*>(&d.prep_board[j * kPrepSlots])[q] = reinterpret_cast<const uint4*>(&s.prep_board[i * kPrepSlots])[q];
+    }
+    if (lane < kPrepSlots) {
+        d.prep_ci[j * kPrepSlots + lane] = s.prep_ci[i * kPrepSlots + lane];
+        d.prep_term[j * kPrepSlots + lane] = s.prep_term[i * kPrepSlots + lane];
+    }
+    __syncwarp();
+    const uint32_t eb = static_cast<uint32_t>(new_eb[i]);
+    if (lane == 0) {
+        d.hdr[j].parent = i == cand ? -1 : new_id[h.parent];
+        d.hdr[j].edge_base = eb;
+    }
+    for (int k = lane; k < h.n_moves; k += 32) {
+        const uint32_t e = h.edge_base + k, f = eb + k;
+        const int c = s.child[e];
+        d.P[f] = s.P[e];
+        d.Q[f] = s.Q[e];
+        d.N[f] = s.N[e];
+        d.move[f] = s.move[e];
+        d.vl[f] = s.vl[e];
+        d.etype[f] = s.etype[e];
+        d.child[f] = c >= 0 ? new_id[c] : c;
+        d.cbase[f] = c >= 0 ? static_cast<uint32_t>(new_eb[c]) : s.cbase[e];
+    }
+}
+__global__ void compact_finish_kernel(TreeState* st, int n_nodes, int n_edges) {
+    st->n_nodes = n_nodes;
+    st->n_edges = n_edges;
+    st->next_root = 0;  // the subtree's root is its first node
+}
+
 // one warp per tree: the sequential part of SearchThread::create_mini_batch
 // EPS: with the epsilon-greedy / epsilon-check exploration (its own kernel: the ordinary select stays as lean as it is)
 template <bool EPS>
@@ -251,6 +351,15 @@ class Search {
     bool primed_ = false;                  // S0 S1 of the current go have been enqueued
     TreeDev* d_trees_slot_[2] = {nullptr, nullptr};
     std::vector<TreeDev> h_trees1_;        // slot 1 views (h_trees_ = slot 0)
+    // node-pool compaction: the second set of pools per tree (allocated at the first compaction), scan scratch
+    std::vector<TreeDev> shadow_;
+    std::vector<char> advanced_;           // ara_search_apply_move since the last go
+    CompactInfo* d_cinfo_ = nullptr;
+    int* d_keep_n_ = nullptr;
+    int* d_keep_e_ = nullptr;
+    int* d_ctotal_ = nullptr;
+    long long compactions = 0;
+    int compact_pools();
     struct SlotArrays {                    // per tree: the batch arrays of slot 1
         int32_t *exp_parent, *new_node, *traj_node, *traj_len, *traj_start;
         uint16_t* traj_ci;
@@ -713,6 +822,62 @@ int Search::iterate(int count) {
     return 0;
 }
 
+// Before a go that may continue on a kept subtree: where the pools have no room for another search, the subtree moves to
+// the front of the tree's second set of pools (see compact_decide_kernel).  h_trees_ is updated; the caller uploads it.
+int Search::compact_pools() {
+    bool any = false;
+    for (char a : advanced_) any = any || a != 0;
+    if (!any) return 0;
+    advanced_.assign(n_trees, 0);
+    if (d_cinfo_ == nullptr) {
+        if (dalloc(&d_cinfo_, n_trees) || dalloc(&d_keep_n_, static_cast<size_t>(max_nodes_) + 1) ||
+            dalloc(&d_keep_e_, static_cast<size_t>(max_nodes_) + 1) || dalloc(&d_ctotal_, 2))
+            return -1;
+        shadow_.resize(n_trees);
+        for (auto& t : shadow_) t.hdr = nullptr;
+    }
+    compact_decide_kernel<<<n_trees, 32, 0, stream_>>>(d_trees_, sp, d_roots_, d_cinfo_);
+    std::vector<CompactInfo> info(n_trees);
+    ARA_CUDA_OK(cudaMemcpyAsync(info.data(), d_cinfo_, sizeof(CompactInfo) * n_trees, cudaMemcpyDeviceToHost, stream_));
+    ARA_CUDA_OK(cudaStreamSynchronize(stream_));
+    ++launches;
+    for (int i = 0; i < n_trees; ++i) {
+        const CompactInfo& c = info[i];
+        if (!c.need || c.n_nodes <= 0) continue;
+        TreeDev& t = h_trees_[i];
+        compact_mark_kernel<<<(c.n_nodes + 255) / 256, 256, 0, stream_>>>(t, c.cand, c.n_nodes, d_keep_n_, d_keep_e_);
+        compact_scan_kernel<<<1, 1024, 0, stream_>>>(d_keep_n_, c.n_nodes, d_ctotal_);
+        compact_scan_kernel<<<1, 1024, 0, stream_>>>(d_keep_e_, c.n_nodes, d_ctotal_ + 1);
+        int total[2] = {0, 0};
+        ARA_CUDA_OK(cudaMemcpyAsync(total, d_ctotal_, sizeof(total), cudaMemcpyDeviceToHost, stream_));
+        ARA_CUDA_OK(cudaStreamSynchronize(stream_));
+        launches += 3;
+        if (!pools_have_room(sp, max_nodes_, max_edges_, total[0], total[1])) continue;  // even the subtree alone is too big: new tree
+        TreeDev& d = shadow_[i];
+        if (d.hdr == nullptr) {
+            d = t;
+            const size_t slots = static_cast<size_t>(max_nodes_) * kPrepSlots;
+            if (dalloc(&d.hdr, max_nodes_) || dalloc(&d.board, max_nodes_) || dalloc(&d.P, max_edges_) || dalloc(&d.Q, max_edges_) ||
+                dalloc(&d.N, max_edges_) || dalloc(&d.child, max_edges_) || dalloc(&d.cbase, max_edges_) || dalloc(&d.move, max_edges_) ||
+                dalloc(&d.vl, max_edges_) || dalloc(&d.etype, max_edges_) || dalloc(&d.prep_board, slots) || dalloc(&d.prep_ci, slots) ||
+                dalloc(&d.prep_term, slots))
+                return -1;
+        }
+        compact_gather_kernel<<<(c.n_nodes + 7) / 8, 256, 0, stream_>>>(t, d, c.cand, c.n_nodes, d_keep_n_, d_keep_e_);
+        compact_finish_kernel<<<1, 1, 0, stream_>>>(t.st, total[0], total[1]);
+        launches += 2;
+        // swap the pools: the tree now lives in what was the second set
+        std::swap(t.hdr, d.hdr), std::swap(t.board, d.board), std::swap(t.P, d.P), std::swap(t.Q, d.Q), std::swap(t.N, d.N);
+        std::swap(t.child, d.child), std::swap(t.cbase, d.cbase), std::swap(t.move, d.move), std::swap(t.vl, d.vl);
+        std::swap(t.etype, d.etype), std::swap(t.prep_board, d.prep_board), std::swap(t.prep_ci, d.prep_ci);
+        std::swap(t.prep_term, d.prep_term);
+        ++compactions;
+    }
+    ARA_CUDA_OK(cudaGetLastError());
+    ARA_CUDA_OK(cudaMemcpyAsync(d_trees_, h_trees_.data(), sizeof(TreeDev) * n_trees, cudaMemcpyHostToDevice, stream_));
+    return 0;
+}
+
 // MCTSAgent::evaluate_board_state up to the first mini-batch: roots created (or taken over), evaluated, noised
 int Search::begin() {
     ARA_CUDA_OK(cudaSetDevice(device_));
@@ -723,6 +888,7 @@ int Search::begin() {
     ARA_CUDA_OK(cudaEventRecord(ev0_, stream_));
     ARA_CUDA_OK(cudaMemcpyAsync(d_trees_, h_trees_.data(), sizeof(TreeDev) * n_trees, cudaMemcpyHostToDevice, stream_));
     ARA_CUDA_OK(cudaMemcpyAsync(d_roots_, h_roots_.data(), sizeof(Board) * n_trees, cudaMemcpyHostToDevice, stream_));
+    if (compact_pools()) return -1;
     if (threads_ == 2) {  // the second thread's views of the trees: same pools, its own batch arrays
         h_trees1_ = h_trees_;
         for (int i = 0; i < n_trees; ++i) {
@@ -921,6 +1087,8 @@ int Search::apply_move(int tree, unsigned short move) {
     if (!searched_) return 0;  // nothing to keep before the first search
     // d_trees_ still holds the descriptors of the last go (pool pointers never change)
     advance_kernel<<<1, 32, 0, stream_>>>(d_trees_, tree, static_cast<Move>(move));
+    if (advanced_.empty()) advanced_.assign(n_trees, 0);
+    advanced_[tree] = 1;
     ++launches;
     ARA_CUDA_OK(cudaGetLastError());
     return 0;
@@ -1092,6 +1260,7 @@ extern "C" int ara_search_debug_cycles(ara_search_t h, int tree, unsigned long l
 }
 extern "C" double ara_search_last_go_ms(ara_search_t h) { return h ? reinterpret_cast<Search*>(h)->last_go_ms : 0.0; }
 extern "C" long long ara_search_launch_count(ara_search_t h) { return h ? reinterpret_cast<Search*>(h)->launches : 0; }
+extern "C" long long ara_search_compaction_count(ara_search_t h) { return h ? reinterpret_cast<Search*>(h)->compactions : 0; }
 
 // ---- debug / unit-test entry: the device build of the glibc powf / logf restatement (glibc_flt32.cuh) on host buffers
 __global__ void glibc_flt32_kernel(const float* x, const float* y, int n, float* pow_out, float* log_out) {

@@ -1463,19 +1463,28 @@ ARA_HD void advance_root(const TreeDev& t, Move move) {
 // MCTSAgent::init_root_node / get_root_node_from_tree (mctsagent.cpp:113-160): if the candidate root is the searched
 // position, is a playout node with visits of its own and the pools have room for another search, the subtree is kept
 // (make_to_root) and the search continues on its statistics.  Returns 1 if the tree is reused.  Warp-uniform.
+// room in the pools for another search on top of n_nodes / n_edges entries in use
+ARA_HD bool pools_have_room(const SearchParams& sp, int max_nodes, int max_edges, int n_nodes, long long n_edges) {
+    // a time-limited search has no visit budget: it keeps the tree only while half of the pool is still free
+    const unsigned limit = sp.simulations ? sp.simulations : sp.nodes;
+    const unsigned budget = limit ? limit : static_cast<unsigned>(max_nodes / 2);
+    return n_nodes + static_cast<long long>(budget) + 4 * sp.batch_size + 64 <= max_nodes &&
+           n_edges + (static_cast<long long>(budget) + 4 * sp.batch_size + 64) * (sp.mode == 1 ? 128 : 320) <= max_edges;
+}
+// the candidate root of the next search (ara_search_apply_move) if it is the searched position and a playout node with
+// visits of its own, else -1
+ARA_HD int kept_subtree_root(const TreeDev& t, const Board* root_board) {
+    const TreeState& st = *t.st;
+    const int cand = (st.next_valid && st.n_nodes > 0 && !st.error) ? st.next_root : -1;
+    if (cand < 0) return -1;
+    const NodeHdr& h = t.hdr[cand];
+    const bool ok = h.key == root_board->key && (h.flags & NF_HAS_D) && (h.flags & NF_HAS_NN) && h.visit_sum - h.free_visits > 0;
+    return ok ? cand : -1;
+}
 ARA_HD int reuse_root(const TreeDev& t, const SearchParams& sp, const Board* root_board) {
     TreeState& st = *t.st;
-    const int cand = (st.next_valid && st.n_nodes > 0 && !st.error) ? st.next_root : -1;
-    int ok = 0;
-    if (cand >= 0) {
-        const NodeHdr& h = t.hdr[cand];
-        // a time-limited search has no visit budget: it keeps the tree only while half of the pool is still free
-        const unsigned limit = sp.simulations ? sp.simulations : sp.nodes;
-        const unsigned budget = limit ? limit : static_cast<unsigned>(t.max_nodes / 2);
-        const bool room = st.n_nodes + static_cast<int>(budget) + 4 * sp.batch_size + 64 <= t.max_nodes &&
-                          st.n_edges + (static_cast<long long>(budget) + 4 * sp.batch_size + 64) * (sp.mode == 1 ? 128 : 320) <= t.max_edges;
-        ok = h.key == root_board->key && (h.flags & NF_HAS_D) && (h.flags & NF_HAS_NN) && h.visit_sum - h.free_visits > 0 && room;
-    }
+    const int cand = kept_subtree_root(t, root_board);
+    const int ok = cand >= 0 && pools_have_room(sp, t.max_nodes, t.max_edges, st.n_nodes, st.n_edges) ? 1 : 0;
     ARA_WARP_SYNC();
     if (ARA_LANE == 0) {
         st.next_root = -1;

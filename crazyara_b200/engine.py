@@ -131,6 +131,8 @@ def _L():
         L.ara_search_last_go_ms.argtypes = [vp]
         L.ara_search_launch_count.restype = ctypes.c_longlong
         L.ara_search_launch_count.argtypes = [vp]
+        L.ara_search_compaction_count.restype = ctypes.c_longlong
+        L.ara_search_compaction_count.argtypes = [vp]
         _SIGS = True
     return L
 
@@ -397,6 +399,10 @@ class MCTSAgent:
 
     def launch_count(self):
         return _L().ara_search_launch_count(self._h)
+
+    def compaction_count(self):
+        """kept subtrees moved to the front of the node pools so far (ara_search_compaction_count)"""
+        return _L().ara_search_compaction_count(self._h)
 
     def close(self):
         if getattr(self, "_h", None):

@@ -109,7 +109,8 @@ int main() {
             net.reset(new NeuralNetAPI("gpu", opt.i("First_Device_ID"), static_cast<unsigned>(s.batch_size), opt.kv["Model_Path"],
                                        opt.kv["Precision"]));
         // a time-limited search has no visit budget to size the node pool from
-        // a kept subtree lives in the same pools as the next search: room for a few searches before a fresh tree
+        // a kept subtree lives in the same pools as the next search: room for a few searches, then the library compacts
+        // the subtree to the front of its second set of pools (ara_search_apply_move)
         const long budget = s.simulations ? s.simulations : s.nodes;
         const int pool = timed ? opt.i("Timed_Search_Nodes")
                                : (opt.b("Reuse_Tree") ? static_cast<int>(std::min(8 * budget + 4L * s.batch_size + 64, 1L << 24)) : 0);

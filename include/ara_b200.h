@@ -237,7 +237,10 @@ int ara_search_node(ara_search_t s, int tree, int node_id, ara_node_view_t* out)
 /* MCTSAgent::apply_move_to_tree (agents/mctsagent.cpp:230-247): tells the tree which move was played.  The next go
  * on the position after that move (after both moves, when called twice) continues on the subtree behind it
  * (init_root_node / get_root_node_from_tree, :113-160) instead of starting a new tree -- provided the subtree's root is
- * that position, has been visited, and the node pool (ara_search_create max_nodes) has room for another search.
+ * that position, has been visited, and the node pool (ara_search_create max_nodes) has room for another search.  When
+ * the dead siblings of the played moves have eaten that room, the kept subtree is first copied to the front of a second
+ * set of pools (compaction; allocated at the first need), so a long game keeps its statistics as long as the subtree
+ * itself plus one search fits.
  * `move` is the engine's 16-bit move code (ara_search_result_t.moves). */
 int ara_search_apply_move(ara_search_t s, int tree, unsigned short move);
 /* ThreadManager's time stop (manager/threadmanager.cpp, SearchLimits::movetime): ms > 0 makes the following go calls
@@ -286,6 +289,9 @@ int ara_search_profile(ara_search_t s, double* select_ms, double* net_ms, double
 int ara_search_debug_cycles(ara_search_t s, int tree, unsigned long long* out8);
 double ara_search_last_go_ms(ara_search_t s);       /* device time of the last go (CUDA events) */
 long long ara_search_launch_count(ara_search_t s); /* search kernels launched so far */
+/* How often a kept subtree (ara_search_apply_move) was moved to the front of the node / edge pools because they had no
+ * room left for another search on top of the dead siblings (instead of giving the tree up). */
+long long ara_search_compaction_count(ara_search_t s);
 
 /* ---- debug / unit-test entries (one tcgen05 convolution layer on caller-provided device buffers) */
 int ara_debug_conv(const void* act_half, int boards_cap, int boards, int cin, const void* w_half, int w_rows, int n_out,

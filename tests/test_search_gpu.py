@@ -259,6 +259,39 @@ def test_gpu_tree_reuse_equals_oracle(variant, vid, mode, batch, sims, extra):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("threads", [1, 2])
+def test_gpu_tree_reuse_survives_full_pools_by_compaction(threads):
+    """A long game on node pools that hold barely three searches: the kept subtree is copied to the front of the second
+    set of pools whenever the dead siblings have eaten the room (search.cu, compact_pools), so EVERY search continues on
+    the kept statistics like the oracle's (whose pool is unbounded) -- bit-exact, node ids aside."""
+    from crazyara_b200.engine import BoardState, MCTSAgent, SearchSettings
+    st = osr.default_settings("crazyhouse", batch_size=16, simulations=400, node_policy_temperature=1.0, threads=threads)
+    s = SearchSettings()
+    for f, _ in s._fields_:
+        setattr(s, f, getattr(st, f))
+    pos = Position(None, "crazyhouse", False)
+    bs = BoardState().set("", False, 1)
+    S = osr.Search(st)
+    agent = MCTSAgent(None, s, 0, 1, 1400)
+    for ply in range(24):
+        ro = S.run(pos, osr.fake_net(S.n_labels), with_keys=True, threads=threads)
+        rg = agent.evaluate_board_state(bs)
+        if agent.compaction_count() > 0:   # (the pool usage is the one statistic a compaction changes: dead nodes are gone)
+            assert rg["tree_nodes"] <= ro["tree_nodes"]
+            ro["tree_nodes"] = rg["tree_nodes"]
+        assert_same_search(ro, rg)
+        assert S.reused == (ply > 0) and rg["nodes_pre_search"] == S.nodes_pre_search
+        order = np.argsort(-ro["visits"].astype(np.int64), kind="stable")
+        uci = ro["moves"][int(order[0])]
+        assert S.apply_move(pos.move_from_uci(uci))
+        agent.apply_move_to_tree(uci)
+        pos.push_uci(uci)
+        bs.do_uci(uci)
+    assert agent.compaction_count() >= 5
+    agent.close()
+
+
+@pytest.mark.gpu
 def test_gpu_time_manager_early_stop_and_veto():
     """ThreadManager on the device search: with a (deliberately tiny) NPS estimate the early-stopping rules fire at the
     first update interval at which the most visited move also looks best; a dropped evaluation vetoes the stop once

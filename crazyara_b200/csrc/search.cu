@@ -173,21 +173,25 @@ __global__ void compact_finish_kernel(TreeState* st, int n_nodes, int n_edges) {
 
 // one warp per tree: the sequential part of SearchThread::create_mini_batch
 // EPS: with the epsilon-greedy / epsilon-check exploration (its own kernel: the ordinary select stays as lean as it is)
+// count != nullptr (single-tree searches): the number of new leaves for the network kernels, what pack_kernel computes
+// for many trees
 template <bool EPS>
-__global__ void __launch_bounds__(32) select_kernel(const TreeDev* trees, SearchParams sp) {
+__global__ void __launch_bounds__(32) select_kernel(const TreeDev* trees, SearchParams sp, int* count) {
     __shared__ WarpScratch ws;
     const TreeDev t = trees[blockIdx.x];
     create_mini_batch<EPS>(t, sp, ws);
+    if (count != nullptr && threadIdx.x == 0) *count = t.st->error ? 0 : t.bs->n_new;
 }
 
 // The same mini-batch by kWaveWarps warps per tree (search_wave.cuh): consecutive playouts of one tree overlap, the result
 // is the sequential one.  Used when there are too few trees to fill the SMs with one warp each.
-__global__ void __launch_bounds__(32 * kWaveWarps) select_wave_kernel(const TreeDev* trees, SearchParams sp) {
+__global__ void __launch_bounds__(32 * kWaveWarps) select_wave_kernel(const TreeDev* trees, SearchParams sp, int* count) {
     extern __shared__ __align__(16) unsigned char wave_smem[];
     WaveShared& S = *reinterpret_cast<WaveShared*>(wave_smem);
     WaveWarp& W = reinterpret_cast<WaveWarp*>(wave_smem + kWaveSharedBytes)[threadIdx.x >> 5];
     const TreeDev t = trees[blockIdx.x];
     wave_mini_batch(t, sp, S, W);
+    if (count != nullptr && threadIdx.x == 0) *count = t.st->error ? 0 : t.bs->n_new;  // (thread 0 wrote both at the end)
 }
 
 // Multi-tree searches: the new leaves of all trees are packed into consecutive rows of the network batch (tree i gets
@@ -343,10 +347,10 @@ class Search {
     int threads_ = 1;
     bool eps_ = false;  // epsilon-greedy / epsilon-check exploration on: the select_kernel<true> instantiation
     bool wave_ = false;  // few trees: select_wave_kernel (several warps per tree) instead of one warp per tree
-    void launch_select(const TreeDev* trees) {
-        if (eps_) select_kernel<true><<<n_trees, 32, 0, stream_>>>(trees, sp);
-        else if (wave_) select_wave_kernel<<<n_trees, 32 * kWaveWarps, kWaveSmemBytes, stream_>>>(trees, sp);
-        else select_kernel<false><<<n_trees, 32, 0, stream_>>>(trees, sp);
+    void launch_select(const TreeDev* trees, int* count = nullptr) {
+        if (eps_) select_kernel<true><<<n_trees, 32, 0, stream_>>>(trees, sp, count);
+        else if (wave_) select_wave_kernel<<<n_trees, 32 * kWaveWarps, kWaveSmemBytes, stream_>>>(trees, sp, count);
+        else select_kernel<false><<<n_trees, 32, 0, stream_>>>(trees, sp, count);
     }
     bool primed_ = false;                  // S0 S1 of the current go have been enqueued
     TreeDev* d_trees_slot_[2] = {nullptr, nullptr};
@@ -721,8 +725,12 @@ int Search::enqueue_slot_tree_ops(int slot, bool with_update) {
         scatter_prepare_kernel<<<n_trees * 4 * B, 32, 0, stream_>>>(trees, sp, B, 4 * B, values, probs, n_labels_);
         ARA_CUDA_OK(cudaStreamWaitEvent(stream_, ev_join_, 0));
     }
-    launch_select(trees);
-    pack_kernel<<<1, 32, 0, stream_>>>(trees, n_trees, d_count_slot_[slot]);
+    if (n_trees == 1) {  // (one tree: its rows start at 0, the select kernel itself leaves the count)
+        launch_select(trees, d_count_slot_[slot]);
+    } else {
+        launch_select(trees);
+        pack_kernel<<<1, 32, 0, stream_>>>(trees, n_trees, d_count_slot_[slot]);
+    }
     expand_kernel<<<n_trees * B, 32, 0, stream_>>>(trees, sp, B, net_ ? net_->io_in_h[slot] : nullptr, net_ ? net_->cin_pad : 0,
                                                     net_ ? net_->precision : 0);
     return 0;
@@ -752,7 +760,7 @@ int Search::enqueue_slot(int slot, bool with_update) {
         if (enqueue_slot_tree_ops(slot, with_update)) return -1;
     }
     if (profile) prof_event();
-    launches += 3 + (with_update ? 2 : 0);
+    launches += (n_trees == 1 ? 2 : 3) + (with_update ? 2 : 0);
     ARA_CUDA_OK(cudaEventRecord(ev_sel_[slot], stream_));
     ARA_CUDA_OK(cudaStreamWaitEvent(net_stream_, ev_sel_[slot], 0));
     if (profile) {

@@ -1323,6 +1323,13 @@ ARA_HD void backup_results(const TreeDev& t, const SearchParams& sp, const float
         float leaf_n = n_new > 0 ? leaf_values[0] : 0.0f, leaf_nn = n_new > 1 ? leaf_values[1] : 0.0f;
         int nid_n = n_new > 0 ? t.traj_node[dd] : -1, nid_nn = n_new > 1 ? t.traj_node[kMaxDepth + dd] : -1;
         uint32_t e_n = n_new > 0 ? t.traj_edge[dd] : 0, e_nn = n_new > 1 ? t.traj_edge[kMaxDepth + dd] : 0;
+#if defined(__CUDA_ARCH__)
+        // further ahead: the lines of trajectories b+3 / b+4 are pulled into L1 (prefetch hints, no registers tied up), so
+        // that the pre-loads above find them there.  This lane is the only writer of those lines; a load after its own
+        // store returns the stored value whatever the hint fetched.
+        int nid_3 = n_new > 2 ? t.traj_node[2 * kMaxDepth + dd] : -1, nid_4 = n_new > 3 ? t.traj_node[3 * kMaxDepth + dd] : -1;
+        uint32_t e_3 = n_new > 2 ? t.traj_edge[2 * kMaxDepth + dd] : 0, e_4 = n_new > 3 ? t.traj_edge[3 * kMaxDepth + dd] : 0;
+#endif
         double p_vsum = 0.0;
         uint32_t p_rv = 0, p_n = 0;
         float p_q = 0.0f;
@@ -1340,6 +1347,25 @@ ARA_HD void backup_results(const TreeDev& t, const SearchParams& sp, const float
             const float l_q = p_q;
             const uint8_t l_vl = p_vl;
             len_n = len_nn, start_n = start_nn, leaf_n = leaf_nn, nid_n = nid_nn, e_n = e_nn;
+#if defined(__CUDA_ARCH__)
+            if (b + 2 < n_new) {
+                len_nn = t.traj_len[b + 2];
+                start_nn = t.traj_start[b + 2];
+                leaf_nn = leaf_values[b + 2];
+                nid_nn = nid_3, e_nn = e_3;
+            }
+            nid_3 = nid_4, e_3 = e_4;
+            if (b + 4 < n_new) {
+                nid_4 = t.traj_node[(b + 4) * kMaxDepth + dd];
+                e_4 = t.traj_edge[(b + 4) * kMaxDepth + dd];
+            }
+            if (b + 3 < n_new && nid_3 >= 0 && d < kMaxDepth) {  // (nid_3 / e_3: trajectory b+3, indices requested two iterations ago)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(&t.hdr[nid_3].value_sum));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(&t.Q[e_3]));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(&t.N[e_3]));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(&t.vl[e_3]));
+            }
+#else
             if (b + 2 < n_new) {
                 len_nn = t.traj_len[b + 2];
                 start_nn = t.traj_start[b + 2];
@@ -1347,6 +1373,7 @@ ARA_HD void backup_results(const TreeDev& t, const SearchParams& sp, const float
                 nid_nn = t.traj_node[(b + 2) * kMaxDepth + dd];
                 e_nn = t.traj_edge[(b + 2) * kMaxDepth + dd];
             }
+#endif
             const bool active = d < len && d >= start;
             if (active) {  // move the register copies on to this trajectory's node / edge (stores first)
                 if (nid != c_nid) {

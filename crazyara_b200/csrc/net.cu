@@ -380,8 +380,12 @@ int Net::enable_second_io() {
     if (dalloc(&io_in_h[1], rows * cin)) return -1;
     if (dalloc(&io_prob[1], static_cast<size_t>(batch) * n_labels())) return -1;
     if (dalloc(&io_value[1], batch) || dalloc(&io_aux[1], static_cast<size_t>(batch) * 4)) return -1;
-    stem_conv2 = stem_conv;  // same weights, epilogue and outputs; only the activation map differs
+    stem_conv2 = stem_conv;  // same weights and epilogue; the activation map differs ...
     if (make_act_tensor_map(&stem_conv2.tm_a, io_in_h[1], batch_cap, cin)) return -1;
+    if (precision == 0) {  // ... and the output buffer: the two sets' stems may then run while the other set's tower reads its own
+        if (dalloc(&d_x0_alt, rows * static_cast<size_t>(hdr.channels))) return -1;
+        stem_conv2.args.out_h = d_x0_alt;
+    }
     return 0;
 }
 
@@ -423,15 +427,24 @@ int Net::enqueue_precise(int n, cudaStream_t s, bool from_f32, const int* cnt, i
     return 0;
 }
 
-int Net::enqueue(int n, cudaStream_t s, bool from_f32, const int* cnt, int io) {
+int Net::stem_device(int n, cudaStream_t s, const int* cnt, int io) {
+    if (!stem_splittable() || io < 0 || io > 1) return set_error("stem_device: needs Precision float16 and two input / output sets");
+    if (conv_layer_launch(io ? &stem_conv2 : &stem_conv, n, s, cnt)) return -1;
+    return 0;  // (the caller counts the launch: it may sit in a captured graph)
+}
+
+int Net::enqueue(int n, cudaStream_t s, bool from_f32, const int* cnt, int io, bool stem_done) {
     if (precision == 1) return enqueue_precise(n, s, from_f32, cnt, io);
     if (from_f32) {
         ARA_CUDA_OK(launch_pdl(nchw_f32_to_nhwc_f16_kernel, dim3(n), dim3(256), hdr.in_channels * 65 * 4, s, d_in_f32, io_in_h[io], hdr.in_channels, cin_pad));
         ++launches;
     }
-    if (conv_layer_launch(io ? &stem_conv2 : &stem_conv, n, s, cnt)) return -1;
-    if (rise_trunk_launch(&trunk_, n, s, cnt)) return -1;
-    launches += 2;
+    if (!stem_done) {
+        if (conv_layer_launch(io ? &stem_conv2 : &stem_conv, n, s, cnt)) return -1;
+        ++launches;
+    }
+    if (rise_trunk_launch(&trunk_, n, s, cnt, (io == 1 && d_x0_alt != nullptr) ? d_x0_alt : nullptr)) return -1;
+    ++launches;
     __half* xfinal = d_x[1];
     ValueHeadW vw{vh_wv, vh_bv, vh_w1t, vh_b1, vh_w2, vh_b2, vh_wdl_w, vh_wdl_b, vh_plys_w, vh_plys_b, hdr.wdl_mode};
     if (fork_heads) {  // value head on the side stream (a second branch of the captured graph), policy head on s
@@ -451,21 +464,22 @@ int Net::enqueue(int n, cudaStream_t s, bool from_f32, const int* cnt, int io) {
     return 0;
 }
 
-int Net::forward_device(int n, cudaStream_t s, const int* cnt, int io) {
+int Net::forward_device(int n, cudaStream_t s, const int* cnt, int io, bool stem_done) {
+    if (stem_done && !stem_splittable()) return set_error("forward: stem_done needs Precision float16 and two input / output sets");
     if (n < 1 || n > batch) return set_error("forward: n=%d outside [1,%d]", n, batch);
     if (io != 0 && (io != 1 || io_in_h[1] == nullptr)) return set_error("forward: input/output set %d not enabled", io);
     // two input / output sets = a search with Threads = 2: this forward runs on the network stream beside the other
     // thread's tree kernels (see PdlSuspend)
     PdlSuspend no_pdl(io_in_h[1] != nullptr);
-    if (!use_graph) return enqueue(n, s, false, cnt, io);
+    if (!use_graph) return enqueue(n, s, false, cnt, io, stem_done);
     {   // inside somebody else's capture (the search's iteration graph) the kernels go in directly
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
         ARA_CUDA_OK(cudaStreamIsCapturing(s, &cs));
-        if (cs == cudaStreamCaptureStatusActive) return enqueue(n, s, false, cnt, io);
+        if (cs == cudaStreamCaptureStatusActive) return enqueue(n, s, false, cnt, io, stem_done);
     }
-    const int gk = io == 1 ? 3 : (cnt != nullptr ? 2 : 0);
-    const int*& baked = io == 1 ? count_ptr2_ : count_ptr_;
-    if ((gk == 3 || cnt != nullptr) && cnt != baked) {  // graphs captured with another counter are of no use
+    const int gk = stem_done ? 4 + io : (io == 1 ? 3 : (cnt != nullptr ? 2 : 0));
+    const int*& baked = baked_[gk];
+    if ((gk >= 3 || cnt != nullptr) && cnt != baked) {  // graphs captured with another counter are of no use
         for (auto& g : graphs_[gk]) cudaGraphExecDestroy(g.second);
         graphs_[gk].clear();
         baked = cnt;
@@ -474,12 +488,12 @@ int Net::forward_device(int n, cudaStream_t s, const int* cnt, int io) {
     auto it = graphs.find(n);
     if (it == graphs.end()) {
         // warm-up launch outside capture (sets function attributes), then capture
-        if (enqueue(n, s, false, cnt, io)) return -1;
+        if (enqueue(n, s, false, cnt, io, stem_done)) return -1;
         ARA_CUDA_OK(cudaStreamSynchronize(s));
         const long long before = launches;
         cudaGraph_t g;
         ARA_CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-        int rc = enqueue(n, s, false, cnt, io);
+        int rc = enqueue(n, s, false, cnt, io, stem_done);
         cudaError_t e = cudaStreamEndCapture(s, &g);
         launches = before;
         if (rc) return -1;
@@ -490,7 +504,7 @@ int Net::forward_device(int n, cudaStream_t s, const int* cnt, int io) {
         it = graphs.emplace(n, ge).first;
     }
     ARA_CUDA_OK(cudaGraphLaunch(it->second, s));
-    launches += kernels_per_forward(false);
+    launches += kernels_per_forward(false) - (stem_done ? 1 : 0);
     return 0;
 }
 

@@ -65,7 +65,14 @@ class Net {
     // sized for n, thread blocks of the rows beyond the count leave at once; the pointer is baked into the CUDA graph
     // io: which input / output buffer set (0, or 1 after enable_second_io()): a search with Threads = 2 keeps two
     // batches in flight -- one set is being written / read by the tree kernels while the other is at the network
-    int forward_device(int n, cudaStream_t stream, const int* boards_dev = nullptr, int io = 0);
+    // stem_done: the stem convolution of this batch has already run (stem_device, on the caller's own stream)
+    int forward_device(int n, cudaStream_t stream, const int* boards_dev = nullptr, int io = 0, bool stem_done = false);
+    // The stem convolution alone, into the stem-output buffer of input / output set `io` (Precision float16 with two
+    // sets enabled): a search with two logical threads runs it on its tree stream right behind the plane encoding, which
+    // takes it off the network stream's critical path.
+    int stem_device(int n, cudaStream_t stream, const int* boards_dev, int io);
+    bool stem_splittable() const { return precision == 0 && d_x0_alt != nullptr; }
+    __half* d_x0_alt = nullptr;  // stem output of set 1 (set 0: d_x[0])
     int enable_second_io();
     int forward_from_f32_device(int n, cudaStream_t stream);  // converts d_in_f32 -> in_h first
 
@@ -114,7 +121,7 @@ class Net {
     bool use_graph = true;
 
    private:
-    int enqueue(int n, cudaStream_t s, bool from_f32, const int* boards_dev = nullptr, int io = 0);
+    int enqueue(int n, cudaStream_t s, bool from_f32, const int* boards_dev = nullptr, int io = 0, bool stem_done = false);
     int read_blob(const char* blob_path, HostWeights* hw);
     int build_half(const HostWeights& hw);
     int build_precise(const HostWeights& hw);
@@ -133,9 +140,8 @@ class Net {
     __half *pol_w1 = nullptr, *pol_w2 = nullptr;
     float* pol_b1 = nullptr;
     ConvLayer pol_conv1, pol_conv2;
-    std::map<int, cudaGraphExec_t> graphs_[4];  // plain, from fp32 input, with a device-side count (io 0), the same for io 1
-    const int* count_ptr2_ = nullptr;
-    const int* count_ptr_ = nullptr;            // the pointer the graphs_[2] entries were captured with
+    std::map<int, cudaGraphExec_t> graphs_[6];  // plain, from fp32 input, with a device-side count (io 0), the same for io 1
+    const int* baked_[6] = {};                  // the counter pointer each graph family was captured with
     template <typename T>
     int dalloc(T** p, size_t count);
     int upload_conv_w(const float* w, int n_out, int cin, int ksize, __half** dst, int* rows);

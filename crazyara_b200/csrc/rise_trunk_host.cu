@@ -199,8 +199,9 @@ int rise_trunk_init(RiseTrunk* T, const std::vector<TrunkBlockHost>& blocks, con
     return 0;
 }
 
-int rise_trunk_launch(const RiseTrunk* T, int boards, cudaStream_t stream, const int* boards_dev) {
+int rise_trunk_launch(const RiseTrunk* T, int boards, cudaStream_t stream, const int* boards_dev, const __half* x_in) {
     TrunkArgs a = T->args;
+    if (x_in != nullptr) a.x_in = x_in;
     a.M = boards * 64;
     a.boards_dev = boards_dev;
     // one board per CTA while that still fits the GPU in one wave (twice the SMs on a small batch), else two

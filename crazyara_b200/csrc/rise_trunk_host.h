@@ -39,7 +39,8 @@ struct RiseTrunk {
 // x_in: [boards_cap, 8, 8, 256] fp16 (stem output); out: [boards*64, 256] fp16 (may alias x_in: every CTA reads its
 // own rows before it writes them)
 int rise_trunk_init(RiseTrunk* T, const std::vector<TrunkBlockHost>& blocks, const __half* x_in, int boards_cap, __half* out);
-int rise_trunk_launch(const RiseTrunk* T, int boards, cudaStream_t stream, const int* boards_dev = nullptr);
+// x_in (optional): another stem-output buffer than the one given to rise_trunk_init (a second input / output set)
+int rise_trunk_launch(const RiseTrunk* T, int boards, cudaStream_t stream, const int* boards_dev = nullptr, const __half* x_in = nullptr);
 void rise_trunk_destroy(RiseTrunk* T);
 
 }  // namespace ara

@@ -733,6 +733,9 @@ int Search::enqueue_slot_tree_ops(int slot, bool with_update) {
     }
     expand_kernel<<<n_trees * B, 32, 0, stream_>>>(trees, sp, B, net_ ? net_->io_in_h[slot] : nullptr, net_ ? net_->cin_pad : 0,
                                                     net_ ? net_->precision : 0);
+    // the stem convolution of the new batch right here, on the tree stream (which has the slack): the network stream's
+    // chain starts at the tower
+    if (net_ && net_->stem_splittable() && net_->stem_device(n_trees * B, stream_, d_count_slot_[slot], slot)) return -1;
     return 0;
 }
 
@@ -761,6 +764,7 @@ int Search::enqueue_slot(int slot, bool with_update) {
     }
     if (profile) prof_event();
     launches += (n_trees == 1 ? 2 : 3) + (with_update ? 2 : 0);
+    if (net_ && net_->stem_splittable()) ++net_->launches;  // (the stem ran with the tree kernels, possibly from their graph)
     ARA_CUDA_OK(cudaEventRecord(ev_sel_[slot], stream_));
     ARA_CUDA_OK(cudaStreamWaitEvent(net_stream_, ev_sel_[slot], 0));
     if (profile) {
@@ -768,7 +772,7 @@ int Search::enqueue_slot(int slot, bool with_update) {
         ARA_CUDA_OK(cudaEventRecord(e, net_stream_));
     }
     if (net_) {
-        if (net_->forward_device(n_trees * B, net_stream_, d_count_slot_[slot], slot)) return -1;
+        if (net_->forward_device(n_trees * B, net_stream_, d_count_slot_[slot], slot, net_->stem_splittable())) return -1;
     } else {
         fake_eval_kernel<<<n_trees * B, 128, 0, net_stream_>>>(d_trees_slot_[slot], n_trees, B, d_values_slot_[slot],
                                                                d_probs_slot_[slot], n_labels_);

@@ -126,8 +126,8 @@ def test_uci_go_infinite_and_stop_on_the_device():
     e.send("setoption name UCI_Variant value crazyhouse")
     e.send("setoption name Batch_Size value 16")
     e.send("position startpos moves e2e4")
-    e.send("go nodes 200")                                # (creates the device context and the search handle: seconds on a cold box)
-    e.read_until("bestmove", timeout=120)
+    e.send("go movetime 100")                             # (creates the device context and the handle for time-limited searches --
+    e.read_until("bestmove", timeout=120)                 #  gigabytes of node pools: seconds on a cold box -- ahead of the timed part)
     e.lines.clear()
     e.send("go infinite")
     time.sleep(0.5)

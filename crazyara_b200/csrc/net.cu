@@ -443,7 +443,12 @@ int Net::enqueue(int n, cudaStream_t s, bool from_f32, const int* cnt, int io, b
         if (conv_layer_launch(io ? &stem_conv2 : &stem_conv, n, s, cnt)) return -1;
         ++launches;
     }
-    if (rise_trunk_launch(&trunk_, n, s, cnt, (io == 1 && d_x0_alt != nullptr) ? d_x0_alt : nullptr)) return -1;
+    {   // two input / output sets = a search with Threads = 2: the tower is the first kernel of this stream's chain and
+        // must not sit on its SMs waiting for the tree stream's event (see PdlSuspend); the small kernels behind it keep
+        // their programmatic launches (the tower triggers them at its last block)
+        PdlSuspend no_pdl(io_in_h[1] != nullptr);
+        if (rise_trunk_launch(&trunk_, n, s, cnt, (io == 1 && d_x0_alt != nullptr) ? d_x0_alt : nullptr)) return -1;
+    }
     ++launches;
     __half* xfinal = d_x[1];
     ValueHeadW vw{vh_wv, vh_bv, vh_w1t, vh_b1, vh_w2, vh_b2, vh_wdl_w, vh_wdl_b, vh_plys_w, vh_plys_b, hdr.wdl_mode};
@@ -470,7 +475,7 @@ int Net::forward_device(int n, cudaStream_t s, const int* cnt, int io, bool stem
     if (io != 0 && (io != 1 || io_in_h[1] == nullptr)) return set_error("forward: input/output set %d not enabled", io);
     // two input / output sets = a search with Threads = 2: this forward runs on the network stream beside the other
     // thread's tree kernels (see PdlSuspend)
-    PdlSuspend no_pdl(io_in_h[1] != nullptr);
+    PdlSuspend no_pdl(io_in_h[1] != nullptr && (precision != 0 || !stem_done));  // (not split: everything plain, as before)
     if (!use_graph) return enqueue(n, s, false, cnt, io, stem_done);
     {   // inside somebody else's capture (the search's iteration graph) the kernels go in directly
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;

@@ -123,7 +123,6 @@ __global__ void __launch_bounds__(kRtcThreads, 1) rise_trunk_c_kernel(const __gr
     const uint32_t tmem_base = *tmem_slot;
     cluster_sync_all();  // the partner's barriers exist before anything arrives on them
     pdl_wait();
-    pdl_launch_dependents();
 
     if (warp == 0 || (warp >= kRttComputeWarps + 2 && warp < kRtcExchangeWarp)) {
         // ---------------------------------------------------------------- producers: unit u of this CTA's stream: producer u % 3
@@ -243,6 +242,9 @@ __global__ void __launch_bounds__(kRtcThreads, 1) rise_trunk_c_kernel(const __gr
             for (int i = P > kTrunkCLag ? P - kTrunkCLag : 0; i < P; ++i) mma2(i);
             if (lane == 0) umma_commit_mc(blk_done, 3);
             __syncwarp();
+            // the kernels behind this one may be scheduled now (programmatic dependent launch): triggered late -- by this
+            // one thread, at the last block -- so that their thread blocks do not sit on SMs while the tower still runs
+            if (lane == 0 && b == n_blocks - 1) pdl_launch_dependents();
         }
         RT_PROF(0);
         RT_PROF_FLUSH(0);

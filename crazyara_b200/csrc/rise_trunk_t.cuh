@@ -171,7 +171,6 @@ __global__ void __launch_bounds__(kRttThreads, 1) rise_trunk_t_kernel(const __gr
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();
-    pdl_launch_dependents();
 
     if (warp == 0 || warp >= kRttComputeWarps + 2) {
         // ---------------------------------------------------------------- producers: unit u belongs to producer u % 3
@@ -259,6 +258,9 @@ __global__ void __launch_bounds__(kRttThreads, 1) rise_trunk_t_kernel(const __gr
             for (int i = P > kTrunkTLag ? P - kTrunkTLag : 0; i < P; ++i) mma2(i);
             if (lane == 0) umma_commit(d2_full);
             __syncwarp();
+            // the kernels behind this one may be scheduled now (programmatic dependent launch): triggered late -- by this
+            // one thread, at the last block -- so that their thread blocks do not sit on SMs while the tower still runs
+            if (lane == 0 && b == n_blocks - 1) pdl_launch_dependents();
         }
         RT_PROF(0);
         RT_PROF_FLUSH(0);

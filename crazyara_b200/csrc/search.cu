@@ -275,6 +275,29 @@ __global__ void __launch_bounds__(32) scatter_prepare_kernel(const TreeDev* tree
     prepare_item(t, sp, ws, item);
 }
 
+// The whole update step of an iteration in ONE launch: the first n_trees warps run the value backups (one per tree, the
+// long pole: scheduled first), the others scatter + prepare.  Backups read nothing the scatter / prepare steps write and
+// write nothing they read (backup_results), so they need no order between them -- and no second stream with its fork /
+// join events either.
+__global__ void __launch_bounds__(32) update_kernel(const TreeDev* trees, SearchParams sp, int n_trees, int batch, int items,
+                                                    const float* values, const float* probs, int n_labels) {
+    __shared__ WarpScratch ws;
+    if (static_cast<int>(blockIdx.x) < n_trees) {
+        backup_results(trees[blockIdx.x], sp, values);
+        return;
+    }
+    const int blk = static_cast<int>(blockIdx.x) - n_trees;
+    const int tree = blk / items, item = blk - tree * items;
+    const TreeDev t = trees[tree];
+    if (t.st->error) return;
+    if (item < batch) {
+        if (item >= t.bs->n_new) return;
+        scatter_pending(t, sp, ws, item, values, probs, n_labels);
+        __syncwarp();
+    }
+    prepare_item(t, sp, ws, item);
+}
+
 __global__ void __launch_bounds__(32) result_kernel(const TreeDev* trees, SearchParams sp, SearchResult* out) {
     const TreeDev t = trees[blockIdx.x];
     if (threadIdx.x == 0) collect_result(t, sp, &out[blockIdx.x]);
@@ -697,12 +720,7 @@ int Search::enqueue_iteration(bool with_events) {
     if (with_events) prof_event();
     // the value backups (one warp per tree, a latency chain) run beside scatter -> prepare: neither reads what the
     // other writes (backup_results); a second branch of the iteration graph
-    ARA_CUDA_OK(cudaEventRecord(ev_fork_, stream_));
-    ARA_CUDA_OK(cudaStreamWaitEvent(side_stream_, ev_fork_, 0));
-    backup_kernel<<<n_trees, 32, 0, side_stream_>>>(d_trees_, sp, 0, values);
-    ARA_CUDA_OK(cudaEventRecord(ev_join_, side_stream_));
-    scatter_prepare_kernel<<<n_trees * 4 * B, 32, 0, stream_>>>(d_trees_, sp, B, 4 * B, values, probs, n_labels_);
-    ARA_CUDA_OK(cudaStreamWaitEvent(stream_, ev_join_, 0));
+    update_kernel<<<n_trees + n_trees * 4 * B, 32, 0, stream_>>>(d_trees_, sp, n_trees, B, 4 * B, values, probs, n_labels_);
     if (with_events) prof_event();
     return 0;
 }
@@ -718,12 +736,7 @@ int Search::enqueue_slot_tree_ops(int slot, bool with_update) {
     const float* values = net_ ? net_->io_value[slot] : d_values_slot_[slot];
     const float* probs = net_ ? net_->io_prob[slot] : d_probs_slot_[slot];
     if (with_update) {
-        ARA_CUDA_OK(cudaEventRecord(ev_fork_, stream_));
-        ARA_CUDA_OK(cudaStreamWaitEvent(side_stream_, ev_fork_, 0));
-        backup_kernel<<<n_trees, 32, 0, side_stream_>>>(trees, sp, 0, values);
-        ARA_CUDA_OK(cudaEventRecord(ev_join_, side_stream_));
-        scatter_prepare_kernel<<<n_trees * 4 * B, 32, 0, stream_>>>(trees, sp, B, 4 * B, values, probs, n_labels_);
-        ARA_CUDA_OK(cudaStreamWaitEvent(stream_, ev_join_, 0));
+        update_kernel<<<n_trees + n_trees * 4 * B, 32, 0, stream_>>>(trees, sp, n_trees, B, 4 * B, values, probs, n_labels_);
     }
     if (n_trees == 1) {  // (one tree: its rows start at 0, the select kernel itself leaves the count)
         launch_select(trees, d_count_slot_[slot]);
@@ -763,7 +776,7 @@ int Search::enqueue_slot(int slot, bool with_update) {
         if (enqueue_slot_tree_ops(slot, with_update)) return -1;
     }
     if (profile) prof_event();
-    launches += (n_trees == 1 ? 2 : 3) + (with_update ? 2 : 0);
+    launches += (n_trees == 1 ? 2 : 3) + (with_update ? 1 : 0);
     if (net_ && net_->stem_splittable()) ++net_->launches;  // (the stem ran with the tree kernels, possibly from their graph)
     ARA_CUDA_OK(cudaEventRecord(ev_sel_[slot], stream_));
     ARA_CUDA_OK(cudaStreamWaitEvent(net_stream_, ev_sel_[slot], 0));
@@ -803,7 +816,7 @@ int Search::iterate2(int cycles) {
 
 int Search::iterate(int count) {
     if (threads_ == 2) return iterate2((count + 1) / 2);
-    const int search_kernels = 4 + (n_trees > 1 ? 1 : 0) + (net_ ? 0 : 1);
+    const int search_kernels = 3 + (n_trees > 1 ? 1 : 0) + (net_ ? 0 : 1);
     const bool graphed = use_iter_graph_ && !profile;
     for (int it = 0; it < count; ++it) {
         if (graphed && iter_graph_ != nullptr) {

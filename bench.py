@@ -513,7 +513,7 @@ def main():
         # achieved = the FLOPs of the leaves the search evaluated (not of the padded rows of its forwards) / forward time
         conv_tflops = evals * flops_pos / (net_ms * 1e-3) / 1e12 if net_ms > 0 else 0.0
         traffic = None  # DRAM bytes per launch of the dominant tensor kernel, from the committed `ncu --set full` capture
-        for prof_file in ("r02_ncu_rise_trunk_kernel.json", "r01_ncu_rise_trunk_kernel.json"):
+        for prof_file in ("r02_ncu_trunk_pair.json", "r02_ncu_trunk.json", "r01_ncu_rise_trunk_kernel.json"):
             try:
                 k = json.load(open(os.path.join(ROOT, "profiles", prof_file)))["kernels"][0]
                 scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
@@ -540,10 +540,11 @@ def main():
             "clocks": sampler.summary(),
             "roofline": {"bound": "tensor", "achieved": conv_tflops, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": conv_tflops / peak_tf if peak_tf else None, "traffic": traffic,
-                         "traffic_note": "rise_trunk_kernel, one launch of 64 positions, dram__bytes_read+write "
-                                         "(profiles/*_ncu_rise_trunk_kernel.json; cold L2: the weights + the input tile)",
-                         "kernel": f"{net_name} conv stack per forward of {batch} positions: rise_trunk_kernel (all bottleneck "
-                                   "blocks, tcgen05 TS/SS MMAs, one launch) + stem/policy conv_gemm_kernel + head kernels",
+                         "traffic_note": "rise_trunk_c_kernel, one launch of 64 positions, dram__bytes_read+write "
+                                         "(profiles/r02_ncu_trunk_pair.json; cold L2: the weights + the input tile)",
+                         "kernel": f"{net_name} conv stack per forward of {batch} positions: rise_trunk_c_kernel (all bottleneck "
+                                   "blocks on CTA pairs, tcgen05 SS MMAs with the channels in M, one launch) + stem/policy "
+                                   "conv_gemm_kernel + head kernels",
                          "achieved_from": "evaluated leaves x FLOP per position / device time of the forwards",
                          "flop_per_position": flops_pos, "peak_source": peak_src},
         }

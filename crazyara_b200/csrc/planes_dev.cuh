@@ -184,13 +184,40 @@ ARA_HD void for_each_plane(const PlaneCtx& p, int version, Sink& sink) {
 }
 
 // ---- sinks ------------------------------------------------------------------------------------------------------
-struct NchwF32Sink {  // [C, 8, 8] fp32; all lanes take part, 2 squares each
+struct NchwF32Sink {  // [C, 8, 8] fp32
     float* out;
     int c = 0;
+#if defined(__CUDA_ARCH__)
+    // Two planes per store instruction: lanes 0..15 write the pending plane, lanes 16..31 the current one, four squares
+    // (16 bytes) each -- 512 contiguous bytes per warp instruction instead of 128, a quarter of the store instructions.
+    uint64_t pm = 0;
+    float pv = 0.0f;
+    __device__ __forceinline__ void emit(uint64_t mask, float v, int plane, int quarter) {
+        const unsigned bits = static_cast<unsigned>(mask >> (4 * quarter)) & 15u;
+        const float4 o = make_float4((bits & 1u) ? v : 0.0f, (bits & 2u) ? v : 0.0f, (bits & 4u) ? v : 0.0f, (bits & 8u) ? v : 0.0f);
+        __stcs(reinterpret_cast<float4*>(out + plane * 64) + quarter, o);  // (streamed: nothing reads the planes back soon)
+    }
+    __device__ __forceinline__ void operator()(uint64_t mask, float v) {
+        if (c & 1) {
+            const int lane = threadIdx.x & 31;
+            if (lane < 16) emit(pm, pv, c - 1, lane);
+            else emit(mask, v, c, lane - 16);
+        } else {
+            pm = mask, pv = v;
+        }
+        ++c;
+    }
+    __device__ __forceinline__ void flush() {  // an odd number of planes: the last one is still pending
+        const int lane = threadIdx.x & 31;
+        if ((c & 1) && lane < 16) emit(pm, pv, c - 1, lane);
+    }
+#else
     ARA_HD void operator()(uint64_t mask, float v) {
         for (int sq = ARA_LANE; sq < 64; sq += ARA_WARP_N) out[c * 64 + sq] = ((mask >> sq) & 1) ? v : 0.0f;
         ++c;
     }
+    ARA_HD void flush() {}
+#endif
 };
 
 struct LaneCaptureSink {  // keeps the descriptors of channels lane, lane+32, lane+64
@@ -211,28 +238,46 @@ ARA_HD void encode_planes_nchw_f32(const Board& b, int mode, int version, bool n
     const PlaneCtx p = make_plane_ctx(b, mode, normalize);
     NchwF32Sink sink{out};
     for_each_plane(p, version, sink);
+    sink.flush();
 }
 
 #if defined(__CUDACC__)
 // [64, cpad] fp16 rows (cpad = 64 or 128); channels >= C are written as zero.  Device only, warp-collective.
 __device__ __forceinline__ void encode_planes_nhwc_f16(const Board& b, int mode, int version, __half* out, int cpad) {
+    // (callers run at most four warps per thread block: encode_planes_f16_kernel, expand_kernel)
+    __shared__ uint64_t s_mask[4][96];
+    __shared__ uint16_t s_val[4][96];
     const PlaneCtx p = make_plane_ctx(b, mode, true);
     LaneCaptureSink sink;
     sink.lane = threadIdx.x & 31;
     for_each_plane(p, version, sink);
-    const int lane = sink.lane;
-    const __half h0 = __float2half_rn(sink.v0), h1 = __float2half_rn(sink.v1), h2 = __float2half_rn(sink.v2);
-    const __half z = __float2half_rn(0.0f);
-#pragma unroll 4
-    for (int sq = 0; sq < 64; ++sq) {
-        __half* row = out + sq * cpad;
-        row[lane] = ((sink.m0 >> sq) & 1) ? h0 : z;
-        row[lane + 32] = ((sink.m1 >> sq) & 1) ? h1 : z;
-        if (cpad > 64) {
-            row[lane + 64] = ((sink.m2 >> sq) & 1) ? h2 : z;
-            row[lane + 96] = z;
-        }
+    const int lane = sink.lane, w = (threadIdx.x >> 5) & 3;
+    // every lane has computed the descriptors (square mask, value) of three channels; a row of the output is written in
+    // 16-byte pieces of eight channels, so the descriptors change hands through shared memory once per board ...
+    s_mask[w][lane] = sink.m0, s_mask[w][lane + 32] = sink.m1, s_mask[w][lane + 64] = sink.m2;
+    s_val[w][lane] = __half_as_ushort(__float2half_rn(sink.v0));
+    s_val[w][lane + 32] = __half_as_ushort(__float2half_rn(sink.v1));
+    s_val[w][lane + 64] = __half_as_ushort(__float2half_rn(sink.v2));
+    __syncwarp();
+    const int chunks = cpad >> 3;                                // pieces per row: 8 (cpad 64) or 16 (cpad 128)
+    const int j = lane % chunks, s0 = lane / chunks, step = 32 / chunks;
+    uint64_t m[8];
+    uint32_t v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int ch = 8 * j + i;
+        m[i] = ch < 96 ? s_mask[w][ch] : 0ull;
+        v[i] = ch < 96 ? s_val[w][ch] : 0u;
     }
+    // ... and every store instruction of the warp writes 512 contiguous bytes (4 or 2 whole rows)
+    for (int sq = s0; sq < 64; sq += step) {
+        uint32_t h[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) h[i] = ((m[i] >> sq) & 1ull) ? v[i] : 0u;
+        const uint4 o = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+        *reinterpret_cast<uint4*>(out + sq * cpad + 8 * j) = o;
+    }
+    __syncwarp();
 }
 // Precision float32: the same rows with every channel as the fp16 pair hi | hi | lo (conv_gemm.cuh), [64, 3 * cpad]
 __device__ __forceinline__ void encode_planes_nhwc_split(const Board& b, int mode, int version, __half* out, int cpad) {

@@ -545,9 +545,10 @@ int Search::init(Net* net, const SearchParams& params, int device, int trees, in
         if (prop.major < 10) return set_error("ara_search_create: device %d is not sm_100 (B200)", device_);
     }
     // few trees cannot fill 148 SMs with one warp each: their playouts overlap inside a CTA instead (search_wave.cuh)
-    // (narrow mini-batches -- self-play's Batch_Size 8 -- leave nothing to overlap: a playout may only start while the
-    // batch cannot end before its turn)
-    wave_ = !eps_ && n_trees <= 32 && sp.batch_size >= 16;
+    // (measured: up to 16 trees it pays from Batch_Size 8 on -- self-play with 8 / 16 games per GPU: +14 % / +8 % games per
+    // hour; with 32 trees of narrow mini-batches the one-warp kernel is faster, a playout may only start while the batch
+    // cannot end before its turn)
+    wave_ = !eps_ && ((n_trees <= 16 && sp.batch_size >= 8) || (n_trees <= 32 && sp.batch_size >= 16));
     if (const char* e = getenv("ARA_WAVE")) wave_ = !eps_ && atoi(e) != 0;
     if (wave_)
         ARA_CUDA_OK(cudaFuncSetAttribute(select_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kWaveSmemBytes)));

@@ -1,11 +1,16 @@
 // GPU MCTS engine: kernels around search_dev.cuh, the host-side driver (MCTSAgent::evaluate_board_state /
 // SearchThread::thread_iteration of the reference) and the C-ABI.
 //
-// Per search iteration three things are enqueued on one stream, with no host round trip in between:
-//   select_kernel  (one warp per tree: create_mini_batch -> planes written straight into the network's NHWC input)
-//   network        (tcgen05 conv stack, CUDA graph; or the hash-derived fake backend for search-parity tests)
-//   apply_kernel   (scatter priors/values into the new nodes, backups, collision reverts)
-// The host only looks at the per-tree `done` flag once per chunk of iterations.
+// Per search iteration these are enqueued, with no host round trip in between:
+//   select   create_mini_batch: one warp per tree (select_kernel), or a wavefront of 12 warps per tree when there are few
+//            trees (select_wave_kernel, search_wave.cuh) -- sequential semantics either way
+//   (pack)   many trees: the new leaves' rows of the network batch; expand: move lists, edges, planes written straight into
+//            the network's NHWC input, one warp per new leaf
+//   network  tcgen05 conv stack (CUDA graph), or the hash-derived fake backend for search-parity tests
+//   update   scatter priors / values into the new nodes, prepare their next children, backups, collision reverts
+// Threads = 1: all on one stream.  Threads = 2: the two logical threads' tree kernels on one stream in the fixed schedule
+// of oracle/mcts.h, their forwards on a second stream (enqueue_slot).  The host only looks at the per-tree `done` flag
+// once per chunk of iterations.
 // This translation unit is compiled with -fmad=false: the PUCT / Q arithmetic must round exactly like the
 // reference's (and the oracle's) scalar C++ code.
 #include <atomic>

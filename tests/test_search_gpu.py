@@ -383,3 +383,49 @@ def test_gpu_wavefront_select_with_many_terminal_playouts(case, threads, monkeyp
     monkeypatch.setenv("ARA_WAVE", "0")
     rs = _gpu_search(vid, fen, False, [], st)[0]          # one warp per tree
     assert_same_search(ro, rs)
+
+
+def _random_gpu_case(seed):
+    """random position (legal random play, every variant) and settings; wide mini-batches so that the wavefront select
+    (Batch_Size >= 8 for one tree) has playouts in flight, one or two logical threads"""
+    rng = np.random.default_rng(1000 + seed)
+    variant, vid, mode = [("crazyhouse", 1, "crazyhouse"), ("chess", 0, "chess"), ("kingofthehill", 2, "lichess"),
+                          ("3check", 3, "lichess")][seed % 4]
+    pos = Position(None, variant, False)
+    played = []
+    for _ in range(int(rng.integers(0, 60))):
+        moves = pos.legal_uci()
+        if not moves or pos.terminal(len(moves)) != 4:
+            break
+        u = moves[int(rng.integers(0, len(moves)))]
+        nxt = pos.clone().push_uci(u)
+        nm = nxt.legal_uci()
+        if not nm or nxt.terminal(len(nm)) != 4:
+            continue
+        pos.push_uci(u)
+        played.append(u)
+    batch = int(rng.choice([8, 16, 32, 64, 100]))
+    threads = int(rng.choice([1, 2])) if 2 * batch < 256 else 1
+    extra = dict(threads=threads)
+    if rng.random() < 0.4:
+        extra["virtual_style"] = int(rng.choice([0, 1, 3]))
+    if rng.random() < 0.4:
+        extra["virtual_mix_threshold"] = int(rng.choice([3, 20, 1000]))
+    if rng.random() < 0.3:
+        extra["mcts_solver"] = 0
+    temp = float(rng.choice([1.0, 1.7, 1.7, 0.8]))
+    if rng.random() < 0.3:
+        extra.update(dirichlet_epsilon=0.25, dirichlet_alpha=float(rng.choice([0.2, 0.3, 1.0])), seed=int(rng.integers(1, 2**31 - 2)))
+    sims = int(rng.choice([300, 800, 1500]))
+    st = osr.default_settings(mode, batch_size=batch, simulations=sims, node_policy_temperature=temp, **extra)
+    return pos, vid, played, st, threads
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(32))
+def test_gpu_random_positions_and_settings_equal_oracle(seed):
+    pos, vid, played, st, threads = _random_gpu_case(seed)
+    S = osr.Search(st)
+    ro = S.run(pos, osr.fake_net(S.n_labels), with_keys=True, threads=threads)
+    rg = _gpu_search(vid, None, False, played, st)[0]
+    assert_same_search(ro, rg)
